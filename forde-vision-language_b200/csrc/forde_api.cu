@@ -1,0 +1,369 @@
+// C-ABI entry points for the tcgen05 GEMM family (see include/forde_b200.h).
+// Host side only: argument validation, TMA tensor-map construction (cached), launch configuration.
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <unordered_map>
+
+#include "../../include/forde_b200.h"
+#include "forde_gemm.cuh"
+#include "forde_host.h"
+
+namespace forde {
+
+thread_local char g_last_err[256] = {0};
+
+void record_cuda_error(const char* what, const char* msg) {
+  std::snprintf(g_last_err, sizeof(g_last_err), "%s: %s", what, msg);
+}
+
+int check_launch(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    record_cuda_error(what, cudaGetErrorString(e));
+    return FORDE_ECUDA;
+  }
+  return FORDE_OK;
+}
+
+int sm_count() {
+  static int cached[64] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 0;
+  if (cached[dev] == 0) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 0;
+    cached[dev] = n;
+  }
+  return cached[dev];
+}
+
+// ------------------------------------------------------------------ tensor maps
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess) {
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+  });
+  return fn;
+}
+
+struct TmapKey {
+  const void* ptr;
+  uint64_t inner, outer, ld;
+  uint32_t box_inner, box_outer;
+  int dev;
+  bool operator==(const TmapKey& o) const {
+    return ptr == o.ptr && inner == o.inner && outer == o.outer && ld == o.ld && box_inner == o.box_inner &&
+           box_outer == o.box_outer && dev == o.dev;
+  }
+};
+struct TmapKeyHash {
+  size_t operator()(const TmapKey& k) const {
+    size_t h = reinterpret_cast<size_t>(k.ptr);
+    auto mix = [&h](uint64_t v) { h ^= v + 0x9e3779b97f4a7c15ull + (h << 6) + (h >> 2); };
+    mix(k.inner); mix(k.outer); mix(k.ld); mix(k.box_inner); mix(k.box_outer); mix(static_cast<uint64_t>(k.dev));
+    return h;
+  }
+};
+
+// 2-D row-major bf16 tensor [outer][inner] with row pitch `ld` elements, 128B swizzle, zero OOB fill.
+// The encoded map depends only on the key, so it is cached (one-time descriptor cache, mutex guarded).
+int make_tmap_bf16(CUtensorMap* out, const void* ptr, uint64_t inner, uint64_t outer, uint64_t ld,
+                   uint32_t box_inner, uint32_t box_outer) {
+  static std::mutex mu;
+  static std::unordered_map<TmapKey, CUtensorMap, TmapKeyHash> cache;
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) != 0 || (ld % 8) != 0) return FORDE_EALIGN;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  TmapKey key{ptr, inner, outer, ld, box_inner, box_outer, dev};
+  {
+    std::lock_guard<std::mutex> lock(mu);
+    auto it = cache.find(key);
+    if (it != cache.end()) {
+      std::memcpy(out, &it->second, sizeof(CUtensorMap));
+      return FORDE_OK;
+    }
+  }
+  EncodeTiledFn enc = get_encode_fn();
+  if (enc == nullptr) {
+    record_cuda_error("cuTensorMapEncodeTiled", "driver entry point not available");
+    return FORDE_ECUDA;
+  }
+  cuuint64_t dims[2] = {inner, outer};
+  cuuint64_t strides[1] = {ld * 2};
+  cuuint32_t box[2] = {box_inner, box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUtensorMap m;
+  CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    char buf[64];
+    std::snprintf(buf, sizeof(buf), "CUresult %d", static_cast<int>(r));
+    record_cuda_error("cuTensorMapEncodeTiled", buf);
+    return FORDE_ECUDA;
+  }
+  {
+    std::lock_guard<std::mutex> lock(mu);
+    if (cache.size() > 4096) cache.clear();
+    cache[key] = m;
+  }
+  std::memcpy(out, &m, sizeof(CUtensorMap));
+  return FORDE_OK;
+}
+
+// operand map: `rows` is the M (or N) extent, `k` the reduction extent.
+//   K-major : memory [rows][k]  -> dims {k, rows},  box {64, tile_rows}
+//   MN-major: memory [k][rows]  -> dims {rows, k},  box {64, 64}
+static int make_operand_map(CUtensorMap* out, const void* ptr, bool mn_major, long long ld, int rows, int k,
+                            int tile_rows) {
+  if (mn_major) return make_tmap_bf16(out, ptr, rows, k, ld, 64, BK);
+  return make_tmap_bf16(out, ptr, k, rows, ld, BK, tile_rows);
+}
+
+template <bool A_MN, bool B_MN, int EPI>
+static int launch_inst(const GemmParams& p, cudaStream_t stream) {
+  static std::once_flag once;
+  static cudaError_t attr_err = cudaSuccess;
+  constexpr int smem = gemm_smem_bytes(EPI);
+  // the attribute is per device function (per context); set once per process/device is enough for one GPU
+  // per process, which is the deployment model (one process per GPU).
+  std::call_once(once, [] {
+    attr_err = cudaFuncSetAttribute(forde_gemm_kernel<A_MN, B_MN, EPI>,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  });
+  if (attr_err != cudaSuccess) {
+    record_cuda_error("cudaFuncSetAttribute", cudaGetErrorString(attr_err));
+    return FORDE_ECUDA;
+  }
+  const int total = p.m_blocks * p.n_blocks * p.split_k;
+  int grid = sm_count();
+  if (grid <= 0) return FORDE_ENODEV;
+  if (total < grid) grid = total;
+  forde_gemm_kernel<A_MN, B_MN, EPI><<<grid, NUM_THREADS, smem, stream>>>(p);
+  return check_launch("forde_gemm_kernel");
+}
+
+template <int EPI>
+static int launch_epi(const GemmParams& p, bool a_mn, bool b_mn, cudaStream_t stream) {
+  if (a_mn) {
+    if (b_mn) return launch_inst<true, true, EPI>(p, stream);
+    return launch_inst<true, false, EPI>(p, stream);
+  }
+  if (b_mn) return launch_inst<false, true, EPI>(p, stream);
+  return launch_inst<false, false, EPI>(p, stream);
+}
+
+
+static int fill_common(GemmParams& p, const GemmArgs& g) {
+  if (g.A == nullptr || g.B == nullptr || g.M <= 0 || g.N <= 0 || g.K <= 0) return FORDE_EINVAL;
+  std::memset(&p, 0, sizeof(p));
+  int rc = make_operand_map(&p.tmA, g.A, g.a_mn, g.lda, g.M, g.K, BM);
+  if (rc != FORDE_OK) return rc;
+  rc = make_operand_map(&p.tmB, g.B, g.b_mn, g.ldb, g.N, g.K, BN);
+  if (rc != FORDE_OK) return rc;
+  p.M = g.M; p.N = g.N; p.K = g.K;
+  p.m_blocks = (g.M + BM - 1) / BM;
+  p.n_blocks = (g.N + BN - 1) / BN;
+  p.k_blocks = (g.K + BK - 1) / BK;
+  p.split_k = 1;
+  p.kb_per_split = p.k_blocks;
+  p.raster_m_fast = g.raster_m_fast ? 1 : 0;
+  p.hintA = g.hintA; p.hintB = g.hintB;
+  p.scale = 1.f;
+  p.gate_generalist = 1.0f;
+  p.gate_specialist = 0.1f;
+  return FORDE_OK;
+}
+
+static void choose_split_k(GemmParams& p) {
+  const int tiles = p.m_blocks * p.n_blocks;
+  const int sms = sm_count();
+  int split = sms / tiles;
+  const int max_split = p.k_blocks / 8 > 0 ? p.k_blocks / 8 : 1;  // at least 8 k-blocks per split
+  if (split > max_split) split = max_split;
+  if (split < 1) split = 1;
+  p.kb_per_split = (p.k_blocks + split - 1) / split;
+  p.split_k = (p.k_blocks + p.kb_per_split - 1) / p.kb_per_split;
+}
+
+int gemm_store_bf16(cudaStream_t stream, const GemmArgs& g, void* D, long long ldd, const float* bias_col) {
+  GemmParams p;
+  int rc = fill_common(p, g);
+  if (rc != FORDE_OK) return rc;
+  if (D == nullptr) return FORDE_EINVAL;
+  rc = make_tmap_bf16(&p.tmC0, D, g.N, g.M, ldd, CHUNK, 32);
+  if (rc != FORDE_OK) return rc;
+  p.bias_col = bias_col;
+  return launch_epi<EPI_STORE>(p, g.a_mn, g.b_mn, stream);
+}
+
+int gemm_f32(cudaStream_t stream, const GemmArgs& g, float* D, long long ldd, const float* row_scale,
+             const float* col_scale, float scale, bool accumulate) {
+  GemmParams p;
+  int rc = fill_common(p, g);
+  if (rc != FORDE_OK) return rc;
+  if (D == nullptr) return FORDE_EINVAL;
+  p.out_f32 = D; p.ldc = ldd; p.row_scale = row_scale; p.col_scale = col_scale; p.scale = scale;
+  p.atomic_out = accumulate ? 1 : 0;
+  if (accumulate) choose_split_k(p);
+  return launch_epi<EPI_F32>(p, g.a_mn, g.b_mn, stream);
+}
+
+}  // namespace forde
+
+using namespace forde;
+
+extern "C" {
+
+int forde_version(void) { return 100; }
+
+const char* forde_error_string(int code) {
+  switch (code) {
+    case FORDE_OK: return "ok";
+    case FORDE_EINVAL: return "invalid argument (null pointer or non-positive dimension)";
+    case FORDE_EALIGN: return "alignment violation (bf16 matrices need 16-byte bases and pitches that are multiples of 8)";
+    case FORDE_ECUDA: return "CUDA error (see forde_last_cuda_error)";
+    case FORDE_ENODEV: return "no CUDA device";
+    default: return "unknown error";
+  }
+}
+
+const char* forde_last_cuda_error(void) { return g_last_err; }
+
+int forde_sm_count(void) { return sm_count(); }
+
+int forde_sl_num_partials(int M) { return M <= 0 ? 0 : (M + BN - 1) / BN; }
+
+int forde_gemm_bf16(void* stream, const void* A, int a_mn_major, long long lda, const void* B, int b_mn_major,
+                    long long ldb, void* D, long long ldd, const float* bias_col, int M, int N, int K) {
+  GemmArgs g{A, a_mn_major != 0, lda, B, b_mn_major != 0, ldb, M, N, K, false, kEvictNormal, kEvictNormal};
+  return gemm_store_bf16(static_cast<cudaStream_t>(stream), g, D, ldd, bias_col);
+}
+
+int forde_gemm_f32(void* stream, const void* A, int a_mn_major, long long lda, const void* B, int b_mn_major,
+                   long long ldb, float* D, long long ldd, const float* row_scale, const float* col_scale,
+                   float scale, int accumulate, int M, int N, int K) {
+  GemmArgs g{A, a_mn_major != 0, lda, B, b_mn_major != 0, ldb, M, N, K, false, kEvictNormal, kEvictNormal};
+  return gemm_f32(static_cast<cudaStream_t>(stream), g, D, ldd, row_scale, col_scale, scale, accumulate != 0);
+}
+
+// zT[H][M] = (x . w_up + b)^T :  A = w_up [d][H] as (m = neuron, k = d) -> MN-major ; B = x [M][d] -> K-major
+int forde_sl_up_fwd(void* stream, const void* x, const void* w_up, const float* b_up, const int8_t* assign,
+                    void* zT, void* hT, float* act_partials, int M, int d, int H, long long ldz) {
+  if (assign == nullptr || zT == nullptr || hT == nullptr || ldz < M) return FORDE_EINVAL;
+  GemmArgs g{w_up, true, H, x, false, d, H, M, d, /*raster_m_fast=*/true, kEvictLast, kEvictLast};
+  GemmParams p;
+  int rc = fill_common(p, g);
+  if (rc != FORDE_OK) return rc;
+  rc = make_tmap_bf16(&p.tmC0, zT, M, H, ldz, CHUNK, 32);
+  if (rc != FORDE_OK) return rc;
+  rc = make_tmap_bf16(&p.tmC1, hT, M, H, ldz, CHUNK, 32);
+  if (rc != FORDE_OK) return rc;
+  p.bias_row = b_up;
+  p.assign = assign;
+  p.partials = act_partials;
+  return launch_epi<EPI_UP_FWD>(p, true, false, static_cast<cudaStream_t>(stream));
+}
+
+// y[M][d] = h . w_down + b :  A = hT [H][M] as (m = sample, k = neuron) -> MN-major ; B = w_down [H][d] -> MN-major
+int forde_sl_down_fwd(void* stream, const void* hT, const void* w_down, const float* b_down, void* y, int M,
+                      int d, int H, long long ldz) {
+  if (ldz < M) return FORDE_EINVAL;
+  GemmArgs g{hT, true, ldz, w_down, true, d, M, d, H, /*raster_m_fast=*/false, kEvictFirst, kEvictLast};
+  return gemm_store_bf16(static_cast<cudaStream_t>(stream), g, y, d, b_down);
+}
+
+int forde_sl_fwd(void* stream, const void* x, const void* w_up, const float* b_up, const void* w_down,
+                 const float* b_down, const int8_t* assign, void* zT, void* hT, void* y, float* act_partials,
+                 int M, int d, int H, long long ldz) {
+  int rc = forde_sl_up_fwd(stream, x, w_up, b_up, assign, zT, hT, act_partials, M, d, H, ldz);
+  if (rc != FORDE_OK) return rc;
+  return forde_sl_down_fwd(stream, hT, w_down, b_down, y, M, d, H, ldz);
+}
+
+// dzT[H][M] = (dy . w_down^T)^T * (F'(z) + gate) : A = w_down [H][d] (m = neuron, k = d) K-major ; B = dy [M][d] K-major
+int forde_sl_dz_bwd(void* stream, const void* dy, const void* w_down, const void* zT, const int8_t* assign,
+                    void* dzT, float* grad_partials, int M, int d, int H, long long ldz) {
+  if (assign == nullptr || zT == nullptr || dzT == nullptr || ldz < M) return FORDE_EINVAL;
+  GemmArgs g{w_down, false, d, dy, false, d, H, M, d, /*raster_m_fast=*/true, kEvictLast, kEvictLast};
+  GemmParams p;
+  int rc = fill_common(p, g);
+  if (rc != FORDE_OK) return rc;
+  rc = make_tmap_bf16(&p.tmC0, dzT, M, H, ldz, CHUNK, 32);
+  if (rc != FORDE_OK) return rc;
+  rc = make_tmap_bf16(&p.tmZ, zT, M, H, ldz, CHUNK, 32);
+  if (rc != FORDE_OK) return rc;
+  p.assign = assign;
+  p.partials = grad_partials;
+  return launch_epi<EPI_DZ_BWD>(p, false, false, static_cast<cudaStream_t>(stream));
+}
+
+// dx[M][d] = dz . w_up^T : A = dzT [H][M] (m = sample, k = neuron) MN-major ; B = w_up [d][H] (n = d, k = neuron) K-major
+int forde_sl_dx_bwd(void* stream, const void* dzT, const void* w_up, void* dx, int M, int d, int H,
+                    long long ldz) {
+  if (ldz < M) return FORDE_EINVAL;
+  GemmArgs g{dzT, true, ldz, w_up, false, H, M, d, H, /*raster_m_fast=*/false, kEvictFirst, kEvictLast};
+  return gemm_store_bf16(static_cast<cudaStream_t>(stream), g, dx, d, nullptr);
+}
+
+// dw_up[d][H] += x^T . dz : A = x [M][d] (m = d, k = sample) MN-major ; B = dzT [H][M] (n = neuron, k = sample) K-major
+int forde_sl_dw_up(void* stream, const void* x, const void* dzT, float* dw_up, int M, int d, int H,
+                   long long ldz) {
+  if (ldz < M) return FORDE_EINVAL;
+  GemmArgs g{x, true, d, dzT, false, ldz, d, H, M, /*raster_m_fast=*/true, kEvictNormal, kEvictNormal};
+  return gemm_f32(static_cast<cudaStream_t>(stream), g, dw_up, H, nullptr, nullptr, 1.f, true);
+}
+
+// dw_down[H][d] += h^T . dy : A = hT [H][M] (m = neuron, k = sample) K-major ; B = dy [M][d] (n = d, k = sample) MN-major
+int forde_sl_dw_down(void* stream, const void* hT, const void* dy, float* dw_down, int M, int d, int H,
+                     long long ldz) {
+  if (ldz < M) return FORDE_EINVAL;
+  GemmArgs g{hT, false, ldz, dy, true, d, H, d, M, /*raster_m_fast=*/false, kEvictNormal, kEvictNormal};
+  return gemm_f32(static_cast<cudaStream_t>(stream), g, dw_down, d, nullptr, nullptr, 1.f, true);
+}
+
+int forde_sl_bwd(void* stream, const void* x, const void* dy, const void* w_up, const void* w_down,
+                 const void* zT, const void* hT, const int8_t* assign, void* dzT, void* dx, float* dw_up,
+                 float* db_up, float* dw_down, float* db_down, float* grad_partials, int M, int d, int H,
+                 long long ldz) {
+  int rc = forde_sl_dz_bwd(stream, dy, w_down, zT, assign, dzT, grad_partials, M, d, H, ldz);
+  if (rc != FORDE_OK) return rc;
+  if (dx != nullptr) {
+    rc = forde_sl_dx_bwd(stream, dzT, w_up, dx, M, d, H, ldz);
+    if (rc != FORDE_OK) return rc;
+  }
+  if (dw_up != nullptr) {
+    rc = forde_sl_dw_up(stream, x, dzT, dw_up, M, d, H, ldz);
+    if (rc != FORDE_OK) return rc;
+  }
+  if (dw_down != nullptr) {
+    rc = forde_sl_dw_down(stream, hT, dy, dw_down, M, d, H, ldz);
+    if (rc != FORDE_OK) return rc;
+  }
+  if (db_down != nullptr) {
+    rc = forde_colsum_bf16(stream, dy, d, db_down, M, d);
+    if (rc != FORDE_OK) return rc;
+  }
+  if (db_up != nullptr && grad_partials != nullptr) {
+    rc = forde_stats_finalize(stream, nullptr, grad_partials, forde_sl_num_partials(M), H, M, nullptr, nullptr,
+                              nullptr, nullptr, nullptr, db_up);
+    if (rc != FORDE_OK) return rc;
+  }
+  return FORDE_OK;
+}
+
+}  // extern "C"

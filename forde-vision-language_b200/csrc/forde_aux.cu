@@ -1,0 +1,357 @@
+// HBM-bound helper kernels of the FORDE hot path: sensing finalisation, bias-gradient column sums and the
+// row/column log-softmax side of the CLIP contrastive loss.  All are simple coalesced streaming kernels; the
+// heavy lifting (GEMMs + fused epilogues) lives in forde_gemm.cuh.
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+#include "../../include/forde_b200.h"
+#include "forde_host.h"
+
+namespace forde {
+
+// ------------------------------------------------------------------ sensing (sensing.py:5-69)
+// Hoyer sparsity of a length-n vector from its L1 norm and squared L2 norm, with the reference's guards:
+// returns 0 for the all-zero vector (sensing.py:22,30) and for n == 1 (sensing.py:25,32).  fp32 like the
+// reference (sensing.py:53-54).
+__device__ __forceinline__ float hoyer_from_norms(float l1, float l2sq, int n) {
+  if (n == 1) return 0.f;
+  const float l2 = sqrtf(l2sq);
+  if (l2 == 0.f) return 0.f;
+  const float sn = sqrtf(static_cast<float>(n));
+  return (sn - l1 / l2) / (sn - 1.f);
+}
+
+// stats row order (sensing.py:65-67): [grad_gini, grad_gdp, act_gini, act_gdp, act_variance]
+__device__ __forceinline__ void stats_from_sums(double a_abs, double a_sum, double a_sq, double g_abs, double g_sq,
+                                                int n, float* out5) {
+  const double inv_n = 1.0 / static_cast<double>(n);
+  const double mean = a_sum * inv_n;
+  double var = a_sq * inv_n - mean * mean;  // jnp.var, ddof = 0 (sensing.py:59)
+  if (var < 0.0) var = 0.0;
+  out5[0] = hoyer_from_norms(static_cast<float>(g_abs), static_cast<float>(g_sq), n);
+  out5[1] = static_cast<float>(g_abs * inv_n);
+  out5[2] = hoyer_from_norms(static_cast<float>(a_abs), static_cast<float>(a_sq), n);
+  out5[3] = static_cast<float>(a_abs * inv_n);
+  out5[4] = static_cast<float>(var);
+}
+
+__global__ void stats_finalize_kernel(const float* __restrict__ act_p, const float* __restrict__ grad_p, int P,
+                                      int H, int M, float* __restrict__ step_stats,
+                                      float* __restrict__ neuron_stats, float* __restrict__ moments,
+                                      int* sample_count, int* step_count, float* __restrict__ db_up) {
+  const int h = blockIdx.x * blockDim.x + threadIdx.x;
+  if (h == 0) {
+    if (sample_count != nullptr) *sample_count += M;
+    if (step_count != nullptr) *step_count += 1;
+  }
+  if (h >= H) return;
+  double a_abs = 0, a_sum = 0, a_sq = 0, g_abs = 0, g_sum = 0, g_sq = 0;
+  // fixed summation order over the partial blocks -> bit-reproducible statistics
+  for (int p = 0; p < P; ++p) {
+    const size_t base = static_cast<size_t>(p) * 3 * H + h;
+    if (act_p != nullptr) {
+      a_abs += act_p[base];
+      a_sum += act_p[base + H];
+      a_sq += act_p[base + 2 * static_cast<size_t>(H)];
+    }
+    if (grad_p != nullptr) {
+      g_abs += grad_p[base];
+      g_sum += grad_p[base + H];
+      g_sq += grad_p[base + 2 * static_cast<size_t>(H)];
+    }
+  }
+  if (db_up != nullptr) db_up[h] += static_cast<float>(g_sum);
+  float s[5];
+  stats_from_sums(a_abs, a_sum, a_sq, g_abs, g_sq, M, s);
+  if (step_stats != nullptr) {
+#pragma unroll
+    for (int k = 0; k < 5; ++k) step_stats[h * 5 + k] = s[k];
+  }
+  if (neuron_stats != nullptr) {
+#pragma unroll
+    for (int k = 0; k < 5; ++k) neuron_stats[h * 5 + k] += s[k];
+  }
+  if (moments != nullptr) {
+    moments[h * 5 + 0] += static_cast<float>(a_abs);
+    moments[h * 5 + 1] += static_cast<float>(a_sum);
+    moments[h * 5 + 2] += static_cast<float>(a_sq);
+    moments[h * 5 + 3] += static_cast<float>(g_abs);
+    moments[h * 5 + 4] += static_cast<float>(g_sq);
+  }
+}
+
+__global__ void stats_from_moments_kernel(const float* __restrict__ moments, const int* __restrict__ sample_count,
+                                          int H, float* __restrict__ out) {
+  const int h = blockIdx.x * blockDim.x + threadIdx.x;
+  if (h >= H) return;
+  const int n = *sample_count;
+  float s[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+  if (n > 0) {
+    stats_from_sums(moments[h * 5 + 0], moments[h * 5 + 1], moments[h * 5 + 2], moments[h * 5 + 3],
+                    moments[h * 5 + 4], n, s);
+  }
+#pragma unroll
+  for (int k = 0; k < 5; ++k) out[h * 5 + k] = s[k];
+}
+
+// ------------------------------------------------------------------ column sums of a bf16 matrix (db_down)
+// block = 32 x 8 threads: 64 columns (bf16x2 per thread) x 8 row lanes; grid.y splits the rows.
+__global__ void colsum_bf16_kernel(const __nv_bfloat16* __restrict__ a, long long lda, float* __restrict__ out,
+                                   int rows, int cols, int rows_per_block) {
+  __shared__ float red[8][64];
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const int c = blockIdx.x * 64 + tx * 2;
+  const int r0 = blockIdx.y * rows_per_block;
+  const int r1 = min(rows, r0 + rows_per_block);
+  float s0 = 0.f, s1 = 0.f;
+  if (c + 1 < cols) {
+    for (int r = r0 + ty; r < r1; r += 8) {
+      const __nv_bfloat162 v = *reinterpret_cast<const __nv_bfloat162*>(a + static_cast<size_t>(r) * lda + c);
+      s0 += __low2float(v);
+      s1 += __high2float(v);
+    }
+  } else if (c < cols) {
+    for (int r = r0 + ty; r < r1; r += 8) s0 += __bfloat162float(a[static_cast<size_t>(r) * lda + c]);
+  }
+  red[ty][tx * 2] = s0;
+  red[ty][tx * 2 + 1] = s1;
+  __syncthreads();
+  if (ty == 0) {
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      float s = 0.f;
+#pragma unroll
+      for (int y = 0; y < 8; ++y) s += red[y][tx * 2 + k];
+      if (c + k < cols) atomicAdd(out + c + k, s);
+    }
+  }
+}
+
+// ------------------------------------------------------------------ CLIP loss helpers (README.md:35)
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// one warp per row: u = x / |x| (bf16), inv_norm = 1 / |x|
+__global__ void l2norm_rows_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ u,
+                                   float* __restrict__ inv_norm, int B, int E) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= B) return;
+  const __nv_bfloat16* xr = x + static_cast<size_t>(row) * E;
+  float ss = 0.f;
+  for (int e = lane; e < E; e += 32) {
+    const float v = __bfloat162float(xr[e]);
+    ss = fmaf(v, v, ss);
+  }
+  ss = warp_sum(ss);
+  const float rn = ss > 0.f ? rsqrtf(ss) : 0.f;
+  for (int e = lane; e < E; e += 32) u[static_cast<size_t>(row) * E + e] = __float2bfloat16(__bfloat162float(xr[e]) * rn);
+  if (lane == 0) inv_norm[row] = rn;
+}
+
+// one warp per row of S: row log-sum-exp and the diagonal (matching pair) logit
+__global__ void row_lse_kernel(const float* __restrict__ S, int Bl, int Bg, int row_offset,
+                               float* __restrict__ row_lse, float* __restrict__ diag) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= Bl) return;
+  const float* sr = S + static_cast<size_t>(row) * Bg;
+  float m = -INFINITY;
+  for (int j = lane; j < Bg; j += 32) m = fmaxf(m, sr[j]);
+  m = warp_max(m);
+  float s = 0.f;
+  for (int j = lane; j < Bg; j += 32) s += __expf(sr[j] - m);
+  s = warp_sum(s);
+  if (lane == 0) {
+    row_lse[row] = m + logf(s);
+    diag[row] = sr[row_offset + row];
+  }
+}
+
+// column max / sum-exp over the local rows.  block = 32 columns x 8 row lanes.
+__global__ void col_lse_kernel(const float* __restrict__ S, int Bl, int Bg, float* __restrict__ col_max,
+                               float* __restrict__ col_sum) {
+  __shared__ float smax[8][32];
+  __shared__ float ssum[8][32];
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const int j = blockIdx.x * 32 + tx;
+  float m = -INFINITY, s = 0.f;
+  if (j < Bg) {
+    for (int i = ty; i < Bl; i += 8) {  // online softmax over the rows
+      const float v = S[static_cast<size_t>(i) * Bg + j];
+      const float nm = fmaxf(m, v);
+      s = s * __expf(m - nm) + __expf(v - nm);
+      m = nm;
+    }
+  }
+  smax[ty][tx] = m;
+  ssum[ty][tx] = s;
+  __syncthreads();
+  if (ty == 0 && j < Bg) {
+    float M = -INFINITY;
+#pragma unroll
+    for (int y = 0; y < 8; ++y) M = fmaxf(M, smax[y][tx]);
+    float T = 0.f;
+#pragma unroll
+    for (int y = 0; y < 8; ++y) T += (smax[y][tx] == -INFINITY) ? 0.f : ssum[y][tx] * __expf(smax[y][tx] - M);
+    col_max[j] = M;
+    col_sum[j] = T;
+  }
+}
+
+// dS = (softmax_row + softmax_col) / (2 Bg) - onehot / Bg  -> bf16 ; d(logit_scale) partial += sum dS * S / scale
+__global__ void clip_ds_kernel(const float* __restrict__ S, const float* __restrict__ row_lse,
+                               const float* __restrict__ col_lse, int Bl, int Bg, int row_offset, float inv_scale,
+                               __nv_bfloat16* __restrict__ dS, float* __restrict__ d_scale) {
+  const size_t total = static_cast<size_t>(Bl) * Bg;
+  const float w = 0.5f / static_cast<float>(Bg);
+  float acc = 0.f;
+  for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int i = static_cast<int>(idx / Bg), j = static_cast<int>(idx % Bg);
+    const float s = S[idx];
+    float g = (__expf(s - row_lse[i]) + __expf(s - col_lse[j])) * w;
+    if (j == row_offset + i) g -= 2.f * w;
+    dS[idx] = __float2bfloat16(g);
+    acc = fmaf(g, s, acc);
+  }
+  acc = warp_sum(acc);
+  __shared__ float part[32];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (lane == 0) part[wid] = acc;
+  __syncthreads();
+  if (wid == 0) {
+    float v = lane < (blockDim.x >> 5) ? part[lane] : 0.f;
+    v = warp_sum(v);
+    if (lane == 0 && d_scale != nullptr) atomicAdd(d_scale, v * inv_scale);
+  }
+}
+
+// d_x = inv_norm * (dU - u (u . dU)); one warp per row
+__global__ void l2norm_bwd_kernel(const __nv_bfloat16* __restrict__ u, const float* __restrict__ inv_norm,
+                                  const float* __restrict__ dU, float* __restrict__ dx, int B, int E) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= B) return;
+  const __nv_bfloat16* ur = u + static_cast<size_t>(row) * E;
+  const float* dr = dU + static_cast<size_t>(row) * E;
+  float dot = 0.f;
+  for (int e = lane; e < E; e += 32) dot = fmaf(__bfloat162float(ur[e]), dr[e], dot);
+  dot = warp_sum(dot);
+  const float rn = inv_norm[row];
+  for (int e = lane; e < E; e += 32)
+    dx[static_cast<size_t>(row) * E + e] = rn * (dr[e] - __bfloat162float(ur[e]) * dot);
+}
+
+}  // namespace forde
+
+using namespace forde;
+
+extern "C" {
+
+int forde_stats_finalize(void* stream, const float* act_partials, const float* grad_partials, int num_partials,
+                         int H, int M, float* step_stats, float* neuron_stats, float* moments,
+                         int* sample_count, int* step_count, float* db_up) {
+  if (H <= 0 || M <= 0 || num_partials <= 0) return FORDE_EINVAL;
+  if (act_partials == nullptr && grad_partials == nullptr) return FORDE_EINVAL;
+  const int threads = 128;
+  stats_finalize_kernel<<<(H + threads - 1) / threads, threads, 0, static_cast<cudaStream_t>(stream)>>>(
+      act_partials, grad_partials, num_partials, H, M, step_stats, neuron_stats, moments, sample_count,
+      step_count, db_up);
+  return check_launch("stats_finalize_kernel");
+}
+
+int forde_stats_from_moments(void* stream, const float* moments, const int* sample_count, int H,
+                             float* stats_out) {
+  if (moments == nullptr || sample_count == nullptr || stats_out == nullptr || H <= 0) return FORDE_EINVAL;
+  const int threads = 128;
+  stats_from_moments_kernel<<<(H + threads - 1) / threads, threads, 0, static_cast<cudaStream_t>(stream)>>>(
+      moments, sample_count, H, stats_out);
+  return check_launch("stats_from_moments_kernel");
+}
+
+int forde_colsum_bf16(void* stream, const void* a, long long lda, float* out, int rows, int cols) {
+  if (a == nullptr || out == nullptr || rows <= 0 || cols <= 0) return FORDE_EINVAL;
+  if ((lda & 1) != 0 || (reinterpret_cast<uintptr_t>(a) & 3) != 0) return FORDE_EALIGN;
+  const int col_blocks = (cols + 63) / 64;
+  int sms = sm_count();
+  if (sms <= 0) return FORDE_ENODEV;
+  int row_blocks = (4 * sms + col_blocks - 1) / col_blocks;
+  const int max_row_blocks = (rows + 63) / 64;
+  if (row_blocks > max_row_blocks) row_blocks = max_row_blocks;
+  if (row_blocks < 1) row_blocks = 1;
+  const int rows_per_block = (rows + row_blocks - 1) / row_blocks;
+  row_blocks = (rows + rows_per_block - 1) / rows_per_block;
+  colsum_bf16_kernel<<<dim3(col_blocks, row_blocks), dim3(32, 8), 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(a), lda, out, rows, cols, rows_per_block);
+  return check_launch("colsum_bf16_kernel");
+}
+
+int forde_clip_fwd(void* stream, const void* img, const void* txt, float logit_scale, int Bl, int Bg, int E,
+                   int row_offset, void* u, void* v, float* inv_norm_img, float* inv_norm_txt, float* S,
+                   float* row_lse, float* col_max, float* col_sum, float* diag) {
+  if (img == nullptr || txt == nullptr || u == nullptr || v == nullptr || inv_norm_img == nullptr ||
+      inv_norm_txt == nullptr || S == nullptr || row_lse == nullptr || col_max == nullptr || col_sum == nullptr ||
+      diag == nullptr || Bl <= 0 || Bg <= 0 || E <= 0 || row_offset < 0 || row_offset + Bl > Bg)
+    return FORDE_EINVAL;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  l2norm_rows_kernel<<<(Bl + 7) / 8, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(img),
+                                                  static_cast<__nv_bfloat16*>(u), inv_norm_img, Bl, E);
+  l2norm_rows_kernel<<<(Bg + 7) / 8, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(txt),
+                                                  static_cast<__nv_bfloat16*>(v), inv_norm_txt, Bg, E);
+  int rc = check_launch("l2norm_rows_kernel");
+  if (rc != FORDE_OK) return rc;
+  // S[Bl][Bg] = logit_scale * u . v^T  : both operands K-major (k = E)
+  GemmArgs g{u, false, E, v, false, E, Bl, Bg, E, true, 0x1000000000000000ull, 0x1000000000000000ull};
+  rc = gemm_f32(st, g, S, Bg, nullptr, nullptr, logit_scale, false);
+  if (rc != FORDE_OK) return rc;
+  row_lse_kernel<<<(Bl + 7) / 8, 256, 0, st>>>(S, Bl, Bg, row_offset, row_lse, diag);
+  col_lse_kernel<<<(Bg + 31) / 32, dim3(32, 8), 0, st>>>(S, Bl, Bg, col_max, col_sum);
+  return check_launch("clip lse kernels");
+}
+
+int forde_clip_bwd(void* stream, const void* u, const void* v, const float* S, const float* row_lse,
+                   const float* col_lse, float logit_scale, int Bl, int Bg, int E, int row_offset, void* dS,
+                   float* dU, float* dV, float* d_logit_scale) {
+  if (u == nullptr || v == nullptr || S == nullptr || row_lse == nullptr || col_lse == nullptr ||
+      dS == nullptr || dU == nullptr || dV == nullptr || Bl <= 0 || Bg <= 0 || E <= 0)
+    return FORDE_EINVAL;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int sms = sm_count();
+  if (sms <= 0) return FORDE_ENODEV;
+  const size_t total = static_cast<size_t>(Bl) * Bg;
+  int blocks = static_cast<int>((total + 255) / 256);
+  if (blocks > 8 * sms) blocks = 8 * sms;
+  clip_ds_kernel<<<blocks, 256, 0, st>>>(S, row_lse, col_lse, Bl, Bg, row_offset, 1.f / logit_scale,
+                                         static_cast<__nv_bfloat16*>(dS), d_logit_scale);
+  int rc = check_launch("clip_ds_kernel");
+  if (rc != FORDE_OK) return rc;
+  // dU[Bl][E] = logit_scale * dS . v   : A = dS [Bl][Bg] K-major ; B = v [Bg][E] as (n = e, k = j) MN-major
+  GemmArgs gu{dS, false, Bg, v, true, E, Bl, E, Bg, true, 0x1000000000000000ull, 0x1000000000000000ull};
+  rc = gemm_f32(st, gu, dU, E, nullptr, nullptr, logit_scale, false);
+  if (rc != FORDE_OK) return rc;
+  // dV[Bg][E] = logit_scale * dS^T . u : A = dS as (m = j, k = i) MN-major ; B = u [Bl][E] as (n = e, k = i) MN-major
+  GemmArgs gv{dS, true, Bg, u, true, E, Bg, E, Bl, true, 0x1000000000000000ull, 0x1000000000000000ull};
+  return gemm_f32(st, gv, dV, E, nullptr, nullptr, logit_scale, false);
+}
+
+int forde_l2norm_bwd(void* stream, const void* u, const float* inv_norm, const float* dU, float* d_x, int B,
+                     int E) {
+  if (u == nullptr || inv_norm == nullptr || dU == nullptr || d_x == nullptr || B <= 0 || E <= 0)
+    return FORDE_EINVAL;
+  l2norm_bwd_kernel<<<(B + 7) / 8, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(u), inv_norm, dU, d_x, B, E);
+  return check_launch("l2norm_bwd_kernel");
+}
+
+}  // extern "C"

@@ -1,0 +1,508 @@
+// Persistent warp-specialised tcgen05 GEMM for sm_100a with the FORDE StatefulLayer epilogues.
+//
+//   D[m, n] = sum_k A[m, k] * B[n, k]        (bf16 operands, fp32 accumulation in TMEM)
+//
+// Roles (192 threads, one CTA per SM):
+//   warp 0     : TMA producer  (cp.async.bulk.tensor -> 128B-swizzled smem ring, mbarrier complete_tx)
+//   warp 1     : TMEM allocator + single-thread tcgen05.mma issuer (128 x 256 x 16 per instruction)
+//   warps 2..5 : epilogue: tcgen05.ld the accumulator (one TMEM lane quarter per warp, one row per thread),
+//                apply the fused epilogue, stage through swizzled smem and TMA-store.
+// The accumulator is double buffered in TMEM (2 x 256 columns) so the epilogue of tile i overlaps the
+// main loop of tile i+1.
+//
+// Either operand may be K-major (reduction index contiguous in global memory) or MN-major (row index
+// contiguous); the smem tile layout and the UMMA descriptors are derived from that, so no operand is ever
+// transposed in HBM.
+//
+// Epilogues (reference: StatefulLayer spec, /root/reference/README.md:47-56; sensing.py:34-69):
+//   EPI_STORE   : D (+ per-column bias) -> bf16, TMA store.                       (down projection, dx)
+//   EPI_UP_FWD  : rows are neurons. z = acc + b[row] -> bf16; h = F_a(z) + gate_a * z -> bf16;
+//                 per-neuron sum|z|, sum z, sum z^2 over the tile's samples -> partials[nb][3][H].
+//   EPI_DZ_BWD  : rows are neurons. reads z^T tile, dz = acc * (F_a'(z) + gate_a) (binary_step uses the
+//                 straight-through estimator) -> bf16; per-neuron sum|dz|, sum dz, sum dz^2 -> partials.
+//   EPI_F32     : D * row_scale[m] * col_scale[n] * scale -> fp32, plain store or red.add (split-K dW).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <cstdint>
+
+#include "sm100_ptx.cuh"
+
+namespace forde {
+
+enum EpiKind : int { EPI_STORE = 0, EPI_UP_FWD = 1, EPI_DZ_BWD = 2, EPI_F32 = 3 };
+
+constexpr int BM = 128;
+constexpr int BN = 256;
+constexpr int BK = 64;
+constexpr int UMMA_K = 16;
+constexpr int A_TILE_BYTES = BM * BK * 2;  // 16 KB
+constexpr int B_TILE_BYTES = BN * BK * 2;  // 32 KB
+constexpr int STAGE_BYTES = A_TILE_BYTES + B_TILE_BYTES;
+constexpr int CHUNK = 64;                         // epilogue column chunk (one 128-byte bf16 row)
+constexpr int BOX_BYTES = 32 * CHUNK * 2;         // one warp's staging box: 32 rows x 64 bf16 = 4 KB
+constexpr int NUM_THREADS = 192;
+constexpr int TMEM_COLS = 512;
+
+__host__ __device__ constexpr int epi_warp_staging_bytes(int epi) {
+  return epi == EPI_STORE ? 2 * BOX_BYTES : (epi == EPI_UP_FWD || epi == EPI_DZ_BWD) ? 4 * BOX_BYTES : 0;
+}
+__host__ __device__ constexpr int gemm_stages(int epi) {
+  return (epi == EPI_UP_FWD || epi == EPI_DZ_BWD) ? 3 : 4;
+}
+__host__ __device__ constexpr int gemm_smem_bytes(int epi) {
+  // ring + staging + column bias (BN fp32) + barriers/pointers (256 B) + 1 KB alignment slack
+  return gemm_stages(epi) * STAGE_BYTES + 4 * epi_warp_staging_bytes(epi) + BN * 4 + 256 + 1024;
+}
+
+struct GemmParams {
+  CUtensorMap tmA;   // operand A   (box 64 x BM for K-major, 64 x 64 for MN-major)
+  CUtensorMap tmB;   // operand B
+  CUtensorMap tmC0;  // bf16 output 0 (box 64 x 32): y / dx / z^T / dz^T
+  CUtensorMap tmC1;  // bf16 output 1 (box 64 x 32): h^T               (EPI_UP_FWD)
+  CUtensorMap tmZ;   // bf16 input z^T (box 64 x 32)                   (EPI_DZ_BWD)
+  int M, N, K;       // D is M x N, reduction length K
+  int m_blocks, n_blocks, k_blocks;
+  int split_k, kb_per_split;
+  int raster_m_fast;  // 1: consecutive work items walk M first (share the B slab), 0: walk N first
+  uint64_t hintA, hintB;
+  const float* bias_col;    // [N]  EPI_STORE (may be null)
+  const float* bias_row;    // [M]  EPI_UP_FWD (may be null)
+  const int8_t* assign;     // [M]  EPI_UP_FWD / EPI_DZ_BWD: 0 relu, 1 tanh, else binary step
+  float* partials;          // [n_blocks][3][M]  EPI_UP_FWD / EPI_DZ_BWD (may be null)
+  float* out_f32;           // EPI_F32
+  long long ldc;            // EPI_F32 row pitch in elements
+  const float* row_scale;   // EPI_F32 (may be null)
+  const float* col_scale;   // EPI_F32 (may be null)
+  float scale;              // EPI_F32
+  int atomic_out;           // EPI_F32: 1 = red.add, 0 = store
+  float gate_generalist;    // 1.0
+  float gate_specialist;    // 0.1
+};
+
+struct WorkItem {
+  int m0, n0, nb, kb0, kb1;
+};
+
+__device__ __forceinline__ WorkItem decode_work(const GemmParams& p, int t) {
+  const int n_tiles = p.m_blocks * p.n_blocks;
+  const int tile = t % n_tiles;
+  const int ks = t / n_tiles;
+  int mb, nb;
+  if (p.raster_m_fast) {
+    mb = tile % p.m_blocks;
+    nb = tile / p.m_blocks;
+  } else {
+    nb = tile % p.n_blocks;
+    mb = tile / p.n_blocks;
+  }
+  WorkItem w;
+  w.m0 = mb * BM;
+  w.n0 = nb * BN;
+  w.nb = nb;
+  w.kb0 = ks * p.kb_per_split;
+  w.kb1 = min(w.kb0 + p.kb_per_split, p.k_blocks);
+  return w;
+}
+
+// Per-thread activation constants derived from the neuron's assignment (README.md:51-56).
+struct ActConst {
+  bool is_tanh;
+  bool is_step;
+  float gate;
+};
+__device__ __forceinline__ ActConst make_act(int a, float g_gen, float g_spec) {
+  ActConst c;
+  c.is_tanh = (a == 1);
+  c.is_step = (a != 0 && a != 1);  // anything outside {0,1} falls to the last branch of the nested where
+  c.gate = c.is_step ? g_spec : g_gen;
+  return c;
+}
+
+template <bool A_MN, bool B_MN, int EPI>
+__global__ void __launch_bounds__(NUM_THREADS, 1) forde_gemm_kernel(const __grid_constant__ GemmParams p) {
+  constexpr int STAGES = gemm_stages(EPI);
+  constexpr int WARP_STAGING = epi_warp_staging_bytes(EPI);
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* staging = smem + STAGES * STAGE_BYTES;
+  float* bias_s = reinterpret_cast<float*>(staging + 4 * WARP_STAGING);  // [BN]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(bias_s) + BN * 4);
+  uint64_t* full_bar = bars;                 // [STAGES]
+  uint64_t* empty_bar = bars + STAGES;       // [STAGES]
+  uint64_t* tfull_bar = bars + 2 * STAGES;   // [2]
+  uint64_t* tempty_bar = tfull_bar + 2;      // [2]
+  uint64_t* z_bar = tempty_bar + 2;          // [4 warps][2]
+  uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(z_bar + 8);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int total_work = p.m_blocks * p.n_blocks * p.split_k;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.tmA);
+    tma_prefetch_desc(&p.tmB);
+    if (EPI != EPI_F32) tma_prefetch_desc(&p.tmC0);
+    if (EPI == EPI_UP_FWD) tma_prefetch_desc(&p.tmC1);
+    if (EPI == EPI_DZ_BWD) tma_prefetch_desc(&p.tmZ);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tfull_bar[a], 1);
+      mbar_init(&tempty_bar[a], 4);
+    }
+    for (int i = 0; i < 8; ++i) mbar_init(&z_bar[i], 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_ptr_s, TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_s;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = blockIdx.x; t < total_work; t += gridDim.x) {
+        const WorkItem w = decode_work(p, t);
+        for (int kb = w.kb0; kb < w.kb1; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
+          uint8_t* sa = smem + stage * STAGE_BYTES;
+          uint8_t* sb = sa + A_TILE_BYTES;
+          const int k0 = kb * BK;
+          if (A_MN) {
+#pragma unroll
+            for (int j = 0; j < BM / 64; ++j)
+              tma_load_2d(&p.tmA, &full_bar[stage], sa + j * (BK * 128), w.m0 + j * 64, k0, p.hintA);
+          } else {
+            tma_load_2d(&p.tmA, &full_bar[stage], sa, k0, w.m0, p.hintA);
+          }
+          if (B_MN) {
+#pragma unroll
+            for (int j = 0; j < BN / 64; ++j)
+              tma_load_2d(&p.tmB, &full_bar[stage], sb + j * (BK * 128), w.n0 + j * 64, k0, p.hintB);
+          } else {
+            tma_load_2d(&p.tmB, &full_bar[stage], sb, k0, w.n0, p.hintB);
+          }
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    constexpr uint32_t idesc = make_idesc_bf16(BM, BN, A_MN, B_MN);
+    // K-major tile: rows of 128 B, 8-row swizzle atoms 1024 B apart; one UMMA_K step = 32 B inside the row.
+    // MN-major tile: 64-element (128 B) row per k, 8-k atoms 1024 B apart (SBO), 64-wide MN chunks
+    //                BK*128 B apart (LBO); one UMMA_K step = 16 k-rows = 2048 B.
+    constexpr uint32_t a_lbo = A_MN ? BK * 128 : 0, b_lbo = B_MN ? BK * 128 : 0;
+    constexpr uint32_t a_kstep = A_MN ? UMMA_K * 128 : UMMA_K * 2, b_kstep = B_MN ? UMMA_K * 128 : UMMA_K * 2;
+    int stage = 0;
+    uint32_t phase = 0;
+    int it = 0;
+    for (int t = blockIdx.x; t < total_work; t += gridDim.x, ++it) {
+      const WorkItem w = decode_work(p, t);
+      const int as = it & 1;
+      const uint32_t aphase = (it >> 1) & 1;
+      mbar_wait(&tempty_bar[as], aphase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + as * BN;
+      for (int kb = w.kb0; kb < w.kb1; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t a_base = smem_u32(smem + stage * STAGE_BYTES);
+          const uint32_t b_base = a_base + A_TILE_BYTES;
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            const uint64_t adesc = make_smem_desc_sw128(a_base + k * a_kstep, a_lbo, 1024);
+            const uint64_t bdesc = make_smem_desc_sw128(b_base + k * b_kstep, b_lbo, 1024);
+            umma_bf16(d_tmem, adesc, bdesc, idesc, (kb > w.kb0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);
+          if (kb == w.kb1 - 1) umma_commit(&tfull_bar[as]);
+        }
+        __syncwarp();
+        if (++stage == STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue warps
+    const int q = warp & 3;          // TMEM lane quarter owned by this warp
+    const int ew = warp - 2;         // staging region index
+    uint8_t* wst = staging + ew * WARP_STAGING;
+    const uint32_t lane_taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+    const uint32_t sw = static_cast<uint32_t>(lane & 7);
+    int it = 0;
+    int out_slot = 0;  // double-buffered output staging slot
+
+    // z^T prefetch state (EPI_DZ_BWD): g = running chunk index of this warp
+    int g = 0;
+    uint64_t* zb = z_bar + ew * 2;
+    if (EPI == EPI_DZ_BWD) {
+      if (lane == 0 && static_cast<int>(blockIdx.x) < total_work) {
+        const WorkItem w0 = decode_work(p, blockIdx.x);
+        mbar_expect_tx(&zb[0], BOX_BYTES);
+        tma_load_2d(&p.tmZ, &zb[0], wst, w0.n0, w0.m0 + q * 32, kEvictFirst);
+      }
+    }
+
+    for (int t = blockIdx.x; t < total_work; t += gridDim.x, ++it) {
+      const WorkItem w = decode_work(p, t);
+      const int as = it & 1;
+      const uint32_t aphase = (it >> 1) & 1;
+      const int row = w.m0 + q * 32 + lane;
+
+      // per-tile, per-thread constants
+      float bias_r = 0.f;
+      ActConst act = make_act(0, p.gate_generalist, p.gate_specialist);
+      bool warp_has_tanh = false;
+      float s_abs = 0.f, s_sum = 0.f, s_sq = 0.f;
+      if (EPI == EPI_UP_FWD || EPI == EPI_DZ_BWD) {
+        int a = 0;
+        if (row < p.M) {
+          a = p.assign[row];
+          if (EPI == EPI_UP_FWD && p.bias_row != nullptr) bias_r = p.bias_row[row];
+        }
+        act = make_act(a, p.gate_generalist, p.gate_specialist);
+        warp_has_tanh = __any_sync(0xffffffffu, act.is_tanh);
+      }
+      if (EPI == EPI_STORE) {
+        // stage this tile's column bias once for the four epilogue warps
+        asm volatile("bar.sync 1, 128;" ::: "memory");  // everyone is done reading the previous tile's bias
+        float* bdst = bias_s;
+        const int e = threadIdx.x - 64;
+#pragma unroll
+        for (int r = 0; r < BN / 128; ++r) {
+          const int c = e + r * 128;
+          const int col = w.n0 + c;
+          bdst[c] = (p.bias_col != nullptr && col < p.N) ? p.bias_col[col] : 0.f;
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+      }
+
+      mbar_wait(&tfull_bar[as], aphase);
+      tc_fence_after();
+      const uint32_t taddr = lane_taddr + as * BN;
+
+#pragma unroll 1
+      for (int c = 0; c < BN / CHUNK; ++c) {
+        const int col0 = w.n0 + c * CHUNK;
+        const int nvalid = p.N - col0;  // valid columns in this chunk (may be <= 0 or >= CHUNK)
+
+        if (EPI == EPI_DZ_BWD) {
+          // prefetch the next z^T box into the other input buffer
+          const int b = g & 1;
+          if (lane == 0) {
+            int nt = t, nc = c + 1;
+            if (nc == BN / CHUNK) {
+              nc = 0;
+              nt = t + gridDim.x;
+            }
+            if (nt < total_work) {
+              const WorkItem wn = (nt == t) ? w : decode_work(p, nt);
+              mbar_expect_tx(&zb[b ^ 1], BOX_BYTES);
+              tma_load_2d(&p.tmZ, &zb[b ^ 1], wst + (b ^ 1) * BOX_BYTES, wn.n0 + nc * CHUNK, wn.m0 + q * 32,
+                          kEvictFirst);
+            }
+          }
+        }
+
+        uint32_t v[CHUNK];
+        tmem_ld32(taddr + c * CHUNK, v);
+        tmem_ld32(taddr + c * CHUNK + 32, v + 32);
+        tmem_wait_ld();
+
+        if (EPI == EPI_F32) {
+          if (row < p.M && nvalid > 0) {
+            const float rs = (p.row_scale != nullptr ? p.row_scale[row] : 1.f) * p.scale;
+            float* orow = p.out_f32 + static_cast<long long>(row) * p.ldc + col0;
+            const bool vec_ok = (nvalid >= CHUNK) && ((p.ldc & 3) == 0) &&
+                                ((reinterpret_cast<uintptr_t>(p.out_f32) & 15) == 0);
+            if (vec_ok) {
+#pragma unroll
+              for (int j = 0; j < CHUNK; j += 4) {
+                float f0 = __uint_as_float(v[j]) * rs, f1 = __uint_as_float(v[j + 1]) * rs;
+                float f2 = __uint_as_float(v[j + 2]) * rs, f3 = __uint_as_float(v[j + 3]) * rs;
+                if (p.col_scale != nullptr) {
+                  const float4 cs = *reinterpret_cast<const float4*>(p.col_scale + col0 + j);
+                  f0 *= cs.x; f1 *= cs.y; f2 *= cs.z; f3 *= cs.w;
+                }
+                if (p.atomic_out) {
+                  red_add_v4_f32(orow + j, f0, f1, f2, f3);
+                } else {
+                  *reinterpret_cast<float4*>(orow + j) = make_float4(f0, f1, f2, f3);
+                }
+              }
+            } else {
+              for (int j = 0; j < CHUNK; ++j) {
+                if (j < nvalid) {
+                  float f = __uint_as_float(v[j]) * rs;
+                  if (p.col_scale != nullptr) f *= p.col_scale[col0 + j];
+                  if (p.atomic_out) atomicAdd(orow + j, f);
+                  else orow[j] = f;
+                }
+              }
+            }
+          }
+        } else {
+          // ---- bf16 outputs staged through swizzled smem
+          // staging map per warp: EPI_STORE  [out0][out1]
+          //                       EPI_UP_FWD [z0][h0][z1][h1]
+          //                       EPI_DZ_BWD [zin0][zin1][out0][out1]
+          uint8_t* obuf = (EPI == EPI_STORE)    ? (wst + out_slot * BOX_BYTES)
+                          : (EPI == EPI_UP_FWD) ? (wst + out_slot * 2 * BOX_BYTES)
+                                                : (wst + 2 * BOX_BYTES + out_slot * BOX_BYTES);
+          // the TMA store issued two chunks ago read this slot; make sure it is done
+          if (lane == 0) tma_wait_read<1>();
+          __syncwarp();
+          const uint32_t orow_s = smem_u32(obuf) + lane * 128;
+
+          if (EPI == EPI_STORE) {
+            const float* bsrc = bias_s + c * CHUNK;
+#pragma unroll
+            for (int j8 = 0; j8 < CHUNK / 8; ++j8) {
+              const float4 b0 = *reinterpret_cast<const float4*>(bsrc + j8 * 8);
+              const float4 b1 = *reinterpret_cast<const float4*>(bsrc + j8 * 8 + 4);
+              const uint32_t w0 = pack_bf16x2(__uint_as_float(v[j8 * 8 + 0]) + b0.x, __uint_as_float(v[j8 * 8 + 1]) + b0.y);
+              const uint32_t w1 = pack_bf16x2(__uint_as_float(v[j8 * 8 + 2]) + b0.z, __uint_as_float(v[j8 * 8 + 3]) + b0.w);
+              const uint32_t w2 = pack_bf16x2(__uint_as_float(v[j8 * 8 + 4]) + b1.x, __uint_as_float(v[j8 * 8 + 5]) + b1.y);
+              const uint32_t w3 = pack_bf16x2(__uint_as_float(v[j8 * 8 + 6]) + b1.z, __uint_as_float(v[j8 * 8 + 7]) + b1.w);
+              st_shared_v4(orow_s + ((static_cast<uint32_t>(j8) ^ sw) << 4), w0, w1, w2, w3);
+            }
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_2d(&p.tmC0, obuf, col0, w.m0 + q * 32);
+              tma_commit();
+            }
+          } else if (EPI == EPI_UP_FWD) {
+            // z slot at obuf, h slot at obuf + BOX_BYTES
+            const bool full = nvalid >= CHUNK;
+#pragma unroll
+            for (int j8 = 0; j8 < CHUNK / 8; ++j8) {
+              uint32_t zw[4], hw[4];
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const int j = j8 * 8 + i * 2;
+                const uint32_t zp = pack_bf16x2(__uint_as_float(v[j]) + bias_r, __uint_as_float(v[j + 1]) + bias_r);
+                const float z0 = bf16lo_to_f32(zp), z1 = bf16hi_to_f32(zp);
+                // F_a(z): relu -> z if z>0 ; binary_step -> 1 if z>0 ; else 0.  tanh lanes overwrite below.
+                float f0 = (z0 > 0.f) ? (act.is_step ? 1.f : z0) : 0.f;
+                float f1 = (z1 > 0.f) ? (act.is_step ? 1.f : z1) : 0.f;
+                if (warp_has_tanh) {
+                  const float t0 = tanh_approx(z0), t1 = tanh_approx(z1);
+                  f0 = act.is_tanh ? t0 : f0;
+                  f1 = act.is_tanh ? t1 : f1;
+                }
+                const float h0 = fmaf(act.gate, z0, f0), h1 = fmaf(act.gate, z1, f1);
+                zw[i] = zp;
+                hw[i] = pack_bf16x2(h0, h1);
+                if (full) {
+                  s_abs += fabsf(z0) + fabsf(z1);
+                  s_sum += z0 + z1;
+                  s_sq = fmaf(z0, z0, s_sq);
+                  s_sq = fmaf(z1, z1, s_sq);
+                } else {
+                  if (j < nvalid) { s_abs += fabsf(z0); s_sum += z0; s_sq = fmaf(z0, z0, s_sq); }
+                  if (j + 1 < nvalid) { s_abs += fabsf(z1); s_sum += z1; s_sq = fmaf(z1, z1, s_sq); }
+                }
+              }
+              const uint32_t off = (static_cast<uint32_t>(j8) ^ sw) << 4;
+              st_shared_v4(orow_s + off, zw[0], zw[1], zw[2], zw[3]);
+              st_shared_v4(orow_s + BOX_BYTES + off, hw[0], hw[1], hw[2], hw[3]);
+            }
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_2d(&p.tmC0, obuf, col0, w.m0 + q * 32);
+              tma_store_2d(&p.tmC1, obuf + BOX_BYTES, col0, w.m0 + q * 32);
+              tma_commit();
+            }
+          } else {  // EPI_DZ_BWD
+            const int b = g & 1;
+            mbar_wait(&zb[b], (g >> 1) & 1);
+            const uint32_t zrow_s = smem_u32(wst + b * BOX_BYTES) + lane * 128;
+            const bool full = nvalid >= CHUNK;
+#pragma unroll
+            for (int j8 = 0; j8 < CHUNK / 8; ++j8) {
+              const uint32_t off = (static_cast<uint32_t>(j8) ^ sw) << 4;
+              uint32_t zw[4], dw[4];
+              ld_shared_v4(zrow_s + off, zw[0], zw[1], zw[2], zw[3]);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const int j = j8 * 8 + i * 2;
+                const float z0 = bf16lo_to_f32(zw[i]), z1 = bf16hi_to_f32(zw[i]);
+                // F_a'(z) + gate_a : relu 1[z>0] + 1 ; binary_step (STE) 1 + 0.1 ; tanh (1 - t^2) + 1
+                float m0 = act.is_step ? (1.f + act.gate) : ((z0 > 0.f ? 1.f : 0.f) + act.gate);
+                float m1 = act.is_step ? (1.f + act.gate) : ((z1 > 0.f ? 1.f : 0.f) + act.gate);
+                if (warp_has_tanh) {
+                  const float t0 = tanh_approx(z0), t1 = tanh_approx(z1);
+                  m0 = act.is_tanh ? (fmaf(-t0, t0, 1.f) + act.gate) : m0;
+                  m1 = act.is_tanh ? (fmaf(-t1, t1, 1.f) + act.gate) : m1;
+                }
+                const uint32_t dp = pack_bf16x2(__uint_as_float(v[j]) * m0, __uint_as_float(v[j + 1]) * m1);
+                dw[i] = dp;
+                const float d0 = bf16lo_to_f32(dp), d1 = bf16hi_to_f32(dp);
+                if (full) {
+                  s_abs += fabsf(d0) + fabsf(d1);
+                  s_sum += d0 + d1;
+                  s_sq = fmaf(d0, d0, s_sq);
+                  s_sq = fmaf(d1, d1, s_sq);
+                } else {
+                  if (j < nvalid) { s_abs += fabsf(d0); s_sum += d0; s_sq = fmaf(d0, d0, s_sq); }
+                  if (j + 1 < nvalid) { s_abs += fabsf(d1); s_sum += d1; s_sq = fmaf(d1, d1, s_sq); }
+                }
+              }
+              st_shared_v4(orow_s + off, dw[0], dw[1], dw[2], dw[3]);
+            }
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_2d(&p.tmC0, obuf, col0, w.m0 + q * 32);
+              tma_commit();
+            }
+            ++g;
+          }
+          out_slot ^= 1;
+        }
+      }
+
+      // accumulator drained: hand the TMEM buffer back to the MMA warp
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[as]);
+
+      if ((EPI == EPI_UP_FWD || EPI == EPI_DZ_BWD) && p.partials != nullptr && row < p.M) {
+        float* dst = p.partials + (static_cast<long long>(w.nb) * 3) * p.M + row;
+        dst[0] = s_abs;
+        dst[p.M] = s_sum;
+        dst[2 * static_cast<long long>(p.M)] = s_sq;
+      }
+    }
+    if (EPI != EPI_F32 && lane == 0) tma_wait_all<0>();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+}  // namespace forde

@@ -1,0 +1,199 @@
+"""Thin torch-tensor wrappers over the C ABI (include/forde_b200.h).
+
+PyTorch is plumbing here: it owns device memory and the CUDA stream; every computation below is one of the
+hand-written sm_100a kernels in csrc/.  Tensors must live on a CUDA device; nothing falls back to torch math.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t):
+    return 0 if t is None else t.data_ptr()
+
+
+def _req(t: torch.Tensor, dtype, name: str) -> None:
+    if not t.is_cuda:
+        raise _lib.FordeError(f"{name} must be a CUDA tensor (the FORDE hot path has no CPU fallback)")
+    if t.dtype != dtype:
+        raise _lib.FordeError(f"{name} must be {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise _lib.FordeError(f"{name} must be contiguous")
+
+
+def round_up(v: int, m: int) -> int:
+    return (v + m - 1) // m * m
+
+
+def num_partials(M: int) -> int:
+    return _lib.load().forde_sl_num_partials(M)
+
+
+def sample_pitch(M: int) -> int:
+    """Row pitch (in elements) of the neuron-major zT / hT / dzT buffers for M samples."""
+    return round_up(M, 8)
+
+
+# ------------------------------------------------------------------------------------------ generic GEMM
+def gemm_bf16(A: torch.Tensor, B: torch.Tensor, a_mn_major: bool, b_mn_major: bool, bias_col=None) -> torch.Tensor:
+    """D[M,N] = sum_k A(m,k) B(n,k) -> bf16.  K-major operands are [rows, K]; MN-major operands are [K, rows]."""
+    _req(A, torch.bfloat16, "A"); _req(B, torch.bfloat16, "B")
+    M, K = (A.shape[1], A.shape[0]) if a_mn_major else (A.shape[0], A.shape[1])
+    N, Kb = (B.shape[1], B.shape[0]) if b_mn_major else (B.shape[0], B.shape[1])
+    assert K == Kb, "reduction extents differ"
+    ldd = round_up(N, 8)
+    D = torch.empty((M, ldd), dtype=torch.bfloat16, device=A.device)
+    if bias_col is not None:
+        _req(bias_col, torch.float32, "bias_col")
+    rc = _lib.load().forde_gemm_bf16(_stream(), A.data_ptr(), int(a_mn_major), A.stride(0), B.data_ptr(),
+                                     int(b_mn_major), B.stride(0), D.data_ptr(), ldd, _ptr(bias_col), M, N, K)
+    _lib.check(rc, "forde_gemm_bf16")
+    return D[:, :N]
+
+
+def gemm_f32(A, B, a_mn_major, b_mn_major, out=None, scale=1.0, accumulate=False, row_scale=None, col_scale=None):
+    _req(A, torch.bfloat16, "A"); _req(B, torch.bfloat16, "B")
+    M, K = (A.shape[1], A.shape[0]) if a_mn_major else (A.shape[0], A.shape[1])
+    N, Kb = (B.shape[1], B.shape[0]) if b_mn_major else (B.shape[0], B.shape[1])
+    assert K == Kb, "reduction extents differ"
+    if out is None:
+        out = torch.zeros((M, N), dtype=torch.float32, device=A.device)
+    _req(out, torch.float32, "out")
+    rc = _lib.load().forde_gemm_f32(_stream(), A.data_ptr(), int(a_mn_major), A.stride(0), B.data_ptr(),
+                                    int(b_mn_major), B.stride(0), out.data_ptr(), out.stride(0), _ptr(row_scale),
+                                    _ptr(col_scale), float(scale), int(accumulate), M, N, K)
+    _lib.check(rc, "forde_gemm_f32")
+    return out
+
+
+# ------------------------------------------------------------------------------------------ StatefulLayer
+def sl_up_fwd(x, w_up, b_up, assign_i8, zT, hT, act_partials):
+    M, d = x.shape
+    H = w_up.shape[1]
+    _req(x, torch.bfloat16, "x"); _req(w_up, torch.bfloat16, "w_up"); _req(assign_i8, torch.int8, "assign")
+    _req(zT, torch.bfloat16, "zT"); _req(hT, torch.bfloat16, "hT")
+    if b_up is not None:
+        _req(b_up, torch.float32, "b_up")
+    rc = _lib.load().forde_sl_up_fwd(_stream(), x.data_ptr(), w_up.data_ptr(), _ptr(b_up), assign_i8.data_ptr(),
+                                     zT.data_ptr(), hT.data_ptr(), _ptr(act_partials), M, d, H, zT.stride(0))
+    _lib.check(rc, "forde_sl_up_fwd")
+
+
+def sl_down_fwd(hT, w_down, b_down, y, M):
+    H, d = w_down.shape
+    _req(hT, torch.bfloat16, "hT"); _req(w_down, torch.bfloat16, "w_down"); _req(y, torch.bfloat16, "y")
+    if b_down is not None:
+        _req(b_down, torch.float32, "b_down")
+    rc = _lib.load().forde_sl_down_fwd(_stream(), hT.data_ptr(), w_down.data_ptr(), _ptr(b_down), y.data_ptr(), M, d,
+                                       H, hT.stride(0))
+    _lib.check(rc, "forde_sl_down_fwd")
+
+
+def sl_dz_bwd(dy, w_down, zT, assign_i8, dzT, grad_partials):
+    M, d = dy.shape
+    H = w_down.shape[0]
+    _req(dy, torch.bfloat16, "dy"); _req(zT, torch.bfloat16, "zT"); _req(dzT, torch.bfloat16, "dzT")
+    rc = _lib.load().forde_sl_dz_bwd(_stream(), dy.data_ptr(), w_down.data_ptr(), zT.data_ptr(), assign_i8.data_ptr(),
+                                     dzT.data_ptr(), _ptr(grad_partials), M, d, H, zT.stride(0))
+    _lib.check(rc, "forde_sl_dz_bwd")
+
+
+def sl_dx_bwd(dzT, w_up, dx, M):
+    d, H = w_up.shape
+    _req(dzT, torch.bfloat16, "dzT"); _req(dx, torch.bfloat16, "dx")
+    rc = _lib.load().forde_sl_dx_bwd(_stream(), dzT.data_ptr(), w_up.data_ptr(), dx.data_ptr(), M, d, H, dzT.stride(0))
+    _lib.check(rc, "forde_sl_dx_bwd")
+
+
+def sl_dw_up(x, dzT, dw_up):
+    M, d = x.shape
+    H = dzT.shape[0]
+    _req(x, torch.bfloat16, "x"); _req(dzT, torch.bfloat16, "dzT"); _req(dw_up, torch.float32, "dw_up")
+    rc = _lib.load().forde_sl_dw_up(_stream(), x.data_ptr(), dzT.data_ptr(), dw_up.data_ptr(), M, d, H, dzT.stride(0))
+    _lib.check(rc, "forde_sl_dw_up")
+
+
+def sl_dw_down(hT, dy, dw_down):
+    M, d = dy.shape
+    H = hT.shape[0]
+    _req(hT, torch.bfloat16, "hT"); _req(dy, torch.bfloat16, "dy"); _req(dw_down, torch.float32, "dw_down")
+    rc = _lib.load().forde_sl_dw_down(_stream(), hT.data_ptr(), dy.data_ptr(), dw_down.data_ptr(), M, d, H,
+                                      hT.stride(0))
+    _lib.check(rc, "forde_sl_dw_down")
+
+
+def colsum_bf16(a, out):
+    _req(a, torch.bfloat16, "a"); _req(out, torch.float32, "out")
+    rc = _lib.load().forde_colsum_bf16(_stream(), a.data_ptr(), a.stride(0), out.data_ptr(), a.shape[0], a.shape[1])
+    _lib.check(rc, "forde_colsum_bf16")
+
+
+def stats_finalize(act_partials, grad_partials, P, H, M, step_stats=None, neuron_stats=None, moments=None,
+                   sample_count=None, step_count=None, db_up=None):
+    rc = _lib.load().forde_stats_finalize(_stream(), _ptr(act_partials), _ptr(grad_partials), P, H, M,
+                                          _ptr(step_stats), _ptr(neuron_stats), _ptr(moments), _ptr(sample_count),
+                                          _ptr(step_count), _ptr(db_up))
+    _lib.check(rc, "forde_stats_finalize")
+
+
+def stats_from_moments(moments, sample_count, out=None):
+    H = moments.shape[0]
+    if out is None:
+        out = torch.empty((H, 5), dtype=torch.float32, device=moments.device)
+    rc = _lib.load().forde_stats_from_moments(_stream(), moments.data_ptr(), sample_count.data_ptr(), H, out.data_ptr())
+    _lib.check(rc, "forde_stats_from_moments")
+    return out
+
+
+# ------------------------------------------------------------------------------------------ CLIP loss
+def clip_fwd(img, txt_all, logit_scale: float, row_offset: int):
+    """Returns a dict of the forward intermediates (all device tensors)."""
+    _req(img, torch.bfloat16, "img"); _req(txt_all, torch.bfloat16, "txt")
+    Bl, E = img.shape
+    Bg = txt_all.shape[0]
+    dev = img.device
+    r = {
+        "u": torch.empty_like(img), "v": torch.empty_like(txt_all),
+        "rn_i": torch.empty(Bl, dtype=torch.float32, device=dev), "rn_t": torch.empty(Bg, dtype=torch.float32, device=dev),
+        "S": torch.empty((Bl, Bg), dtype=torch.float32, device=dev),
+        "row_lse": torch.empty(Bl, dtype=torch.float32, device=dev),
+        "col_max": torch.empty(Bg, dtype=torch.float32, device=dev),
+        "col_sum": torch.empty(Bg, dtype=torch.float32, device=dev),
+        "diag": torch.empty(Bl, dtype=torch.float32, device=dev),
+    }
+    rc = _lib.load().forde_clip_fwd(_stream(), img.data_ptr(), txt_all.data_ptr(), float(logit_scale), Bl, Bg, E,
+                                    int(row_offset), r["u"].data_ptr(), r["v"].data_ptr(), r["rn_i"].data_ptr(),
+                                    r["rn_t"].data_ptr(), r["S"].data_ptr(), r["row_lse"].data_ptr(),
+                                    r["col_max"].data_ptr(), r["col_sum"].data_ptr(), r["diag"].data_ptr())
+    _lib.check(rc, "forde_clip_fwd")
+    return r
+
+
+def clip_bwd(fwd, col_lse, logit_scale: float, row_offset: int):
+    u, v, S = fwd["u"], fwd["v"], fwd["S"]
+    Bl, E = u.shape
+    Bg = v.shape[0]
+    dev = u.device
+    dS = torch.empty((Bl, Bg), dtype=torch.bfloat16, device=dev)
+    dU = torch.empty((Bl, E), dtype=torch.float32, device=dev)
+    dV = torch.empty((Bg, E), dtype=torch.float32, device=dev)
+    dscale = torch.zeros(1, dtype=torch.float32, device=dev)
+    rc = _lib.load().forde_clip_bwd(_stream(), u.data_ptr(), v.data_ptr(), S.data_ptr(), fwd["row_lse"].data_ptr(),
+                                    col_lse.data_ptr(), float(logit_scale), Bl, Bg, E, int(row_offset), dS.data_ptr(),
+                                    dU.data_ptr(), dV.data_ptr(), dscale.data_ptr())
+    _lib.check(rc, "forde_clip_bwd")
+    return dU, dV, dscale
+
+
+def l2norm_bwd(u, inv_norm, dU):
+    B, E = u.shape
+    out = torch.empty((B, E), dtype=torch.float32, device=u.device)
+    rc = _lib.load().forde_l2norm_bwd(_stream(), u.data_ptr(), inv_norm.data_ptr(), dU.data_ptr(), out.data_ptr(), B, E)
+    _lib.check(rc, "forde_l2norm_bwd")
+    return out

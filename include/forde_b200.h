@@ -1,0 +1,131 @@
+/* forde_b200.h -- C ABI of the B200-native FORDE fast-loop hot path.
+ *
+ * This is the boundary a jax.ffi / XLA custom-call shim (or ctypes, as in this repository) binds.
+ * The reference has no native layer; every entry point names the reference code (or README spec)
+ * it stands in for.  Conventions for every function:
+ *   - `stream` is a cudaStream_t passed as void*; kernels are only ENQUEUED on it.  No entry point
+ *     synchronises, allocates device memory or touches host memory other than its arguments.
+ *   - the caller owns and pre-allocates every buffer (inputs, outputs, scratch).
+ *   - all matrices are row-major; bf16 matrices need 16-byte aligned base pointers and a row pitch
+ *     (in elements) that is a multiple of 8.
+ *   - return value: 0 on success, a negative FORDE_E* code on a shape / alignment / launch error.
+ *     An XLA FFI handler maps non-zero to XLA_FFI_Error.
+ *
+ * Data layout of the StatefulLayer (reference spec: /root/reference/README.md:47-56):
+ *   x, y, dy, dx : [M][d]  bf16, one row per token ("sample")
+ *   w_up         : [d][H]  bf16  (Flax Dense `kernel`, (in, out))
+ *   w_down       : [H][d]  bf16
+ *   b_up [H], b_down [d] : fp32
+ *   assign       : [H] int8, 0 = relu (generalist), 1 = tanh (pooling), anything else = binary step
+ *   zT, hT, dzT  : [H][ldz] bf16, NEURON-major (one row per neuron, samples contiguous), ldz >= M.
+ *                  Keeping the per-neuron axis on the TMEM lanes is what lets the sensing statistics be
+ *                  accumulated per thread with no cross-lane reduction.
+ *   partials     : [P][3][H] fp32 with P = forde_sl_num_partials(M): per 256-sample block the per-neuron
+ *                  sum|v|, sum v, sum v^2 (v = z in the forward, v = dL/dz in the backward).  Written,
+ *                  not accumulated: every slot has exactly one writer, so results are deterministic.
+ */
+#ifndef FORDE_B200_H_
+#define FORDE_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FORDE_OK 0
+#define FORDE_EINVAL (-1)   /* null pointer / non-positive dimension */
+#define FORDE_EALIGN (-2)   /* pointer or pitch alignment violated */
+#define FORDE_ECUDA (-3)    /* CUDA runtime / driver error (launch, tensor-map encode) */
+#define FORDE_ENODEV (-4)   /* no sm_100 device */
+
+int forde_version(void);
+const char* forde_error_string(int code);
+/* last CUDA error text recorded by this library on the calling thread ("" if none) */
+const char* forde_last_cuda_error(void);
+int forde_sm_count(void);
+
+/* number of 256-sample partial blocks the forward / backward kernels write for M samples */
+int forde_sl_num_partials(int M);
+
+/* ---- generic GEMM  D[M][N] = sum_k A(m,k) * B(n,k)  (test + building block) -------------------------
+ * a_mn_major = 0: A stored [M][K] (pitch lda);  1: A stored [K][M] (pitch lda).  Same for B with N. */
+int forde_gemm_bf16(void* stream, const void* A, int a_mn_major, long long lda, const void* B, int b_mn_major,
+                    long long ldb, void* D, long long ldd, const float* bias_col, int M, int N, int K);
+int forde_gemm_f32(void* stream, const void* A, int a_mn_major, long long lda, const void* B, int b_mn_major,
+                   long long ldb, float* D, long long ldd, const float* row_scale, const float* col_scale,
+                   float scale, int accumulate, int M, int N, int K);
+
+/* ---- StatefulLayer forward (README.md:47-56; sensing.py:57-59 for the activation moments) ------------
+ * up:   zT = (x . w_up + b_up)^T ; hT = F_assign(zT) + gate_assign * zT ; act_partials (may be NULL)
+ * down: y = h . w_down + b_down */
+int forde_sl_up_fwd(void* stream, const void* x, const void* w_up, const float* b_up, const int8_t* assign,
+                    void* zT, void* hT, float* act_partials, int M, int d, int H, long long ldz);
+int forde_sl_down_fwd(void* stream, const void* hT, const void* w_down, const float* b_down, void* y, int M,
+                      int d, int H, long long ldz);
+/* both of the above */
+int forde_sl_fwd(void* stream, const void* x, const void* w_up, const float* b_up, const void* w_down,
+                 const float* b_down, const int8_t* assign, void* zT, void* hT, void* y, float* act_partials,
+                 int M, int d, int H, long long ldz);
+
+/* ---- StatefulLayer backward (autodiff of the above with the straight-through binary step, README.md:55;
+ *      gradient statistics are those of dL/dz, tests/reproduce_grad_sink.py:16-17, sensing.py:62-63) -----
+ * dz:      dzT = (dy . w_down^T)^T * (F'(zT) + gate) ; grad_partials (sum|dz|, sum dz (= db_up), sum dz^2)
+ * dx:      dx = dz . w_up^T
+ * dw_up:   dw_up[d][H]   += x^T . dz      (fp32, accumulated with red.add: caller zeroes or carries grads)
+ * dw_down: dw_down[H][d] += h^T . dy
+ * db_down: db_down[d]    += sum_m dy */
+int forde_sl_dz_bwd(void* stream, const void* dy, const void* w_down, const void* zT, const int8_t* assign,
+                    void* dzT, float* grad_partials, int M, int d, int H, long long ldz);
+int forde_sl_dx_bwd(void* stream, const void* dzT, const void* w_up, void* dx, int M, int d, int H,
+                    long long ldz);
+int forde_sl_dw_up(void* stream, const void* x, const void* dzT, float* dw_up, int M, int d, int H,
+                   long long ldz);
+int forde_sl_dw_down(void* stream, const void* hT, const void* dy, float* dw_down, int M, int d, int H,
+                     long long ldz);
+int forde_colsum_bf16(void* stream, const void* a, long long lda, float* out, int rows, int cols);
+/* all of the above; db_up[H] += sum dz is taken from grad_partials */
+int forde_sl_bwd(void* stream, const void* x, const void* dy, const void* w_up, const void* w_down,
+                 const void* zT, const void* hT, const int8_t* assign, void* dzT, void* dx, float* dw_up,
+                 float* db_up, float* dw_down, float* db_down, float* grad_partials, int M, int d, int H,
+                 long long ldz);
+
+/* ---- sensing finalisation (sensing.py:5-69) --------------------------------------------------------
+ * Reduces the partials in a fixed order and produces this step's (H,5) statistics
+ *   [grad_gini, grad_gdp, act_gini, act_gdp, act_variance]   (gini = Hoyer sparsity over the M samples)
+ * then accumulates the stats_buffer leaves (moe.py:265-279 pattern): neuron_stats (H,5) += step stats,
+ * moments (H,5) += [sum|z|, sum z, sum z^2, sum|g|, sum g^2], sample_count += M, step_count += 1.
+ * step_stats / neuron_stats / moments / counters may each be NULL.  db_up (may be NULL) += sum g. */
+int forde_stats_finalize(void* stream, const float* act_partials, const float* grad_partials, int num_partials,
+                         int H, int M, float* step_stats, float* neuron_stats, float* moments,
+                         int* sample_count, int* step_count, float* db_up);
+/* stats from already pooled moments (used after the cross-rank all-reduce of the accumulators) */
+int forde_stats_from_moments(void* stream, const float* moments, const int* sample_count, int H,
+                             float* stats_out);
+
+/* ---- CLIP contrastive loss (README.md:35) ------------------------------------------------
+ * img [Bl][E], txt [Bg][E] bf16 (txt already all-gathered; Bl = Bg on one GPU), row_offset = global index
+ * of local image row 0.  logit_scale = exp(tau).
+ * fwd:  u = img/|img|, v = txt/|txt| (bf16), S = logit_scale * u . v^T (fp32 [Bl][Bg]),
+ *       row_lse[Bl], col_max[Bg], col_sum[Bg] (partial over the local rows; all-reduce across ranks),
+ *       diag[Bl] = S[i][row_offset+i].
+ * The caller combines: loss = 1/(2 Bg) * (sum_i (row_lse_i - diag_i) + sum_j (col_lse_j - diag_j)). */
+int forde_clip_fwd(void* stream, const void* img, const void* txt, float logit_scale, int Bl, int Bg, int E,
+                   int row_offset, void* u, void* v, float* inv_norm_img, float* inv_norm_txt, float* S,
+                   float* row_lse, float* col_max, float* col_sum, float* diag);
+/* bwd:  dS = (softmax_row + softmax_col)/(2 Bg) - onehot/Bg  (bf16 scratch [Bl][Bg]); col_lse is the GLOBAL
+ *       column log-sum-exp (col_max + log col_sum after the cross-rank combine);
+ *       dU [Bl][E] = logit_scale * dS . v (fp32, complete), dV [Bg][E] = logit_scale * dS^T . u (fp32, partial
+ *       over ranks: reduce-scatter it), d_logit_scale[1] += sum dS * S / logit_scale (may be NULL).
+ *       Follow with forde_l2norm_bwd to go from dU / dV to the gradients of the un-normalised embeddings. */
+int forde_clip_bwd(void* stream, const void* u, const void* v, const float* S, const float* row_lse,
+                   const float* col_lse, float logit_scale, int Bl, int Bg, int E, int row_offset, void* dS,
+                   float* dU, float* dV, float* d_logit_scale);
+/* normalisation backward for rows of an embedding: d_x = inv_norm * (dU - u (u . dU)) */
+int forde_l2norm_bwd(void* stream, const void* u, const float* inv_norm, const float* dU, float* d_x, int B,
+                     int E);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FORDE_B200_H_ */
