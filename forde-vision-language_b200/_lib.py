@@ -37,8 +37,10 @@ SIGNATURES = {
     "forde_sl_bwd": (_i, [_vp] * 15 + [_i, _i, _i, _ll]),
     "forde_stats_finalize": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "forde_stats_from_moments": (_i, [_vp, _vp, _vp, _i, _vp]),
-    "forde_clip_fwd": (_i, [_vp, _vp, _vp, _f, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
-    "forde_clip_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _f, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
+    "forde_clip_fwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i] + [_vp] * 10),
+    "forde_clip_col_rescale": (_i, [_vp, _vp, _vp, _vp, _i]),
+    "forde_clip_loss": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp]),
+    "forde_clip_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "forde_l2norm_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i]),
 }
 

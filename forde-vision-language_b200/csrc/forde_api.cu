@@ -212,12 +212,12 @@ int gemm_store_bf16(cudaStream_t stream, const GemmArgs& g, void* D, long long l
 }
 
 int gemm_f32(cudaStream_t stream, const GemmArgs& g, float* D, long long ldd, const float* row_scale,
-             const float* col_scale, float scale, bool accumulate) {
+             const float* col_scale, float scale, const float* scale_dev, bool accumulate) {
   GemmParams p;
   int rc = fill_common(p, g);
   if (rc != FORDE_OK) return rc;
   if (D == nullptr) return FORDE_EINVAL;
-  p.out_f32 = D; p.ldc = ldd; p.row_scale = row_scale; p.col_scale = col_scale; p.scale = scale;
+  p.out_f32 = D; p.ldc = ldd; p.row_scale = row_scale; p.col_scale = col_scale; p.scale = scale; p.scale_dev = scale_dev;
   p.atomic_out = accumulate ? 1 : 0;
   if (accumulate) choose_split_k(p);
   return launch_epi<EPI_F32>(p, g.a_mn, g.b_mn, stream);
@@ -258,7 +258,7 @@ int forde_gemm_f32(void* stream, const void* A, int a_mn_major, long long lda, c
                    long long ldb, float* D, long long ldd, const float* row_scale, const float* col_scale,
                    float scale, int accumulate, int M, int N, int K) {
   GemmArgs g{A, a_mn_major != 0, lda, B, b_mn_major != 0, ldb, M, N, K, false, kEvictNormal, kEvictNormal};
-  return gemm_f32(static_cast<cudaStream_t>(stream), g, D, ldd, row_scale, col_scale, scale, accumulate != 0);
+  return gemm_f32(static_cast<cudaStream_t>(stream), g, D, ldd, row_scale, col_scale, scale, nullptr, accumulate != 0);
 }
 
 // zT[H][M] = (x . w_up + b)^T :  A = w_up [d][H] as (m = neuron, k = d) -> MN-major ; B = x [M][d] -> K-major
@@ -325,7 +325,7 @@ int forde_sl_dw_up(void* stream, const void* x, const void* dzT, float* dw_up, i
                    long long ldz) {
   if (ldz < M) return FORDE_EINVAL;
   GemmArgs g{x, true, d, dzT, false, ldz, d, H, M, /*raster_m_fast=*/true, kEvictNormal, kEvictNormal};
-  return gemm_f32(static_cast<cudaStream_t>(stream), g, dw_up, H, nullptr, nullptr, 1.f, true);
+  return gemm_f32(static_cast<cudaStream_t>(stream), g, dw_up, H, nullptr, nullptr, 1.f, nullptr, true);
 }
 
 // dw_down[H][d] += h^T . dy : A = hT [H][M] (m = neuron, k = sample) K-major ; B = dy [M][d] (n = d, k = sample) MN-major
@@ -333,7 +333,7 @@ int forde_sl_dw_down(void* stream, const void* hT, const void* dy, float* dw_dow
                      long long ldz) {
   if (ldz < M) return FORDE_EINVAL;
   GemmArgs g{hT, false, ldz, dy, true, d, H, d, M, /*raster_m_fast=*/false, kEvictNormal, kEvictNormal};
-  return gemm_f32(static_cast<cudaStream_t>(stream), g, dw_down, d, nullptr, nullptr, 1.f, true);
+  return gemm_f32(static_cast<cudaStream_t>(stream), g, dw_down, d, nullptr, nullptr, 1.f, nullptr, true);
 }
 
 int forde_sl_bwd(void* stream, const void* x, const void* dy, const void* w_up, const void* w_down,

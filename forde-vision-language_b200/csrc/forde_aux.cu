@@ -143,9 +143,11 @@ __device__ __forceinline__ float warp_max(float v) {
 
 // one warp per row: u = x / |x| (bf16), inv_norm = 1 / |x|
 __global__ void l2norm_rows_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ u,
-                                   float* __restrict__ inv_norm, int B, int E) {
+                                   float* __restrict__ inv_norm, int B, int E, const float* __restrict__ log_temp,
+                                   float* __restrict__ logit_scale_out) {
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
+  if (logit_scale_out != nullptr && blockIdx.x == 0 && threadIdx.x == 0) *logit_scale_out = expf(*log_temp);
   if (row >= B) return;
   const __nv_bfloat16* xr = x + static_cast<size_t>(row) * E;
   float ss = 0.f;
@@ -209,9 +211,43 @@ __global__ void col_lse_kernel(const float* __restrict__ S, int Bl, int Bg, floa
   }
 }
 
-// dS = (softmax_row + softmax_col) / (2 Bg) - onehot / Bg  -> bf16 ; d(logit_scale) partial += sum dS * S / scale
+// rescale a rank's column sum-exp to the global column max (before the cross-rank SUM all-reduce)
+__global__ void clip_col_rescale_kernel(const float* __restrict__ col_max_local, const float* __restrict__ col_max_global,
+                                        float* __restrict__ col_sum, int Bg) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < Bg) {
+    const float ml = col_max_local[j];
+    col_sum[j] = (ml == -INFINITY) ? 0.f : col_sum[j] * __expf(ml - col_max_global[j]);
+  }
+}
+
+// col_lse = col_max + log(col_sum); loss += (sum_i (row_lse_i - diag_i) + sum_{j local} (col_lse_j - diag_j)) / (2 Bg)
+// single block; B is at most a few thousand.
+__global__ void clip_loss_kernel(const float* __restrict__ row_lse, const float* __restrict__ diag,
+                                 const float* __restrict__ col_max, const float* __restrict__ col_sum, int Bl, int Bg,
+                                 int row_offset, float* __restrict__ col_lse, float* __restrict__ loss) {
+  float acc = 0.f;
+  for (int j = threadIdx.x; j < Bg; j += blockDim.x) {
+    const float l = col_max[j] + logf(col_sum[j]);
+    col_lse[j] = l;
+    const int i = j - row_offset;
+    if (i >= 0 && i < Bl) acc += (l - diag[i]) + (row_lse[i] - diag[i]);
+  }
+  acc = warp_sum(acc);
+  __shared__ float part[32];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (lane == 0) part[wid] = acc;
+  __syncthreads();
+  if (wid == 0) {
+    float v = lane < (blockDim.x >> 5) ? part[lane] : 0.f;
+    v = warp_sum(v);
+    if (lane == 0) atomicAdd(loss, v * 0.5f / static_cast<float>(Bg));
+  }
+}
+
+// dS = (softmax_row + softmax_col) / (2 Bg) - onehot / Bg  -> bf16 ; d(log_temp) partial += sum dS * S
 __global__ void clip_ds_kernel(const float* __restrict__ S, const float* __restrict__ row_lse,
-                               const float* __restrict__ col_lse, int Bl, int Bg, int row_offset, float inv_scale,
+                               const float* __restrict__ col_lse, int Bl, int Bg, int row_offset,
                                __nv_bfloat16* __restrict__ dS, float* __restrict__ d_scale) {
   const size_t total = static_cast<size_t>(Bl) * Bg;
   const float w = 0.5f / static_cast<float>(Bg);
@@ -233,7 +269,7 @@ __global__ void clip_ds_kernel(const float* __restrict__ S, const float* __restr
   if (wid == 0) {
     float v = lane < (blockDim.x >> 5) ? part[lane] : 0.f;
     v = warp_sum(v);
-    if (lane == 0 && d_scale != nullptr) atomicAdd(d_scale, v * inv_scale);
+    if (lane == 0 && d_scale != nullptr) atomicAdd(d_scale, v);
   }
 }
 
@@ -297,34 +333,55 @@ int forde_colsum_bf16(void* stream, const void* a, long long lda, float* out, in
   return check_launch("colsum_bf16_kernel");
 }
 
-int forde_clip_fwd(void* stream, const void* img, const void* txt, float logit_scale, int Bl, int Bg, int E,
-                   int row_offset, void* u, void* v, float* inv_norm_img, float* inv_norm_txt, float* S,
-                   float* row_lse, float* col_max, float* col_sum, float* diag) {
-  if (img == nullptr || txt == nullptr || u == nullptr || v == nullptr || inv_norm_img == nullptr ||
-      inv_norm_txt == nullptr || S == nullptr || row_lse == nullptr || col_max == nullptr || col_sum == nullptr ||
-      diag == nullptr || Bl <= 0 || Bg <= 0 || E <= 0 || row_offset < 0 || row_offset + Bl > Bg)
+int forde_clip_fwd(void* stream, const void* img, const void* txt, const float* log_temp, int Bl, int Bg, int E,
+                   int row_offset, void* u, void* v, float* inv_norm_img, float* inv_norm_txt,
+                   float* logit_scale_out, float* S, float* row_lse, float* col_max, float* col_sum, float* diag) {
+  if (img == nullptr || txt == nullptr || log_temp == nullptr || u == nullptr || v == nullptr ||
+      inv_norm_img == nullptr || inv_norm_txt == nullptr || logit_scale_out == nullptr || S == nullptr ||
+      row_lse == nullptr || col_max == nullptr || col_sum == nullptr || diag == nullptr || Bl <= 0 || Bg <= 0 ||
+      E <= 0 || row_offset < 0 || row_offset + Bl > Bg)
     return FORDE_EINVAL;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   l2norm_rows_kernel<<<(Bl + 7) / 8, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(img),
-                                                  static_cast<__nv_bfloat16*>(u), inv_norm_img, Bl, E);
+                                                  static_cast<__nv_bfloat16*>(u), inv_norm_img, Bl, E, log_temp,
+                                                  logit_scale_out);
   l2norm_rows_kernel<<<(Bg + 7) / 8, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(txt),
-                                                  static_cast<__nv_bfloat16*>(v), inv_norm_txt, Bg, E);
+                                                  static_cast<__nv_bfloat16*>(v), inv_norm_txt, Bg, E, nullptr,
+                                                  nullptr);
   int rc = check_launch("l2norm_rows_kernel");
   if (rc != FORDE_OK) return rc;
-  // S[Bl][Bg] = logit_scale * u . v^T  : both operands K-major (k = E)
+  // S[Bl][Bg] = exp(log_temp) * u . v^T  : both operands K-major (k = E)
   GemmArgs g{u, false, E, v, false, E, Bl, Bg, E, true, 0x1000000000000000ull, 0x1000000000000000ull};
-  rc = gemm_f32(st, g, S, Bg, nullptr, nullptr, logit_scale, false);
+  rc = gemm_f32(st, g, S, Bg, nullptr, nullptr, 1.f, logit_scale_out, false);
   if (rc != FORDE_OK) return rc;
   row_lse_kernel<<<(Bl + 7) / 8, 256, 0, st>>>(S, Bl, Bg, row_offset, row_lse, diag);
   col_lse_kernel<<<(Bg + 31) / 32, dim3(32, 8), 0, st>>>(S, Bl, Bg, col_max, col_sum);
   return check_launch("clip lse kernels");
 }
 
+int forde_clip_col_rescale(void* stream, const float* col_max_local, const float* col_max_global, float* col_sum,
+                           int Bg) {
+  if (col_max_local == nullptr || col_max_global == nullptr || col_sum == nullptr || Bg <= 0) return FORDE_EINVAL;
+  clip_col_rescale_kernel<<<(Bg + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      col_max_local, col_max_global, col_sum, Bg);
+  return check_launch("clip_col_rescale_kernel");
+}
+
+int forde_clip_loss(void* stream, const float* row_lse, const float* diag, const float* col_max,
+                    const float* col_sum, int Bl, int Bg, int row_offset, float* col_lse, float* loss) {
+  if (row_lse == nullptr || diag == nullptr || col_max == nullptr || col_sum == nullptr || col_lse == nullptr ||
+      loss == nullptr || Bl <= 0 || Bg <= 0)
+    return FORDE_EINVAL;
+  clip_loss_kernel<<<1, 1024, 0, static_cast<cudaStream_t>(stream)>>>(row_lse, diag, col_max, col_sum, Bl, Bg,
+                                                                     row_offset, col_lse, loss);
+  return check_launch("clip_loss_kernel");
+}
+
 int forde_clip_bwd(void* stream, const void* u, const void* v, const float* S, const float* row_lse,
-                   const float* col_lse, float logit_scale, int Bl, int Bg, int E, int row_offset, void* dS,
-                   float* dU, float* dV, float* d_logit_scale) {
+                   const float* col_lse, const float* logit_scale, int Bl, int Bg, int E, int row_offset, void* dS,
+                   float* dU, float* dV, float* d_log_temp) {
   if (u == nullptr || v == nullptr || S == nullptr || row_lse == nullptr || col_lse == nullptr ||
-      dS == nullptr || dU == nullptr || dV == nullptr || Bl <= 0 || Bg <= 0 || E <= 0)
+      logit_scale == nullptr || dS == nullptr || dU == nullptr || dV == nullptr || Bl <= 0 || Bg <= 0 || E <= 0)
     return FORDE_EINVAL;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   int sms = sm_count();
@@ -332,17 +389,17 @@ int forde_clip_bwd(void* stream, const void* u, const void* v, const float* S, c
   const size_t total = static_cast<size_t>(Bl) * Bg;
   int blocks = static_cast<int>((total + 255) / 256);
   if (blocks > 8 * sms) blocks = 8 * sms;
-  clip_ds_kernel<<<blocks, 256, 0, st>>>(S, row_lse, col_lse, Bl, Bg, row_offset, 1.f / logit_scale,
-                                         static_cast<__nv_bfloat16*>(dS), d_logit_scale);
+  clip_ds_kernel<<<blocks, 256, 0, st>>>(S, row_lse, col_lse, Bl, Bg, row_offset, static_cast<__nv_bfloat16*>(dS),
+                                         d_log_temp);
   int rc = check_launch("clip_ds_kernel");
   if (rc != FORDE_OK) return rc;
-  // dU[Bl][E] = logit_scale * dS . v   : A = dS [Bl][Bg] K-major ; B = v [Bg][E] as (n = e, k = j) MN-major
+  // dU[Bl][E] = scale * dS . v   : A = dS [Bl][Bg] K-major ; B = v [Bg][E] as (n = e, k = j) MN-major
   GemmArgs gu{dS, false, Bg, v, true, E, Bl, E, Bg, true, 0x1000000000000000ull, 0x1000000000000000ull};
-  rc = gemm_f32(st, gu, dU, E, nullptr, nullptr, logit_scale, false);
+  rc = gemm_f32(st, gu, dU, E, nullptr, nullptr, 1.f, logit_scale, false);
   if (rc != FORDE_OK) return rc;
-  // dV[Bg][E] = logit_scale * dS^T . u : A = dS as (m = j, k = i) MN-major ; B = u [Bl][E] as (n = e, k = i) MN-major
+  // dV[Bg][E] = scale * dS^T . u : A = dS as (m = j, k = i) MN-major ; B = u [Bl][E] as (n = e, k = i) MN-major
   GemmArgs gv{dS, true, Bg, u, true, E, Bg, E, Bl, true, 0x1000000000000000ull, 0x1000000000000000ull};
-  return gemm_f32(st, gv, dV, E, nullptr, nullptr, logit_scale, false);
+  return gemm_f32(st, gv, dV, E, nullptr, nullptr, 1.f, logit_scale, false);
 }
 
 int forde_l2norm_bwd(void* stream, const void* u, const float* inv_norm, const float* dU, float* d_x, int B,

@@ -75,6 +75,7 @@ struct GemmParams {
   const float* row_scale;   // EPI_F32 (may be null)
   const float* col_scale;   // EPI_F32 (may be null)
   float scale;              // EPI_F32
+  const float* scale_dev;   // EPI_F32: optional device scalar multiplied into scale (may be null)
   int atomic_out;           // EPI_F32: 1 = red.add, 0 = store
   float gate_generalist;    // 1.0
   float gate_specialist;    // 0.1
@@ -329,7 +330,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) forde_gemm_kernel(const __grid
 
         if (EPI == EPI_F32) {
           if (row < p.M && nvalid > 0) {
-            const float rs = (p.row_scale != nullptr ? p.row_scale[row] : 1.f) * p.scale;
+            const float rs = (p.row_scale != nullptr ? p.row_scale[row] : 1.f) * p.scale *
+                             (p.scale_dev != nullptr ? *p.scale_dev : 1.f);
             float* orow = p.out_f32 + static_cast<long long>(row) * p.ldc + col0;
             const bool vec_ok = (nvalid >= CHUNK) && ((p.ldc & 3) == 0) &&
                                 ((reinterpret_cast<uintptr_t>(p.out_f32) & 15) == 0);
@@ -349,6 +351,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) forde_gemm_kernel(const __grid
                 }
               }
             } else {
+#pragma unroll
               for (int j = 0; j < CHUNK; ++j) {
                 if (j < nvalid) {
                   float f = __uint_as_float(v[j]) * rs;

@@ -152,30 +152,47 @@ def stats_from_moments(moments, sample_count, out=None):
 
 
 # ------------------------------------------------------------------------------------------ CLIP loss
-def clip_fwd(img, txt_all, logit_scale: float, row_offset: int):
-    """Returns a dict of the forward intermediates (all device tensors)."""
-    _req(img, torch.bfloat16, "img"); _req(txt_all, torch.bfloat16, "txt")
+def clip_fwd(img, txt_all, log_temp, row_offset: int):
+    """Launch the forward kernels; returns a dict of the forward intermediates (all device tensors)."""
+    _req(img, torch.bfloat16, "img"); _req(txt_all, torch.bfloat16, "txt"); _req(log_temp, torch.float32, "log_temp")
     Bl, E = img.shape
     Bg = txt_all.shape[0]
     dev = img.device
+    f32 = dict(dtype=torch.float32, device=dev)
     r = {
         "u": torch.empty_like(img), "v": torch.empty_like(txt_all),
-        "rn_i": torch.empty(Bl, dtype=torch.float32, device=dev), "rn_t": torch.empty(Bg, dtype=torch.float32, device=dev),
-        "S": torch.empty((Bl, Bg), dtype=torch.float32, device=dev),
-        "row_lse": torch.empty(Bl, dtype=torch.float32, device=dev),
-        "col_max": torch.empty(Bg, dtype=torch.float32, device=dev),
-        "col_sum": torch.empty(Bg, dtype=torch.float32, device=dev),
-        "diag": torch.empty(Bl, dtype=torch.float32, device=dev),
+        "rn_i": torch.empty(Bl, **f32), "rn_t": torch.empty(Bg, **f32), "scale": torch.empty(1, **f32),
+        "S": torch.empty((Bl, Bg), **f32), "row_lse": torch.empty(Bl, **f32),
+        "col_max": torch.empty(Bg, **f32), "col_sum": torch.empty(Bg, **f32), "diag": torch.empty(Bl, **f32),
     }
-    rc = _lib.load().forde_clip_fwd(_stream(), img.data_ptr(), txt_all.data_ptr(), float(logit_scale), Bl, Bg, E,
+    rc = _lib.load().forde_clip_fwd(_stream(), img.data_ptr(), txt_all.data_ptr(), log_temp.data_ptr(), Bl, Bg, E,
                                     int(row_offset), r["u"].data_ptr(), r["v"].data_ptr(), r["rn_i"].data_ptr(),
-                                    r["rn_t"].data_ptr(), r["S"].data_ptr(), r["row_lse"].data_ptr(),
-                                    r["col_max"].data_ptr(), r["col_sum"].data_ptr(), r["diag"].data_ptr())
+                                    r["rn_t"].data_ptr(), r["scale"].data_ptr(), r["S"].data_ptr(),
+                                    r["row_lse"].data_ptr(), r["col_max"].data_ptr(), r["col_sum"].data_ptr(),
+                                    r["diag"].data_ptr())
     _lib.check(rc, "forde_clip_fwd")
     return r
 
 
-def clip_bwd(fwd, col_lse, logit_scale: float, row_offset: int):
+def clip_col_rescale(col_max_local, col_max_global, col_sum):
+    rc = _lib.load().forde_clip_col_rescale(_stream(), col_max_local.data_ptr(), col_max_global.data_ptr(),
+                                            col_sum.data_ptr(), col_sum.numel())
+    _lib.check(rc, "forde_clip_col_rescale")
+
+
+def clip_loss(fwd, col_max, col_sum, row_offset: int):
+    """Returns (loss_share[1], col_lse[Bg]); loss_share sums to the loss over ranks."""
+    Bl = fwd["row_lse"].numel()
+    Bg = col_max.numel()
+    col_lse = torch.empty_like(col_max)
+    loss = torch.zeros(1, dtype=torch.float32, device=col_max.device)
+    rc = _lib.load().forde_clip_loss(_stream(), fwd["row_lse"].data_ptr(), fwd["diag"].data_ptr(), col_max.data_ptr(),
+                                     col_sum.data_ptr(), Bl, Bg, int(row_offset), col_lse.data_ptr(), loss.data_ptr())
+    _lib.check(rc, "forde_clip_loss")
+    return loss, col_lse
+
+
+def clip_bwd(fwd, col_lse, row_offset: int):
     u, v, S = fwd["u"], fwd["v"], fwd["S"]
     Bl, E = u.shape
     Bg = v.shape[0]
@@ -183,12 +200,12 @@ def clip_bwd(fwd, col_lse, logit_scale: float, row_offset: int):
     dS = torch.empty((Bl, Bg), dtype=torch.bfloat16, device=dev)
     dU = torch.empty((Bl, E), dtype=torch.float32, device=dev)
     dV = torch.empty((Bg, E), dtype=torch.float32, device=dev)
-    dscale = torch.zeros(1, dtype=torch.float32, device=dev)
+    dlog_temp = torch.zeros(1, dtype=torch.float32, device=dev)
     rc = _lib.load().forde_clip_bwd(_stream(), u.data_ptr(), v.data_ptr(), S.data_ptr(), fwd["row_lse"].data_ptr(),
-                                    col_lse.data_ptr(), float(logit_scale), Bl, Bg, E, int(row_offset), dS.data_ptr(),
-                                    dU.data_ptr(), dV.data_ptr(), dscale.data_ptr())
+                                    col_lse.data_ptr(), fwd["scale"].data_ptr(), Bl, Bg, E, int(row_offset),
+                                    dS.data_ptr(), dU.data_ptr(), dV.data_ptr(), dlog_temp.data_ptr())
     _lib.check(rc, "forde_clip_bwd")
-    return dU, dV, dscale
+    return dU, dV, dlog_temp
 
 
 def l2norm_bwd(u, inv_norm, dU):

@@ -1,0 +1,177 @@
+"""Slow loop: Sense -> Cluster -> Smooth -> Actuate -> Reset, every N fast steps (README.md:17-20).
+
+Host-side, exactly like the reference (src/forde/moe_slow_loop.py:253-464 is "non-jit-able" Python around
+scikit-learn and a convolution); it touches (H,5) floats per layer once every ~100 steps, so it is not
+accelerated (out of scope).  What is kept is the INTERFACE:
+
+  * input / output are plain nested dicts of array leaves; layers are found under ``layer_{i}`` keys and the
+    statistics leaves by name (moe_slow_loop.py:145-170); the call returns
+    ``(params, mutable_variables, diagnostics)`` (moe_slow_loop.py:455-464);
+  * Sense consumes the accumulators the fast loop filled (``stats_buffer``), Cluster is
+    ``GaussianMixture(n_components, random_state=seed)`` (clustering.py:27-30), Smooth is the per-cluster box
+    filter + argmax on a 2-D neuron grid (smoothing.py:30-91), Actuate rewrites ``neuron_assignments``
+    (README.md:20), and every leaf of ``stats_buffer`` is zeroed afterwards (moe_slow_loop.py:441-449,
+    tests/verify_reset.py:61-67).
+
+Multi-GPU: the raw-moment accumulators are additive, so ranks all-reduce(SUM) ``moments`` and ``sample_count``
+(never the finished statistics, Hoyer and variance are non-linear) and every rank then runs the same
+deterministic slow loop with the same seed, which keeps ``neuron_assignments`` replicated without a broadcast.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Dict, Optional, Tuple
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import ops
+
+
+@dataclass
+class SlowLoopConfig:
+    num_clusters: int = 3            # README.md:52-54: three processing paths
+    kernel_size: int = 3             # smoothing.py:31
+    pooled: bool = True              # Sense from pooled raw moments (exact across ranks); False = mean of
+                                     # per-step statistics (neuron_stats / step_count, moe_slow_loop.py:298)
+    canonicalize: bool = True        # D10: relabel clusters by ascending mean grad_gini -> 0 relu, 1 tanh, 2 step
+    forde_lite: bool = False         # README.md:58-59 ablation: is_spec = grad_gini > threshold, no GMM
+    forde_lite_threshold: float = 0.8
+
+
+def default_grid(H: int) -> Tuple[int, int]:
+    """Most square factorisation of H (3072 -> 48x64, 2048 -> 32x64, 4096 -> 64x64, 512 -> 16x32)."""
+    best = (1, H)
+    for a in range(1, int(H ** 0.5) + 1):
+        if H % a == 0:
+            best = (a, H // a)
+    return best
+
+
+def box_smooth(grid: np.ndarray, kernel_size: int, num_clusters: int) -> np.ndarray:
+    """Majority-style smoothing of an integer label grid (smoothing.py:30-91): per-label density by a
+    zero-padded k x k box filter, then the label of highest density; ties resolve to the smallest label."""
+    from scipy.signal import convolve2d
+
+    h, w = grid.shape
+    box = np.full((kernel_size, kernel_size), 1.0 / kernel_size ** 2, dtype=np.float32)
+    # the reference pads tiny grids so each side exceeds the kernel (smoothing.py:59-68) and crops back
+    ph, pw = max(0, kernel_size + 1 - h), max(0, kernel_size + 1 - w)
+    top, left = ph // 2, pw // 2
+    dens = np.empty((h, w, num_clusters), dtype=np.float32)
+    for c in range(num_clusters):
+        plane = np.pad((grid == c).astype(np.float32), ((top, ph - top), (left, pw - left)))
+        dens[:, :, c] = convolve2d(plane, box, mode="same")[top:top + h, left:left + w]
+    return dens.argmax(axis=-1).astype(np.int32)
+
+
+def gmm_cluster(stats: np.ndarray, num_clusters: int, seed: int):
+    """Cluster stage (clustering.py:6-39)."""
+    from sklearn.mixture import GaussianMixture
+
+    gmm = GaussianMixture(n_components=num_clusters, random_state=int(seed))
+    gmm.fit(stats)
+    labels = gmm.predict(stats).astype(np.int32)
+    return labels, {"weights": gmm.weights_, "means": gmm.means_, "covariances": gmm.covariances_}
+
+
+def _relabel_by_grad_gini(labels: np.ndarray, stats: np.ndarray, k: int) -> np.ndarray:
+    means = np.array([stats[labels == c, 0].mean() if np.any(labels == c) else np.inf for c in range(k)])
+    order = np.argsort(means, kind="stable")
+    lut = np.empty(k, dtype=np.int32)
+    lut[order] = np.arange(k, dtype=np.int32)
+    return lut[labels]
+
+
+def _seed_from_key(key) -> int:
+    """The reference derives the sklearn seed from a JAX PRNGKey (clustering.py:25); here `key` is an int or a
+    torch.Generator."""
+    if isinstance(key, torch.Generator):
+        return int(torch.randint(0, 2 ** 31 - 1, (), generator=key).item())
+    return int(key) % (2 ** 31 - 1)
+
+
+def sense_layer(stats_leaf: Dict[str, torch.Tensor], pooled: bool, group=None) -> Optional[np.ndarray]:
+    """(H,5) [grad_gini, grad_gdp, act_gini, act_gdp, act_variance] for one layer, or None if nothing was
+    accumulated.  With `pooled`, the raw moments are all-reduced across ranks first."""
+    world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
+    if pooled:
+        moments, count = stats_leaf["moments"], stats_leaf["sample_count"]
+        if world > 1:
+            moments = moments.clone(); count = count.clone()
+            dist.all_reduce(moments, op=dist.ReduceOp.SUM, group=group)
+            dist.all_reduce(count, op=dist.ReduceOp.SUM, group=group)
+        if int(count.item()) == 0:
+            return None
+        if moments.is_cuda:
+            return ops.stats_from_moments(moments.contiguous(), count.reshape(1).contiguous()).cpu().numpy()
+        raise RuntimeError("pooled sensing runs the CUDA finalisation kernel; stats_buffer must be on the GPU")
+    steps = int(stats_leaf["step_count"].item())
+    if steps == 0:
+        return None
+    s = stats_leaf["neuron_stats"] / steps
+    if world > 1:
+        s = s.clone()
+        dist.all_reduce(s, op=dist.ReduceOp.SUM, group=group)
+        s = s / world
+    return s.cpu().numpy()
+
+
+def slow_loop_step(params, mutable_variables, config: SlowLoopConfig, key, epoch: int = 0, step: int = 0,
+                   group=None):
+    """One brain update.  `mutable_variables` holds ``stats_buffer`` and ``neuron_assignments`` trees keyed by
+    ``layer_{i}`` (any nesting above that is walked).  Returns (params, mutable_variables, diagnostics)."""
+    stats_tree = mutable_variables["stats_buffer"]
+    assign_tree = mutable_variables["neuron_assignments"]
+    seed = _seed_from_key(key)
+    diagnostics = {"epoch": epoch, "step": step, "layers": {}}
+
+    def walk(st, asg, path):
+        if isinstance(st, dict) and "neuron_stats" in st:
+            _update_layer(st, asg, path)
+            return
+        if isinstance(st, dict):
+            for k in sorted(st):
+                walk(st[k], asg[k], path + (k,))
+
+    def _update_layer(st, asg, path):
+        stats = sense_layer(st, config.pooled, group)                                   # SENSE
+        name = "/".join(path)
+        if stats is None:
+            diagnostics["layers"][name] = {"skipped": "no statistics accumulated"}
+            return
+        H = stats.shape[0]
+        k = config.num_clusters
+        if config.forde_lite:
+            labels = np.where(stats[:, 0] > config.forde_lite_threshold, 2, 0).astype(np.int32)
+            gmm_params = None
+        else:
+            labels, gmm_params = gmm_cluster(np.nan_to_num(stats), k, seed)             # CLUSTER
+            if config.canonicalize:
+                labels = _relabel_by_grad_gini(labels, stats, k)
+        grid = labels.reshape(default_grid(H))                                          # SMOOTH
+        smoothed = box_smooth(grid, config.kernel_size, max(k, 3) if config.forde_lite else k)
+        tgt = asg["assignments"]
+        new = torch.from_numpy(smoothed.reshape(-1).astype(np.int32)).to(tgt.device)
+        changed = int((new != tgt).sum().item())
+        tgt.copy_(new)                                                                  # ACTUATE (in place: bumps _version)
+        diagnostics["layers"][name] = {
+            "census": np.bincount(smoothed.reshape(-1), minlength=k).tolist(),          # README.md:66 "The Census"
+            "raw_census": np.bincount(labels, minlength=k).tolist(),
+            "changed": changed,
+            "brain_scan": smoothed,                                                     # README.md:64
+            "features": stats,                                                          # README.md:65
+            "gmm": gmm_params,
+        }
+
+    walk(stats_tree, assign_tree, ())
+    # RESET: zero every leaf of stats_buffer (moe_slow_loop.py:441-449)
+    def zero(t):
+        if isinstance(t, dict):
+            for v in t.values():
+                zero(v)
+        else:
+            t.zero_()
+    zero(stats_tree)
+    return params, mutable_variables, diagnostics

@@ -1,0 +1,230 @@
+"""StatefulLayer -- host-side mirror of the reference's Flax module contract for the FFN slot.
+
+Reference interface this keeps:
+  * Flax-linen style ``module.init(key, x) -> variables`` and
+    ``module.apply(variables, x, mutable=[...]) -> (out, updated_collections)``
+    (src/forde/moe.py:225-281; call site src/training/train.py:135-139; tests/verify_init.py:55-57).
+  * variable collections, names verbatim:
+      params/{up_proj,down_proj}/{kernel,bias}      Flax Dense layout, kernel is (in, out)
+      neuron_assignments/assignments                (H,) int32, read in the fast loop, written by the slow loop
+                                                    (README.md:15,20,50); initialised to 0 = generalist (D7)
+      stats_buffer/{neuron_stats (H,5) f32, moments (H,5) f32, sample_count i32, step_count i32}
+                                                    (pattern of moe.py:265-279; D6)
+  * the per-step statistics leave through the mutable collection, not the return value (moe.py:281).
+
+The math (README.md:47-56): z = x W_up + b_up ; F = relu / tanh / binary_step by assignment ;
+h = F(z) + gate * z (gate 0.1 for specialists, 1.0 otherwise) ; y = h W_down + b_down ; backward uses the
+straight-through estimator for binary_step.  All of it runs in the sm_100a kernels of csrc/ through the C ABI;
+torch only owns memory, the stream and the autograd tape.
+
+Difference from Flax that a user must know: JAX is functional, torch autograd is not.  The gradient half of
+the statistics only exists once backward has run, so the ``stats_buffer`` leaves returned by ``apply`` are
+updated IN PLACE when the backward pass of that call finishes (forward-only calls update nothing unless
+``sense_forward_only=True``).
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+from typing import Dict, Iterable, Optional, Tuple, Union
+
+import torch
+
+from . import ops
+
+Collections = Dict[str, Dict[str, torch.Tensor]]
+
+STAT_NAMES = ("grad_gini", "grad_gdp", "act_gini", "act_gdp", "act_variance")  # sensing.py:65-67
+
+
+class _Workspace:
+    """Per-(M, H, device) scratch that is reused every step: the neuron-major residual buffers and partials."""
+
+    def __init__(self, M: int, H: int, device):
+        ld = ops.sample_pitch(M)
+        P = ops.num_partials(M)
+        self.M, self.H, self.ld, self.P = M, H, ld, P
+        self.zT = torch.empty((H, ld), dtype=torch.bfloat16, device=device)
+        self.hT = torch.empty((H, ld), dtype=torch.bfloat16, device=device)
+        self.act_partials = torch.empty((P, 3, H), dtype=torch.float32, device=device)
+        self.grad_partials = torch.empty((P, 3, H), dtype=torch.float32, device=device)
+        self.in_flight = False  # forward done, backward pending: zT / hT must not be overwritten
+
+
+_DZ_POOL: Dict[Tuple[int, int, str], torch.Tensor] = {}
+
+
+def _dz_scratch(H: int, ld: int, device) -> torch.Tensor:
+    """dz^T is consumed inside one layer's backward, so every layer of the same shape shares one buffer."""
+    key = (H, ld, str(device))
+    t = _DZ_POOL.get(key)
+    if t is None:
+        t = torch.empty((H, ld), dtype=torch.bfloat16, device=device)
+        _DZ_POOL[key] = t
+    return t
+
+
+class _StatefulLayerFn(torch.autograd.Function):
+    """fwd: two GEMM launches (up + fused epilogue, down).  bwd: dz (fused), dx, dW_up, dW_down, db, sensing."""
+
+    @staticmethod
+    def forward(ctx, x2d, w_up, b_up, w_down, b_down, layer, stats):
+        M, d = x2d.shape
+        H = w_up.shape[1]
+        ws = layer._workspace(M, H, x2d.device)
+        w_up16 = layer._bf16(w_up, "up")
+        w_down16 = layer._bf16(w_down, "down")
+        b_up32 = b_up.float() if b_up.dtype != torch.float32 else b_up
+        b_down32 = b_down.float() if b_down.dtype != torch.float32 else b_down
+        assign_i8 = layer._assign_i8
+        y = torch.empty((M, w_down.shape[1]), dtype=torch.bfloat16, device=x2d.device)
+        ops.sl_up_fwd(x2d, w_up16, b_up32, assign_i8, ws.zT, ws.hT, ws.act_partials)
+        ops.sl_down_fwd(ws.hT, w_down16, b_down32, y, M)
+        ctx.save_for_backward(x2d, w_up16, w_down16)
+        ctx.layer, ctx.ws, ctx.stats, ctx.assign_i8 = layer, ws, stats, assign_i8
+        ctx.param_dtypes = (w_up.dtype, b_up.dtype, w_down.dtype, b_down.dtype)
+        ctx.needs_dx = ctx.needs_input_grad[0]
+        will_backward = any(ctx.needs_input_grad)
+        ws.in_flight = will_backward
+        if stats is not None and not will_backward and layer.sense_forward_only:
+            layer._finalize(ws, stats, with_grad=False)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2d, w_up16, w_down16 = ctx.saved_tensors
+        layer, ws, stats, assign_i8 = ctx.layer, ctx.ws, ctx.stats, ctx.assign_i8
+        M, d = x2d.shape
+        H = ws.H
+        dy = dy.contiguous()
+        if dy.dtype != torch.bfloat16:
+            dy = dy.to(torch.bfloat16)
+        dev = x2d.device
+        dzT = _dz_scratch(H, ws.ld, dev)
+        ops.sl_dz_bwd(dy, w_down16, ws.zT, assign_i8, dzT, ws.grad_partials)
+        dx = None
+        if ctx.needs_dx:
+            dx = torch.empty((M, d), dtype=torch.bfloat16, device=dev)
+            ops.sl_dx_bwd(dzT, w_up16, dx, M)
+        dw_up = torch.zeros((d, H), dtype=torch.float32, device=dev)
+        d_out = dy.shape[1]
+        dw_down = torch.zeros((H, d_out), dtype=torch.float32, device=dev)
+        db_up = torch.zeros(H, dtype=torch.float32, device=dev)
+        db_down = torch.zeros(d_out, dtype=torch.float32, device=dev)
+        ops.sl_dw_up(x2d, dzT, dw_up)
+        ops.sl_dw_down(ws.hT, dy, dw_down)
+        ops.colsum_bf16(dy, db_down)
+        if stats is not None:
+            layer._finalize(ws, stats, with_grad=True, db_up=db_up)
+        else:
+            ops.stats_finalize(None, ws.grad_partials, ws.P, H, M, db_up=db_up)
+        ws.in_flight = False
+        return dx, dw_up, db_up, dw_down, db_down, None, None
+
+
+@dataclass
+class StatefulLayer:
+    """Drop-in for the reference's FFN-slot module (Flax dataclass-field construction, moe.py:225-243)."""
+
+    hidden_dim: int
+    out_dim: Optional[int] = None          # defaults to the input feature size (D2: d -> H -> d)
+    top_k: Optional[int] = None            # D8 activation sparsification; None = off (vision/text towers)
+    param_dtype: torch.dtype = torch.float32
+    sense_forward_only: bool = False       # also accumulate activation-only stats in no-grad forwards
+    name: str = "stateful_layer"
+
+    def __post_init__(self):
+        self._ws: Dict[Tuple[int, int, str], list] = {}
+        self._bf16_cache: Dict[str, Tuple[int, int, torch.Tensor]] = {}
+        self._assign_i8: Optional[torch.Tensor] = None
+        self._assign_src: Optional[Tuple[int, int]] = None
+        if self.top_k is not None:
+            raise NotImplementedError("top_k sparsification is provided by forde_b200.sparsify (LLM variant)")
+
+    # ------------------------------------------------------------------ Flax-style API
+    def init(self, key: Union[int, torch.Generator], x: torch.Tensor) -> Collections:
+        """Create the variable collections for inputs shaped like ``x`` (..., d)."""
+        d = x.shape[-1]
+        H = self.hidden_dim
+        out = self.out_dim or d
+        dev = x.device
+        gen = key if isinstance(key, torch.Generator) else torch.Generator(device="cpu").manual_seed(int(key))
+
+        def lecun(fan_in, shape):  # flax nn.Dense default kernel_init (lecun_normal), zero bias
+            w = torch.empty(shape, dtype=torch.float32)
+            torch.nn.init.trunc_normal_(w, mean=0.0, std=1.0, a=-2.0, b=2.0, generator=gen)
+            return (w * (math.sqrt(1.0 / fan_in) / 0.87962566103423978)).to(self.param_dtype).to(dev)
+
+        return {
+            "params": {
+                "up_proj": {"kernel": lecun(d, (d, H)), "bias": torch.zeros(H, dtype=self.param_dtype, device=dev)},
+                "down_proj": {"kernel": lecun(H, (H, out)), "bias": torch.zeros(out, dtype=self.param_dtype, device=dev)},
+            },
+            "neuron_assignments": {"assignments": torch.zeros(H, dtype=torch.int32, device=dev)},
+            "stats_buffer": new_stats_buffer(H, dev),
+        }
+
+    def apply(self, variables: Collections, x: torch.Tensor, mutable: Union[bool, Iterable[str]] = False):
+        """Forward pass.  With ``mutable=["stats_buffer"]`` returns ``(y, {"stats_buffer": ...})`` and the
+        sensing statistics of this step are accumulated into those leaves (see module docstring)."""
+        p = variables["params"]
+        mut = set(mutable) if not isinstance(mutable, bool) else (set(variables) - {"params"} if mutable else set())
+        stats = variables.get("stats_buffer") if "stats_buffer" in mut else None
+        self._load_assignments(variables["neuron_assignments"]["assignments"])
+        lead = x.shape[:-1]
+        x2d = x.reshape(-1, x.shape[-1])
+        if x2d.dtype != torch.bfloat16:
+            x2d = x2d.to(torch.bfloat16)
+        x2d = x2d.contiguous()
+        y = _StatefulLayerFn.apply(x2d, p["up_proj"]["kernel"], p["up_proj"]["bias"], p["down_proj"]["kernel"],
+                                   p["down_proj"]["bias"], self, stats)
+        y = y.reshape(*lead, y.shape[-1])
+        if isinstance(mutable, bool) and not mutable:
+            return y
+        return y, {k: variables[k] for k in mut if k in variables}
+
+    __call__ = apply
+
+    # ------------------------------------------------------------------ internals
+    def _workspace(self, M, H, device) -> _Workspace:
+        pool = self._ws.setdefault((M, H, str(device)), [])
+        for ws in pool:
+            if not ws.in_flight:
+                return ws
+        ws = _Workspace(M, H, device)  # the module is applied again before its previous backward ran
+        pool.append(ws)
+        return ws
+
+    def _bf16(self, w: torch.Tensor, tag: str) -> torch.Tensor:
+        if w.dtype == torch.bfloat16 and w.is_contiguous():
+            return w.detach()
+        c = self._bf16_cache.get(tag)
+        if c is not None and c[0] == w.data_ptr() and c[1] == w._version:
+            return c[2]
+        w16 = w.detach().to(torch.bfloat16).contiguous()
+        self._bf16_cache[tag] = (w.data_ptr(), w._version, w16)
+        return w16
+
+    def _load_assignments(self, a: torch.Tensor) -> None:
+        src = (a.data_ptr(), a._version)
+        if self._assign_i8 is None or self._assign_src != src:
+            # D5: values outside {0,1} act as specialists; clamp into int8 range before the narrowing cast
+            self._assign_i8 = a.clamp(-128, 127).to(torch.int8).contiguous()
+            self._assign_src = src
+
+    def _finalize(self, ws: _Workspace, stats: Dict[str, torch.Tensor], with_grad: bool, db_up=None) -> None:
+        ops.stats_finalize(ws.act_partials, ws.grad_partials if with_grad else None, ws.P, ws.H, ws.M,
+                           step_stats=stats.get("last_step_stats"), neuron_stats=stats["neuron_stats"],
+                           moments=stats["moments"], sample_count=stats["sample_count"],
+                           step_count=stats["step_count"], db_up=db_up)
+
+
+def new_stats_buffer(H: int, device) -> Dict[str, torch.Tensor]:
+    """Zero-initialised ``stats_buffer`` leaves for one layer (every leaf is a plain tensor so the slow loop's
+    ``zeros_like`` reset, moe_slow_loop.py:441-449, works unchanged)."""
+    return {
+        "neuron_stats": torch.zeros((H, 5), dtype=torch.float32, device=device),
+        "moments": torch.zeros((H, 5), dtype=torch.float32, device=device),
+        "sample_count": torch.zeros((), dtype=torch.int32, device=device),
+        "step_count": torch.zeros((), dtype=torch.int32, device=device),
+    }

@@ -105,22 +105,29 @@ int forde_stats_from_moments(void* stream, const float* moments, const int* samp
 
 /* ---- CLIP contrastive loss (README.md:35) ------------------------------------------------
  * img [Bl][E], txt [Bg][E] bf16 (txt already all-gathered; Bl = Bg on one GPU), row_offset = global index
- * of local image row 0.  logit_scale = exp(tau).
- * fwd:  u = img/|img|, v = txt/|txt| (bf16), S = logit_scale * u . v^T (fp32 [Bl][Bg]),
- *       row_lse[Bl], col_max[Bg], col_sum[Bg] (partial over the local rows; all-reduce across ranks),
- *       diag[Bl] = S[i][row_offset+i].
- * The caller combines: loss = 1/(2 Bg) * (sum_i (row_lse_i - diag_i) + sum_j (col_lse_j - diag_j)). */
-int forde_clip_fwd(void* stream, const void* img, const void* txt, float logit_scale, int Bl, int Bg, int E,
-                   int row_offset, void* u, void* v, float* inv_norm_img, float* inv_norm_txt, float* S,
-                   float* row_lse, float* col_max, float* col_sum, float* diag);
+ * of local image row 0.  log_temp is a DEVICE scalar (learnable log temperature tau), so no host sync.
+ * fwd:  u = img/|img|, v = txt/|txt| (bf16), logit_scale_out[1] = exp(tau),
+ *       S = exp(tau) * u . v^T (fp32 [Bl][Bg]), row_lse[Bl] (complete: a rank owns whole rows),
+ *       col_max[Bg], col_sum[Bg] (max / sum-exp over the LOCAL rows), diag[Bl] = S[i][row_offset+i].
+ * Across ranks: all-reduce(MAX) col_max -> g; forde_clip_col_rescale(col_max_local, g, col_sum);
+ *       all-reduce(SUM) col_sum.  On one GPU skip both.
+ * loss: col_lse = col_max + log col_sum;  loss[1] += this rank's share of
+ *       1/(2 Bg) (sum_i (row_lse_i - diag_i) + sum_j (col_lse_j - diag_j))   (all-reduce(SUM) across ranks) */
+int forde_clip_fwd(void* stream, const void* img, const void* txt, const float* log_temp, int Bl, int Bg, int E,
+                   int row_offset, void* u, void* v, float* inv_norm_img, float* inv_norm_txt,
+                   float* logit_scale_out, float* S, float* row_lse, float* col_max, float* col_sum, float* diag);
+int forde_clip_col_rescale(void* stream, const float* col_max_local, const float* col_max_global, float* col_sum,
+                           int Bg);
+int forde_clip_loss(void* stream, const float* row_lse, const float* diag, const float* col_max,
+                    const float* col_sum, int Bl, int Bg, int row_offset, float* col_lse, float* loss);
 /* bwd:  dS = (softmax_row + softmax_col)/(2 Bg) - onehot/Bg  (bf16 scratch [Bl][Bg]); col_lse is the GLOBAL
- *       column log-sum-exp (col_max + log col_sum after the cross-rank combine);
- *       dU [Bl][E] = logit_scale * dS . v (fp32, complete), dV [Bg][E] = logit_scale * dS^T . u (fp32, partial
- *       over ranks: reduce-scatter it), d_logit_scale[1] += sum dS * S / logit_scale (may be NULL).
+ *       column log-sum-exp; logit_scale is the device scalar written by forde_clip_fwd;
+ *       dU [Bl][E] = exp(tau) * dS . v (fp32, complete), dV [Bg][E] = exp(tau) * dS^T . u (fp32, partial over
+ *       ranks: reduce-scatter it), d_log_temp[1] += sum dS * S (may be NULL; all-reduce(SUM) across ranks).
  *       Follow with forde_l2norm_bwd to go from dU / dV to the gradients of the un-normalised embeddings. */
 int forde_clip_bwd(void* stream, const void* u, const void* v, const float* S, const float* row_lse,
-                   const float* col_lse, float logit_scale, int Bl, int Bg, int E, int row_offset, void* dS,
-                   float* dU, float* dV, float* d_logit_scale);
+                   const float* col_lse, const float* logit_scale, int Bl, int Bg, int E, int row_offset, void* dS,
+                   float* dU, float* dV, float* d_log_temp);
 /* normalisation backward for rows of an embedding: d_x = inv_norm * (dU - u (u . dU)) */
 int forde_l2norm_bwd(void* stream, const void* u, const float* inv_norm, const float* dU, float* d_x, int B,
                      int E);
