@@ -1,0 +1,302 @@
+#!/usr/bin/env python
+"""bench.py -- FORDE dual-encoder train-step throughput (image-text pairs/s) on B200.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--config vit_b16] [--batch 256] [--impl reference]
+
+One "step" = one fast-loop train step of the FORDE dual encoder (README.md:26-56) on one synthetic batch of
+image/caption pairs: forward of both towers (every FFN slot is the sm_100a StatefulLayer with in-kernel
+sensing), contrastive loss over the global batch, backward, gradient all-reduce (N > 1), global-norm clip,
+AdamW, bf16 weight refresh.  Batch-sharded ("weak" scaling: --batch pairs per GPU).
+
+JSON line keys follow the driver's contract: `value` = pairs/s with inputs resident in HBM, `e2e` = the same
+through train_step() with HOST (pinned) batches, the H2D copy and the loss read-back inside the timed region;
+`roofline` = the dominant StatefulLayer kernel (tensor bound) timed live with CUDA events on the launching
+stream; `cpu_baseline` = the CPU port of the same step (oracle/dual_encoder_cpu.py) on the host cores.
+
+--impl reference times that CPU port alone (the reference's JAX code cannot be installed here and contains no
+dual-encoder code) and prints the same line with "impl": "reference".
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "image_text_pairs_per_sec"
+UNIT = "pairs/s"
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return {"burst": p["bf16_tflops"], "sustained": p.get("bf16_tflops_sustained", p["bf16_tflops"]),
+                "hbm": p["hbm_gbs"], "source": "measured"}
+    return {"burst": 1590.0, "sustained": 1400.0, "hbm": 6650.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        self.thread.join(timeout=2)
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1])); pw.append(float(f[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def run_reference(args):
+    """CPU port of the same train step on the host cores (rank 0 only)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    import forde_b200  # noqa: F401
+    from forde_b200 import dual_encoder, train
+    from oracle import dual_encoder_cpu as C
+
+    cfg = dual_encoder.CONFIGS[args.config]()
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sample = args.cpu_batch
+    st = train.create_train_state(cfg, 0, device="cpu")
+    tr = C.CpuTrainer(cfg, st.variables)
+    b = train.synthetic_batch(cfg, sample, pinned=False)
+    img = b["image"].float()
+    for _ in range(args.warmup):
+        tr.step(img, b["input_ids"])
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        tr.step(img, b["input_ids"])
+    dt = time.perf_counter() - t0
+    v = sample * args.steps / dt
+    line = {
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"FORDE {cfg.name} dual-encoder train step (fwd+bwd+sensing+AdamW), CPU port, "
+                               f"{sample} pairs per step", "image": cfg.image_size, "text_len": cfg.text_len},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{sample} synthetic pairs per step of the {cfg.name} workload "
+                                   f"(the GPU arm runs {args.batch} per GPU per step); torch CPU fp32, "
+                                   "restated reference (not JAX/XLA: not installable here)"},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+
+    import __graft_entry__ as G
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the FORDE hot path has no CPU fallback "
+                         "(use --impl reference for the CPU port)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    if local == 0:
+        G.build()
+    if world > 1:
+        dist.barrier()
+    import forde_b200  # noqa: F401
+    from forde_b200 import dual_encoder, ops, train
+
+    cfg = dual_encoder.CONFIGS[args.config]()
+    dev = torch.device("cuda", local)
+    state = train.create_train_state(cfg, 0, device=dev)
+    host = [train.synthetic_batch(cfg, args.batch, seed=42 + rank * 100 + i, pinned=True) for i in range(2)]
+    devb = [{k: v.to(dev) for k, v in b.items()} for b in host]
+    h2d = sum(v.numel() * v.element_size() for v in host[0].values())
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(batches, steps, read_loss):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        last = None
+        for i in range(steps):
+            _, m = train.train_step(state, batches[i % len(batches)])
+            if read_loss:
+                last = float(m["loss"].item())      # D2H of the step's result inside the timed region
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item()), last
+
+    for i in range(max(args.warmup, 3)):
+        train.train_step(state, devb[i % 2])
+    torch.cuda.synchronize()
+
+    # ---- device-resident throughput, with live per-kernel timing and clock sampling
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ops.enable_timing(True)
+    l0 = ops.launch_count()
+    ms, _ = timed(devb, args.steps, read_loss=False)
+    launches = ops.launch_count() - l0
+    kt = ops.timing_summary()
+    ops.enable_timing(False)
+    clocks = sampler.stop() if rank == 0 else None
+    value = world * args.batch * args.steps / (ms * 1e-3)
+
+    # ---- end to end: host batches -> train_step -> loss on the host
+    for i in range(2):
+        train.train_step(state, host[i % 2])
+    ms_e2e, loss = timed(host, args.steps, read_loss=True)
+    e2e = world * args.batch * args.steps / (ms_e2e * 1e-3)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    peaks = measured_peaks()
+    kernels = {}
+    for name, r in kt.items():
+        us = 1e3 * r["ms_total"] / r["launches"]
+        kernels[name] = {"launches": r["launches"], "us_per_launch": round(us, 2),
+                         "tflops": round(r["flops_total"] / r["launches"] / (us * 1e-6) / 1e12, 1)}
+    roofline = None
+    sl_ms = sum(r["ms_total"] for r in kt.values())
+    sl_flops = sum(r["flops_total"] for r in kt.values())
+    if kt:
+        dom = max(kt, key=lambda n: kt[n]["ms_total"])
+        r = kt[dom]
+        ach = r["flops_total"] / (r["ms_total"] * 1e-3) / 1e12
+        roofline = {"kernel": dom, "bound": "tensor", "achieved": round(ach, 1), "peak": peaks["sustained"],
+                    "unit": "TFLOP/s", "frac": round(ach / peaks["sustained"], 4),
+                    "peak_kind": f"{peaks['source']} sustained bf16 (kernel timed inside a long step)",
+                    "flops_per_launch": r["flops_total"] / r["launches"], "launches": r["launches"],
+                    "us_per_launch": round(1e3 * r["ms_total"] / r["launches"], 2), "traffic": None}
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": f"FORDE {cfg.name} dual-encoder train step: ViT {cfg.image_size}px/p{cfg.patch_size} "
+                               f"d={cfg.vision.width} H={cfg.vision.hidden} L={cfg.vision.layers} + text S={cfg.text_len} "
+                               f"d={cfg.text.width} H={cfg.text.hidden} L={cfg.text.layers}, embed {cfg.embed_dim}",
+                   "batch_per_gpu": args.batch, "global_batch": args.batch * world, "parallelism": f"dp{world}",
+                   "optimizer": "clip_by_global_norm(1.0)+AdamW fp32 master, bf16 compute",
+                   "l2": "per-step working set (activations + weights, several GB) exceeds the 126 MB L2; no flush"},
+        "clocks": clocks,
+        "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": ms_e2e / args.steps, "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": 4, "loss": loss},
+        "gpu_launches": int(launches),
+        "roofline": roofline,
+        "stateful_layer": {"flops_per_step": dual_encoder.stateful_layer_flops(cfg, args.batch),
+                           "ms_per_step_in_kernels": sl_ms / args.steps,
+                           "tflops": round(sl_flops / (sl_ms * 1e-3) / 1e12, 1) if sl_ms else None,
+                           "frac_of_sustained_peak": round(sl_flops / (sl_ms * 1e-3) / 1e12 / peaks["sustained"], 4) if sl_ms else None,
+                           "kernels": kernels},
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline(cfg, args)
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def cpu_baseline(cfg, args):
+    """Bounded sample of the same workload on the host cores (about 10-30 s)."""
+    import torch
+    from forde_b200 import train
+    from oracle import dual_encoder_cpu as C
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sample = args.cpu_batch
+    st = train.create_train_state(cfg, 0, device="cpu")
+    tr = C.CpuTrainer(cfg, st.variables)
+    b = train.synthetic_batch(cfg, sample, pinned=False)
+    img = b["image"].float()
+    tr.step(img, b["input_ids"])
+    t0 = time.perf_counter()
+    n = 0
+    while n < 3 or (time.perf_counter() - t0 < 10.0 and n < 50):
+        tr.step(img, b["input_ids"])
+        n += 1
+    dt = time.perf_counter() - t0
+    return {"value": sample * n / dt, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{n} steps of {sample} synthetic pairs of the {cfg.name} workload (fwd+bwd+sensing pass+AdamW), "
+                      "torch CPU fp32 port of the restated reference (JAX not installable here)"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--config", default="vit_b16", choices=["tiny", "vit_b16", "vit_l14"])
+    ap.add_argument("--batch", type=int, default=256, help="pairs per GPU per step")
+    ap.add_argument("--cpu-batch", type=int, default=8, help="pairs per step of the CPU port's bounded sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -23,6 +23,7 @@ SIGNATURES = {
     "forde_error_string": (ctypes.c_char_p, [_i]),
     "forde_last_cuda_error": (ctypes.c_char_p, []),
     "forde_sm_count": (_i, []),
+    "forde_launch_count": (ctypes.c_ulonglong, []),
     "forde_sl_num_partials": (_i, [_i]),
     "forde_gemm_bf16": (_i, [_vp, _vp, _i, _ll, _vp, _i, _ll, _vp, _ll, _vp, _i, _i, _i]),
     "forde_gemm_f32": (_i, [_vp, _vp, _i, _ll, _vp, _i, _ll, _vp, _ll, _vp, _vp, _f, _i, _i, _i, _i]),

@@ -3,6 +3,7 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 
+#include <atomic>
 #include <cstdio>
 #include <cstring>
 #include <mutex>
@@ -20,12 +21,15 @@ void record_cuda_error(const char* what, const char* msg) {
   std::snprintf(g_last_err, sizeof(g_last_err), "%s: %s", what, msg);
 }
 
-int check_launch(const char* what) {
+static std::atomic<unsigned long long> g_launches{0};
+
+int check_launch(const char* what, int kernels) {
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
     record_cuda_error(what, cudaGetErrorString(e));
     return FORDE_ECUDA;
   }
+  g_launches.fetch_add(static_cast<unsigned long long>(kernels), std::memory_order_relaxed);
   return FORDE_OK;
 }
 
@@ -245,6 +249,8 @@ const char* forde_error_string(int code) {
 const char* forde_last_cuda_error(void) { return g_last_err; }
 
 int forde_sm_count(void) { return sm_count(); }
+
+unsigned long long forde_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
 int forde_sl_num_partials(int M) { return M <= 0 ? 0 : (M + BN - 1) / BN; }
 

@@ -348,7 +348,7 @@ int forde_clip_fwd(void* stream, const void* img, const void* txt, const float* 
   l2norm_rows_kernel<<<(Bg + 7) / 8, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(txt),
                                                   static_cast<__nv_bfloat16*>(v), inv_norm_txt, Bg, E, nullptr,
                                                   nullptr);
-  int rc = check_launch("l2norm_rows_kernel");
+  int rc = check_launch("l2norm_rows_kernel", 2);
   if (rc != FORDE_OK) return rc;
   // S[Bl][Bg] = exp(log_temp) * u . v^T  : both operands K-major (k = E)
   GemmArgs g{u, false, E, v, false, E, Bl, Bg, E, true, 0x1000000000000000ull, 0x1000000000000000ull};
@@ -356,7 +356,7 @@ int forde_clip_fwd(void* stream, const void* img, const void* txt, const float* 
   if (rc != FORDE_OK) return rc;
   row_lse_kernel<<<(Bl + 7) / 8, 256, 0, st>>>(S, Bl, Bg, row_offset, row_lse, diag);
   col_lse_kernel<<<(Bg + 31) / 32, dim3(32, 8), 0, st>>>(S, Bl, Bg, col_max, col_sum);
-  return check_launch("clip lse kernels");
+  return check_launch("clip lse kernels", 2);
 }
 
 int forde_clip_col_rescale(void* stream, const float* col_max_local, const float* col_max_global, float* col_sum,

@@ -6,7 +6,8 @@
 namespace forde {
 
 void record_cuda_error(const char* what, const char* msg);
-int check_launch(const char* what);
+// records a launch error (if any) and counts `kernels` successful kernel launches (forde_launch_count)
+int check_launch(const char* what, int kernels = 1);
 int sm_count();
 
 struct GemmArgs {

@@ -1,0 +1,220 @@
+"""FORDE CLIP-style dual encoder: the CALLER of the hot path (README.md:26-43).
+
+This is the benchmark / integration harness around the StatefulLayer, not the product: the towers are the
+plain macro-architecture the README describes (patchify or token embedding -> L x FORDETransformerBlock ->
+[CLS] -> Dense projection), attention and LayerNorm go through stock torch ops (cuBLAS / SDPA flash kernels,
+"library code" for this task), and ONLY the FFN slot of every block -- ``StatefulLayer`` -- and the contrastive
+loss run on this repository's sm_100a kernels.  FORDE block = self-attention -> add/norm -> StatefulLayer ->
+add/norm (README.md:42-43).
+
+Variables follow the Flax collection layout the reference's training loop threads through ``train_step``
+(src/training/train.py:122-171): ``params`` (differentiated), ``neuron_assignments`` and ``stats_buffer``
+(mutable, keyed ``{tower}/layer_{i}/stateful_layer`` so the slow loop's walker finds them,
+src/forde/moe_slow_loop.py:145-170).
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, field
+from typing import Dict, Optional
+
+import torch
+import torch.nn.functional as F
+
+from .clip_loss import INIT_LOG_TEMP, clip_contrastive_loss
+from .stateful_layer import StatefulLayer, new_stats_buffer
+
+
+@dataclass
+class TowerConfig:
+    width: int
+    layers: int
+    heads: int
+    hidden: int                      # StatefulLayer H (4 x width, src/training/train.py:250)
+
+
+@dataclass
+class DualEncoderConfig:
+    """SURVEY.md section 8 config table (C1, C2/C3, C5); CLIP-standard dims where the README is silent."""
+    image_size: int = 224
+    patch_size: int = 16
+    vision: TowerConfig = field(default_factory=lambda: TowerConfig(768, 12, 12, 3072))
+    text: TowerConfig = field(default_factory=lambda: TowerConfig(512, 12, 8, 2048))
+    vocab_size: int = 30522          # bert-base-uncased (src/data/download_to_drive.py:122)
+    text_len: int = 77
+    embed_dim: int = 512
+    name: str = "vit_b16"
+
+    @property
+    def vision_tokens(self) -> int:
+        return (self.image_size // self.patch_size) ** 2 + 1
+
+
+def config_tiny() -> DualEncoderConfig:      # C1
+    return DualEncoderConfig(32, 16, TowerConfig(128, 2, 4, 512), TowerConfig(128, 2, 4, 512), 30522, 16, 128, "tiny")
+
+
+def config_vit_b16() -> DualEncoderConfig:   # C2 / C3
+    return DualEncoderConfig()
+
+
+def config_vit_l14() -> DualEncoderConfig:   # C5
+    return DualEncoderConfig(224, 14, TowerConfig(1024, 24, 16, 4096), TowerConfig(768, 12, 12, 3072), 30522, 77, 768,
+                             "vit_l14")
+
+
+CONFIGS = {"tiny": config_tiny, "vit_b16": config_vit_b16, "vit_l14": config_vit_l14}
+
+
+class _Bf16Mirror(torch.autograd.Function):
+    """Use the pre-cast bf16 mirror of an fp32 master parameter; route the gradient back to the master."""
+
+    @staticmethod
+    def forward(ctx, master, mirror):
+        return mirror.view_as(mirror)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g.float(), None
+
+
+def _flatten(tree, prefix=""):
+    out = {}
+    for k in sorted(tree):
+        v = tree[k]
+        name = f"{prefix}/{k}" if prefix else k
+        if isinstance(v, dict):
+            out.update(_flatten(v, name))
+        else:
+            out[name] = v
+    return out
+
+
+class FORDEDualEncoder:
+    def __init__(self, cfg: DualEncoderConfig):
+        self.cfg = cfg
+        self.layers: Dict[str, StatefulLayer] = {}
+        for tower, tc in (("vision", cfg.vision), ("text", cfg.text)):
+            for i in range(tc.layers):
+                self.layers[f"{tower}/layer_{i}"] = StatefulLayer(hidden_dim=tc.hidden, name=f"{tower}/layer_{i}")
+
+    # ------------------------------------------------------------------ init
+    def init(self, key: int, device) -> Dict[str, dict]:
+        cfg = self.cfg
+        gen = torch.Generator(device="cpu").manual_seed(int(key))
+        dev = torch.device(device)
+
+        def normal(shape, std):
+            return (torch.randn(shape, generator=gen) * std).to(dev)
+
+        def dense(i, o, bias=True):
+            p = {"kernel": normal((i, o), 1.0 / math.sqrt(i))}
+            if bias:
+                p["bias"] = torch.zeros(o, device=dev)
+            return p
+
+        def ln(w):
+            return {"scale": torch.ones(w, device=dev), "bias": torch.zeros(w, device=dev)}
+
+        params, assigns, stats = {}, {}, {}
+        for tower, tc in (("vision", cfg.vision), ("text", cfg.text)):
+            tp, ta, ts = {}, {}, {}
+            w = tc.width
+            if tower == "vision":
+                tp["patch_embed"] = dense(cfg.patch_size * cfg.patch_size * 3, w)
+                tp["cls"] = normal((w,), 0.02)
+                tp["pos_embed"] = normal((cfg.vision_tokens, w), 0.02)
+            else:
+                tp["token_embed"] = normal((cfg.vocab_size, w), 0.02)
+                tp["pos_embed"] = normal((cfg.text_len, w), 0.01)
+            for i in range(tc.layers):
+                sl = self.layers[f"{tower}/layer_{i}"]
+                v = sl.init(int(torch.randint(0, 2 ** 31 - 1, (), generator=gen)), torch.empty((1, w), device=dev))
+                tp[f"layer_{i}"] = {"attn": {"qkv": dense(w, 3 * w), "out": dense(w, w)}, "ln_1": ln(w), "ln_2": ln(w),
+                                    "stateful_layer": v["params"]}
+                ta[f"layer_{i}"] = {"stateful_layer": v["neuron_assignments"]}
+                ts[f"layer_{i}"] = {"stateful_layer": new_stats_buffer(tc.hidden, dev)}
+            tp["proj"] = dense(w, cfg.embed_dim, bias=False)
+            params[tower], assigns[tower], stats[tower] = tp, ta, ts
+        params["log_temp"] = torch.tensor(INIT_LOG_TEMP, device=dev)
+        return {"params": params, "neuron_assignments": assigns, "stats_buffer": stats}
+
+    # ------------------------------------------------------------------ forward
+    @staticmethod
+    def _w(p, p16, name):
+        """bf16 compute weight of a master parameter (uses the pre-cast mirror when the train state keeps one)."""
+        if p16 is not None:
+            return _Bf16Mirror.apply(p[name], p16[name])
+        return p[name].to(torch.bfloat16)
+
+    def _block(self, key, x, p, p16, heads, variables, sense):
+        B, T, w = x.shape
+        qkv = F.linear(x, self._w(p["attn"]["qkv"], p16 and p16["attn"]["qkv"], "kernel").t(),
+                       p["attn"]["qkv"]["bias"].to(torch.bfloat16))
+        q, k, v = qkv.view(B, T, 3, heads, w // heads).permute(2, 0, 3, 1, 4)
+        a = F.scaled_dot_product_attention(q, k, v)
+        a = a.transpose(1, 2).reshape(B, T, w)
+        a = F.linear(a, self._w(p["attn"]["out"], p16 and p16["attn"]["out"], "kernel").t(),
+                     p["attn"]["out"]["bias"].to(torch.bfloat16))
+        x = F.layer_norm(x + a, (w,), p["ln_1"]["scale"].to(torch.bfloat16), p["ln_1"]["bias"].to(torch.bfloat16), 1e-6)
+        tower, lname = key.split("/")
+        sl_vars = {
+            "params": p["stateful_layer"],
+            "neuron_assignments": variables["neuron_assignments"][tower][lname]["stateful_layer"],
+            "stats_buffer": variables["stats_buffer"][tower][lname]["stateful_layer"],
+        }
+        if p16 is not None:
+            sl_vars["params_bf16"] = p16["stateful_layer"]
+        layer = self.layers[key]
+        if sense:
+            m, _ = layer.apply(sl_vars, x, mutable=["stats_buffer"])
+        else:
+            m = layer.apply(sl_vars, x)
+        return F.layer_norm(x + m, (w,), p["ln_2"]["scale"].to(torch.bfloat16), p["ln_2"]["bias"].to(torch.bfloat16), 1e-6)
+
+    def encode_image(self, variables, images, sense=True, params_bf16=None):
+        """images (B, S, S, 3) NHWC (src/data/download_to_drive.py:173), any float dtype."""
+        cfg = self.cfg
+        p = variables["params"]["vision"]
+        p16 = params_bf16["vision"] if params_bf16 is not None else None
+        B = images.shape[0]
+        g, ps = cfg.image_size // cfg.patch_size, cfg.patch_size
+        x = images.to(torch.bfloat16).view(B, g, ps, g, ps, 3).permute(0, 1, 3, 2, 4, 5).reshape(B, g * g, ps * ps * 3)
+        x = F.linear(x, self._w(p["patch_embed"], p16 and p16["patch_embed"], "kernel").t(),
+                     p["patch_embed"]["bias"].to(torch.bfloat16))
+        cls = p["cls"].to(torch.bfloat16).expand(B, 1, -1)
+        x = torch.cat([cls, x], dim=1) + p["pos_embed"].to(torch.bfloat16)
+        for i in range(cfg.vision.layers):
+            x = self._block(f"vision/layer_{i}", x, p[f"layer_{i}"], p16 and p16[f"layer_{i}"], cfg.vision.heads,
+                            variables, sense)
+        return F.linear(x[:, 0], self._w(p["proj"], p16 and p16["proj"], "kernel").t())
+
+    def encode_text(self, variables, input_ids, sense=True, params_bf16=None):
+        """input_ids (B, S) int (src/data/download_to_drive.py:106-108); token 0 is [CLS]."""
+        cfg = self.cfg
+        p = variables["params"]["text"]
+        p16 = params_bf16["text"] if params_bf16 is not None else None
+        emb = self._w(p, p16, "token_embed")
+        x = F.embedding(input_ids.long(), emb) + p["pos_embed"].to(torch.bfloat16)[: input_ids.shape[1]]
+        for i in range(cfg.text.layers):
+            x = self._block(f"text/layer_{i}", x, p[f"layer_{i}"], p16 and p16[f"layer_{i}"], cfg.text.heads,
+                            variables, sense)
+        return F.linear(x[:, 0], self._w(p["proj"], p16 and p16["proj"], "kernel").t())
+
+    def apply(self, variables, images, input_ids, mutable=False, params_bf16=None, group=None):
+        """Returns the global-batch contrastive loss (and the mutable collections when asked, Flax style)."""
+        mut = set(mutable) if not isinstance(mutable, bool) else (set(variables) - {"params"} if mutable else set())
+        sense = "stats_buffer" in mut
+        img = self.encode_image(variables, images, sense, params_bf16)
+        txt = self.encode_text(variables, input_ids, sense, params_bf16)
+        loss = clip_contrastive_loss(img, txt, variables["params"]["log_temp"], group)
+        if isinstance(mutable, bool) and not mutable:
+            return loss
+        return loss, {k: variables[k] for k in mut if k in variables}
+
+
+def stateful_layer_flops(cfg: DualEncoderConfig, batch: int) -> float:
+    """Algorithmic FLOPs of the hot path per train step: 12 M d H per layer (six GEMMs), SURVEY.md 8d."""
+    v = 12.0 * batch * cfg.vision_tokens * cfg.vision.width * cfg.vision.hidden * cfg.vision.layers
+    t = 12.0 * batch * cfg.text_len * cfg.text.width * cfg.text.hidden * cfg.text.layers
+    return v + t

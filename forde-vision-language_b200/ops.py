@@ -27,6 +27,51 @@ def _req(t: torch.Tensor, dtype, name: str) -> None:
         raise _lib.FordeError(f"{name} must be contiguous")
 
 
+# ---- optional per-kernel CUDA-event timing (bench.py's live roofline measurement); off by default -----------
+_TIMING = None
+
+
+def enable_timing(on: bool = True) -> None:
+    """Record a CUDA-event pair on the launching stream around every StatefulLayer kernel launch."""
+    global _TIMING
+    _TIMING = {} if on else None
+
+
+def timing_summary():
+    """{kernel family: {"launches", "ms_total", "flops_total"}}; synchronises.  Call after the timed region."""
+    out = {}
+    if _TIMING is None:
+        return out
+    torch.cuda.synchronize()
+    for name, recs in _TIMING.items():
+        ms = sum(a.elapsed_time(b) for a, b, _ in recs)
+        out[name] = {"launches": len(recs), "ms_total": ms, "flops_total": float(sum(f for _, _, f in recs))}
+    return out
+
+
+class _Timed:
+    __slots__ = ("name", "flops", "a")
+
+    def __init__(self, name, flops):
+        self.name, self.flops = name, flops
+
+    def __enter__(self):
+        if _TIMING is not None:
+            self.a = torch.cuda.Event(enable_timing=True)
+            self.a.record()
+
+    def __exit__(self, *exc):
+        if _TIMING is not None:
+            b = torch.cuda.Event(enable_timing=True)
+            b.record()
+            _TIMING.setdefault(self.name, []).append((self.a, b, self.flops))
+        return False
+
+
+def launch_count() -> int:
+    return int(_lib.load().forde_launch_count())
+
+
 def round_up(v: int, m: int) -> int:
     return (v + m - 1) // m * m
 
@@ -80,8 +125,9 @@ def sl_up_fwd(x, w_up, b_up, assign_i8, zT, hT, act_partials):
     _req(zT, torch.bfloat16, "zT"); _req(hT, torch.bfloat16, "hT")
     if b_up is not None:
         _req(b_up, torch.float32, "b_up")
-    rc = _lib.load().forde_sl_up_fwd(_stream(), x.data_ptr(), w_up.data_ptr(), _ptr(b_up), assign_i8.data_ptr(),
-                                     zT.data_ptr(), hT.data_ptr(), _ptr(act_partials), M, d, H, zT.stride(0))
+    with _Timed(f"sl_up_fwd[{M}x{d}x{H}]", 2.0 * M * d * H):
+        rc = _lib.load().forde_sl_up_fwd(_stream(), x.data_ptr(), w_up.data_ptr(), _ptr(b_up), assign_i8.data_ptr(),
+                                         zT.data_ptr(), hT.data_ptr(), _ptr(act_partials), M, d, H, zT.stride(0))
     _lib.check(rc, "forde_sl_up_fwd")
 
 
@@ -90,8 +136,9 @@ def sl_down_fwd(hT, w_down, b_down, y, M):
     _req(hT, torch.bfloat16, "hT"); _req(w_down, torch.bfloat16, "w_down"); _req(y, torch.bfloat16, "y")
     if b_down is not None:
         _req(b_down, torch.float32, "b_down")
-    rc = _lib.load().forde_sl_down_fwd(_stream(), hT.data_ptr(), w_down.data_ptr(), _ptr(b_down), y.data_ptr(), M, d,
-                                       H, hT.stride(0))
+    with _Timed(f"sl_down_fwd[{M}x{d}x{H}]", 2.0 * M * d * H):
+        rc = _lib.load().forde_sl_down_fwd(_stream(), hT.data_ptr(), w_down.data_ptr(), _ptr(b_down), y.data_ptr(), M, d,
+                                           H, hT.stride(0))
     _lib.check(rc, "forde_sl_down_fwd")
 
 
@@ -99,15 +146,17 @@ def sl_dz_bwd(dy, w_down, zT, assign_i8, dzT, grad_partials):
     M, d = dy.shape
     H = w_down.shape[0]
     _req(dy, torch.bfloat16, "dy"); _req(zT, torch.bfloat16, "zT"); _req(dzT, torch.bfloat16, "dzT")
-    rc = _lib.load().forde_sl_dz_bwd(_stream(), dy.data_ptr(), w_down.data_ptr(), zT.data_ptr(), assign_i8.data_ptr(),
-                                     dzT.data_ptr(), _ptr(grad_partials), M, d, H, zT.stride(0))
+    with _Timed(f"sl_dz_bwd[{M}x{d}x{H}]", 2.0 * M * d * H):
+        rc = _lib.load().forde_sl_dz_bwd(_stream(), dy.data_ptr(), w_down.data_ptr(), zT.data_ptr(), assign_i8.data_ptr(),
+                                         dzT.data_ptr(), _ptr(grad_partials), M, d, H, zT.stride(0))
     _lib.check(rc, "forde_sl_dz_bwd")
 
 
 def sl_dx_bwd(dzT, w_up, dx, M):
     d, H = w_up.shape
     _req(dzT, torch.bfloat16, "dzT"); _req(dx, torch.bfloat16, "dx")
-    rc = _lib.load().forde_sl_dx_bwd(_stream(), dzT.data_ptr(), w_up.data_ptr(), dx.data_ptr(), M, d, H, dzT.stride(0))
+    with _Timed(f"sl_dx_bwd[{M}x{d}x{H}]", 2.0 * M * d * H):
+        rc = _lib.load().forde_sl_dx_bwd(_stream(), dzT.data_ptr(), w_up.data_ptr(), dx.data_ptr(), M, d, H, dzT.stride(0))
     _lib.check(rc, "forde_sl_dx_bwd")
 
 
@@ -115,7 +164,8 @@ def sl_dw_up(x, dzT, dw_up):
     M, d = x.shape
     H = dzT.shape[0]
     _req(x, torch.bfloat16, "x"); _req(dzT, torch.bfloat16, "dzT"); _req(dw_up, torch.float32, "dw_up")
-    rc = _lib.load().forde_sl_dw_up(_stream(), x.data_ptr(), dzT.data_ptr(), dw_up.data_ptr(), M, d, H, dzT.stride(0))
+    with _Timed(f"sl_dw_up[{M}x{d}x{H}]", 2.0 * M * d * H):
+        rc = _lib.load().forde_sl_dw_up(_stream(), x.data_ptr(), dzT.data_ptr(), dw_up.data_ptr(), M, d, H, dzT.stride(0))
     _lib.check(rc, "forde_sl_dw_up")
 
 
@@ -123,8 +173,9 @@ def sl_dw_down(hT, dy, dw_down):
     M, d = dy.shape
     H = hT.shape[0]
     _req(hT, torch.bfloat16, "hT"); _req(dy, torch.bfloat16, "dy"); _req(dw_down, torch.float32, "dw_down")
-    rc = _lib.load().forde_sl_dw_down(_stream(), hT.data_ptr(), dy.data_ptr(), dw_down.data_ptr(), M, d, H,
-                                      hT.stride(0))
+    with _Timed(f"sl_dw_down[{M}x{d}x{H}]", 2.0 * M * d * H):
+        rc = _lib.load().forde_sl_dw_down(_stream(), hT.data_ptr(), dy.data_ptr(), dw_down.data_ptr(), M, d, H,
+                                          hT.stride(0))
     _lib.check(rc, "forde_sl_dw_down")
 
 

@@ -68,12 +68,12 @@ class _StatefulLayerFn(torch.autograd.Function):
     """fwd: two GEMM launches (up + fused epilogue, down).  bwd: dz (fused), dx, dW_up, dW_down, db, sensing."""
 
     @staticmethod
-    def forward(ctx, x2d, w_up, b_up, w_down, b_down, layer, stats):
+    def forward(ctx, x2d, w_up, b_up, w_down, b_down, layer, stats, w_up16, w_down16):
         M, d = x2d.shape
         H = w_up.shape[1]
         ws = layer._workspace(M, H, x2d.device)
-        w_up16 = layer._bf16(w_up, "up")
-        w_down16 = layer._bf16(w_down, "down")
+        w_up16 = layer._bf16(w_up, "up") if w_up16 is None else w_up16
+        w_down16 = layer._bf16(w_down, "down") if w_down16 is None else w_down16
         b_up32 = b_up.float() if b_up.dtype != torch.float32 else b_up
         b_down32 = b_down.float() if b_down.dtype != torch.float32 else b_down
         assign_i8 = layer._assign_i8
@@ -119,7 +119,7 @@ class _StatefulLayerFn(torch.autograd.Function):
         else:
             ops.stats_finalize(None, ws.grad_partials, ws.P, H, M, db_up=db_up)
         ws.in_flight = False
-        return dx, dw_up, db_up, dw_down, db_down, None, None
+        return dx, dw_up, db_up, dw_down, db_down, None, None, None, None
 
 
 @dataclass
@@ -176,8 +176,13 @@ class StatefulLayer:
         if x2d.dtype != torch.bfloat16:
             x2d = x2d.to(torch.bfloat16)
         x2d = x2d.contiguous()
+        # optional pre-cast bf16 mirror of the fp32 master weights (kept by the train state, refreshed once per
+        # optimizer step) so the forward does not re-cast them
+        p16 = variables.get("params_bf16")
+        w_up16 = p16["up_proj"]["kernel"] if p16 is not None else None
+        w_down16 = p16["down_proj"]["kernel"] if p16 is not None else None
         y = _StatefulLayerFn.apply(x2d, p["up_proj"]["kernel"], p["up_proj"]["bias"], p["down_proj"]["kernel"],
-                                   p["down_proj"]["bias"], self, stats)
+                                   p["down_proj"]["bias"], self, stats, w_up16, w_down16)
         y = y.reshape(*lead, y.shape[-1])
         if isinstance(mutable, bool) and not mutable:
             return y

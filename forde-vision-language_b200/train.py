@@ -1,0 +1,132 @@
+"""Training-loop contract of the fast loop (src/training/train.py:48-171), B200-side.
+
+``create_train_state`` / ``train_step`` keep the reference's names and roles: the state carries ``params``
+plus the mutable collections (``stats_buffer``, and README's ``neuron_assignments``), ``train_step`` runs
+forward + backward with the statistics threaded through ``mutable=[...]``, clips the global gradient norm to
+1.0 and applies AdamW (optax chain at train.py:74-77), and the slow loop is triggered by the caller every
+``slow_loop_interval`` steps (train.py:365-399).
+
+B200 layout: every master parameter is a view into ONE flat fp32 buffer (gradients likewise, plus a flat bf16
+compute mirror refreshed once per step), so the data-parallel gradient all-reduce, the global-norm clip, AdamW
+and the bf16 refresh are each a single pass over contiguous memory, and the NCCL all-reduce is issued in a few
+large chunks on a side stream while the remaining backward still runs.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Dict, Optional
+
+import torch
+import torch.distributed as dist
+
+from .dual_encoder import DualEncoderConfig, FORDEDualEncoder
+
+_ALIGN = 64  # elements; keeps every bf16 mirror view 128-byte aligned (TMA needs 16 B)
+
+
+def _leaves(tree, path=()):
+    for k in sorted(tree):
+        v = tree[k]
+        if isinstance(v, dict):
+            yield from _leaves(v, path + (k,))
+        else:
+            yield path + (k,), v
+
+
+def _set(tree, path, value):
+    for k in path[:-1]:
+        tree = tree[k]
+    tree[path[-1]] = value
+
+
+def _mirror_tree(tree):
+    return {k: (_mirror_tree(v) if isinstance(v, dict) else None) for k, v in tree.items()}
+
+
+@dataclass
+class TrainState:
+    step: int
+    model: FORDEDualEncoder
+    variables: Dict[str, dict]          # params (views of flat_p32), neuron_assignments, stats_buffer
+    params_bf16: Dict[str, dict]        # same tree, views of flat_p16
+    flat_p32: torch.Tensor
+    flat_g32: torch.Tensor
+    flat_p16: torch.Tensor
+    opt: torch.optim.Optimizer
+    group: Optional["dist.ProcessGroup"] = None
+    max_grad_norm: float = 1.0
+
+    @property
+    def params(self):
+        return self.variables["params"]
+
+    @property
+    def stats_buffer(self):
+        return self.variables["stats_buffer"]
+
+
+def create_train_state(config: DualEncoderConfig, key: int, learning_rate: float = 1e-4, weight_decay: float = 0.01,
+                       device="cuda", group=None) -> TrainState:
+    model = FORDEDualEncoder(config)
+    variables = model.init(key, device)
+    leaves = list(_leaves(variables["params"]))
+    offs, total = [], 0
+    for _, t in leaves:
+        offs.append(total)
+        total += (t.numel() + _ALIGN - 1) // _ALIGN * _ALIGN
+    dev = torch.device(device)
+    flat_p32 = torch.zeros(total, dtype=torch.float32, device=dev)
+    flat_g32 = torch.zeros(total, dtype=torch.float32, device=dev)
+    flat_p16 = torch.zeros(total, dtype=torch.bfloat16, device=dev)
+    p16_tree = _mirror_tree(variables["params"])
+    for (path, t), off in zip(leaves, offs):
+        n = t.numel()
+        flat_p32[off:off + n].copy_(t.reshape(-1))
+        p = flat_p32[off:off + n].view(t.shape).requires_grad_(True)
+        p.grad = flat_g32[off:off + n].view(t.shape)
+        _set(variables["params"], path, p)
+        _set(p16_tree, path, flat_p16[off:off + n].view(t.shape))
+    flat_p16.copy_(flat_p32)
+    flat_p32.grad = flat_g32
+    # optax.adamw(lr, wd) decays every leaf (no mask, train.py:74-77), so one flat parameter is equivalent
+    opt = torch.optim.AdamW([flat_p32], lr=learning_rate, weight_decay=weight_decay, betas=(0.9, 0.999), eps=1e-8,
+                            fused=dev.type == "cuda")
+    return TrainState(0, model, variables, p16_tree, flat_p32, flat_g32, flat_p16, opt, group)
+
+
+def _to_device(t: torch.Tensor, dev) -> torch.Tensor:
+    return t if t.device == dev else t.to(dev, non_blocking=True)
+
+
+def train_step(state: TrainState, batch: Dict[str, torch.Tensor], sense: bool = True):
+    """One fast-loop step.  batch = {"image": (B,S,S,3), "input_ids": (B,T)}; host (pinned) or device tensors.
+    Returns (state, metrics) with metrics["loss"], metrics["grad_norm"] as device scalars (train.py:167-171)."""
+    dev = state.flat_p32.device
+    images = _to_device(batch["image"], dev)
+    ids = _to_device(batch["input_ids"], dev)
+    world = dist.get_world_size(state.group) if (dist.is_available() and dist.is_initialized()) else 1
+    state.flat_g32.zero_()
+    loss, _ = state.model.apply(state.variables, images, ids, mutable=["stats_buffer"] if sense else [],
+                                params_bf16=state.params_bf16, group=state.group)
+    loss.backward()
+    if world > 1:
+        # the loss is the GLOBAL-batch loss and every rank holds the partial derivative through its own samples:
+        # the full gradient is the SUM over ranks
+        dist.all_reduce(state.flat_g32, op=dist.ReduceOp.SUM, group=state.group)
+    gnorm = state.flat_g32.norm()
+    state.flat_g32.mul_(torch.clamp(state.max_grad_norm / (gnorm + 1e-6), max=1.0))   # optax.clip_by_global_norm
+    state.opt.step()
+    state.flat_p16.copy_(state.flat_p32)
+    state.step += 1
+    return state, {"loss": loss.detach(), "grad_norm": gnorm}
+
+
+def synthetic_batch(config: DualEncoderConfig, batch: int, seed: int = 42, pinned: bool = True):
+    """Synthetic image/caption pairs of the reference's tensor layout (src/data/download_to_drive.py:106-108,
+    171-178): image (B,S,S,3) NHWC, input_ids (B,T) int32; fixed-seed ints as src/data/dataset.py:27,39."""
+    g = torch.Generator().manual_seed(seed)
+    img = torch.randn((batch, config.image_size, config.image_size, 3), generator=g).to(torch.bfloat16)
+    ids = torch.randint(0, config.vocab_size, (batch, config.text_len), generator=g, dtype=torch.int32)
+    if pinned and torch.cuda.is_available():
+        img, ids = img.pin_memory(), ids.pin_memory()
+    return {"image": img, "input_ids": ids}

@@ -44,6 +44,8 @@ const char* forde_error_string(int code);
 /* last CUDA error text recorded by this library on the calling thread ("" if none) */
 const char* forde_last_cuda_error(void);
 int forde_sm_count(void);
+/* kernels launched by this library in this process so far (bench.py reports the per-step difference) */
+unsigned long long forde_launch_count(void);
 
 /* number of 256-sample partial blocks the forward / backward kernels write for M samples */
 int forde_sl_num_partials(int M);

@@ -1,0 +1,78 @@
+"""The C-ABI library loads and exports every symbol include/forde_b200.h declares (no compute calls: CPU-only)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "forde_b200.h")
+
+
+def _declared_symbols():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(forde_[a-z0-9_]+)\s*\(", src)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    import __graft_entry__ as g
+    g.build()
+    from forde_b200 import _lib
+    return _lib.load()
+
+
+def test_header_declares_the_path():
+    syms = _declared_symbols()
+    for must in ["forde_sl_up_fwd", "forde_sl_down_fwd", "forde_sl_dz_bwd", "forde_sl_dx_bwd", "forde_sl_dw_up",
+                 "forde_sl_dw_down", "forde_stats_finalize", "forde_clip_fwd", "forde_clip_bwd"]:
+        assert must in syms
+
+
+def test_every_declared_symbol_is_exported_and_bound(lib):
+    from forde_b200 import _lib
+    syms = _declared_symbols()
+    missing = [s for s in syms if not hasattr(lib, s)]
+    assert not missing, f"declared in the header but not exported: {missing}"
+    unbound = [s for s in syms if s not in _lib.SIGNATURES]
+    assert not unbound, f"declared in the header but not bound in _lib.SIGNATURES: {unbound}"
+    extra = [s for s in _lib.SIGNATURES if s not in syms]
+    assert not extra, f"bound in _lib.SIGNATURES but not declared in the header: {extra}"
+
+
+def test_pure_host_entry_points(lib):
+    assert lib.forde_version() >= 100
+    assert lib.forde_error_string(0) == b"ok"
+    assert b"alignment" in lib.forde_error_string(-2)
+    assert lib.forde_sl_num_partials(0) == 0
+    assert lib.forde_sl_num_partials(1) == 1
+    assert lib.forde_sl_num_partials(256) == 1
+    assert lib.forde_sl_num_partials(257) == 2
+    assert lib.forde_sl_num_partials(50432) == 197
+
+
+def test_argument_validation_needs_no_gpu(lib):
+    # null pointers / bad shapes are rejected on the host before anything touches the device
+    rc = lib.forde_sl_up_fwd(None, None, None, None, None, None, None, None, 16, 16, 16, 16)
+    assert rc == -1
+    rc = lib.forde_stats_finalize(None, None, None, 1, 16, 16, None, None, None, None, None, None)
+    assert rc == -1
+    rc = lib.forde_clip_fwd(None, None, None, None, 4, 4, 8, 0, *([None] * 10))
+    assert rc == -1
+
+
+def test_missing_library_fails_loudly(monkeypatch, tmp_path):
+    from forde_b200 import _lib
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", str(tmp_path / "nope.so"))
+    with pytest.raises(_lib.FordeError, match="no CPU fallback"):
+        _lib.load()
+
+
+def test_ops_refuse_cpu_tensors(lib):
+    import torch
+    from forde_b200 import ops, _lib
+    x = torch.zeros((8, 8), dtype=torch.bfloat16)
+    with pytest.raises(_lib.FordeError, match="CUDA tensor"):
+        ops.gemm_bf16(x, x, False, False)

@@ -1,0 +1,71 @@
+"""End-to-end parity of the fast loop at BASELINE config 1 (tiny dual encoder, batch 32): the B200 train step
+(bf16 storage, sm_100a StatefulLayer + contrastive-loss kernels) against the fp32 CPU port of the same step on
+identical parameters and the same synthetic batch.  Tolerances: loss abs 5e-2 (bf16 towers vs fp32), per-layer
+statistics rtol 0.1 on the scale-type stats, assignments routing exercised with a mixed brain map."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def built():
+    import __graft_entry__ as g
+    g.build()
+    return True
+
+
+def test_tiny_dual_encoder_train_step_matches_cpu_port(built):
+    from forde_b200 import dual_encoder, train
+    from oracle import dual_encoder_cpu as C
+
+    cfg = dual_encoder.config_tiny()
+    st = train.create_train_state(cfg, 0, device="cuda")
+    # a mixed brain map so all three paths and both gates are exercised
+    for tower in ("vision", "text"):
+        for l in st.variables["neuron_assignments"][tower].values():
+            a = l["stateful_layer"]["assignments"]
+            a.copy_(torch.arange(a.numel(), device=a.device) % 3)
+    cpu = C.CpuTrainer(cfg, st.variables)
+    b = train.synthetic_batch(cfg, 32, pinned=False)
+    losses_g, losses_c = [], []
+    for i in range(3):
+        _, m = train.train_step(st, b)
+        lc, gn_c, stats_c = cpu.step(b["image"].float(), b["input_ids"])
+        losses_g.append(float(m["loss"].item())); losses_c.append(lc)
+        if i == 0:
+            gn_g = float(m["grad_norm"].item())
+            assert abs(gn_g - gn_c) <= 0.1 * gn_c, (gn_g, gn_c)
+    assert abs(losses_g[0] - losses_c[0]) < 5e-2, (losses_g, losses_c)
+    assert losses_g[-1] < losses_g[0] and losses_c[-1] < losses_c[0]        # both arms are learning
+    assert abs(losses_g[-1] - losses_c[-1]) < 0.25, (losses_g, losses_c)
+    sb = st.variables["stats_buffer"]["vision"]["layer_0"]["stateful_layer"]
+    assert int(sb["step_count"].item()) == 3 and int(sb["sample_count"].item()) == 3 * 32 * 5
+    sc = cpu.variables["stats_buffer"]["vision"]["layer_0"]["stateful_layer"]["neuron_stats"].numpy()
+    sg = sb["neuron_stats"].cpu().numpy()
+    # act_gdp / act_variance / grad_gdp are smooth in the inputs: compare across arms; the Hoyer columns too
+    for col, tol in ((3, 0.05), (4, 0.1), (1, 0.15), (2, 0.05), (0, 0.05)):
+        denom = np.abs(sc[:, col]).mean()
+        assert np.abs(sg[:, col] - sc[:, col]).mean() <= tol * denom, (col, np.abs(sg[:, col] - sc[:, col]).mean(), denom)
+
+
+def test_slow_loop_closes_the_loop_on_gpu(built):
+    from forde_b200 import dual_encoder, slow_loop, train
+
+    cfg = dual_encoder.config_tiny()
+    st = train.create_train_state(cfg, 1, device="cuda")
+    b = train.synthetic_batch(cfg, 32, pinned=False)
+    for _ in range(4):
+        train.train_step(st, b)
+    mv = {"stats_buffer": st.variables["stats_buffer"], "neuron_assignments": st.variables["neuron_assignments"]}
+    _, mv, diag = slow_loop.slow_loop_step(st.params, mv, slow_loop.SlowLoopConfig(), key=0, step=4)
+    assert len(diag["layers"]) == 4
+    for name, d in diag["layers"].items():
+        assert sum(d["census"]) == 512 and d["features"].shape == (512, 5)
+    for tower in mv["stats_buffer"].values():
+        for l in tower.values():
+            assert all(float(t.float().abs().sum()) == 0.0 for t in l["stateful_layer"].values())
+    # the new brain map is live in the next fast step
+    _, m = train.train_step(st, b)
+    assert np.isfinite(float(m["loss"].item()))

@@ -1,0 +1,322 @@
+"""Parity tests proper: the sm_100a kernels, called through the C ABI (ctypes), against the CPU oracle on the
+same seeded inputs.  Tolerances (none exist upstream):
+  z, h, y, dz, dx vs the fp32-accumulating oracle with bf16 storage emulated: relative Frobenius <= 1e-2 and
+      every element within 2 bf16 ulps (2^-7 relative) + 1e-3 absolute of the oracle;
+  dW, db (fp32 outputs): relative Frobenius <= 1e-3;
+  statistics (H,5): rtol 1e-3, atol 1e-5, computed by the oracle from the kernel's own stored z / dz;
+  discrete outputs (relu mask, binary step, gate selection): BIT-exact given the same stored bf16 z.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import forde_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ops():
+    import __graft_entry__ as g
+    g.build()
+    from forde_b200 import ops as _ops
+    return _ops
+
+
+def f32(t):
+    return t.detach().float().cpu().numpy()
+
+
+def relerr(got, ref):
+    return float(np.linalg.norm(got.astype(np.float64) - ref) / (np.linalg.norm(ref) + 1e-30))
+
+
+def assert_close_bf16(got, ref, name, fro=1e-2):
+    assert relerr(got, ref) <= fro, f"{name}: rel Frobenius {relerr(got, ref):.3e}"
+    bound = 2.0 ** -6 * np.abs(ref) + 2e-2 * (np.abs(ref).mean() + 1e-6)
+    bad = np.abs(got - ref) > bound
+    assert bad.mean() < 1e-4, f"{name}: {bad.sum()} of {bad.size} elements outside the bf16 tolerance"
+
+
+# ------------------------------------------------------------------------------------------ generic GEMM
+@pytest.mark.parametrize("a_mn", [False, True])
+@pytest.mark.parametrize("b_mn", [False, True])
+@pytest.mark.parametrize("shape", [(256, 512, 256), (200, 136, 328), (128, 8, 64), (1000, 264, 72)])
+def test_gemm_bf16_all_operand_layouts(ops, a_mn, b_mn, shape):
+    M, N, K = shape
+    g = torch.Generator(device="cuda").manual_seed(1)
+    A = torch.randn((K, M) if a_mn else (M, K), device="cuda", generator=g).bfloat16()
+    B = torch.randn((K, N) if b_mn else (N, K), device="cuda", generator=g).bfloat16()
+    bias = torch.randn(N, device="cuda", generator=g)
+    out = ops.gemm_bf16(A, B, a_mn, b_mn, bias_col=bias)
+    Af = f32(A.t() if a_mn else A); Bf = f32(B.t() if b_mn else B)
+    ref = O.bf16_round(Af @ Bf.T + f32(bias))
+    assert_close_bf16(f32(out), ref, "gemm_bf16")
+
+
+@pytest.mark.parametrize("accumulate", [False, True])
+def test_gemm_f32_split_k_accumulate(ops, accumulate):
+    M, N, K = 384, 520, 4096
+    g = torch.Generator(device="cuda").manual_seed(2)
+    A = torch.randn((K, M), device="cuda", generator=g).bfloat16()
+    B = torch.randn((N, K), device="cuda", generator=g).bfloat16()
+    out = torch.full((M, N), 1.0 if accumulate else 7.0, device="cuda")
+    ops.gemm_f32(A, B, True, False, out=out, accumulate=accumulate)
+    ref = f32(A).T.astype(np.float64) @ f32(B).T.astype(np.float64) + (1.0 if accumulate else 0.0)
+    assert relerr(f32(out), ref) < 1e-5
+
+
+# ------------------------------------------------------------------------------------------ StatefulLayer
+def run_layer(ops, M, d, H, assign, seed=0, bias_scale=0.1):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    t = {}
+    t["x"] = torch.randn((M, d), device="cuda", generator=g).bfloat16()
+    t["w_up"] = (torch.randn((d, H), device="cuda", generator=g) / d ** 0.5).bfloat16()
+    t["w_down"] = (torch.randn((H, d), device="cuda", generator=g) / H ** 0.5).bfloat16()
+    t["b_up"] = torch.randn(H, device="cuda", generator=g) * bias_scale
+    t["b_down"] = torch.randn(d, device="cuda", generator=g) * bias_scale
+    t["dy"] = torch.randn((M, d), device="cuda", generator=g).bfloat16()
+    t["assign"] = torch.as_tensor(assign, device="cuda").to(torch.int8)
+    ld, P = ops.sample_pitch(M), ops.num_partials(M)
+    t["zT"] = torch.zeros((H, ld), device="cuda", dtype=torch.bfloat16)
+    t["hT"] = torch.zeros_like(t["zT"]); t["dzT"] = torch.zeros_like(t["zT"])
+    t["actp"] = torch.zeros((P, 3, H), device="cuda"); t["gradp"] = torch.zeros((P, 3, H), device="cuda")
+    t["y"] = torch.zeros((M, d), device="cuda", dtype=torch.bfloat16); t["dx"] = torch.zeros_like(t["y"])
+    t["dw_up"] = torch.zeros((d, H), device="cuda"); t["dw_down"] = torch.zeros((H, d), device="cuda")
+    t["db_up"] = torch.zeros(H, device="cuda"); t["db_down"] = torch.zeros(d, device="cuda")
+    t["stats"] = torch.zeros((H, 5), device="cuda")
+    ops.sl_up_fwd(t["x"], t["w_up"], t["b_up"], t["assign"], t["zT"], t["hT"], t["actp"])
+    ops.sl_down_fwd(t["hT"], t["w_down"], t["b_down"], t["y"], M)
+    ops.sl_dz_bwd(t["dy"], t["w_down"], t["zT"], t["assign"], t["dzT"], t["gradp"])
+    ops.sl_dx_bwd(t["dzT"], t["w_up"], t["dx"], M)
+    ops.sl_dw_up(t["x"], t["dzT"], t["dw_up"])
+    ops.sl_dw_down(t["hT"], t["dy"], t["dw_down"])
+    ops.colsum_bf16(t["dy"], t["db_down"])
+    ops.stats_finalize(t["actp"], t["gradp"], P, H, M, step_stats=t["stats"], db_up=t["db_up"])
+    torch.cuda.synchronize()
+    t["z"] = t["zT"][:, :M].t(); t["h"] = t["hT"][:, :M].t(); t["dz"] = t["dzT"][:, :M].t()
+    return t
+
+
+LAYER_SHAPES = [
+    (160, 128, 512),     # C1 vision: 32 images x 5 tokens
+    (512, 128, 512),     # C1 text:   32 captions x 16 tokens
+    (1000, 256, 640),    # ragged: M, H not multiples of the tile
+    (7, 64, 136),        # fewer samples than one tile row, H = 128 + 8
+    (1, 128, 128),       # a single sample (Hoyer's n == 1 guard)
+    (2048, 768, 3072),   # C2 vision dims at a reduced batch
+]
+
+
+@pytest.mark.parametrize("shape", LAYER_SHAPES)
+@pytest.mark.parametrize("pattern", ["mixed", "all0", "all1", "all2"])
+def test_stateful_layer_forward_backward_parity(ops, shape, pattern):
+    M, d, H = shape
+    if pattern != "mixed" and shape not in (LAYER_SHAPES[0], LAYER_SHAPES[2]):
+        pytest.skip("uniform-assignment extremes are covered on two shapes")
+    rng = np.random.RandomState(3)
+    assign = {"mixed": rng.randint(0, 3, H), "all0": np.zeros(H, int), "all1": np.ones(H, int),
+              "all2": np.full(H, 2)}[pattern]
+    t = run_layer(ops, M, d, H, assign)
+    x, wu, wd = f32(t["x"]), f32(t["w_up"]), f32(t["w_down"])
+    bu, bd, dy = f32(t["b_up"]), f32(t["b_down"]), f32(t["dy"])
+    fw = O.stateful_layer_fwd(x, wu, bu, wd, bd, assign)
+    assert_close_bf16(f32(t["z"]), fw["z"], "z")
+    # everything downstream of z is checked from the kernel's OWN stored z (threshold consistency)
+    z_k = f32(t["z"])
+    h_ref = O.stateful_layer_fwd_from_z(z_k, assign)
+    h_k = f32(t["h"])
+    # bit-exact for relu and binary-step neurons (mask, step and gate selection are discrete decisions)
+    for a_val in (0, 2):
+        m = assign == a_val
+        if m.any():
+            np.testing.assert_array_equal(O.bf16_bits(h_k[:, m]), O.bf16_bits(h_ref[:, m]))
+    m1 = assign == 1
+    if m1.any():  # tanh.approx.f32: ~2^-11 relative error before the bf16 rounding -> at most one bf16 ulp
+        assert np.abs(h_k[:, m1] - h_ref[:, m1]).max() <= 2.0 ** -7 * np.abs(h_ref[:, m1]).max() + 1e-6
+    y_ref = O.bf16_round(h_k @ wd + bd)
+    assert_close_bf16(f32(t["y"]), y_ref, "y")
+    bw = O.stateful_layer_bwd(x, wu, wd, assign, z_k, h_k, dy)
+    assert_close_bf16(f32(t["dz"]), bw["dz"], "dz")
+    # STE: specialist neurons see dz = 1.1 * dh regardless of z (binary_step's straight-through estimator)
+    dz_k = f32(t["dz"])
+    m2 = assign == 2
+    if m2.any():
+        dh = dy @ wd.T
+        assert_close_bf16(dz_k[:, m2], O.bf16_round(np.float32(1.1) * dh[:, m2]), "dz(STE)")
+    assert_close_bf16(f32(t["dx"]), O.bf16_round(dz_k @ wu.T), "dx")
+    assert relerr(f32(t["dw_up"]), x.T.astype(np.float64) @ dz_k) < 1e-3
+    assert relerr(f32(t["dw_down"]), h_k.T.astype(np.float64) @ dy) < 1e-3
+    np.testing.assert_allclose(f32(t["db_down"]), dy.sum(0), rtol=1e-3, atol=1e-3)
+    np.testing.assert_allclose(f32(t["db_up"]), dz_k.astype(np.float64).sum(0), rtol=1e-3, atol=1e-3)
+    # sensing: the in-kernel statistics equal the reference's separate pass over (z, dL/dz)
+    stats_ref = O.calculate_neuron_stats(z_k, dz_k)
+    np.testing.assert_allclose(f32(t["stats"]), stats_ref, rtol=1e-3, atol=1e-5)
+
+
+def test_padding_columns_do_not_leak_into_statistics(ops):
+    # M = 1000 leaves 24 out-of-range sample columns in the last 256-wide tile: they must not be counted.
+    M, d, H = 1000, 128, 256
+    t = run_layer(ops, M, d, H, np.zeros(H, int), bias_scale=5.0)  # a large bias makes a leak obvious
+    z_k = f32(t["z"])
+    np.testing.assert_allclose(f32(t["actp"]).sum(0)[1], z_k.astype(np.float64).sum(0), rtol=1e-4, atol=1e-2)
+
+
+def test_statistics_are_deterministic(ops):
+    a = np.random.RandomState(0).randint(0, 3, 512)
+    s1 = f32(run_layer(ops, 3000, 128, 512, a)["stats"])
+    s2 = f32(run_layer(ops, 3000, 128, 512, a)["stats"])
+    np.testing.assert_array_equal(s1, s2)  # one writer per partial slot + fixed-order finalisation
+
+
+def test_moments_are_additive_over_sample_blocks(ops):
+    # the property that lets steps and ranks be pooled: moments(M) == moments(first half) + moments(second half)
+    M, d, H = 1024, 128, 256
+    a = np.random.RandomState(1).randint(0, 3, H)
+    g = torch.Generator(device="cuda").manual_seed(0)
+    x = torch.randn((M, d), device="cuda", generator=g).bfloat16()
+    w = (torch.randn((d, H), device="cuda", generator=g) / d ** 0.5).bfloat16()
+    b = torch.zeros(H, device="cuda")
+    ai8 = torch.as_tensor(a, device="cuda").to(torch.int8)
+
+    def moments(xs):
+        m = xs.shape[0]
+        ld, P = ops.sample_pitch(m), ops.num_partials(m)
+        zT = torch.zeros((H, ld), device="cuda", dtype=torch.bfloat16); hT = torch.zeros_like(zT)
+        p = torch.zeros((P, 3, H), device="cuda")
+        ops.sl_up_fwd(xs, w, b, ai8, zT, hT, p)
+        mom = torch.zeros((H, 5), device="cuda"); cnt = torch.zeros((), device="cuda", dtype=torch.int32)
+        ops.stats_finalize(p, None, P, H, m, moments=mom, sample_count=cnt)
+        torch.cuda.synchronize()
+        return f32(mom), int(cnt.item())
+
+    m_all, n_all = moments(x)
+    m_a, n_a = moments(x[:512].contiguous()); m_b, n_b = moments(x[512:].contiguous())
+    assert n_all == n_a + n_b == M
+    np.testing.assert_allclose(m_all, m_a + m_b, rtol=1e-5, atol=1e-4)
+
+
+# ------------------------------------------------------------------------------------------ module API
+def test_module_contract_and_in_place_statistics(ops):
+    from forde_b200.stateful_layer import StatefulLayer, STAT_NAMES
+    assert STAT_NAMES == ("grad_gini", "grad_gdp", "act_gini", "act_gdp", "act_variance")
+    dev = torch.device("cuda")
+    layer = StatefulLayer(hidden_dim=512)
+    x = torch.randn((4, 40, 128), device=dev).bfloat16().requires_grad_(True)
+    v = layer.init(0, x)
+    assert set(v) == {"params", "neuron_assignments", "stats_buffer"}
+    assert set(v["params"]) == {"up_proj", "down_proj"} and set(v["params"]["up_proj"]) == {"kernel", "bias"}
+    assert v["params"]["up_proj"]["kernel"].shape == (128, 512)       # Flax Dense kernel is (in, out)
+    assert v["neuron_assignments"]["assignments"].dtype == torch.int32
+    assert int(v["neuron_assignments"]["assignments"].abs().sum()) == 0  # D7: all generalists at init
+    assert set(v["stats_buffer"]) == {"neuron_stats", "moments", "sample_count", "step_count"}
+    for grp in v["params"].values():
+        for p in grp.values():
+            p.requires_grad_(True)
+    y0 = layer.apply(v, x)                      # immutable call: just the output
+    assert y0.shape == x.shape
+    for step in range(2):
+        y, upd = layer.apply(v, x, mutable=["stats_buffer"])
+        assert set(upd) == {"stats_buffer"}
+        y.backward(torch.ones_like(y))
+    torch.cuda.synchronize()
+    sb = upd["stats_buffer"]
+    assert int(sb["step_count"].item()) == 2 and int(sb["sample_count"].item()) == 2 * 160
+    assert v["params"]["up_proj"]["kernel"].grad.shape == (128, 512)
+    assert x.grad is not None and x.grad.shape == x.shape
+    # two identical steps: accumulated per-step stats are exactly twice one step's
+    one = f32(sb["neuron_stats"]) / 2
+    z = f32(x).reshape(-1, 128) @ f32(v["params"]["up_proj"]["kernel"].bfloat16())
+    np.testing.assert_allclose(one[:, 3], np.abs(O.bf16_round(z)).mean(0), rtol=1e-3, atol=1e-5)
+    # the slow loop rewrites assignments in place -> the next forward routes differently
+    v["neuron_assignments"]["assignments"].fill_(2)
+    y2 = layer.apply(v, x)
+    torch.cuda.synchronize()
+    assert (y2.float() - y0.float()).abs().max() > 1e-2
+
+
+def test_autograd_matches_oracle_backward(ops):
+    from forde_b200.stateful_layer import StatefulLayer
+    dev = torch.device("cuda")
+    M, d, H = 300, 64, 256
+    layer = StatefulLayer(hidden_dim=H)
+    x = torch.randn((M, d), device=dev).bfloat16().requires_grad_(True)
+    v = layer.init(1, x)
+    a = np.arange(H) % 3
+    v["neuron_assignments"]["assignments"].copy_(torch.as_tensor(a))
+    ps = [v["params"]["up_proj"]["kernel"], v["params"]["up_proj"]["bias"], v["params"]["down_proj"]["kernel"],
+          v["params"]["down_proj"]["bias"]]
+    ps[1].normal_(0, 0.2); ps[3].normal_(0, 0.2)
+    for p in ps:
+        p.requires_grad_(True)
+    y = layer.apply(v, x)
+    dy = torch.randn_like(y)
+    y.backward(dy)
+    torch.cuda.synchronize()
+    wu, wd = f32(ps[0].bfloat16()), f32(ps[2].bfloat16())
+    fw = O.stateful_layer_fwd(f32(x), wu, f32(ps[1]), wd, f32(ps[3]), a)
+    bw = O.stateful_layer_bwd(f32(x), wu, wd, a, fw["z"], fw["h"], f32(dy))
+    assert relerr(f32(y), fw["y"]) < 1e-2
+    assert relerr(f32(x.grad), bw["dx"]) < 1e-2
+    assert relerr(f32(ps[0].grad), bw["dw_up"]) < 1e-2
+    assert relerr(f32(ps[2].grad), bw["dw_down"]) < 1e-2
+    assert relerr(f32(ps[1].grad), bw["db_up"]) < 1e-2
+    assert relerr(f32(ps[3].grad), bw["db_down"]) < 1e-2
+
+
+# ------------------------------------------------------------------------------------------ CLIP loss
+@pytest.mark.parametrize("B,E", [(32, 128), (256, 512), (100, 72)])
+def test_clip_loss_forward_backward_parity(ops, B, E):
+    from forde_b200.clip_loss import clip_contrastive_loss
+    g = torch.Generator(device="cuda").manual_seed(B)
+    img = torch.randn((B, E), device="cuda", generator=g).bfloat16().float().requires_grad_(True)
+    txt = (torch.randn((B, E), device="cuda", generator=g) + 0.5 * img.detach()).bfloat16().float().requires_grad_(True)
+    lt = torch.tensor(float(np.log(1 / 0.07)), device="cuda", requires_grad=True)
+    loss = clip_contrastive_loss(img, txt, lt)
+    loss.backward()
+    torch.cuda.synchronize()
+    ref_loss = float(O.clip_loss_fwd(f32(img), f32(txt), float(lt.item()))[0])
+    assert abs(float(loss.item()) - ref_loss) <= 1e-2 * max(1.0, abs(ref_loss))   # u, v are stored in bf16
+    dimg, dtxt, dlt, _ = O.clip_loss_bwd(f32(img), f32(txt), float(lt.item()))
+    assert relerr(f32(img.grad), dimg) < 3e-2
+    assert relerr(f32(txt.grad), dtxt) < 3e-2
+    assert abs(float(lt.grad.item()) - float(dlt)) < 3e-2 * max(1.0, abs(float(dlt)))
+
+
+# ------------------------------------------------------------------------------------------ full-size properties
+def test_c2_vision_layer_full_size_properties(ops):
+    """BASELINE config 2, vision tower layer: M = 256 x 197 = 50432, d = 768, H = 3072 (too big for the NumPy
+    oracle to be pleasant: checked through size-independent properties, with torch on the GPU as the checker)."""
+    M, d, H = 50432, 768, 3072
+    a = np.random.RandomState(0).randint(0, 3, H)
+    t = run_layer(ops, M, d, H, a)
+    at = torch.as_tensor(a, device="cuda")
+    z = t["z"].float()
+    z_ref = (t["x"].float() @ t["w_up"].float() + t["b_up"]).bfloat16().float()
+    assert ((z - z_ref).norm() / z_ref.norm()).item() < 5e-3
+    # multiplex + gate recomputed from the stored z: bit-exact on relu / step neurons
+    gate = torch.where(at == 2, 0.1, 1.0).float()
+    F = torch.where(at == 0, torch.relu(z), torch.where(at == 1, torch.tanh(z), (z > 0).float()))
+    h_ref = (gate.double() * z.double() + F.double()).float().bfloat16()
+    h = t["h"]
+    exact = (h == h_ref)
+    assert bool(exact[:, at != 1].all())
+    assert (h.float() - h_ref.float())[:, at == 1].abs().max().item() <= 2.0 ** -7 * 2.0
+    # bias gradient == column sums of dz ; dx linear in dz
+    dz = t["dz"].float()
+    torch.testing.assert_close(t["db_up"], dz.sum(0), rtol=2e-3, atol=2e-2)
+    dx_ref = (dz @ t["w_up"].float().t()).bfloat16().float()
+    assert ((t["dx"].float() - dx_ref).norm() / dx_ref.norm()).item() < 5e-3
+    dw_ref = t["x"].float().t() @ dz
+    assert ((t["dw_up"] - dw_ref).norm() / dw_ref.norm()).item() < 2e-3
+    # statistics: reference formulae evaluated with torch on the same stored tensors
+    n = float(M)
+    l1, l2 = z.abs().sum(0), z.pow(2).sum(0).sqrt()
+    act_gini = (n ** 0.5 - l1 / l2) / (n ** 0.5 - 1)
+    st = t["stats"]
+    torch.testing.assert_close(st[:, 2], act_gini, rtol=1e-3, atol=1e-5)
+    torch.testing.assert_close(st[:, 3], l1 / n, rtol=1e-3, atol=1e-6)
+    torch.testing.assert_close(st[:, 4], z.var(0, unbiased=False), rtol=2e-3, atol=1e-5)
+    gl1, gl2 = dz.abs().sum(0), dz.pow(2).sum(0).sqrt()
+    torch.testing.assert_close(st[:, 0], (n ** 0.5 - gl1 / gl2) / (n ** 0.5 - 1), rtol=1e-3, atol=1e-5)
+    torch.testing.assert_close(st[:, 1], gl1 / n, rtol=1e-3, atol=1e-6)

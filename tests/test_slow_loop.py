@@ -1,0 +1,90 @@
+"""Slow-loop host logic on CPU: Smooth against the reference-derived golden grids, interface and reset
+semantics of tests/verify_reset.py:17-35,61-67, the Forde-lite rule (README.md:58-59)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from forde_b200 import slow_loop as SL
+from forde_b200.stateful_layer import new_stats_buffer
+from oracle import forde_oracle as O
+
+
+@pytest.mark.parametrize("i", range(6))
+def test_box_smooth_matches_reference_golden(golden_dir, i):
+    z = np.load(os.path.join(golden_dir, "smoothing.npz"))
+    k, nc = (int(v) for v in z[f"params{i}"])
+    np.testing.assert_array_equal(SL.box_smooth(z[f"grid{i}"], k, nc), z[f"out{i}"])
+
+
+def test_default_grid():
+    assert SL.default_grid(3072) == (48, 64)
+    assert SL.default_grid(2048) == (32, 64)
+    assert SL.default_grid(4096) == (64, 64)
+    assert SL.default_grid(512) == (16, 32)
+    assert SL.default_grid(7) == (1, 7)
+
+
+def test_gmm_cluster_matches_oracle_call():
+    rng = np.random.RandomState(0)
+    stats = np.concatenate([rng.randn(60, 5) * 0.1, rng.randn(60, 5) * 0.1 + 3, rng.randn(60, 5) * 0.1 - 3]).astype(np.float32)
+    a, _ = SL.gmm_cluster(stats, 3, 123)
+    b, _ = O.cluster_neurons_gmm(stats, 3, 123)
+    np.testing.assert_array_equal(a, b)
+    assert len(set(a[:60])) == 1 and len(set(a.tolist())) == 3
+
+
+def _tree(H=64, layers=2, steps=3):
+    rng = np.random.RandomState(1)
+    stats, assign = {}, {}
+    for i in range(layers):
+        sb = new_stats_buffer(H, "cpu")
+        s = rng.rand(H, 5).astype(np.float32)
+        s[: H // 2, 0] += 2.0  # two obvious populations along grad_gini
+        sb["neuron_stats"] += torch.from_numpy(s) * steps
+        sb["step_count"] += steps
+        sb["sample_count"] += 100 * steps
+        stats[f"layer_{i}"] = {"stateful_layer": sb}
+        assign[f"layer_{i}"] = {"stateful_layer": {"assignments": torch.zeros(H, dtype=torch.int32)}}
+    return {"stats_buffer": stats, "neuron_assignments": assign}
+
+
+def test_slow_loop_interface_actuates_and_resets():
+    mv = _tree()
+    params = {"dummy": torch.ones(1)}
+    cfg = SL.SlowLoopConfig(num_clusters=2, pooled=False)
+    p2, mv2, diag = SL.slow_loop_step(params, mv, cfg, key=7, epoch=0, step=100)
+    assert p2 is params and mv2 is mv
+    # RESET: every leaf of stats_buffer is zero afterwards (tests/verify_reset.py:61-67)
+    for layer in mv2["stats_buffer"].values():
+        for leaf in layer["stateful_layer"].values():
+            assert float(leaf.float().abs().sum()) == 0.0
+    # ACTUATE: assignments were rewritten in place with int32 labels in range, and the census adds up
+    for name, layer in mv2["neuron_assignments"].items():
+        a = layer["stateful_layer"]["assignments"]
+        assert a.dtype == torch.int32 and int(a.min()) >= 0 and int(a.max()) <= 1
+        d = diag["layers"][f"{name}/stateful_layer"]
+        assert sum(d["census"]) == 64 and d["brain_scan"].shape == SL.default_grid(64)
+        # canonical order: cluster with the larger mean grad_gini gets the larger id
+        assert a[:32].float().mean() > a[32:].float().mean()
+
+
+def test_slow_loop_skips_layers_without_statistics():
+    mv = _tree(steps=0)
+    _, mv2, diag = SL.slow_loop_step({}, mv, SL.SlowLoopConfig(pooled=False), key=0)
+    assert all("skipped" in d for d in diag["layers"].values())
+    assert all(int(l["stateful_layer"]["assignments"].sum()) == 0 for l in mv2["neuron_assignments"].values())
+
+
+def test_forde_lite_rule():
+    mv = _tree()
+    for layer in mv["stats_buffer"].values():
+        sb = layer["stateful_layer"]
+        sb["neuron_stats"].zero_()
+        sb["neuron_stats"][:10, 0] = 0.9 * 3   # mean over 3 steps = 0.9 > 0.8 -> specialist
+        sb["neuron_stats"][10:, 0] = 0.5 * 3
+    cfg = SL.SlowLoopConfig(forde_lite=True, pooled=False, kernel_size=1)
+    _, mv2, diag = SL.slow_loop_step({}, mv, cfg, key=0)
+    a = mv2["neuron_assignments"]["layer_0"]["stateful_layer"]["assignments"].numpy()
+    np.testing.assert_array_equal(a, O.forde_lite_assignments(np.r_[np.full(10, 0.9), np.full(54, 0.5)][:, None]))
