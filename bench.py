@@ -46,11 +46,19 @@ def measured_peaks():
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
 
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index: int):
         self.index, self.proc, self.lines = index, None, []
+        self.t0 = self.t1 = None
+
+    def mark_begin(self):
+        self.t0 = time.time()
+
+    def mark_end(self):
+        self.t1 = time.time()
 
     def start(self):
         try:
@@ -79,13 +87,16 @@ class ClockSampler:
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for ln in self.lines:
             f = [x.strip() for x in ln.split(",")]
-            if len(f) < 7:
+            if len(f) < 8:
                 continue
             try:
-                sm.append(float(f[0])); mx.append(float(f[1])); pw.append(float(f[2]))
-            except ValueError:
+                ts = time.mktime(time.strptime(f[0].split(".")[0], "%Y/%m/%d %H:%M:%S")) + float("0." + f[0].split(".")[1])
+                if self.t0 is not None and not (self.t0 <= ts <= (self.t1 or ts)):
+                    continue          # keep only samples taken DURING the timed region
+                sm.append(float(f[1])); mx.append(float(f[2])); pw.append(float(f[3]))
+            except (ValueError, IndexError):
                 continue
-            for n, v in zip(names, f[3:7]):
+            for n, v in zip(names, f[4:8]):
                 if v.lower().startswith("active"):
                     reasons.add(n)
         sm.sort()
@@ -183,17 +194,19 @@ def run_gpu(args):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item()), last
 
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()       # started early (nvidia-smi takes a while to come up); samples are filtered by time
     for i in range(max(args.warmup, 3)):
         train.train_step(state, devb[i % 2])
     torch.cuda.synchronize()
 
     # ---- device-resident throughput, with live per-kernel timing and clock sampling
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
     ops.enable_timing(True)
     l0 = ops.launch_count()
+    sampler.mark_begin()
     ms, _ = timed(devb, args.steps, read_loss=False)
+    sampler.mark_end()
     launches = ops.launch_count() - l0
     kt = ops.timing_summary()
     ops.enable_timing(False)
@@ -284,7 +297,7 @@ def cpu_baseline(cfg, args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--config", default="vit_b16", choices=["tiny", "vit_b16", "vit_l14"])

@@ -43,6 +43,9 @@ SIGNATURES = {
     "forde_clip_loss": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp]),
     "forde_clip_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "forde_l2norm_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i]),
+    "forde_ln_num_partials": (_i, [_i]),
+    "forde_add_layernorm_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _f]),
+    "forde_add_layernorm_bwd": (_i, [_vp] * 11 + [_i, _i]),
 }
 
 

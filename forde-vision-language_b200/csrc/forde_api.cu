@@ -101,6 +101,13 @@ int make_tmap_bf16(CUtensorMap* out, const void* ptr, uint64_t inner, uint64_t o
       return FORDE_OK;
     }
   }
+  // cuTensorMapEncodeTiled is a driver call and needs a current context; a thread that has only ever had
+  // cudaSetDevice() called on it (torch's autograd worker threads) may not have the primary context bound yet.
+  static thread_local bool ctx_bound = false;
+  if (!ctx_bound) {
+    cudaFree(nullptr);
+    ctx_bound = true;
+  }
   EncodeTiledFn enc = get_encode_fn();
   if (enc == nullptr) {
     record_cuda_error("cuTensorMapEncodeTiled", "driver entry point not available");

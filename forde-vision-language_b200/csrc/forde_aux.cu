@@ -37,31 +37,50 @@ __device__ __forceinline__ void stats_from_sums(double a_abs, double a_sum, doub
   out5[4] = static_cast<float>(var);
 }
 
-__global__ void stats_finalize_kernel(const float* __restrict__ act_p, const float* __restrict__ grad_p, int P,
-                                      int H, int M, float* __restrict__ step_stats,
-                                      float* __restrict__ neuron_stats, float* __restrict__ moments,
-                                      int* sample_count, int* step_count, float* __restrict__ db_up) {
-  const int h = blockIdx.x * blockDim.x + threadIdx.x;
-  if (h == 0) {
+// block = 32 neurons x FIN_LANES partial-lanes.  Lane y sums partial blocks y, y + FIN_LANES, ... in double,
+// then the lanes are combined in a fixed order: the result does not depend on scheduling (bit-reproducible).
+constexpr int FIN_LANES = 16;
+
+__global__ void __launch_bounds__(32 * FIN_LANES)
+stats_finalize_kernel(const float* __restrict__ act_p, const float* __restrict__ grad_p, int P, int H, int M,
+                      float* __restrict__ step_stats, float* __restrict__ neuron_stats,
+                      float* __restrict__ moments, int* sample_count, int* step_count,
+                      float* __restrict__ db_up) {
+  __shared__ double red[FIN_LANES][6][33];
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const int h = blockIdx.x * 32 + tx;
+  if (blockIdx.x == 0 && tx == 0 && ty == 0) {
     if (sample_count != nullptr) *sample_count += M;
     if (step_count != nullptr) *step_count += 1;
   }
-  if (h >= H) return;
-  double a_abs = 0, a_sum = 0, a_sq = 0, g_abs = 0, g_sum = 0, g_sq = 0;
-  // fixed summation order over the partial blocks -> bit-reproducible statistics
-  for (int p = 0; p < P; ++p) {
-    const size_t base = static_cast<size_t>(p) * 3 * H + h;
-    if (act_p != nullptr) {
-      a_abs += act_p[base];
-      a_sum += act_p[base + H];
-      a_sq += act_p[base + 2 * static_cast<size_t>(H)];
-    }
-    if (grad_p != nullptr) {
-      g_abs += grad_p[base];
-      g_sum += grad_p[base + H];
-      g_sq += grad_p[base + 2 * static_cast<size_t>(H)];
+  double acc[6] = {0, 0, 0, 0, 0, 0};
+  if (h < H) {
+    for (int p = ty; p < P; p += FIN_LANES) {
+      const size_t base = static_cast<size_t>(p) * 3 * H + h;
+      if (act_p != nullptr) {
+        acc[0] += act_p[base];
+        acc[1] += act_p[base + H];
+        acc[2] += act_p[base + 2 * static_cast<size_t>(H)];
+      }
+      if (grad_p != nullptr) {
+        acc[3] += grad_p[base];
+        acc[4] += grad_p[base + H];
+        acc[5] += grad_p[base + 2 * static_cast<size_t>(H)];
+      }
     }
   }
+#pragma unroll
+  for (int k = 0; k < 6; ++k) red[ty][k][tx] = acc[k];
+  __syncthreads();
+  if (ty != 0 || h >= H) return;
+#pragma unroll
+  for (int k = 0; k < 6; ++k) {
+    double t = 0;
+#pragma unroll
+    for (int y = 0; y < FIN_LANES; ++y) t += red[y][k][tx];
+    acc[k] = t;
+  }
+  const double a_abs = acc[0], a_sum = acc[1], a_sq = acc[2], g_abs = acc[3], g_sum = acc[4], g_sq = acc[5];
   if (db_up != nullptr) db_up[h] += static_cast<float>(g_sum);
   float s[5];
   stats_from_sums(a_abs, a_sum, a_sq, g_abs, g_sq, M, s);
@@ -248,7 +267,7 @@ __global__ void clip_loss_kernel(const float* __restrict__ row_lse, const float*
 // dS = (softmax_row + softmax_col) / (2 Bg) - onehot / Bg  -> bf16 ; d(log_temp) partial += sum dS * S
 __global__ void clip_ds_kernel(const float* __restrict__ S, const float* __restrict__ row_lse,
                                const float* __restrict__ col_lse, int Bl, int Bg, int row_offset,
-                               __nv_bfloat16* __restrict__ dS, float* __restrict__ d_scale) {
+                               __nv_bfloat16* __restrict__ dS, int ld_ds, float* __restrict__ d_scale) {
   const size_t total = static_cast<size_t>(Bl) * Bg;
   const float w = 0.5f / static_cast<float>(Bg);
   float acc = 0.f;
@@ -258,7 +277,7 @@ __global__ void clip_ds_kernel(const float* __restrict__ S, const float* __restr
     const float s = S[idx];
     float g = (__expf(s - row_lse[i]) + __expf(s - col_lse[j])) * w;
     if (j == row_offset + i) g -= 2.f * w;
-    dS[idx] = __float2bfloat16(g);
+    dS[static_cast<size_t>(i) * ld_ds + j] = __float2bfloat16(g);
     acc = fmaf(g, s, acc);
   }
   acc = warp_sum(acc);
@@ -300,8 +319,7 @@ int forde_stats_finalize(void* stream, const float* act_partials, const float* g
                          int* sample_count, int* step_count, float* db_up) {
   if (H <= 0 || M <= 0 || num_partials <= 0) return FORDE_EINVAL;
   if (act_partials == nullptr && grad_partials == nullptr) return FORDE_EINVAL;
-  const int threads = 128;
-  stats_finalize_kernel<<<(H + threads - 1) / threads, threads, 0, static_cast<cudaStream_t>(stream)>>>(
+  stats_finalize_kernel<<<(H + 31) / 32, dim3(32, FIN_LANES), 0, static_cast<cudaStream_t>(stream)>>>(
       act_partials, grad_partials, num_partials, H, M, step_stats, neuron_stats, moments, sample_count,
       step_count, db_up);
   return check_launch("stats_finalize_kernel");
@@ -389,16 +407,17 @@ int forde_clip_bwd(void* stream, const void* u, const void* v, const float* S, c
   const size_t total = static_cast<size_t>(Bl) * Bg;
   int blocks = static_cast<int>((total + 255) / 256);
   if (blocks > 8 * sms) blocks = 8 * sms;
+  const int ld_ds = (Bg + 7) / 8 * 8;  // dS row pitch: TMA needs 16-byte pitches
   clip_ds_kernel<<<blocks, 256, 0, st>>>(S, row_lse, col_lse, Bl, Bg, row_offset, static_cast<__nv_bfloat16*>(dS),
-                                         d_log_temp);
+                                         ld_ds, d_log_temp);
   int rc = check_launch("clip_ds_kernel");
   if (rc != FORDE_OK) return rc;
   // dU[Bl][E] = scale * dS . v   : A = dS [Bl][Bg] K-major ; B = v [Bg][E] as (n = e, k = j) MN-major
-  GemmArgs gu{dS, false, Bg, v, true, E, Bl, E, Bg, true, 0x1000000000000000ull, 0x1000000000000000ull};
+  GemmArgs gu{dS, false, ld_ds, v, true, E, Bl, E, Bg, true, 0x1000000000000000ull, 0x1000000000000000ull};
   rc = gemm_f32(st, gu, dU, E, nullptr, nullptr, 1.f, logit_scale, false);
   if (rc != FORDE_OK) return rc;
   // dV[Bg][E] = scale * dS^T . u : A = dS as (m = j, k = i) MN-major ; B = u [Bl][E] as (n = e, k = i) MN-major
-  GemmArgs gv{dS, true, Bg, u, true, E, Bg, E, Bl, true, 0x1000000000000000ull, 0x1000000000000000ull};
+  GemmArgs gv{dS, true, ld_ds, u, true, E, Bg, E, Bl, true, 0x1000000000000000ull, 0x1000000000000000ull};
   return gemm_f32(st, gv, dV, E, nullptr, nullptr, 1.f, logit_scale, false);
 }
 

@@ -2,9 +2,9 @@
 
 This is the benchmark / integration harness around the StatefulLayer, not the product: the towers are the
 plain macro-architecture the README describes (patchify or token embedding -> L x FORDETransformerBlock ->
-[CLS] -> Dense projection), attention and LayerNorm go through stock torch ops (cuBLAS / SDPA flash kernels,
-"library code" for this task), and ONLY the FFN slot of every block -- ``StatefulLayer`` -- and the contrastive
-loss run on this repository's sm_100a kernels.  FORDE block = self-attention -> add/norm -> StatefulLayer ->
+[CLS] -> Dense projection), the attention projections and the attention itself go through stock torch ops
+(cuBLAS / cuDNN flash SDPA, "library code" for this task); the FFN slot of every block -- ``StatefulLayer`` --,
+the `add/norm` either side of it and the contrastive loss run on this repository's sm_100a kernels.  FORDE block = self-attention -> add/norm -> StatefulLayer ->
 add/norm (README.md:42-43).
 
 Variables follow the Flax collection layout the reference's training loop threads through ``train_step``
@@ -21,6 +21,7 @@ from typing import Dict, Optional
 import torch
 import torch.nn.functional as F
 
+from . import ops
 from .clip_loss import INIT_LOG_TEMP, clip_contrastive_loss
 from .stateful_layer import StatefulLayer, new_stats_buffer
 
@@ -78,6 +79,23 @@ class _Bf16Mirror(torch.autograd.Function):
         return g.float(), None
 
 
+class _AddLayerNorm(torch.autograd.Function):
+    """LayerNorm(x + r) on the fused sm_100a kernel (csrc/forde_norm.cu); gamma / beta are fp32 masters."""
+
+    @staticmethod
+    def forward(ctx, x, r, gamma, beta):
+        x = x.contiguous(); r = r.contiguous()
+        out, mean, rstd = ops.add_layernorm_fwd(x, r, gamma, beta, 1e-6)
+        ctx.save_for_backward(x, r, gamma, mean, rstd)
+        return out
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, r, gamma, mean, rstd = ctx.saved_tensors
+        ds, dg, db = ops.add_layernorm_bwd(dy.contiguous(), x, r, gamma, mean, rstd)
+        return ds, ds, dg, db
+
+
 def _flatten(tree, prefix=""):
     out = {}
     for k in sorted(tree):
@@ -130,7 +148,8 @@ class FORDEDualEncoder:
             for i in range(tc.layers):
                 sl = self.layers[f"{tower}/layer_{i}"]
                 v = sl.init(int(torch.randint(0, 2 ** 31 - 1, (), generator=gen)), torch.empty((1, w), device=dev))
-                tp[f"layer_{i}"] = {"attn": {"qkv": dense(w, 3 * w), "out": dense(w, w)}, "ln_1": ln(w), "ln_2": ln(w),
+                tp[f"layer_{i}"] = {"attn": {"query": dense(w, w), "key": dense(w, w), "value": dense(w, w),
+                                             "out": dense(w, w)}, "ln_1": ln(w), "ln_2": ln(w),
                                     "stateful_layer": v["params"]}
                 ta[f"layer_{i}"] = {"stateful_layer": v["neuron_assignments"]}
                 ts[f"layer_{i}"] = {"stateful_layer": new_stats_buffer(tc.hidden, dev)}
@@ -149,14 +168,18 @@ class FORDEDualEncoder:
 
     def _block(self, key, x, p, p16, heads, variables, sense):
         B, T, w = x.shape
-        qkv = F.linear(x, self._w(p["attn"]["qkv"], p16 and p16["attn"]["qkv"], "kernel").t(),
-                       p["attn"]["qkv"]["bias"].to(torch.bfloat16))
-        q, k, v = qkv.view(B, T, 3, heads, w // heads).permute(2, 0, 3, 1, 4)
+        pa, pa16 = p["attn"], (p16["attn"] if p16 is not None else None)
+
+        def proj(t, name):
+            return F.linear(t, self._w(pa[name], pa16 and pa16[name], "kernel").t(),
+                            self._w(pa[name], pa16 and pa16[name], "bias"))
+
+        # Flax MultiHeadDotProductAttention layout: separate query / key / value / out projections.  Heads are a
+        # strided view of the (B, T, w) projections, so nothing is re-packed on the way in or out of the kernel.
+        q, k, v = (proj(x, n).view(B, T, heads, w // heads).transpose(1, 2) for n in ("query", "key", "value"))
         a = F.scaled_dot_product_attention(q, k, v)
-        a = a.transpose(1, 2).reshape(B, T, w)
-        a = F.linear(a, self._w(p["attn"]["out"], p16 and p16["attn"]["out"], "kernel").t(),
-                     p["attn"]["out"]["bias"].to(torch.bfloat16))
-        x = F.layer_norm(x + a, (w,), p["ln_1"]["scale"].to(torch.bfloat16), p["ln_1"]["bias"].to(torch.bfloat16), 1e-6)
+        a = proj(a.transpose(1, 2).reshape(B, T, w), "out")
+        x = _AddLayerNorm.apply(x, a, p["ln_1"]["scale"], p["ln_1"]["bias"])
         tower, lname = key.split("/")
         sl_vars = {
             "params": p["stateful_layer"],
@@ -170,7 +193,7 @@ class FORDEDualEncoder:
             m, _ = layer.apply(sl_vars, x, mutable=["stats_buffer"])
         else:
             m = layer.apply(sl_vars, x)
-        return F.layer_norm(x + m, (w,), p["ln_2"]["scale"].to(torch.bfloat16), p["ln_2"]["bias"].to(torch.bfloat16), 1e-6)
+        return _AddLayerNorm.apply(x, m, p["ln_2"]["scale"], p["ln_2"]["bias"])
 
     def encode_image(self, variables, images, sense=True, params_bf16=None):
         """images (B, S, S, 3) NHWC (src/data/download_to_drive.py:173), any float dtype."""

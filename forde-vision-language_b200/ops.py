@@ -248,7 +248,7 @@ def clip_bwd(fwd, col_lse, row_offset: int):
     Bl, E = u.shape
     Bg = v.shape[0]
     dev = u.device
-    dS = torch.empty((Bl, Bg), dtype=torch.bfloat16, device=dev)
+    dS = torch.zeros((Bl, round_up(Bg, 8)), dtype=torch.bfloat16, device=dev)
     dU = torch.empty((Bl, E), dtype=torch.float32, device=dev)
     dV = torch.empty((Bg, E), dtype=torch.float32, device=dev)
     dlog_temp = torch.zeros(1, dtype=torch.float32, device=dev)
@@ -265,3 +265,37 @@ def l2norm_bwd(u, inv_norm, dU):
     rc = _lib.load().forde_l2norm_bwd(_stream(), u.data_ptr(), inv_norm.data_ptr(), dU.data_ptr(), out.data_ptr(), B, E)
     _lib.check(rc, "forde_l2norm_bwd")
     return out
+
+
+# ------------------------------------------------------------------------------------------ add + LayerNorm
+def add_layernorm_fwd(x, r, gamma, beta, eps: float = 1e-6):
+    """out = LayerNorm(x + r) * gamma + beta over the last axis; returns (out, mean, rstd)."""
+    _req(x, torch.bfloat16, "x"); _req(gamma, torch.float32, "gamma"); _req(beta, torch.float32, "beta")
+    if r is not None:
+        _req(r, torch.bfloat16, "r")
+    cols = x.shape[-1]
+    rows = x.numel() // cols
+    out = torch.empty_like(x)
+    mean = torch.empty(rows, dtype=torch.float32, device=x.device)
+    rstd = torch.empty(rows, dtype=torch.float32, device=x.device)
+    rc = _lib.load().forde_add_layernorm_fwd(_stream(), x.data_ptr(), _ptr(r), gamma.data_ptr(), beta.data_ptr(),
+                                             out.data_ptr(), mean.data_ptr(), rstd.data_ptr(), rows, cols, float(eps))
+    _lib.check(rc, "forde_add_layernorm_fwd")
+    return out, mean, rstd
+
+
+def add_layernorm_bwd(dy, x, r, gamma, mean, rstd):
+    """returns (ds, d_gamma, d_beta); ds is the gradient of both x and r."""
+    _req(dy, torch.bfloat16, "dy")
+    cols = x.shape[-1]
+    rows = x.numel() // cols
+    ds = torch.empty_like(x)
+    nb = _lib.load().forde_ln_num_partials(rows)
+    partials = torch.empty((nb, 2, cols), dtype=torch.float32, device=x.device)
+    d_gamma = torch.zeros(cols, dtype=torch.float32, device=x.device)
+    d_beta = torch.zeros(cols, dtype=torch.float32, device=x.device)
+    rc = _lib.load().forde_add_layernorm_bwd(_stream(), dy.data_ptr(), x.data_ptr(), _ptr(r), gamma.data_ptr(),
+                                             mean.data_ptr(), rstd.data_ptr(), ds.data_ptr(), partials.data_ptr(),
+                                             d_gamma.data_ptr(), d_beta.data_ptr(), rows, cols)
+    _lib.check(rc, "forde_add_layernorm_bwd")
+    return ds, d_gamma, d_beta

@@ -122,7 +122,7 @@ int forde_clip_col_rescale(void* stream, const float* col_max_local, const float
                            int Bg);
 int forde_clip_loss(void* stream, const float* row_lse, const float* diag, const float* col_max,
                     const float* col_sum, int Bl, int Bg, int row_offset, float* col_lse, float* loss);
-/* bwd:  dS = (softmax_row + softmax_col)/(2 Bg) - onehot/Bg  (bf16 scratch [Bl][Bg]); col_lse is the GLOBAL
+/* bwd:  dS = (softmax_row + softmax_col)/(2 Bg) - onehot/Bg  (bf16 scratch [Bl][round_up(Bg, 8)]); col_lse is the GLOBAL
  *       column log-sum-exp; logit_scale is the device scalar written by forde_clip_fwd;
  *       dU [Bl][E] = exp(tau) * dS . v (fp32, complete), dV [Bg][E] = exp(tau) * dS^T . u (fp32, partial over
  *       ranks: reduce-scatter it), d_log_temp[1] += sum dS * S (may be NULL; all-reduce(SUM) across ranks).
@@ -133,6 +133,19 @@ int forde_clip_bwd(void* stream, const void* u, const void* v, const float* S, c
 /* normalisation backward for rows of an embedding: d_x = inv_norm * (dU - u (u . dU)) */
 int forde_l2norm_bwd(void* stream, const void* u, const float* inv_norm, const float* dU, float* d_x, int B,
                      int E);
+
+/* ---- fused residual-add + LayerNorm: the `add/norm` either side of the StatefulLayer in a FORDE block
+ *      (README.md:42-43; flax nn.LayerNorm, eps 1e-6).  Caller side of the path. -------
+ * fwd: out = LayerNorm(x + r) * gamma + beta  (x, r, out bf16 [rows][cols]; r may be NULL; gamma, beta fp32);
+ *      mean[rows], rstd[rows] fp32 are saved for the backward.  cols % 8 == 0, cols <= 1024.
+ * bwd: ds = d(x + r) (the gradient of BOTH x and r), d_gamma[cols] += , d_beta[cols] += ;
+ *      partials is scratch of forde_ln_num_partials(rows) * 2 * cols floats. */
+int forde_ln_num_partials(int rows);
+int forde_add_layernorm_fwd(void* stream, const void* x, const void* r, const float* gamma, const float* beta,
+                            void* out, float* mean, float* rstd, int rows, int cols, float eps);
+int forde_add_layernorm_bwd(void* stream, const void* dy, const void* x, const void* r, const float* gamma,
+                            const float* mean, const float* rstd, void* ds, float* partials, float* d_gamma,
+                            float* d_beta, int rows, int cols);
 
 #ifdef __cplusplus
 }

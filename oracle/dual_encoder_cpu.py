@@ -67,8 +67,8 @@ def stateful_layer(x, p, assign, sink):
 
 def _block(x, p, heads, assign, sink):
     B, T, w = x.shape
-    qkv = x @ p["attn"]["qkv"]["kernel"] + p["attn"]["qkv"]["bias"]
-    q, k, v = qkv.view(B, T, 3, heads, w // heads).permute(2, 0, 3, 1, 4)
+    q, k, v = ((x @ p["attn"][n]["kernel"] + p["attn"][n]["bias"]).view(B, T, heads, w // heads).transpose(1, 2)
+               for n in ("query", "key", "value"))
     a = F.scaled_dot_product_attention(q, k, v).transpose(1, 2).reshape(B, T, w)
     a = a @ p["attn"]["out"]["kernel"] + p["attn"]["out"]["bias"]
     x = F.layer_norm(x + a, (w,), p["ln_1"]["scale"], p["ln_1"]["bias"], 1e-6)

@@ -320,3 +320,28 @@ def test_c2_vision_layer_full_size_properties(ops):
     gl1, gl2 = dz.abs().sum(0), dz.pow(2).sum(0).sqrt()
     torch.testing.assert_close(st[:, 0], (n ** 0.5 - gl1 / gl2) / (n ** 0.5 - 1), rtol=1e-3, atol=1e-5)
     torch.testing.assert_close(st[:, 1], gl1 / n, rtol=1e-3, atol=1e-6)
+
+
+# ------------------------------------------------------------------------------------------ add + LayerNorm
+@pytest.mark.parametrize("rows,cols", [(160, 128), (1000, 768), (77, 512), (3, 1024), (50432, 768)])
+def test_add_layernorm_forward_backward(ops, rows, cols):
+    """The block's add/norm (README.md:42-43): fp32 torch LayerNorm of the fp32 sum as the checker.
+    Tolerance: outputs / ds are bf16 (2^-8 relative rounding); d_gamma / d_beta fp32 sums, rtol 2e-3."""
+    g = torch.Generator(device="cuda").manual_seed(rows)
+    x = torch.randn((rows, cols), device="cuda", generator=g).bfloat16()
+    r = (torch.randn((rows, cols), device="cuda", generator=g) * 0.5 + 0.3).bfloat16()
+    gamma = torch.rand(cols, device="cuda", generator=g) + 0.5
+    beta = torch.randn(cols, device="cuda", generator=g) * 0.1
+    dy = torch.randn((rows, cols), device="cuda", generator=g).bfloat16()
+    out, mean, rstd = ops.add_layernorm_fwd(x, r, gamma, beta, 1e-6)
+    ds, dg, db = ops.add_layernorm_bwd(dy, x, r, gamma, mean, rstd)
+    torch.cuda.synchronize()
+    s = (x.float() + r.float()).requires_grad_(True)
+    gm = gamma.clone().requires_grad_(True); bt = beta.clone().requires_grad_(True)
+    ref = torch.nn.functional.layer_norm(s, (cols,), gm, bt, 1e-6)
+    ref.backward(dy.float())
+    assert_close_bf16(f32(out), f32(ref), "ln out", fro=5e-3)
+    assert_close_bf16(f32(ds), f32(s.grad), "ln ds", fro=5e-3)
+    np.testing.assert_allclose(f32(dg), f32(gm.grad), rtol=2e-3, atol=2e-3 * float(gm.grad.abs().mean()) + 1e-4)
+    np.testing.assert_allclose(f32(db), f32(bt.grad), rtol=2e-3, atol=2e-3 * float(bt.grad.abs().mean()) + 1e-4)
+    np.testing.assert_allclose(f32(mean), f32(s.detach().mean(-1)), rtol=1e-4, atol=1e-5)
