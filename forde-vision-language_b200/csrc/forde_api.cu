@@ -5,6 +5,7 @@
 
 #include <atomic>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <unordered_map>
@@ -197,6 +198,10 @@ static int fill_common(GemmParams& p, const GemmArgs& g) {
   p.scale = 1.f;
   p.gate_generalist = 1.0f;
   p.gate_specialist = 0.1f;
+  {
+    const char* dbg = std::getenv("FORDE_DEBUG");
+    p.debug = dbg ? std::atoi(dbg) : 0;
+  }
   return FORDE_OK;
 }
 
@@ -259,7 +264,7 @@ int forde_sm_count(void) { return sm_count(); }
 
 unsigned long long forde_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
-int forde_sl_num_partials(int M) { return M <= 0 ? 0 : (M + BN - 1) / BN; }
+int forde_sl_num_partials(int M) { return M <= 0 ? 0 : 2 * ((M + BN - 1) / BN); }
 
 int forde_gemm_bf16(void* stream, const void* A, int a_mn_major, long long lda, const void* B, int b_mn_major,
                     long long ldb, void* D, long long ldd, const float* bias_col, int M, int N, int K) {
@@ -289,6 +294,7 @@ int forde_sl_up_fwd(void* stream, const void* x, const void* w_up, const float* 
   p.bias_row = b_up;
   p.assign = assign;
   p.partials = act_partials;
+  if (p.debug & 64) p.raster_m_fast = 0;
   return launch_epi<EPI_UP_FWD>(p, true, false, static_cast<cudaStream_t>(stream));
 }
 
@@ -322,6 +328,7 @@ int forde_sl_dz_bwd(void* stream, const void* dy, const void* w_down, const void
   if (rc != FORDE_OK) return rc;
   p.assign = assign;
   p.partials = grad_partials;
+  if (p.debug & 64) p.raster_m_fast = 0;
   return launch_epi<EPI_DZ_BWD>(p, false, false, static_cast<cudaStream_t>(stream));
 }
 

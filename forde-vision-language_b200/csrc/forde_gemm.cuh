@@ -2,11 +2,14 @@
 //
 //   D[m, n] = sum_k A[m, k] * B[n, k]        (bf16 operands, fp32 accumulation in TMEM)
 //
-// Roles (192 threads, one CTA per SM):
+// Roles (320 threads, one CTA per SM):
 //   warp 0     : TMA producer  (cp.async.bulk.tensor -> 128B-swizzled smem ring, mbarrier complete_tx)
 //   warp 1     : TMEM allocator + single-thread tcgen05.mma issuer (128 x 256 x 16 per instruction)
-//   warps 2..5 : epilogue: tcgen05.ld the accumulator (one TMEM lane quarter per warp, one row per thread),
-//                apply the fused epilogue, stage through swizzled smem and TMA-store.
+//   warps 2..9 : epilogue: tcgen05.ld the accumulator (TMEM lane quarter = warp % 4, one row per thread; the two
+//                warps of a quarter split the tile's 256 columns in halves), apply the fused epilogue, stage
+//                through swizzled smem and TMA-store.  Two epilogue warps per SM sub-partition is what hides the
+//                tcgen05.ld / MUFU / st.shared latencies of the fused epilogues (one warp per scheduler left the
+//                tensor pipe 38 % busy; see profiles/).
 // The accumulator is double buffered in TMEM (2 x 256 columns) so the epilogue of tile i overlaps the
 // main loop of tile i+1.
 //
@@ -41,18 +44,23 @@ constexpr int B_TILE_BYTES = BN * BK * 2;  // 32 KB
 constexpr int STAGE_BYTES = A_TILE_BYTES + B_TILE_BYTES;
 constexpr int CHUNK = 64;                         // epilogue column chunk (one 128-byte bf16 row)
 constexpr int BOX_BYTES = 32 * CHUNK * 2;         // one warp's staging box: 32 rows x 64 bf16 = 4 KB
-constexpr int NUM_THREADS = 192;
+constexpr int EPI_WARPS = 8;                      // 2 per TMEM lane quarter
+constexpr int CPW = (BN / CHUNK) / (EPI_WARPS / 4);  // column chunks per epilogue warp per tile
+constexpr int NUM_THREADS = 64 + 32 * EPI_WARPS;
 constexpr int TMEM_COLS = 512;
 
+// per-warp staging: EPI_STORE [out] ; EPI_UP_FWD [z][h] ; EPI_DZ_BWD [zin/out 0][zin/out 1] (in place)
 __host__ __device__ constexpr int epi_warp_staging_bytes(int epi) {
-  return epi == EPI_STORE ? 2 * BOX_BYTES : (epi == EPI_UP_FWD || epi == EPI_DZ_BWD) ? 4 * BOX_BYTES : 0;
+  return epi == EPI_F32 ? 0 : epi == EPI_STORE ? BOX_BYTES : 2 * BOX_BYTES;
 }
+static_assert(4 * STAGE_BYTES + EPI_WARPS * BOX_BYTES + BN * 4 + 256 + 1024 <= 232448, "EPI_STORE smem budget");
+static_assert(3 * STAGE_BYTES + EPI_WARPS * 2 * BOX_BYTES + BN * 4 + 256 + 1024 <= 232448, "fused smem budget");
 __host__ __device__ constexpr int gemm_stages(int epi) {
   return (epi == EPI_UP_FWD || epi == EPI_DZ_BWD) ? 3 : 4;
 }
 __host__ __device__ constexpr int gemm_smem_bytes(int epi) {
   // ring + staging + column bias (BN fp32) + barriers/pointers (256 B) + 1 KB alignment slack
-  return gemm_stages(epi) * STAGE_BYTES + 4 * epi_warp_staging_bytes(epi) + BN * 4 + 256 + 1024;
+  return gemm_stages(epi) * STAGE_BYTES + EPI_WARPS * epi_warp_staging_bytes(epi) + BN * 4 + 256 + 1024;
 }
 
 struct GemmParams {
@@ -69,7 +77,7 @@ struct GemmParams {
   const float* bias_col;    // [N]  EPI_STORE (may be null)
   const float* bias_row;    // [M]  EPI_UP_FWD (may be null)
   const int8_t* assign;     // [M]  EPI_UP_FWD / EPI_DZ_BWD: 0 relu, 1 tanh, else binary step
-  float* partials;          // [n_blocks][3][M]  EPI_UP_FWD / EPI_DZ_BWD (may be null)
+  float* partials;          // [2 * n_blocks][3][M]  EPI_UP_FWD / EPI_DZ_BWD (may be null): one slot per 128 columns
   float* out_f32;           // EPI_F32
   long long ldc;            // EPI_F32 row pitch in elements
   const float* row_scale;   // EPI_F32 (may be null)
@@ -79,6 +87,7 @@ struct GemmParams {
   int atomic_out;           // EPI_F32: 1 = red.add, 0 = store
   float gate_generalist;    // 1.0
   float gate_specialist;    // 0.1
+  int debug;                // experiment switches (FORDE_DEBUG env), 0 in production
 };
 
 struct WorkItem {
@@ -128,14 +137,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) forde_gemm_kernel(const __grid
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* staging = smem + STAGES * STAGE_BYTES;
-  float* bias_s = reinterpret_cast<float*>(staging + 4 * WARP_STAGING);  // [BN]
+  float* bias_s = reinterpret_cast<float*>(staging + EPI_WARPS * WARP_STAGING);  // [BN]
   uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(bias_s) + BN * 4);
   uint64_t* full_bar = bars;                 // [STAGES]
   uint64_t* empty_bar = bars + STAGES;       // [STAGES]
   uint64_t* tfull_bar = bars + 2 * STAGES;   // [2]
   uint64_t* tempty_bar = tfull_bar + 2;      // [2]
-  uint64_t* z_bar = tempty_bar + 2;          // [4 warps][2]
-  uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(z_bar + 8);
+  uint64_t* z_bar = tempty_bar + 2;          // [EPI_WARPS][2]
+  uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(z_bar + 2 * EPI_WARPS);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -153,9 +162,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) forde_gemm_kernel(const __grid
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull_bar[a], 1);
-      mbar_init(&tempty_bar[a], 4);
+      mbar_init(&tempty_bar[a], EPI_WARPS);
     }
-    for (int i = 0; i < 8; ++i) mbar_init(&z_bar[i], 1);
+    for (int i = 0; i < 2 * EPI_WARPS; ++i) mbar_init(&z_bar[i], 1);
     fence_mbar_init();
   }
   if (warp == 1) {
@@ -245,20 +254,21 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) forde_gemm_kernel(const __grid
     // ------------------------------------------------------------------ epilogue warps
     const int q = warp & 3;          // TMEM lane quarter owned by this warp
     const int ew = warp - 2;         // staging region index
+    const int e = ew >> 2;           // which column half of the tile this warp drains
     uint8_t* wst = staging + ew * WARP_STAGING;
     const uint32_t lane_taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
     const uint32_t sw = static_cast<uint32_t>(lane & 7);
     int it = 0;
-    int out_slot = 0;  // double-buffered output staging slot
 
-    // z^T prefetch state (EPI_DZ_BWD): g = running chunk index of this warp
+    // z^T prefetch state (EPI_DZ_BWD): g = running chunk index of this warp; chunk g lives in buffer g & 1 and
+    // dz is written over it in place.
     int g = 0;
     uint64_t* zb = z_bar + ew * 2;
     if (EPI == EPI_DZ_BWD) {
       if (lane == 0 && static_cast<int>(blockIdx.x) < total_work) {
         const WorkItem w0 = decode_work(p, blockIdx.x);
         mbar_expect_tx(&zb[0], BOX_BYTES);
-        tma_load_2d(&p.tmZ, &zb[0], wst, w0.n0, w0.m0 + q * 32, kEvictFirst);
+        tma_load_2d(&p.tmZ, &zb[0], wst, w0.n0 + e * CPW * CHUNK, w0.m0 + q * 32, kEvictFirst);
       }
     }
 
@@ -283,17 +293,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) forde_gemm_kernel(const __grid
         warp_has_tanh = __any_sync(0xffffffffu, act.is_tanh);
       }
       if (EPI == EPI_STORE) {
-        // stage this tile's column bias once for the four epilogue warps
-        asm volatile("bar.sync 1, 128;" ::: "memory");  // everyone is done reading the previous tile's bias
-        float* bdst = bias_s;
-        const int e = threadIdx.x - 64;
-#pragma unroll
-        for (int r = 0; r < BN / 128; ++r) {
-          const int c = e + r * 128;
+        // stage this tile's column bias once for the epilogue warps
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * EPI_WARPS) : "memory");  // previous tile's bias no longer read
+        const int c = threadIdx.x - 64;
+        if (c < BN) {
           const int col = w.n0 + c;
-          bdst[c] = (p.bias_col != nullptr && col < p.N) ? p.bias_col[col] : 0.f;
+          bias_s[c] = (p.bias_col != nullptr && col < p.N) ? p.bias_col[col] : 0.f;
         }
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * EPI_WARPS) : "memory");
       }
 
       mbar_wait(&tfull_bar[as], aphase);
@@ -301,31 +308,36 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) forde_gemm_kernel(const __grid
       const uint32_t taddr = lane_taddr + as * BN;
 
 #pragma unroll 1
-      for (int c = 0; c < BN / CHUNK; ++c) {
+      for (int cc = 0; cc < CPW; ++cc) {
+        const int c = e * CPW + cc;
         const int col0 = w.n0 + c * CHUNK;
         const int nvalid = p.N - col0;  // valid columns in this chunk (may be <= 0 or >= CHUNK)
 
+        uint32_t v[CHUNK];
+        tmem_ld32(taddr + c * CHUNK, v);
+        tmem_ld32(taddr + c * CHUNK + 32, v + 32);
+
         if (EPI == EPI_DZ_BWD) {
-          // prefetch the next z^T box into the other input buffer
+          // prefetch the next z^T box into the other buffer; the dz store that last read it must have drained
           const int b = g & 1;
           if (lane == 0) {
-            int nt = t, nc = c + 1;
-            if (nc == BN / CHUNK) {
+            int nt = t, nc = cc + 1;
+            if (nc == CPW) {
               nc = 0;
               nt = t + gridDim.x;
             }
             if (nt < total_work) {
               const WorkItem wn = (nt == t) ? w : decode_work(p, nt);
+              tma_wait_read<0>();
               mbar_expect_tx(&zb[b ^ 1], BOX_BYTES);
-              tma_load_2d(&p.tmZ, &zb[b ^ 1], wst + (b ^ 1) * BOX_BYTES, wn.n0 + nc * CHUNK, wn.m0 + q * 32,
-                          kEvictFirst);
+              tma_load_2d(&p.tmZ, &zb[b ^ 1], wst + (b ^ 1) * BOX_BYTES, wn.n0 + (e * CPW + nc) * CHUNK,
+                          wn.m0 + q * 32, kEvictFirst);
             }
           }
         }
-
-        uint32_t v[CHUNK];
-        tmem_ld32(taddr + c * CHUNK, v);
-        tmem_ld32(taddr + c * CHUNK + 32, v + 32);
+        // single-buffered staging: the previous chunk's TMA stores must have read the boxes (the other epilogue
+        // warp of this SM sub-partition covers the wait)
+        if ((EPI == EPI_UP_FWD || EPI == EPI_STORE) && lane == 0 && !(p.debug & 8)) tma_wait_read<0>();
         tmem_wait_ld();
 
         if (EPI == EPI_F32) {
@@ -362,126 +374,123 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) forde_gemm_kernel(const __grid
               }
             }
           }
-        } else {
-          // ---- bf16 outputs staged through swizzled smem
-          // staging map per warp: EPI_STORE  [out0][out1]
-          //                       EPI_UP_FWD [z0][h0][z1][h1]
-          //                       EPI_DZ_BWD [zin0][zin1][out0][out1]
-          uint8_t* obuf = (EPI == EPI_STORE)    ? (wst + out_slot * BOX_BYTES)
-                          : (EPI == EPI_UP_FWD) ? (wst + out_slot * 2 * BOX_BYTES)
-                                                : (wst + 2 * BOX_BYTES + out_slot * BOX_BYTES);
-          // the TMA store issued two chunks ago read this slot; make sure it is done
-          if (lane == 0) tma_wait_read<1>();
+        } else if (EPI == EPI_STORE) {
+          // ---- bf16 output staged through swizzled smem
+          uint8_t* obuf = wst;
           __syncwarp();
           const uint32_t orow_s = smem_u32(obuf) + lane * 128;
-
-          if (EPI == EPI_STORE) {
-            const float* bsrc = bias_s + c * CHUNK;
+          const float* bsrc = bias_s + c * CHUNK;
 #pragma unroll
-            for (int j8 = 0; j8 < CHUNK / 8; ++j8) {
-              const float4 b0 = *reinterpret_cast<const float4*>(bsrc + j8 * 8);
-              const float4 b1 = *reinterpret_cast<const float4*>(bsrc + j8 * 8 + 4);
-              const uint32_t w0 = pack_bf16x2(__uint_as_float(v[j8 * 8 + 0]) + b0.x, __uint_as_float(v[j8 * 8 + 1]) + b0.y);
-              const uint32_t w1 = pack_bf16x2(__uint_as_float(v[j8 * 8 + 2]) + b0.z, __uint_as_float(v[j8 * 8 + 3]) + b0.w);
-              const uint32_t w2 = pack_bf16x2(__uint_as_float(v[j8 * 8 + 4]) + b1.x, __uint_as_float(v[j8 * 8 + 5]) + b1.y);
-              const uint32_t w3 = pack_bf16x2(__uint_as_float(v[j8 * 8 + 6]) + b1.z, __uint_as_float(v[j8 * 8 + 7]) + b1.w);
-              st_shared_v4(orow_s + ((static_cast<uint32_t>(j8) ^ sw) << 4), w0, w1, w2, w3);
-            }
-            fence_proxy_async_smem();
-            __syncwarp();
-            if (lane == 0) {
-              tma_store_2d(&p.tmC0, obuf, col0, w.m0 + q * 32);
-              tma_commit();
-            }
-          } else if (EPI == EPI_UP_FWD) {
-            // z slot at obuf, h slot at obuf + BOX_BYTES
-            const bool full = nvalid >= CHUNK;
+          for (int j8 = 0; j8 < CHUNK / 8; ++j8) {
+            const float4 b0 = *reinterpret_cast<const float4*>(bsrc + j8 * 8);
+            const float4 b1 = *reinterpret_cast<const float4*>(bsrc + j8 * 8 + 4);
+            const uint32_t w0 = pack_bf16x2(__uint_as_float(v[j8 * 8 + 0]) + b0.x, __uint_as_float(v[j8 * 8 + 1]) + b0.y);
+            const uint32_t w1 = pack_bf16x2(__uint_as_float(v[j8 * 8 + 2]) + b0.z, __uint_as_float(v[j8 * 8 + 3]) + b0.w);
+            const uint32_t w2 = pack_bf16x2(__uint_as_float(v[j8 * 8 + 4]) + b1.x, __uint_as_float(v[j8 * 8 + 5]) + b1.y);
+            const uint32_t w3 = pack_bf16x2(__uint_as_float(v[j8 * 8 + 6]) + b1.z, __uint_as_float(v[j8 * 8 + 7]) + b1.w);
+            st_shared_v4(orow_s + ((static_cast<uint32_t>(j8) ^ sw) << 4), w0, w1, w2, w3);
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(&p.tmC0, obuf, col0, w.m0 + q * 32);
+            tma_commit();
+          }
+        } else if (EPI == EPI_UP_FWD) {
+          // z box at wst, h box at wst + BOX_BYTES (single buffered: the other warp of this SM sub-partition
+          // covers the wait for the previous chunk's stores to have read them)
+          __syncwarp();
+          const uint32_t orow_s = smem_u32(wst) + lane * 128;
+          const bool full = nvalid >= CHUNK;
 #pragma unroll
-            for (int j8 = 0; j8 < CHUNK / 8; ++j8) {
-              uint32_t zw[4], hw[4];
+          for (int j8 = 0; j8 < CHUNK / 8; ++j8) {
+            uint32_t zw[4], hw[4];
 #pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                const int j = j8 * 8 + i * 2;
-                const uint32_t zp = pack_bf16x2(__uint_as_float(v[j]) + bias_r, __uint_as_float(v[j + 1]) + bias_r);
-                const float z0 = bf16lo_to_f32(zp), z1 = bf16hi_to_f32(zp);
-                // F_a(z): relu -> z if z>0 ; binary_step -> 1 if z>0 ; else 0.  tanh lanes overwrite below.
-                float f0 = (z0 > 0.f) ? (act.is_step ? 1.f : z0) : 0.f;
-                float f1 = (z1 > 0.f) ? (act.is_step ? 1.f : z1) : 0.f;
-                if (warp_has_tanh) {
-                  const float t0 = tanh_approx(z0), t1 = tanh_approx(z1);
-                  f0 = act.is_tanh ? t0 : f0;
-                  f1 = act.is_tanh ? t1 : f1;
-                }
-                const float h0 = fmaf(act.gate, z0, f0), h1 = fmaf(act.gate, z1, f1);
-                zw[i] = zp;
-                hw[i] = pack_bf16x2(h0, h1);
-                if (full) {
-                  s_abs += fabsf(z0) + fabsf(z1);
-                  s_sum += z0 + z1;
-                  s_sq = fmaf(z0, z0, s_sq);
-                  s_sq = fmaf(z1, z1, s_sq);
-                } else {
-                  if (j < nvalid) { s_abs += fabsf(z0); s_sum += z0; s_sq = fmaf(z0, z0, s_sq); }
-                  if (j + 1 < nvalid) { s_abs += fabsf(z1); s_sum += z1; s_sq = fmaf(z1, z1, s_sq); }
-                }
+            for (int i = 0; i < 4; ++i) {
+              const int j = j8 * 8 + i * 2;
+              const uint32_t zp = pack_bf16x2(__uint_as_float(v[j]) + bias_r, __uint_as_float(v[j + 1]) + bias_r);
+              const float z0 = bf16lo_to_f32(zp), z1 = bf16hi_to_f32(zp);
+              // F_a(z): relu -> z if z>0 ; binary_step -> 1 if z>0 ; else 0.  tanh lanes overwrite below.
+              float f0 = (z0 > 0.f) ? (act.is_step ? 1.f : z0) : 0.f;
+              float f1 = (z1 > 0.f) ? (act.is_step ? 1.f : z1) : 0.f;
+              if (warp_has_tanh && !(p.debug & 32)) {
+                const float t0 = tanh_approx(z0), t1 = tanh_approx(z1);
+                f0 = act.is_tanh ? t0 : f0;
+                f1 = act.is_tanh ? t1 : f1;
               }
-              const uint32_t off = (static_cast<uint32_t>(j8) ^ sw) << 4;
+              const float h0 = fmaf(act.gate, z0, f0), h1 = fmaf(act.gate, z1, f1);
+              zw[i] = zp;
+              hw[i] = pack_bf16x2(h0, h1);
+              if (p.debug & 16) continue;
+              if (full) {
+                s_abs += fabsf(z0) + fabsf(z1);
+                s_sum += z0 + z1;
+                s_sq = fmaf(z0, z0, s_sq);
+                s_sq = fmaf(z1, z1, s_sq);
+              } else {
+                if (j < nvalid) { s_abs += fabsf(z0); s_sum += z0; s_sq = fmaf(z0, z0, s_sq); }
+                if (j + 1 < nvalid) { s_abs += fabsf(z1); s_sum += z1; s_sq = fmaf(z1, z1, s_sq); }
+              }
+            }
+            const uint32_t off = (static_cast<uint32_t>(j8) ^ sw) << 4;
+            if (!(p.debug & 2)) {
               st_shared_v4(orow_s + off, zw[0], zw[1], zw[2], zw[3]);
               st_shared_v4(orow_s + BOX_BYTES + off, hw[0], hw[1], hw[2], hw[3]);
+            } else {
+              s_sum += __uint_as_float(zw[0] ^ zw[1] ^ zw[2] ^ zw[3] ^ hw[0] ^ hw[1] ^ hw[2] ^ hw[3]);
             }
-            fence_proxy_async_smem();
-            __syncwarp();
-            if (lane == 0) {
-              tma_store_2d(&p.tmC0, obuf, col0, w.m0 + q * 32);
-              tma_store_2d(&p.tmC1, obuf + BOX_BYTES, col0, w.m0 + q * 32);
-              tma_commit();
-            }
-          } else {  // EPI_DZ_BWD
-            const int b = g & 1;
-            mbar_wait(&zb[b], (g >> 1) & 1);
-            const uint32_t zrow_s = smem_u32(wst + b * BOX_BYTES) + lane * 128;
-            const bool full = nvalid >= CHUNK;
-#pragma unroll
-            for (int j8 = 0; j8 < CHUNK / 8; ++j8) {
-              const uint32_t off = (static_cast<uint32_t>(j8) ^ sw) << 4;
-              uint32_t zw[4], dw[4];
-              ld_shared_v4(zrow_s + off, zw[0], zw[1], zw[2], zw[3]);
-#pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                const int j = j8 * 8 + i * 2;
-                const float z0 = bf16lo_to_f32(zw[i]), z1 = bf16hi_to_f32(zw[i]);
-                // F_a'(z) + gate_a : relu 1[z>0] + 1 ; binary_step (STE) 1 + 0.1 ; tanh (1 - t^2) + 1
-                float m0 = act.is_step ? (1.f + act.gate) : ((z0 > 0.f ? 1.f : 0.f) + act.gate);
-                float m1 = act.is_step ? (1.f + act.gate) : ((z1 > 0.f ? 1.f : 0.f) + act.gate);
-                if (warp_has_tanh) {
-                  const float t0 = tanh_approx(z0), t1 = tanh_approx(z1);
-                  m0 = act.is_tanh ? (fmaf(-t0, t0, 1.f) + act.gate) : m0;
-                  m1 = act.is_tanh ? (fmaf(-t1, t1, 1.f) + act.gate) : m1;
-                }
-                const uint32_t dp = pack_bf16x2(__uint_as_float(v[j]) * m0, __uint_as_float(v[j + 1]) * m1);
-                dw[i] = dp;
-                const float d0 = bf16lo_to_f32(dp), d1 = bf16hi_to_f32(dp);
-                if (full) {
-                  s_abs += fabsf(d0) + fabsf(d1);
-                  s_sum += d0 + d1;
-                  s_sq = fmaf(d0, d0, s_sq);
-                  s_sq = fmaf(d1, d1, s_sq);
-                } else {
-                  if (j < nvalid) { s_abs += fabsf(d0); s_sum += d0; s_sq = fmaf(d0, d0, s_sq); }
-                  if (j + 1 < nvalid) { s_abs += fabsf(d1); s_sum += d1; s_sq = fmaf(d1, d1, s_sq); }
-                }
-              }
-              st_shared_v4(orow_s + off, dw[0], dw[1], dw[2], dw[3]);
-            }
-            fence_proxy_async_smem();
-            __syncwarp();
-            if (lane == 0) {
-              tma_store_2d(&p.tmC0, obuf, col0, w.m0 + q * 32);
-              tma_commit();
-            }
-            ++g;
           }
-          out_slot ^= 1;
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0 && !(p.debug & 1)) {
+            tma_store_2d(&p.tmC0, wst, col0, w.m0 + q * 32);
+            if (!(p.debug & 4)) tma_store_2d(&p.tmC1, wst + BOX_BYTES, col0, w.m0 + q * 32);
+            tma_commit();
+          }
+        } else {  // EPI_DZ_BWD
+          const int b = g & 1;
+          mbar_wait(&zb[b], (g >> 1) & 1);
+          const uint32_t zrow_s = smem_u32(wst + b * BOX_BYTES) + lane * 128;
+          const bool full = nvalid >= CHUNK;
+#pragma unroll
+          for (int j8 = 0; j8 < CHUNK / 8; ++j8) {
+            const uint32_t off = (static_cast<uint32_t>(j8) ^ sw) << 4;
+            uint32_t zw[4], dw[4];
+            ld_shared_v4(zrow_s + off, zw[0], zw[1], zw[2], zw[3]);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int j = j8 * 8 + i * 2;
+              const float z0 = bf16lo_to_f32(zw[i]), z1 = bf16hi_to_f32(zw[i]);
+              // F_a'(z) + gate_a : relu 1[z>0] + 1 ; binary_step (STE) 1 + 0.1 ; tanh (1 - t^2) + 1
+              float m0 = act.is_step ? (1.f + act.gate) : ((z0 > 0.f ? 1.f : 0.f) + act.gate);
+              float m1 = act.is_step ? (1.f + act.gate) : ((z1 > 0.f ? 1.f : 0.f) + act.gate);
+              if (warp_has_tanh) {
+                const float t0 = tanh_approx(z0), t1 = tanh_approx(z1);
+                m0 = act.is_tanh ? (fmaf(-t0, t0, 1.f) + act.gate) : m0;
+                m1 = act.is_tanh ? (fmaf(-t1, t1, 1.f) + act.gate) : m1;
+              }
+              const uint32_t dp = pack_bf16x2(__uint_as_float(v[j]) * m0, __uint_as_float(v[j + 1]) * m1);
+              dw[i] = dp;
+              const float d0 = bf16lo_to_f32(dp), d1 = bf16hi_to_f32(dp);
+              if (full) {
+                s_abs += fabsf(d0) + fabsf(d1);
+                s_sum += d0 + d1;
+                s_sq = fmaf(d0, d0, s_sq);
+                s_sq = fmaf(d1, d1, s_sq);
+              } else {
+                if (j < nvalid) { s_abs += fabsf(d0); s_sum += d0; s_sq = fmaf(d0, d0, s_sq); }
+                if (j + 1 < nvalid) { s_abs += fabsf(d1); s_sum += d1; s_sq = fmaf(d1, d1, s_sq); }
+              }
+            }
+            st_shared_v4(zrow_s + off, dw[0], dw[1], dw[2], dw[3]);  // dz over z, in place (same thread, same bytes)
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(&p.tmC0, wst + b * BOX_BYTES, col0, w.m0 + q * 32);
+            tma_commit();
+          }
+          ++g;
         }
       }
 
@@ -491,7 +500,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) forde_gemm_kernel(const __grid
       if (lane == 0) mbar_arrive(&tempty_bar[as]);
 
       if ((EPI == EPI_UP_FWD || EPI == EPI_DZ_BWD) && p.partials != nullptr && row < p.M) {
-        float* dst = p.partials + (static_cast<long long>(w.nb) * 3) * p.M + row;
+        float* dst = p.partials + (static_cast<long long>(w.nb * 2 + e) * 3) * p.M + row;
         dst[0] = s_abs;
         dst[p.M] = s_sum;
         dst[2 * static_cast<long long>(p.M)] = s_sq;
