@@ -194,6 +194,7 @@ def stats_finalize(act_partials, grad_partials, P, H, M, step_stats=None, neuron
 
 
 def stats_from_moments(moments, sample_count, out=None):
+    _req(moments, torch.float32, "moments"); _req(sample_count, torch.int32, "sample_count")
     H = moments.shape[0]
     if out is None:
         out = torch.empty((H, 5), dtype=torch.float32, device=moments.device)

@@ -104,9 +104,8 @@ def sense_layer(stats_leaf: Dict[str, torch.Tensor], pooled: bool, group=None) -
             dist.all_reduce(count, op=dist.ReduceOp.SUM, group=group)
         if int(count.item()) == 0:
             return None
-        if moments.is_cuda:
-            return ops.stats_from_moments(moments.contiguous(), count.reshape(1).contiguous()).cpu().numpy()
-        raise RuntimeError("pooled sensing runs the CUDA finalisation kernel; stats_buffer must be on the GPU")
+        # finalisation runs in the CUDA kernel (ops rejects host tensors: no CPU fallback)
+        return ops.stats_from_moments(moments.contiguous(), count.reshape(1).contiguous()).cpu().numpy()
     steps = int(stats_leaf["step_count"].item())
     if steps == 0:
         return None

@@ -94,6 +94,14 @@ def create_train_state(config: DualEncoderConfig, key: int, learning_rate: float
     return TrainState(0, model, variables, p16_tree, flat_p32, flat_g32, flat_p16, opt, group)
 
 
+def sync_gradients(flat_g32: torch.Tensor, group=None) -> None:
+    """Data-parallel gradient exchange.  The loss every rank differentiates is the GLOBAL-batch loss and each
+    rank holds the partial derivative through its own samples, so the full gradient is the SUM over ranks
+    (not the mean).  One all-reduce over the flat buffer; no-op on a single process."""
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(flat_g32, op=dist.ReduceOp.SUM, group=group)
+
+
 def _to_device(t: torch.Tensor, dev) -> torch.Tensor:
     return t if t.device == dev else t.to(dev, non_blocking=True)
 
@@ -104,15 +112,11 @@ def train_step(state: TrainState, batch: Dict[str, torch.Tensor], sense: bool = 
     dev = state.flat_p32.device
     images = _to_device(batch["image"], dev)
     ids = _to_device(batch["input_ids"], dev)
-    world = dist.get_world_size(state.group) if (dist.is_available() and dist.is_initialized()) else 1
     state.flat_g32.zero_()
     loss, _ = state.model.apply(state.variables, images, ids, mutable=["stats_buffer"] if sense else [],
                                 params_bf16=state.params_bf16, group=state.group)
     loss.backward()
-    if world > 1:
-        # the loss is the GLOBAL-batch loss and every rank holds the partial derivative through its own samples:
-        # the full gradient is the SUM over ranks
-        dist.all_reduce(state.flat_g32, op=dist.ReduceOp.SUM, group=state.group)
+    sync_gradients(state.flat_g32, state.group)
     gnorm = state.flat_g32.norm()
     state.flat_g32.mul_(torch.clamp(state.max_grad_norm / (gnorm + 1e-6), max=1.0))   # optax.clip_by_global_norm
     state.opt.step()
