@@ -178,13 +178,14 @@ def run_gpu(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(batches, steps, read_loss):
+    def timed(batches, steps, read_loss, step_fn=None):
+        step_fn = step_fn or (lambda b: train.train_step(state, b))
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         last = None
         for i in range(steps):
-            _, m = train.train_step(state, batches[i % len(batches)])
+            _, m = step_fn(batches[i % len(batches)])
             if read_loss:
                 last = float(m["loss"].item())      # D2H of the step's result inside the timed region
         e1.record()
@@ -201,22 +202,38 @@ def run_gpu(args):
         train.train_step(state, devb[i % 2])
     torch.cuda.synchronize()
 
-    # ---- device-resident throughput, with live per-kernel timing and clock sampling
+    # ---- per-kernel pass (eager launches, CUDA events around every StatefulLayer kernel on the launching stream):
+    #      the same K steps as the timed region below, which replays them as one CUDA graph and so cannot be
+    #      instrumented per kernel.  Launch counts come from this pass too (a replay launches the same kernels).
     ops.enable_timing(True)
     l0 = ops.launch_count()
-    sampler.mark_begin()
-    ms, _ = timed(devb, args.steps, read_loss=False)
-    sampler.mark_end()
+    ms_eager, _ = timed(devb, args.steps, read_loss=False)
     launches = ops.launch_count() - l0
     kt = ops.timing_summary()
     ops.enable_timing(False)
+
+    step_fn, graphed = None, False
+    if not args.no_graph:
+        try:
+            step_fn = train.GraphedTrainStep(state, devb[0])
+            graphed = True
+        except Exception as e:  # noqa: BLE001  (report and fall back to eager launches)
+            print(f"[bench] CUDA graph capture failed, timing eager launches: {type(e).__name__}: {e}", file=sys.stderr)
+            step_fn = None
+
+    # ---- device-resident throughput (the metric), with clock sampling
+    for i in range(2):
+        (step_fn or (lambda b: train.train_step(state, b)))(devb[i % 2])
+    sampler.mark_begin()
+    ms, _ = timed(devb, args.steps, read_loss=False, step_fn=step_fn)
+    sampler.mark_end()
     clocks = sampler.stop() if rank == 0 else None
     value = world * args.batch * args.steps / (ms * 1e-3)
 
-    # ---- end to end: host batches -> train_step -> loss on the host
+    # ---- end to end: host (pinned) batches -> public train-step API -> loss on the host, every step
     for i in range(2):
-        train.train_step(state, host[i % 2])
-    ms_e2e, loss = timed(host, args.steps, read_loss=True)
+        (step_fn or (lambda b: train.train_step(state, b)))(host[i % 2])
+    ms_e2e, loss = timed(host, args.steps, read_loss=True, step_fn=step_fn)
     e2e = world * args.batch * args.steps / (ms_e2e * 1e-3)
 
     if rank != 0:
@@ -250,6 +267,8 @@ def run_gpu(args):
                                f"d={cfg.text.width} H={cfg.text.hidden} L={cfg.text.layers}, embed {cfg.embed_dim}",
                    "batch_per_gpu": args.batch, "global_batch": args.batch * world, "parallelism": f"dp{world}",
                    "optimizer": "clip_by_global_norm(1.0)+AdamW fp32 master, bf16 compute",
+                   "launch": "whole step replayed as one CUDA graph" if graphed else "eager launches",
+                   "ms_per_step_eager_instrumented": ms_eager / args.steps,
                    "l2": "per-step working set (activations + weights, several GB) exceeds the 126 MB L2; no flush"},
         "clocks": clocks,
         "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": ms_e2e / args.steps, "h2d_bytes_per_step": h2d,
@@ -304,6 +323,7 @@ def main():
     ap.add_argument("--batch", type=int, default=256, help="pairs per GPU per step")
     ap.add_argument("--cpu-batch", type=int, default=8, help="pairs per step of the CPU port's bounded sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of the CUDA-graph replay")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

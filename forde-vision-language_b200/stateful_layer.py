@@ -211,10 +211,16 @@ class StatefulLayer:
         return w16
 
     def _load_assignments(self, a: torch.Tensor) -> None:
+        """int8 mirror of the (H,) int32 brain map for the kernels.  Refreshed when the collection leaf changed
+        (the slow loop writes it in place); while a CUDA graph is being captured the conversion is always
+        recorded, so replays pick up whatever the slow loop wrote since."""
         src = (a.data_ptr(), a._version)
-        if self._assign_i8 is None or self._assign_src != src:
+        if self._assign_i8 is None or self._assign_i8.numel() != a.numel() or self._assign_i8.device != a.device:
+            self._assign_i8 = torch.empty(a.numel(), dtype=torch.int8, device=a.device)
+            self._assign_src = None
+        if self._assign_src != src or (a.is_cuda and torch.cuda.is_current_stream_capturing()):
             # D5: values outside {0,1} act as specialists; clamp into int8 range before the narrowing cast
-            self._assign_i8 = a.clamp(-128, 127).to(torch.int8).contiguous()
+            self._assign_i8.copy_(a.clamp(-128, 127))
             self._assign_src = src
 
     def _finalize(self, ws: _Workspace, stats: Dict[str, torch.Tensor], with_grad: bool, db_up=None) -> None:

@@ -90,7 +90,7 @@ def create_train_state(config: DualEncoderConfig, key: int, learning_rate: float
     flat_p32.grad = flat_g32
     # optax.adamw(lr, wd) decays every leaf (no mask, train.py:74-77), so one flat parameter is equivalent
     opt = torch.optim.AdamW([flat_p32], lr=learning_rate, weight_decay=weight_decay, betas=(0.9, 0.999), eps=1e-8,
-                            fused=dev.type == "cuda")
+                            fused=dev.type == "cuda", capturable=dev.type == "cuda")
     return TrainState(0, model, variables, p16_tree, flat_p32, flat_g32, flat_p16, opt, group)
 
 
@@ -123,6 +123,44 @@ def train_step(state: TrainState, batch: Dict[str, torch.Tensor], sense: bool = 
     state.flat_p16.copy_(state.flat_p32)
     state.step += 1
     return state, {"loss": loss.detach(), "grad_norm": gnorm}
+
+
+class GraphedTrainStep:
+    """The whole fast-loop step (forward, loss, backward, gradient all-reduce, clip, AdamW, bf16 refresh, in-kernel
+    sensing and stats accumulation) captured ONCE into a CUDA graph and replayed per step: the step is ~1600
+    kernel launches, and launching them from Python costs more than running them on a B200.
+
+    Usage: ``g = GraphedTrainStep(state, example_batch); state, metrics = g(batch)``.  ``batch`` may live on the
+    host (pinned) or the device; it is copied into the graph's static input buffers on the current stream.
+    ``metrics`` are the graph's static output scalars (valid until the next call).  The slow loop may rewrite
+    ``neuron_assignments`` in place and zero ``stats_buffer`` between replays; both are read/updated by kernels
+    inside the graph."""
+
+    def __init__(self, state: TrainState, example_batch: Dict[str, torch.Tensor], sense: bool = True, warmup: int = 3):
+        dev = state.flat_p32.device
+        self.state = state
+        self.static = {k: torch.empty_like(v, device=dev) for k, v in example_batch.items()}
+        for k, v in example_batch.items():
+            self.static[k].copy_(v, non_blocking=True)
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                train_step(state, self.static, sense)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            _, self.metrics = train_step(state, self.static, sense)
+        torch.cuda.synchronize(dev)
+
+    def __call__(self, batch: Dict[str, torch.Tensor]):
+        for k, v in batch.items():
+            if v.data_ptr() != self.static[k].data_ptr():
+                self.static[k].copy_(v, non_blocking=True)
+        self.graph.replay()
+        self.state.step += 1
+        return self.state, self.metrics
 
 
 def synthetic_batch(config: DualEncoderConfig, batch: int, seed: int = 42, pinned: bool = True):

@@ -69,3 +69,34 @@ def test_slow_loop_closes_the_loop_on_gpu(built):
     # the new brain map is live in the next fast step
     _, m = train.train_step(st, b)
     assert np.isfinite(float(m["loss"].item()))
+
+
+def test_cuda_graph_replay_matches_eager_steps(built):
+    """The captured step must be the same computation: identical losses and statistics as eager launches, and it
+    must see the slow loop's in-place rewrite of neuron_assignments and reset of stats_buffer."""
+    from forde_b200 import dual_encoder, train
+
+    cfg = dual_encoder.config_tiny()
+    b = {k: v.cuda() for k, v in train.synthetic_batch(cfg, 32, pinned=False).items()}
+    warm = 3
+    eager = train.create_train_state(cfg, 5, device="cuda")
+    le = [float(train.train_step(eager, b)[1]["loss"].item()) for _ in range(warm + 3)]
+    gs = train.create_train_state(cfg, 5, device="cuda")
+    g = train.GraphedTrainStep(gs, b, warmup=warm)          # warm-up (3 eager) + capture (not a step)
+    lg = [float(g(b)[1]["loss"].item()) for _ in range(3)]
+    np.testing.assert_allclose(lg, le[warm:warm + 3], rtol=2e-3, atol=2e-3)
+    sb_e = eager.variables["stats_buffer"]["text"]["layer_1"]["stateful_layer"]
+    sb_g = gs.variables["stats_buffer"]["text"]["layer_1"]["stateful_layer"]
+    assert int(sb_g["step_count"].item()) == int(sb_e["step_count"].item()) == warm + 3
+    np.testing.assert_allclose(sb_g["moments"].cpu().numpy(), sb_e["moments"].cpu().numpy(), rtol=2e-2, atol=1e-3)
+    # slow-loop side effects between replays: new brain map + zeroed statistics
+    for tower in gs.variables["neuron_assignments"].values():
+        for l in tower.values():
+            l["stateful_layer"]["assignments"].fill_(2)
+    for tower in gs.variables["stats_buffer"].values():
+        for l in tower.values():
+            for t in l["stateful_layer"].values():
+                t.zero_()
+    l2 = float(g(b)[1]["loss"].item())
+    assert int(sb_g["step_count"].item()) == 1
+    assert abs(l2 - lg[-1]) > 1e-4 and np.isfinite(l2)       # routing changed, so the loss moved
