@@ -236,9 +236,17 @@ def run_gpu(args):
     ms_e2e, loss = timed(host, args.steps, read_loss=True, step_fn=step_fn)
     e2e = world * args.batch * args.steps / (ms_e2e * 1e-3)
 
-    if rank != 0:
+    def finish():
+        # NCCL communicators that were captured into a CUDA graph can hang in their destructor at interpreter
+        # exit; everything is measured and printed by now, so synchronise, meet at a barrier and leave.
+        sys.stdout.flush(); sys.stderr.flush()
         if world > 1:
-            dist.destroy_process_group()
+            torch.cuda.synchronize()
+            dist.barrier()
+            os._exit(0)
+
+    if rank != 0:
+        finish()
         return
     peaks = measured_peaks()
     kernels = {}
@@ -284,8 +292,7 @@ def run_gpu(args):
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(cfg, args)
     print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    finish()
 
 
 def cpu_baseline(cfg, args):

@@ -9,7 +9,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libforde_b200.so")
+LIB_PATH = os.environ.get("FORDE_LIB", os.path.join(_HERE, "libforde_b200.so"))  # FORDE_LIB: A/B builds (tools/)
 
 _vp = ctypes.c_void_p
 _i = ctypes.c_int

@@ -146,15 +146,15 @@ static int make_operand_map(CUtensorMap* out, const void* ptr, bool mn_major, lo
   return make_tmap_bf16(out, ptr, k, rows, ld, BK, tile_rows);
 }
 
-template <bool A_MN, bool B_MN, int EPI>
+template <bool A_MN, bool B_MN, int EPI, bool PAIR>
 static int launch_inst(const GemmParams& p, cudaStream_t stream) {
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
-  constexpr int smem = gemm_smem_bytes(EPI);
+  constexpr int smem = gemm_smem_bytes(EPI, PAIR);
   // the attribute is per device function (per context); set once per process/device is enough for one GPU
   // per process, which is the deployment model (one process per GPU).
   std::call_once(once, [] {
-    attr_err = cudaFuncSetAttribute(forde_gemm_kernel<A_MN, B_MN, EPI>,
+    attr_err = cudaFuncSetAttribute(forde_gemm_kernel<A_MN, B_MN, EPI, PAIR>,
                                     cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   });
   if (attr_err != cudaSuccess) {
@@ -162,33 +162,77 @@ static int launch_inst(const GemmParams& p, cudaStream_t stream) {
     return FORDE_ECUDA;
   }
   const int total = p.m_blocks * p.n_blocks * p.split_k;
-  int grid = sm_count();
-  if (grid <= 0) return FORDE_ENODEV;
-  if (total < grid) grid = total;
-  forde_gemm_kernel<A_MN, B_MN, EPI><<<grid, NUM_THREADS, smem, stream>>>(p);
+  const int sms = sm_count();
+  if (sms <= 0) return FORDE_ENODEV;
+  cudaLaunchConfig_t cfg = {};
+  cfg.blockDim = dim3(num_threads(EPI, PAIR));
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  if (PAIR) {
+    int pairs = sms / 2;
+    if (total < pairs) pairs = total;
+    cfg.gridDim = dim3(2 * pairs);
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+  } else {
+    cfg.gridDim = dim3(total < sms ? total : sms);
+  }
+  cudaError_t e = cudaLaunchKernelEx(&cfg, forde_gemm_kernel<A_MN, B_MN, EPI, PAIR>, p);
+  if (e != cudaSuccess) {
+    record_cuda_error("cudaLaunchKernelEx(forde_gemm_kernel)", cudaGetErrorString(e));
+    return FORDE_ECUDA;
+  }
   return check_launch("forde_gemm_kernel");
+}
+
+template <int EPI, bool PAIR>
+static int launch_layouts(const GemmParams& p, bool a_mn, bool b_mn, cudaStream_t stream) {
+  if (a_mn) {
+    if (b_mn) return launch_inst<true, true, EPI, PAIR>(p, stream);
+    return launch_inst<true, false, EPI, PAIR>(p, stream);
+  }
+  if (b_mn) return launch_inst<false, true, EPI, PAIR>(p, stream);
+  return launch_inst<false, false, EPI, PAIR>(p, stream);
 }
 
 template <int EPI>
 static int launch_epi(const GemmParams& p, bool a_mn, bool b_mn, cudaStream_t stream) {
-  if (a_mn) {
-    if (b_mn) return launch_inst<true, true, EPI>(p, stream);
-    return launch_inst<true, false, EPI>(p, stream);
-  }
-  if (b_mn) return launch_inst<false, true, EPI>(p, stream);
-  return launch_inst<false, false, EPI>(p, stream);
+  if (p.pair) return launch_layouts<EPI, true>(p, a_mn, b_mn, stream);
+  return launch_layouts<EPI, false>(p, a_mn, b_mn, stream);
 }
 
+// CTA pairs (256-row tiles) once there are enough of them to fill the 74 SM pairs; single CTAs below that.
+// FORDE_PAIR=0/1 overrides (bring-up and A/B measurements).
+static bool choose_pair(int M, int N, int K, bool can_split_k) {
+  static const int forced = [] {
+    const char* e = std::getenv("FORDE_PAIR");
+    return e ? std::atoi(e) : -1;
+  }();
+  if (forced >= 0) return forced != 0;
+  long long work = static_cast<long long>((M + 2 * BM - 1) / (2 * BM)) * ((N + BN - 1) / BN);
+  if (can_split_k) {  // split-K (fp32 accumulate outputs) multiplies the work items; >= 8 k-blocks per split
+    const int max_split = ((K + BK - 1) / BK) / 8;
+    if (max_split > 1) work *= max_split;
+  }
+  return work >= sm_count() / 2;
+}
 
-static int fill_common(GemmParams& p, const GemmArgs& g) {
+static int fill_common(GemmParams& p, const GemmArgs& g, bool can_split_k = false) {
   if (g.A == nullptr || g.B == nullptr || g.M <= 0 || g.N <= 0 || g.K <= 0) return FORDE_EINVAL;
   std::memset(&p, 0, sizeof(p));
+  p.pair = choose_pair(g.M, g.N, g.K, can_split_k) ? 1 : 0;
   int rc = make_operand_map(&p.tmA, g.A, g.a_mn, g.lda, g.M, g.K, BM);
   if (rc != FORDE_OK) return rc;
-  rc = make_operand_map(&p.tmB, g.B, g.b_mn, g.ldb, g.N, g.K, BN);
+  rc = make_operand_map(&p.tmB, g.B, g.b_mn, g.ldb, g.N, g.K, p.pair ? BN / 2 : BN);  // a pair CTA stages half of B
   if (rc != FORDE_OK) return rc;
   p.M = g.M; p.N = g.N; p.K = g.K;
-  p.m_blocks = (g.M + BM - 1) / BM;
+  const int tile_m = p.pair ? 2 * BM : BM;
+  p.m_blocks = (g.M + tile_m - 1) / tile_m;
   p.n_blocks = (g.N + BN - 1) / BN;
   p.k_blocks = (g.K + BK - 1) / BK;
   p.split_k = 1;
@@ -198,17 +242,13 @@ static int fill_common(GemmParams& p, const GemmArgs& g) {
   p.scale = 1.f;
   p.gate_generalist = 1.0f;
   p.gate_specialist = 0.1f;
-  {
-    const char* dbg = std::getenv("FORDE_DEBUG");
-    p.debug = dbg ? std::atoi(dbg) : 0;
-  }
   return FORDE_OK;
 }
 
 static void choose_split_k(GemmParams& p) {
   const int tiles = p.m_blocks * p.n_blocks;
-  const int sms = sm_count();
-  int split = sms / tiles;
+  const int workers = p.pair ? sm_count() / 2 : sm_count();
+  int split = workers / tiles;
   const int max_split = p.k_blocks / 8 > 0 ? p.k_blocks / 8 : 1;  // at least 8 k-blocks per split
   if (split > max_split) split = max_split;
   if (split < 1) split = 1;
@@ -230,7 +270,7 @@ int gemm_store_bf16(cudaStream_t stream, const GemmArgs& g, void* D, long long l
 int gemm_f32(cudaStream_t stream, const GemmArgs& g, float* D, long long ldd, const float* row_scale,
              const float* col_scale, float scale, const float* scale_dev, bool accumulate) {
   GemmParams p;
-  int rc = fill_common(p, g);
+  int rc = fill_common(p, g, accumulate);
   if (rc != FORDE_OK) return rc;
   if (D == nullptr) return FORDE_EINVAL;
   p.out_f32 = D; p.ldc = ldd; p.row_scale = row_scale; p.col_scale = col_scale; p.scale = scale; p.scale_dev = scale_dev;
@@ -264,7 +304,7 @@ int forde_sm_count(void) { return sm_count(); }
 
 unsigned long long forde_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
-int forde_sl_num_partials(int M) { return M <= 0 ? 0 : 2 * ((M + BN - 1) / BN); }
+int forde_sl_num_partials(int M) { return M <= 0 ? 0 : PARTIALS_PER_TILE * ((M + BN - 1) / BN); }
 
 int forde_gemm_bf16(void* stream, const void* A, int a_mn_major, long long lda, const void* B, int b_mn_major,
                     long long ldb, void* D, long long ldd, const float* bias_col, int M, int N, int K) {
@@ -294,7 +334,6 @@ int forde_sl_up_fwd(void* stream, const void* x, const void* w_up, const float* 
   p.bias_row = b_up;
   p.assign = assign;
   p.partials = act_partials;
-  if (p.debug & 64) p.raster_m_fast = 0;
   return launch_epi<EPI_UP_FWD>(p, true, false, static_cast<cudaStream_t>(stream));
 }
 
@@ -328,7 +367,6 @@ int forde_sl_dz_bwd(void* stream, const void* dy, const void* w_down, const void
   if (rc != FORDE_OK) return rc;
   p.assign = assign;
   p.partials = grad_partials;
-  if (p.debug & 64) p.raster_m_fast = 0;
   return launch_epi<EPI_DZ_BWD>(p, false, false, static_cast<cudaStream_t>(stream));
 }
 

@@ -2,6 +2,15 @@
 //
 //   D[m, n] = sum_k A[m, k] * B[n, k]        (bf16 operands, fp32 accumulation in TMEM)
 //
+// Two instantiations of the tile engine:
+//   PAIR = true  (default for large problems): a 2-CTA cluster works on one 256 x 256 tile with
+//                tcgen05.mma.cta_group::2 -- each CTA stages its own 128 rows of A and only HALF of B (128 of the 256
+//                columns), the leader CTA's single thread issues the MMA for both SMs, and each CTA's TMEM receives
+//                its 128 x 256 half of the accumulator.  Halving the B traffic is what takes the 128 x 256
+//                cta_group::1 tile off the SM<->L2 operand-bandwidth limit (576 KB -> 384 KB of loads per
+//                128 x 256 x 768 tile).
+//   PAIR = false : one CTA per 128 x 256 tile (small problems, where 256-row tiles would leave SMs idle).
+//
 // Roles (320 threads, one CTA per SM):
 //   warp 0     : TMA producer  (cp.async.bulk.tensor -> 128B-swizzled smem ring, mbarrier complete_tx)
 //   warp 1     : TMEM allocator + single-thread tcgen05.mma issuer (128 x 256 x 16 per instruction)
@@ -40,28 +49,56 @@ constexpr int BN = 256;
 constexpr int BK = 64;
 constexpr int UMMA_K = 16;
 constexpr int A_TILE_BYTES = BM * BK * 2;  // 16 KB
-constexpr int B_TILE_BYTES = BN * BK * 2;  // 32 KB
-constexpr int STAGE_BYTES = A_TILE_BYTES + B_TILE_BYTES;
+__host__ __device__ constexpr int b_tile_bytes(bool pair) { return (pair ? BN / 2 : BN) * BK * 2; }  // 16 / 32 KB
+__host__ __device__ constexpr int stage_bytes(bool pair) { return A_TILE_BYTES + b_tile_bytes(pair); }
 constexpr int CHUNK = 64;                         // epilogue column chunk (one 128-byte bf16 row)
 constexpr int BOX_BYTES = 32 * CHUNK * 2;         // one warp's staging box: 32 rows x 64 bf16 = 4 KB
-constexpr int EPI_WARPS = 8;                      // 2 per TMEM lane quarter
-constexpr int CPW = (BN / CHUNK) / (EPI_WARPS / 4);  // column chunks per epilogue warp per tile
-constexpr int NUM_THREADS = 64 + 32 * EPI_WARPS;
 constexpr int TMEM_COLS = 512;
+// Epilogue warps per CTA.  The fused epilogues are instruction/latency heavy (bf16 round trip, multiplex, gate FMA,
+// three running sums per element); 8 warps = 2 per SM sub-partition, 16 = 4 (one 64-column chunk each per tile).
+// More warps cost staging smem, i.e. main-loop stages; the trade-off differs per kernel, see below.
+// Measured at C2 dims (profiles/r1_exp7_variants.txt): up_fwd 8 warps / 5 stages 217 us vs 16 / 3 251 us (its
+// main loop starves with 3 stages); dz_bwd 16 / 3 226 us vs 8 / 5 245 us.  -D overrides are for A/B builds.
+#ifndef FORDE_UP_WARPS
+#define FORDE_UP_WARPS 8
+#endif
+#ifndef FORDE_DZ_WARPS
+#define FORDE_DZ_WARPS 16
+#endif
+#ifndef FORDE_UP_STAGES
+#define FORDE_UP_STAGES 5
+#endif
+#ifndef FORDE_DZ_STAGES
+#define FORDE_DZ_STAGES 3
+#endif
+__host__ __device__ constexpr int epi_warps(int epi, bool pair) {
+  return !pair ? 8 : epi == EPI_UP_FWD ? FORDE_UP_WARPS : epi == EPI_DZ_BWD ? FORDE_DZ_WARPS : 8;
+}
+__host__ __device__ constexpr int num_threads(int epi, bool pair) { return 64 + 32 * epi_warps(epi, pair); }
+// number of per-neuron partial-sum slots per 256-column tile: always 4 (one per 64-column chunk)
+constexpr int PARTIALS_PER_TILE = BN / CHUNK;
 
-// per-warp staging: EPI_STORE [out] ; EPI_UP_FWD [z][h] ; EPI_DZ_BWD [zin/out 0][zin/out 1] (in place)
-__host__ __device__ constexpr int epi_warp_staging_bytes(int epi) {
-  return epi == EPI_F32 ? 0 : epi == EPI_STORE ? BOX_BYTES : 2 * BOX_BYTES;
+// EPI_DZ_BWD keeps a per-warp ring of z^T boxes: chunk g is TMA-loaded DZ_DIST chunks ahead into box g % ring,
+// multiplied in place into dz and TMA-stored from there.  ring - DZ_DIST - 1 stores may still be reading smem
+// when a box is refilled, so with ring 4 / distance 2 the refill never waits on the store just issued.
+__host__ __device__ constexpr int dz_ring(bool pair) { return 2; }
+__host__ __device__ constexpr int dz_dist(bool pair) { return 1; }
+// per-warp staging: EPI_STORE [out] ; EPI_UP_FWD [z][h] ; EPI_DZ_BWD [ring of zin/out boxes]
+__host__ __device__ constexpr int epi_warp_staging_bytes(int epi, bool pair) {
+  return epi == EPI_F32 ? 0 : epi == EPI_STORE ? BOX_BYTES : epi == EPI_DZ_BWD ? dz_ring(pair) * BOX_BYTES : 2 * BOX_BYTES;
 }
-static_assert(4 * STAGE_BYTES + EPI_WARPS * BOX_BYTES + BN * 4 + 256 + 1024 <= 232448, "EPI_STORE smem budget");
-static_assert(3 * STAGE_BYTES + EPI_WARPS * 2 * BOX_BYTES + BN * 4 + 256 + 1024 <= 232448, "fused smem budget");
-__host__ __device__ constexpr int gemm_stages(int epi) {
-  return (epi == EPI_UP_FWD || epi == EPI_DZ_BWD) ? 3 : 4;
+
+__host__ __device__ constexpr int gemm_stages(int epi, bool pair) {
+  return epi == EPI_UP_FWD ? (pair ? FORDE_UP_STAGES : 3) : epi == EPI_DZ_BWD ? (pair ? FORDE_DZ_STAGES : 3) : (pair ? 6 : 4);
 }
-__host__ __device__ constexpr int gemm_smem_bytes(int epi) {
-  // ring + staging + column bias (BN fp32) + barriers/pointers (256 B) + 1 KB alignment slack
-  return gemm_stages(epi) * STAGE_BYTES + EPI_WARPS * epi_warp_staging_bytes(epi) + BN * 4 + 256 + 1024;
+__host__ __device__ constexpr int gemm_smem_bytes(int epi, bool pair) {
+  // ring + staging + column bias (BN fp32) + barriers/pointers (512 B) + 1 KB alignment slack
+  return gemm_stages(epi, pair) * stage_bytes(pair) + epi_warps(epi, pair) * epi_warp_staging_bytes(epi, pair) + BN * 4 + 512 + 1024;
 }
+static_assert(gemm_smem_bytes(EPI_STORE, false) <= 232448 && gemm_smem_bytes(EPI_STORE, true) <= 232448, "smem");
+static_assert(gemm_smem_bytes(EPI_UP_FWD, false) <= 232448 && gemm_smem_bytes(EPI_UP_FWD, true) <= 232448, "smem");
+static_assert(gemm_smem_bytes(EPI_F32, false) <= 232448 && gemm_smem_bytes(EPI_F32, true) <= 232448, "smem");
+static_assert(gemm_smem_bytes(EPI_DZ_BWD, false) <= 232448 && gemm_smem_bytes(EPI_DZ_BWD, true) <= 232448, "smem");
 
 struct GemmParams {
   CUtensorMap tmA;   // operand A   (box 64 x BM for K-major, 64 x 64 for MN-major)
@@ -73,11 +110,12 @@ struct GemmParams {
   int m_blocks, n_blocks, k_blocks;
   int split_k, kb_per_split;
   int raster_m_fast;  // 1: consecutive work items walk M first (share the B slab), 0: walk N first
+  int pair;           // 1: launched as 2-CTA clusters (256-row tiles, cta_group::2)
   uint64_t hintA, hintB;
   const float* bias_col;    // [N]  EPI_STORE (may be null)
   const float* bias_row;    // [M]  EPI_UP_FWD (may be null)
   const int8_t* assign;     // [M]  EPI_UP_FWD / EPI_DZ_BWD: 0 relu, 1 tanh, else binary step
-  float* partials;          // [2 * n_blocks][3][M]  EPI_UP_FWD / EPI_DZ_BWD (may be null): one slot per 128 columns
+  float* partials;          // [4 * n_blocks][3][M]  EPI_UP_FWD / EPI_DZ_BWD (may be null): one slot per 64 columns
   float* out_f32;           // EPI_F32
   long long ldc;            // EPI_F32 row pitch in elements
   const float* row_scale;   // EPI_F32 (may be null)
@@ -87,14 +125,14 @@ struct GemmParams {
   int atomic_out;           // EPI_F32: 1 = red.add, 0 = store
   float gate_generalist;    // 1.0
   float gate_specialist;    // 0.1
-  int debug;                // experiment switches (FORDE_DEBUG env), 0 in production
 };
 
 struct WorkItem {
   int m0, n0, nb, kb0, kb1;
 };
 
-__device__ __forceinline__ WorkItem decode_work(const GemmParams& p, int t) {
+// `tile_m` = rows of D per work item (128, or 256 for a CTA pair); `m_off` = this CTA's row offset inside it.
+__device__ __forceinline__ WorkItem decode_work(const GemmParams& p, int t, int tile_m, int m_off) {
   const int n_tiles = p.m_blocks * p.n_blocks;
   const int tile = t % n_tiles;
   const int ks = t / n_tiles;
@@ -107,7 +145,7 @@ __device__ __forceinline__ WorkItem decode_work(const GemmParams& p, int t) {
     mb = tile / p.n_blocks;
   }
   WorkItem w;
-  w.m0 = mb * BM;
+  w.m0 = mb * tile_m + m_off;
   w.n0 = nb * BN;
   w.nb = nb;
   w.kb0 = ks * p.kb_per_split;
@@ -129,10 +167,15 @@ __device__ __forceinline__ ActConst make_act(int a, float g_gen, float g_spec) {
   return c;
 }
 
-template <bool A_MN, bool B_MN, int EPI>
-__global__ void __launch_bounds__(NUM_THREADS, 1) forde_gemm_kernel(const __grid_constant__ GemmParams p) {
-  constexpr int STAGES = gemm_stages(EPI);
-  constexpr int WARP_STAGING = epi_warp_staging_bytes(EPI);
+template <bool A_MN, bool B_MN, int EPI, bool PAIR>
+__global__ void __launch_bounds__(num_threads(EPI, PAIR), 1) forde_gemm_kernel(const __grid_constant__ GemmParams p) {
+  constexpr int EPI_WARPS = epi_warps(EPI, PAIR);
+  constexpr int CPW = (BN / CHUNK) / (EPI_WARPS / 4);  // 64-column chunks per epilogue warp per tile
+  constexpr int STAGES = gemm_stages(EPI, PAIR);
+  constexpr int WARP_STAGING = epi_warp_staging_bytes(EPI, PAIR);
+  constexpr int STAGE_BYTES = stage_bytes(PAIR);
+  constexpr int BNL = PAIR ? BN / 2 : BN;       // B rows (D columns) staged by this CTA
+  constexpr int TILE_M = PAIR ? 2 * BM : BM;    // D rows per work item
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -143,12 +186,18 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) forde_gemm_kernel(const __grid
   uint64_t* empty_bar = bars + STAGES;       // [STAGES]
   uint64_t* tfull_bar = bars + 2 * STAGES;   // [2]
   uint64_t* tempty_bar = tfull_bar + 2;      // [2]
-  uint64_t* z_bar = tempty_bar + 2;          // [EPI_WARPS][2]
-  uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(z_bar + 2 * EPI_WARPS);
+  constexpr int ZR = dz_ring(PAIR), ZD = dz_dist(PAIR);
+  uint64_t* z_bar = tempty_bar + 2;          // [EPI_WARPS][ZR]
+  uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(z_bar + 2 * 16);
+  static_assert(2 * 6 + 4 + 2 * 16 <= 62, "barrier block is 512 bytes");
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int total_work = p.m_blocks * p.n_blocks * p.split_k;
+  const int cta_rank = PAIR ? static_cast<int>(cluster_ctarank()) : 0;
+  const int m_off = cta_rank * BM;
+  const int worker = PAIR ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+  const int num_workers = PAIR ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.tmA);
@@ -162,17 +211,23 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) forde_gemm_kernel(const __grid
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull_bar[a], 1);
-      mbar_init(&tempty_bar[a], EPI_WARPS);
+      mbar_init(&tempty_bar[a], PAIR ? 2 * EPI_WARPS : EPI_WARPS);  // pair: both CTAs' epilogues release the leader
     }
-    for (int i = 0; i < 2 * EPI_WARPS; ++i) mbar_init(&z_bar[i], 1);
+    for (int i = 0; i < ZR * EPI_WARPS; ++i) mbar_init(&z_bar[i], 1);
     fence_mbar_init();
   }
   if (warp == 1) {
-    tmem_alloc(tmem_ptr_s, TMEM_COLS);
-    tmem_relinquish();
+    if (PAIR) {
+      tmem_alloc_pair(tmem_ptr_s, TMEM_COLS);
+      tmem_relinquish_pair();
+    } else {
+      tmem_alloc(tmem_ptr_s, TMEM_COLS);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync_all();  // the peer's barriers are initialised before anything arrives on them remotely
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_s;
 
@@ -181,27 +236,31 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) forde_gemm_kernel(const __grid
     if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int t = blockIdx.x; t < total_work; t += gridDim.x) {
-        const WorkItem w = decode_work(p, t);
+      for (int t = worker; t < total_work; t += num_workers) {
+        const WorkItem w = decode_work(p, t, TILE_M, m_off);
+        const int nb0 = w.n0 + (PAIR ? cta_rank * BNL : 0);  // first B row (D column) this CTA stages
         for (int kb = w.kb0; kb < w.kb1; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
-          mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
+          // pair: both CTAs' bytes are counted on the leader's barrier; only the leader arms it
+          if (!PAIR || cta_rank == 0) mbar_expect_tx(&full_bar[stage], (PAIR ? 2 : 1) * STAGE_BYTES);
           uint8_t* sa = smem + stage * STAGE_BYTES;
           uint8_t* sb = sa + A_TILE_BYTES;
           const int k0 = kb * BK;
+          auto load = [&](const CUtensorMap* tm, void* dst, int c0, int c1, uint64_t hint) {
+            if (PAIR) tma_load_2d_pair(tm, &full_bar[stage], dst, c0, c1, hint);
+            else tma_load_2d(tm, &full_bar[stage], dst, c0, c1, hint);
+          };
           if (A_MN) {
 #pragma unroll
-            for (int j = 0; j < BM / 64; ++j)
-              tma_load_2d(&p.tmA, &full_bar[stage], sa + j * (BK * 128), w.m0 + j * 64, k0, p.hintA);
+            for (int j = 0; j < BM / 64; ++j) load(&p.tmA, sa + j * (BK * 128), w.m0 + j * 64, k0, p.hintA);
           } else {
-            tma_load_2d(&p.tmA, &full_bar[stage], sa, k0, w.m0, p.hintA);
+            load(&p.tmA, sa, k0, w.m0, p.hintA);
           }
           if (B_MN) {
 #pragma unroll
-            for (int j = 0; j < BN / 64; ++j)
-              tma_load_2d(&p.tmB, &full_bar[stage], sb + j * (BK * 128), w.n0 + j * 64, k0, p.hintB);
+            for (int j = 0; j < BNL / 64; ++j) load(&p.tmB, sb + j * (BK * 128), nb0 + j * 64, k0, p.hintB);
           } else {
-            tma_load_2d(&p.tmB, &full_bar[stage], sb, k0, w.n0, p.hintB);
+            load(&p.tmB, sb, k0, nb0, p.hintB);
           }
           if (++stage == STAGES) {
             stage = 0;
@@ -212,7 +271,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) forde_gemm_kernel(const __grid
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
-    constexpr uint32_t idesc = make_idesc_bf16(BM, BN, A_MN, B_MN);
+    constexpr uint32_t idesc = make_idesc_bf16(TILE_M, BN, A_MN, B_MN);
     // K-major tile: rows of 128 B, 8-row swizzle atoms 1024 B apart; one UMMA_K step = 32 B inside the row.
     // MN-major tile: 64-element (128 B) row per k, 8-k atoms 1024 B apart (SBO), 64-wide MN chunks
     //                BK*128 B apart (LBO); one UMMA_K step = 16 k-rows = 2048 B.
@@ -221,32 +280,40 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) forde_gemm_kernel(const __grid
     int stage = 0;
     uint32_t phase = 0;
     int it = 0;
-    for (int t = blockIdx.x; t < total_work; t += gridDim.x, ++it) {
-      const WorkItem w = decode_work(p, t);
-      const int as = it & 1;
-      const uint32_t aphase = (it >> 1) & 1;
-      mbar_wait(&tempty_bar[as], aphase ^ 1);
-      tc_fence_after();
-      const uint32_t d_tmem = tmem_base + as * BN;
-      for (int kb = w.kb0; kb < w.kb1; ++kb) {
-        mbar_wait(&full_bar[stage], phase);
+    if (!PAIR || cta_rank == 0) {  // in a pair only the leader issues; its MMAs drive both SMs' tensor cores
+      for (int t = worker; t < total_work; t += num_workers, ++it) {
+        const WorkItem w = decode_work(p, t, TILE_M, m_off);
+        const int as = it & 1;
+        const uint32_t aphase = (it >> 1) & 1;
+        mbar_wait(&tempty_bar[as], aphase ^ 1);
         tc_fence_after();
-        if (elect_one()) {
-          const uint32_t a_base = smem_u32(smem + stage * STAGE_BYTES);
-          const uint32_t b_base = a_base + A_TILE_BYTES;
+        const uint32_t d_tmem = tmem_base + as * BN;
+        for (int kb = w.kb0; kb < w.kb1; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          if (elect_one()) {
+            const uint32_t a_base = smem_u32(smem + stage * STAGE_BYTES);
+            const uint32_t b_base = a_base + A_TILE_BYTES;
 #pragma unroll
-          for (int k = 0; k < BK / UMMA_K; ++k) {
-            const uint64_t adesc = make_smem_desc_sw128(a_base + k * a_kstep, a_lbo, 1024);
-            const uint64_t bdesc = make_smem_desc_sw128(b_base + k * b_kstep, b_lbo, 1024);
-            umma_bf16(d_tmem, adesc, bdesc, idesc, (kb > w.kb0 || k > 0) ? 1u : 0u);
+            for (int k = 0; k < BK / UMMA_K; ++k) {
+              const uint64_t adesc = make_smem_desc_sw128(a_base + k * a_kstep, a_lbo, 1024);
+              const uint64_t bdesc = make_smem_desc_sw128(b_base + k * b_kstep, b_lbo, 1024);
+              if (PAIR) umma_bf16_pair(d_tmem, adesc, bdesc, idesc, (kb > w.kb0 || k > 0) ? 1u : 0u);
+              else umma_bf16(d_tmem, adesc, bdesc, idesc, (kb > w.kb0 || k > 0) ? 1u : 0u);
+            }
+            if (PAIR) {
+              umma_commit_pair(&empty_bar[stage]);  // frees the stage in BOTH CTAs
+              if (kb == w.kb1 - 1) umma_commit_pair(&tfull_bar[as]);
+            } else {
+              umma_commit(&empty_bar[stage]);
+              if (kb == w.kb1 - 1) umma_commit(&tfull_bar[as]);
+            }
           }
-          umma_commit(&empty_bar[stage]);
-          if (kb == w.kb1 - 1) umma_commit(&tfull_bar[as]);
-        }
-        __syncwarp();
-        if (++stage == STAGES) {
-          stage = 0;
-          phase ^= 1;
+          __syncwarp();
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
         }
       }
     }
@@ -260,20 +327,27 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) forde_gemm_kernel(const __grid
     const uint32_t sw = static_cast<uint32_t>(lane & 7);
     int it = 0;
 
-    // z^T prefetch state (EPI_DZ_BWD): g = running chunk index of this warp; chunk g lives in buffer g & 1 and
-    // dz is written over it in place.
+    // z^T prefetch state (EPI_DZ_BWD): g = running chunk index of this warp (tile g / CPW, chunk g % CPW);
+    // chunk g lives in box g % ZR and dz is written over it in place.
     int g = 0;
-    uint64_t* zb = z_bar + ew * 2;
-    if (EPI == EPI_DZ_BWD) {
-      if (lane == 0 && static_cast<int>(blockIdx.x) < total_work) {
-        const WorkItem w0 = decode_work(p, blockIdx.x);
-        mbar_expect_tx(&zb[0], BOX_BYTES);
-        tma_load_2d(&p.tmZ, &zb[0], wst, w0.n0 + e * CPW * CHUNK, w0.m0 + q * 32, kEvictFirst);
+    uint64_t* zb = z_bar + ew * ZR;
+    auto z_prefetch = [&](int gi) {  // lane 0 only
+      const int nt = worker + (gi / CPW) * num_workers;
+      if (nt < total_work) {
+        const WorkItem wn = decode_work(p, nt, TILE_M, m_off);
+        const int bi = gi % ZR;
+        mbar_expect_tx(&zb[bi], BOX_BYTES);
+        tma_load_2d(&p.tmZ, &zb[bi], wst + bi * BOX_BYTES, wn.n0 + (e * CPW + gi % CPW) * CHUNK, wn.m0 + q * 32,
+                    kEvictFirst);
       }
+    };
+    if (EPI == EPI_DZ_BWD && lane == 0) {
+#pragma unroll
+      for (int i = 0; i < ZD; ++i) z_prefetch(i);
     }
 
-    for (int t = blockIdx.x; t < total_work; t += gridDim.x, ++it) {
-      const WorkItem w = decode_work(p, t);
+    for (int t = worker; t < total_work; t += num_workers, ++it) {
+      const WorkItem w = decode_work(p, t, TILE_M, m_off);
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
       const int row = w.m0 + q * 32 + lane;
@@ -282,7 +356,6 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) forde_gemm_kernel(const __grid
       float bias_r = 0.f;
       ActConst act = make_act(0, p.gate_generalist, p.gate_specialist);
       bool warp_has_tanh = false;
-      float s_abs = 0.f, s_sum = 0.f, s_sq = 0.f;
       if (EPI == EPI_UP_FWD || EPI == EPI_DZ_BWD) {
         int a = 0;
         if (row < p.M) {
@@ -296,7 +369,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) forde_gemm_kernel(const __grid
         // stage this tile's column bias once for the epilogue warps
         asm volatile("bar.sync 1, %0;" ::"n"(32 * EPI_WARPS) : "memory");  // previous tile's bias no longer read
         const int c = threadIdx.x - 64;
-        if (c < BN) {
+        if (c < BN) {  // 8 epilogue warps = 256 threads = BN
           const int col = w.n0 + c;
           bias_s[c] = (p.bias_col != nullptr && col < p.N) ? p.bias_col[col] : 0.f;
         }
@@ -312,208 +385,184 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) forde_gemm_kernel(const __grid
         const int c = e * CPW + cc;
         const int col0 = w.n0 + c * CHUNK;
         const int nvalid = p.N - col0;  // valid columns in this chunk (may be <= 0 or >= CHUNK)
+        const bool full = nvalid >= CHUNK;
+        float s_abs = 0.f, s_sum = 0.f, s_sq = 0.f;  // this chunk's per-neuron sums (fused epilogues)
 
-        uint32_t v[CHUNK];
-        tmem_ld32(taddr + c * CHUNK, v);
-        tmem_ld32(taddr + c * CHUNK + 32, v + 32);
+        if (EPI == EPI_DZ_BWD && lane == 0) {
+          // refill the box chunk g + ZD will use; the dz store that last read it (chunk g + ZD - ZR) must have drained
+          tma_wait_read<ZR - ZD - 1>();
+          z_prefetch(g + ZD);
+        }
+        // single-buffered staging: the previous chunk's TMA stores must have read the boxes (the other epilogue
+        // warps of this SM sub-partition cover the wait)
+        if ((EPI == EPI_UP_FWD || EPI == EPI_STORE) && lane == 0) tma_wait_read<0>();
+        if (EPI == EPI_DZ_BWD) mbar_wait(&zb[g % ZR], (g / ZR) & 1);
+        __syncwarp();
+        uint8_t* obuf = (EPI == EPI_DZ_BWD) ? (wst + (g % ZR) * BOX_BYTES) : wst;
+        const uint32_t orow_s = smem_u32(obuf) + lane * 128;
 
-        if (EPI == EPI_DZ_BWD) {
-          // prefetch the next z^T box into the other buffer; the dz store that last read it must have drained
-          const int b = g & 1;
-          if (lane == 0) {
-            int nt = t, nc = cc + 1;
-            if (nc == CPW) {
-              nc = 0;
-              nt = t + gridDim.x;
+        // the 64-column chunk is drained in two 32-column halves to keep the live registers low
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          uint32_t v[32];
+          tmem_ld32(taddr + c * CHUNK + half * 32, v);
+          tmem_wait_ld();
+          const int jbase = half * 32;  // column offset inside the chunk
+
+          if (EPI == EPI_F32) {
+            if (row < p.M && nvalid > jbase) {
+              const float rs = (p.row_scale != nullptr ? p.row_scale[row] : 1.f) * p.scale *
+                               (p.scale_dev != nullptr ? *p.scale_dev : 1.f);
+              float* orow = p.out_f32 + static_cast<long long>(row) * p.ldc + col0 + jbase;
+              const bool vec_ok = (nvalid >= jbase + 32) && ((p.ldc & 3) == 0) &&
+                                  ((reinterpret_cast<uintptr_t>(p.out_f32) & 15) == 0);
+              if (vec_ok) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                  float f0 = __uint_as_float(v[j]) * rs, f1 = __uint_as_float(v[j + 1]) * rs;
+                  float f2 = __uint_as_float(v[j + 2]) * rs, f3 = __uint_as_float(v[j + 3]) * rs;
+                  if (p.col_scale != nullptr) {
+                    const float4 cs = *reinterpret_cast<const float4*>(p.col_scale + col0 + jbase + j);
+                    f0 *= cs.x; f1 *= cs.y; f2 *= cs.z; f3 *= cs.w;
+                  }
+                  if (p.atomic_out) {
+                    red_add_v4_f32(orow + j, f0, f1, f2, f3);
+                  } else {
+                    *reinterpret_cast<float4*>(orow + j) = make_float4(f0, f1, f2, f3);
+                  }
+                }
+              } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                  if (jbase + j < nvalid) {
+                    float f = __uint_as_float(v[j]) * rs;
+                    if (p.col_scale != nullptr) f *= p.col_scale[col0 + jbase + j];
+                    if (p.atomic_out) atomicAdd(orow + j, f);
+                    else orow[j] = f;
+                  }
+                }
+              }
             }
-            if (nt < total_work) {
-              const WorkItem wn = (nt == t) ? w : decode_work(p, nt);
-              tma_wait_read<0>();
-              mbar_expect_tx(&zb[b ^ 1], BOX_BYTES);
-              tma_load_2d(&p.tmZ, &zb[b ^ 1], wst + (b ^ 1) * BOX_BYTES, wn.n0 + (e * CPW + nc) * CHUNK,
-                          wn.m0 + q * 32, kEvictFirst);
+          } else if (EPI == EPI_STORE) {
+            const float* bsrc = bias_s + c * CHUNK + jbase;
+#pragma unroll
+            for (int j8 = 0; j8 < 4; ++j8) {
+              const float4 b0 = *reinterpret_cast<const float4*>(bsrc + j8 * 8);
+              const float4 b1 = *reinterpret_cast<const float4*>(bsrc + j8 * 8 + 4);
+              const uint32_t w0 = pack_bf16x2(__uint_as_float(v[j8 * 8 + 0]) + b0.x, __uint_as_float(v[j8 * 8 + 1]) + b0.y);
+              const uint32_t w1 = pack_bf16x2(__uint_as_float(v[j8 * 8 + 2]) + b0.z, __uint_as_float(v[j8 * 8 + 3]) + b0.w);
+              const uint32_t w2 = pack_bf16x2(__uint_as_float(v[j8 * 8 + 4]) + b1.x, __uint_as_float(v[j8 * 8 + 5]) + b1.y);
+              const uint32_t w3 = pack_bf16x2(__uint_as_float(v[j8 * 8 + 6]) + b1.z, __uint_as_float(v[j8 * 8 + 7]) + b1.w);
+              st_shared_v4(orow_s + ((static_cast<uint32_t>(half * 4 + j8) ^ sw) << 4), w0, w1, w2, w3);
+            }
+          } else if (EPI == EPI_UP_FWD) {
+            // z box at wst, h box at wst + BOX_BYTES
+#pragma unroll
+            for (int j8 = 0; j8 < 4; ++j8) {
+              uint32_t zw[4], hw[4];
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const int j = j8 * 8 + i * 2;
+                const uint32_t zp = pack_bf16x2(__uint_as_float(v[j]) + bias_r, __uint_as_float(v[j + 1]) + bias_r);
+                const float z0 = bf16lo_to_f32(zp), z1 = bf16hi_to_f32(zp);
+                // F_a(z): relu -> z if z>0 ; binary_step -> 1 if z>0 ; else 0.  tanh lanes overwrite below.
+                float f0 = (z0 > 0.f) ? (act.is_step ? 1.f : z0) : 0.f;
+                float f1 = (z1 > 0.f) ? (act.is_step ? 1.f : z1) : 0.f;
+                if (warp_has_tanh) {
+                  const float t0 = tanh_approx(z0), t1 = tanh_approx(z1);
+                  f0 = act.is_tanh ? t0 : f0;
+                  f1 = act.is_tanh ? t1 : f1;
+                }
+                const float h0 = fmaf(act.gate, z0, f0), h1 = fmaf(act.gate, z1, f1);
+                zw[i] = zp;
+                hw[i] = pack_bf16x2(h0, h1);
+                if (full) {
+                  s_abs += fabsf(z0) + fabsf(z1);
+                  s_sum += z0 + z1;
+                  s_sq = fmaf(z0, z0, s_sq);
+                  s_sq = fmaf(z1, z1, s_sq);
+                } else {
+                  if (jbase + j < nvalid) { s_abs += fabsf(z0); s_sum += z0; s_sq = fmaf(z0, z0, s_sq); }
+                  if (jbase + j + 1 < nvalid) { s_abs += fabsf(z1); s_sum += z1; s_sq = fmaf(z1, z1, s_sq); }
+                }
+              }
+              const uint32_t off = (static_cast<uint32_t>(half * 4 + j8) ^ sw) << 4;
+              st_shared_v4(orow_s + off, zw[0], zw[1], zw[2], zw[3]);
+              st_shared_v4(orow_s + BOX_BYTES + off, hw[0], hw[1], hw[2], hw[3]);
+            }
+          } else {  // EPI_DZ_BWD: dz over z, in place (same thread, same bytes)
+#pragma unroll
+            for (int j8 = 0; j8 < 4; ++j8) {
+              const uint32_t off = (static_cast<uint32_t>(half * 4 + j8) ^ sw) << 4;
+              uint32_t zw[4], dw[4];
+              ld_shared_v4(orow_s + off, zw[0], zw[1], zw[2], zw[3]);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const int j = j8 * 8 + i * 2;
+                const float z0 = bf16lo_to_f32(zw[i]), z1 = bf16hi_to_f32(zw[i]);
+                // F_a'(z) + gate_a : relu 1[z>0] + 1 ; binary_step (STE) 1 + 0.1 ; tanh (1 - t^2) + 1
+                float m0 = act.is_step ? (1.f + act.gate) : ((z0 > 0.f ? 1.f : 0.f) + act.gate);
+                float m1 = act.is_step ? (1.f + act.gate) : ((z1 > 0.f ? 1.f : 0.f) + act.gate);
+                if (warp_has_tanh) {
+                  const float t0 = tanh_approx(z0), t1 = tanh_approx(z1);
+                  m0 = act.is_tanh ? (fmaf(-t0, t0, 1.f) + act.gate) : m0;
+                  m1 = act.is_tanh ? (fmaf(-t1, t1, 1.f) + act.gate) : m1;
+                }
+                const uint32_t dp = pack_bf16x2(__uint_as_float(v[j]) * m0, __uint_as_float(v[j + 1]) * m1);
+                dw[i] = dp;
+                const float d0 = bf16lo_to_f32(dp), d1 = bf16hi_to_f32(dp);
+                if (full) {
+                  s_abs += fabsf(d0) + fabsf(d1);
+                  s_sum += d0 + d1;
+                  s_sq = fmaf(d0, d0, s_sq);
+                  s_sq = fmaf(d1, d1, s_sq);
+                } else {
+                  if (jbase + j < nvalid) { s_abs += fabsf(d0); s_sum += d0; s_sq = fmaf(d0, d0, s_sq); }
+                  if (jbase + j + 1 < nvalid) { s_abs += fabsf(d1); s_sum += d1; s_sq = fmaf(d1, d1, s_sq); }
+                }
+              }
+              st_shared_v4(orow_s + off, dw[0], dw[1], dw[2], dw[3]);
             }
           }
         }
-        // single-buffered staging: the previous chunk's TMA stores must have read the boxes (the other epilogue
-        // warp of this SM sub-partition covers the wait)
-        if ((EPI == EPI_UP_FWD || EPI == EPI_STORE) && lane == 0 && !(p.debug & 8)) tma_wait_read<0>();
-        tmem_wait_ld();
 
-        if (EPI == EPI_F32) {
-          if (row < p.M && nvalid > 0) {
-            const float rs = (p.row_scale != nullptr ? p.row_scale[row] : 1.f) * p.scale *
-                             (p.scale_dev != nullptr ? *p.scale_dev : 1.f);
-            float* orow = p.out_f32 + static_cast<long long>(row) * p.ldc + col0;
-            const bool vec_ok = (nvalid >= CHUNK) && ((p.ldc & 3) == 0) &&
-                                ((reinterpret_cast<uintptr_t>(p.out_f32) & 15) == 0);
-            if (vec_ok) {
-#pragma unroll
-              for (int j = 0; j < CHUNK; j += 4) {
-                float f0 = __uint_as_float(v[j]) * rs, f1 = __uint_as_float(v[j + 1]) * rs;
-                float f2 = __uint_as_float(v[j + 2]) * rs, f3 = __uint_as_float(v[j + 3]) * rs;
-                if (p.col_scale != nullptr) {
-                  const float4 cs = *reinterpret_cast<const float4*>(p.col_scale + col0 + j);
-                  f0 *= cs.x; f1 *= cs.y; f2 *= cs.z; f3 *= cs.w;
-                }
-                if (p.atomic_out) {
-                  red_add_v4_f32(orow + j, f0, f1, f2, f3);
-                } else {
-                  *reinterpret_cast<float4*>(orow + j) = make_float4(f0, f1, f2, f3);
-                }
-              }
-            } else {
-#pragma unroll
-              for (int j = 0; j < CHUNK; ++j) {
-                if (j < nvalid) {
-                  float f = __uint_as_float(v[j]) * rs;
-                  if (p.col_scale != nullptr) f *= p.col_scale[col0 + j];
-                  if (p.atomic_out) atomicAdd(orow + j, f);
-                  else orow[j] = f;
-                }
-              }
-            }
-          }
-        } else if (EPI == EPI_STORE) {
-          // ---- bf16 output staged through swizzled smem
-          uint8_t* obuf = wst;
-          __syncwarp();
-          const uint32_t orow_s = smem_u32(obuf) + lane * 128;
-          const float* bsrc = bias_s + c * CHUNK;
-#pragma unroll
-          for (int j8 = 0; j8 < CHUNK / 8; ++j8) {
-            const float4 b0 = *reinterpret_cast<const float4*>(bsrc + j8 * 8);
-            const float4 b1 = *reinterpret_cast<const float4*>(bsrc + j8 * 8 + 4);
-            const uint32_t w0 = pack_bf16x2(__uint_as_float(v[j8 * 8 + 0]) + b0.x, __uint_as_float(v[j8 * 8 + 1]) + b0.y);
-            const uint32_t w1 = pack_bf16x2(__uint_as_float(v[j8 * 8 + 2]) + b0.z, __uint_as_float(v[j8 * 8 + 3]) + b0.w);
-            const uint32_t w2 = pack_bf16x2(__uint_as_float(v[j8 * 8 + 4]) + b1.x, __uint_as_float(v[j8 * 8 + 5]) + b1.y);
-            const uint32_t w3 = pack_bf16x2(__uint_as_float(v[j8 * 8 + 6]) + b1.z, __uint_as_float(v[j8 * 8 + 7]) + b1.w);
-            st_shared_v4(orow_s + ((static_cast<uint32_t>(j8) ^ sw) << 4), w0, w1, w2, w3);
-          }
+        if (EPI != EPI_F32) {
           fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0) {
             tma_store_2d(&p.tmC0, obuf, col0, w.m0 + q * 32);
+            if (EPI == EPI_UP_FWD) tma_store_2d(&p.tmC1, obuf + BOX_BYTES, col0, w.m0 + q * 32);
             tma_commit();
           }
-        } else if (EPI == EPI_UP_FWD) {
-          // z box at wst, h box at wst + BOX_BYTES (single buffered: the other warp of this SM sub-partition
-          // covers the wait for the previous chunk's stores to have read them)
-          __syncwarp();
-          const uint32_t orow_s = smem_u32(wst) + lane * 128;
-          const bool full = nvalid >= CHUNK;
-#pragma unroll
-          for (int j8 = 0; j8 < CHUNK / 8; ++j8) {
-            uint32_t zw[4], hw[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const int j = j8 * 8 + i * 2;
-              const uint32_t zp = pack_bf16x2(__uint_as_float(v[j]) + bias_r, __uint_as_float(v[j + 1]) + bias_r);
-              const float z0 = bf16lo_to_f32(zp), z1 = bf16hi_to_f32(zp);
-              // F_a(z): relu -> z if z>0 ; binary_step -> 1 if z>0 ; else 0.  tanh lanes overwrite below.
-              float f0 = (z0 > 0.f) ? (act.is_step ? 1.f : z0) : 0.f;
-              float f1 = (z1 > 0.f) ? (act.is_step ? 1.f : z1) : 0.f;
-              if (warp_has_tanh && !(p.debug & 32)) {
-                const float t0 = tanh_approx(z0), t1 = tanh_approx(z1);
-                f0 = act.is_tanh ? t0 : f0;
-                f1 = act.is_tanh ? t1 : f1;
-              }
-              const float h0 = fmaf(act.gate, z0, f0), h1 = fmaf(act.gate, z1, f1);
-              zw[i] = zp;
-              hw[i] = pack_bf16x2(h0, h1);
-              if (p.debug & 16) continue;
-              if (full) {
-                s_abs += fabsf(z0) + fabsf(z1);
-                s_sum += z0 + z1;
-                s_sq = fmaf(z0, z0, s_sq);
-                s_sq = fmaf(z1, z1, s_sq);
-              } else {
-                if (j < nvalid) { s_abs += fabsf(z0); s_sum += z0; s_sq = fmaf(z0, z0, s_sq); }
-                if (j + 1 < nvalid) { s_abs += fabsf(z1); s_sum += z1; s_sq = fmaf(z1, z1, s_sq); }
-              }
-            }
-            const uint32_t off = (static_cast<uint32_t>(j8) ^ sw) << 4;
-            if (!(p.debug & 2)) {
-              st_shared_v4(orow_s + off, zw[0], zw[1], zw[2], zw[3]);
-              st_shared_v4(orow_s + BOX_BYTES + off, hw[0], hw[1], hw[2], hw[3]);
-            } else {
-              s_sum += __uint_as_float(zw[0] ^ zw[1] ^ zw[2] ^ zw[3] ^ hw[0] ^ hw[1] ^ hw[2] ^ hw[3]);
-            }
-          }
-          fence_proxy_async_smem();
-          __syncwarp();
-          if (lane == 0 && !(p.debug & 1)) {
-            tma_store_2d(&p.tmC0, wst, col0, w.m0 + q * 32);
-            if (!(p.debug & 4)) tma_store_2d(&p.tmC1, wst + BOX_BYTES, col0, w.m0 + q * 32);
-            tma_commit();
-          }
-        } else {  // EPI_DZ_BWD
-          const int b = g & 1;
-          mbar_wait(&zb[b], (g >> 1) & 1);
-          const uint32_t zrow_s = smem_u32(wst + b * BOX_BYTES) + lane * 128;
-          const bool full = nvalid >= CHUNK;
-#pragma unroll
-          for (int j8 = 0; j8 < CHUNK / 8; ++j8) {
-            const uint32_t off = (static_cast<uint32_t>(j8) ^ sw) << 4;
-            uint32_t zw[4], dw[4];
-            ld_shared_v4(zrow_s + off, zw[0], zw[1], zw[2], zw[3]);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const int j = j8 * 8 + i * 2;
-              const float z0 = bf16lo_to_f32(zw[i]), z1 = bf16hi_to_f32(zw[i]);
-              // F_a'(z) + gate_a : relu 1[z>0] + 1 ; binary_step (STE) 1 + 0.1 ; tanh (1 - t^2) + 1
-              float m0 = act.is_step ? (1.f + act.gate) : ((z0 > 0.f ? 1.f : 0.f) + act.gate);
-              float m1 = act.is_step ? (1.f + act.gate) : ((z1 > 0.f ? 1.f : 0.f) + act.gate);
-              if (warp_has_tanh) {
-                const float t0 = tanh_approx(z0), t1 = tanh_approx(z1);
-                m0 = act.is_tanh ? (fmaf(-t0, t0, 1.f) + act.gate) : m0;
-                m1 = act.is_tanh ? (fmaf(-t1, t1, 1.f) + act.gate) : m1;
-              }
-              const uint32_t dp = pack_bf16x2(__uint_as_float(v[j]) * m0, __uint_as_float(v[j + 1]) * m1);
-              dw[i] = dp;
-              const float d0 = bf16lo_to_f32(dp), d1 = bf16hi_to_f32(dp);
-              if (full) {
-                s_abs += fabsf(d0) + fabsf(d1);
-                s_sum += d0 + d1;
-                s_sq = fmaf(d0, d0, s_sq);
-                s_sq = fmaf(d1, d1, s_sq);
-              } else {
-                if (j < nvalid) { s_abs += fabsf(d0); s_sum += d0; s_sq = fmaf(d0, d0, s_sq); }
-                if (j + 1 < nvalid) { s_abs += fabsf(d1); s_sum += d1; s_sq = fmaf(d1, d1, s_sq); }
-              }
-            }
-            st_shared_v4(zrow_s + off, dw[0], dw[1], dw[2], dw[3]);  // dz over z, in place (same thread, same bytes)
-          }
-          fence_proxy_async_smem();
-          __syncwarp();
-          if (lane == 0) {
-            tma_store_2d(&p.tmC0, wst + b * BOX_BYTES, col0, w.m0 + q * 32);
-            tma_commit();
-          }
-          ++g;
+        }
+        if (EPI == EPI_DZ_BWD) ++g;
+
+        if ((EPI == EPI_UP_FWD || EPI == EPI_DZ_BWD) && p.partials != nullptr && row < p.M) {
+          float* dst = p.partials + (static_cast<long long>(w.nb * PARTIALS_PER_TILE + c) * 3) * p.M + row;
+          dst[0] = s_abs;
+          dst[p.M] = s_sum;
+          dst[2 * static_cast<long long>(p.M)] = s_sq;
         }
       }
 
       // accumulator drained: hand the TMEM buffer back to the MMA warp
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[as]);
-
-      if ((EPI == EPI_UP_FWD || EPI == EPI_DZ_BWD) && p.partials != nullptr && row < p.M) {
-        float* dst = p.partials + (static_cast<long long>(w.nb * 2 + e) * 3) * p.M + row;
-        dst[0] = s_abs;
-        dst[p.M] = s_sum;
-        dst[2 * static_cast<long long>(p.M)] = s_sq;
+      if (lane == 0) {
+        if (PAIR) mbar_arrive_leader(&tempty_bar[as]);
+        else mbar_arrive(&tempty_bar[as]);
       }
     }
     if (EPI != EPI_F32 && lane == 0) tma_wait_all<0>();
   }
 
   tc_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync_all();  // neither CTA may leave while the other can still touch its smem / TMEM / barriers
+  else __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, TMEM_COLS);
+    if (PAIR) tmem_dealloc_pair(tmem_base, TMEM_COLS);
+    else tmem_dealloc(tmem_base, TMEM_COLS);
   }
 }
 

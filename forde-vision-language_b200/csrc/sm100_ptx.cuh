@@ -55,6 +55,24 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// ---------------------------------------------------------------- clusters / CTA pairs
+// In a 2-CTA cluster a shared::cta window address is also a valid shared::cluster address of the executing CTA;
+// clearing bit 24 turns it into the same offset in the even ("leader") CTA of the pair.
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.aligned;\n\tbarrier.cluster.wait.aligned;" ::: "memory");
+}
+// arrive on the barrier at this offset in the leader CTA's shared memory (works from either CTA of the pair)
+__device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & kPeerBitMask) : "memory");
+}
+
 // ---------------------------------------------------------------- proxies / fences
 __device__ __forceinline__ void fence_proxy_async_smem() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -83,6 +101,18 @@ __device__ __forceinline__ void tma_load_2d(const void* tmap, uint64_t* bar, voi
       :
       : "r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar)), "r"(c0), "r"(c1),
         "l"(hint)
+      : "memory");
+}
+// Same, issued by either CTA of a pair: data lands in the issuing CTA's shared memory, the transaction bytes are
+// counted on the LEADER CTA's barrier (the one the cta_group::2 MMA issuer waits on).
+__device__ __forceinline__ void tma_load_2d_pair(const void* tmap, uint64_t* bar, void* smem_dst, int c0, int c1,
+                                                 uint64_t hint) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+      " [%0], [%1, {%3, %4}], [%2], %5;"
+      :
+      : "r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0),
+        "r"(c1), "l"(hint)
       : "memory");
 }
 // 2-D tiled store shared -> global (bulk async group).
@@ -131,6 +161,40 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                : "memory");
+}
+// ---- cta_group::2 (CTA pair) variants: allocation is issued by the same warp of BOTH CTAs, the MMA by the leader.
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t* smem_dst, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)),
+               "r"(ncols)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish_pair() {
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// D[tmem of both CTAs] (+)= A[256 rows: 128 per CTA] * B[N columns: N/2 per CTA]; descriptors are the leader's,
+// the peer's tiles sit at the same shared-memory offsets.
+__device__ __forceinline__ void umma_bf16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                               uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}\n"
+      :
+      : "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive (once all previously issued MMAs completed) on the barrier at this offset in BOTH CTAs of the pair
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+          smem_u32(bar)),
+      "h"(static_cast<uint16_t>(3))
+      : "memory");
 }
 // 32 lanes x 32 consecutive fp32 columns: thread l of the warp gets row (lane_base + l).
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
