@@ -40,6 +40,7 @@ __device__ __forceinline__ uint4 pack8(const float* f) {
   return make_uint4(w[0], w[1], w[2], w[3]);
 }
 
+template <int NV>  // 16-byte vectors per lane actually used: ceil(cols / 256)
 __global__ void __launch_bounds__(LN_WARPS * 32)
 add_layernorm_fwd_kernel(const uint4* __restrict__ x, const uint4* __restrict__ r, const float* __restrict__ gamma,
                          const float* __restrict__ beta, uint4* __restrict__ out, float* __restrict__ mean_out,
@@ -49,10 +50,10 @@ add_layernorm_fwd_kernel(const uint4* __restrict__ x, const uint4* __restrict__ 
   const float inv_n = 1.f / static_cast<float>(cols);
   for (int row = blockIdx.x * LN_WARPS + warp; row < rows; row += gridDim.x * LN_WARPS) {
     const size_t base = static_cast<size_t>(row) * nvec;
-    float s[LN_MAXV][8];
+    float s[NV][8];
     float sum = 0.f;
 #pragma unroll
-    for (int i = 0; i < LN_MAXV; ++i) {
+    for (int i = 0; i < NV; ++i) {
       const int v = lane + i * 32;
       if (v < nvec) {
         float a[8], b[8];
@@ -72,7 +73,7 @@ add_layernorm_fwd_kernel(const uint4* __restrict__ x, const uint4* __restrict__ 
     const float mean = wsum(sum) * inv_n;
     float sq = 0.f;
 #pragma unroll
-    for (int i = 0; i < LN_MAXV; ++i) {
+    for (int i = 0; i < NV; ++i) {
       if (lane + i * 32 < nvec) {
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
@@ -83,7 +84,7 @@ add_layernorm_fwd_kernel(const uint4* __restrict__ x, const uint4* __restrict__ 
     }
     const float rstd = rsqrtf(wsum(sq) * inv_n + eps);
 #pragma unroll
-    for (int i = 0; i < LN_MAXV; ++i) {
+    for (int i = 0; i < NV; ++i) {
       const int v = lane + i * 32;
       if (v < nvec) {
         const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma) + 2 * v);
@@ -106,7 +107,8 @@ add_layernorm_fwd_kernel(const uint4* __restrict__ x, const uint4* __restrict__ 
 }
 
 // partials: [gridDim.x][2][cols]  (d_gamma, d_beta)
-__global__ void __launch_bounds__(LN_WARPS * 32)
+template <int NV>
+__global__ void __launch_bounds__(LN_WARPS * 32, NV <= 3 ? 2 : 1)
 add_layernorm_bwd_kernel(const uint4* __restrict__ dy, const uint4* __restrict__ x, const uint4* __restrict__ r,
                          const float* __restrict__ gamma, const float* __restrict__ mean_in,
                          const float* __restrict__ rstd_in, uint4* __restrict__ ds, float* __restrict__ partials,
@@ -115,9 +117,9 @@ add_layernorm_bwd_kernel(const uint4* __restrict__ dy, const uint4* __restrict__
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int nvec = cols >> 3;
   const float inv_n = 1.f / static_cast<float>(cols);
-  float dg[LN_MAXV][8], db[LN_MAXV][8], g[LN_MAXV][8];
+  float dg[NV][8], db[NV][8], g[NV][8];
 #pragma unroll
-  for (int i = 0; i < LN_MAXV; ++i) {
+  for (int i = 0; i < NV; ++i) {
     const int v = lane + i * 32;
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
@@ -129,10 +131,10 @@ add_layernorm_bwd_kernel(const uint4* __restrict__ dy, const uint4* __restrict__
   for (int row = blockIdx.x * LN_WARPS + warp; row < rows; row += gridDim.x * LN_WARPS) {
     const size_t base = static_cast<size_t>(row) * nvec;
     const float mean = mean_in[row], rstd = rstd_in[row];
-    float xh[LN_MAXV][8], gy[LN_MAXV][8];
+    float xh[NV][8], gy[NV][8];
     float c1 = 0.f, c2 = 0.f;
 #pragma unroll
-    for (int i = 0; i < LN_MAXV; ++i) {
+    for (int i = 0; i < NV; ++i) {
       const int v = lane + i * 32;
       if (v < nvec) {
         float a[8], b[8], d[8];
@@ -159,7 +161,7 @@ add_layernorm_bwd_kernel(const uint4* __restrict__ dy, const uint4* __restrict__
     c1 = wsum(c1) * inv_n;
     c2 = wsum(c2) * inv_n;
 #pragma unroll
-    for (int i = 0; i < LN_MAXV; ++i) {
+    for (int i = 0; i < NV; ++i) {
       const int v = lane + i * 32;
       if (v < nvec) {
         float o[8];
@@ -171,7 +173,7 @@ add_layernorm_bwd_kernel(const uint4* __restrict__ dy, const uint4* __restrict__
   }
   // CTA reduction of d_gamma / d_beta over the warps, fixed order
 #pragma unroll
-  for (int i = 0; i < LN_MAXV; ++i) {
+  for (int i = 0; i < NV; ++i) {
     const int v = lane + i * 32;
     if (v < nvec) {
 #pragma unroll
@@ -191,21 +193,31 @@ add_layernorm_bwd_kernel(const uint4* __restrict__ dy, const uint4* __restrict__
   }
 }
 
+// d_gamma / d_beta from the per-CTA partials: block = 32 columns x 8 lanes over the CTAs, fixed combination order.
 __global__ void ln_param_grad_kernel(const float* __restrict__ partials, int nblocks, int cols,
                                      float* __restrict__ d_gamma, float* __restrict__ d_beta) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= 2 * cols) return;
-  const int which = c / cols, col = c - which * cols;
+  __shared__ float red[8][33];
+  const int c = blockIdx.x * 32 + threadIdx.x;  // index into [2][cols]
   float t = 0.f;
-  for (int b = 0; b < nblocks; ++b) t += partials[(static_cast<size_t>(b) * 2 + which) * cols + col];
-  float* dst = which == 0 ? d_gamma : d_beta;
-  dst[col] += t;
+  if (c < 2 * cols) {
+    const int which = c / cols, col = c - which * cols;
+    for (int b = threadIdx.y; b < nblocks; b += 8) t += partials[(static_cast<size_t>(b) * 2 + which) * cols + col];
+  }
+  red[threadIdx.y][threadIdx.x] = t;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < 2 * cols) {
+    float r = 0.f;
+#pragma unroll
+    for (int y = 0; y < 8; ++y) r += red[y][threadIdx.x];
+    const int which = c / cols, col = c - which * cols;
+    (which == 0 ? d_gamma : d_beta)[col] += r;
+  }
 }
 
 static int ln_grid(int rows) {
   const int sms = sm_count();
   if (sms <= 0) return 0;
-  int grid = 2 * sms;
+  int grid = 4 * sms;
   const int need = (rows + LN_WARPS - 1) / LN_WARPS;
   return grid < need ? grid : need;
 }
@@ -229,9 +241,16 @@ int forde_add_layernorm_fwd(void* stream, const void* x, const void* r, const fl
     return FORDE_EALIGN;
   const int grid = ln_grid(rows);
   if (grid <= 0) return FORDE_ENODEV;
-  add_layernorm_fwd_kernel<<<grid, LN_WARPS * 32, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const uint4*>(x), static_cast<const uint4*>(r), gamma, beta, static_cast<uint4*>(out), mean, rstd,
-      rows, cols, eps);
+  const int nv = (cols / 8 + 31) / 32;
+#define FORDE_LN_FWD(NV)                                                                                      \
+  add_layernorm_fwd_kernel<NV><<<grid, LN_WARPS * 32, 0, static_cast<cudaStream_t>(stream)>>>(               \
+      static_cast<const uint4*>(x), static_cast<const uint4*>(r), gamma, beta, static_cast<uint4*>(out), mean, \
+      rstd, rows, cols, eps)
+  if (nv == 1) FORDE_LN_FWD(1);
+  else if (nv == 2) FORDE_LN_FWD(2);
+  else if (nv == 3) FORDE_LN_FWD(3);
+  else FORDE_LN_FWD(4);
+#undef FORDE_LN_FWD
   return check_launch("add_layernorm_fwd_kernel");
 }
 
@@ -248,17 +267,27 @@ int forde_add_layernorm_bwd(void* stream, const void* dy, const void* x, const v
   const int grid = ln_grid(rows);
   if (grid <= 0) return FORDE_ENODEV;
   const int smem = LN_WARPS * 2 * cols * static_cast<int>(sizeof(float));
+  const int max_smem = LN_WARPS * 2 * 32 * LN_MAXV * 8 * static_cast<int>(sizeof(float));
   static bool attr_set = false;
   if (!attr_set) {
-    cudaFuncSetAttribute(add_layernorm_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                         LN_WARPS * 2 * 32 * LN_MAXV * 8 * static_cast<int>(sizeof(float)));
+    cudaFuncSetAttribute(add_layernorm_bwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+    cudaFuncSetAttribute(add_layernorm_bwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+    cudaFuncSetAttribute(add_layernorm_bwd_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+    cudaFuncSetAttribute(add_layernorm_bwd_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
     attr_set = true;
   }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  add_layernorm_bwd_kernel<<<grid, LN_WARPS * 32, smem, st>>>(
-      static_cast<const uint4*>(dy), static_cast<const uint4*>(x), static_cast<const uint4*>(r), gamma, mean, rstd,
-      static_cast<uint4*>(ds), partials, rows, cols);
-  ln_param_grad_kernel<<<(2 * cols + 127) / 128, 128, 0, st>>>(partials, grid, cols, d_gamma, d_beta);
+  const int nv = (cols / 8 + 31) / 32;
+#define FORDE_LN_BWD(NV)                                                                                         \
+  add_layernorm_bwd_kernel<NV><<<grid, LN_WARPS * 32, smem, st>>>(                                               \
+      static_cast<const uint4*>(dy), static_cast<const uint4*>(x), static_cast<const uint4*>(r), gamma, mean, rstd, \
+      static_cast<uint4*>(ds), partials, rows, cols)
+  if (nv == 1) FORDE_LN_BWD(1);
+  else if (nv == 2) FORDE_LN_BWD(2);
+  else if (nv == 3) FORDE_LN_BWD(3);
+  else FORDE_LN_BWD(4);
+#undef FORDE_LN_BWD
+  ln_param_grad_kernel<<<(2 * cols + 31) / 32, dim3(32, 8), 0, st>>>(partials, grid, cols, d_gamma, d_beta);
   return check_launch("add_layernorm_bwd_kernel", 2);
 }
 

@@ -79,6 +79,61 @@ class _Bf16Mirror(torch.autograd.Function):
         return g.float(), None
 
 
+def _colsum(dy2d):
+    out = torch.zeros(dy2d.shape[1], dtype=torch.float32, device=dy2d.device)
+    ops.colsum_bf16(dy2d, out)
+    return out
+
+
+class _Dense(torch.autograd.Function):
+    """y = x W + b for bf16 activations (cuBLAS GEMMs; the bias gradient is this repository's column-sum kernel
+    instead of a generic strided reduction).  `w16` is the bf16 mirror (in, out); gradients go to the fp32 masters."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, w16, b16):
+        x2 = x.reshape(-1, x.shape[-1])
+        y = torch.addmm(b16, x2, w16)
+        ctx.save_for_backward(x2, w16)
+        ctx.lead = x.shape[:-1]
+        return y.view(*x.shape[:-1], w16.shape[1])
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, w16 = ctx.saved_tensors
+        dy2 = dy.reshape(-1, dy.shape[-1])
+        if not dy2.is_contiguous():
+            dy2 = dy2.contiguous()
+        dx = torch.mm(dy2, w16.t()).view(*ctx.lead, w16.shape[0])
+        dw = torch.mm(x2.t(), dy2).float()
+        return dx, dw, _colsum(dy2), None, None
+
+
+class _QKVDense(torch.autograd.Function):
+    """The three attention input projections sharing one input: forward three GEMMs, backward accumulates dx with
+    beta = 1 inside the GEMMs (no separate add passes over the (M, w) gradient)."""
+
+    @staticmethod
+    def forward(ctx, x, wq, bq, wk, bk, wv, bv, wq16, bq16, wk16, bk16, wv16, bv16):
+        x2 = x.reshape(-1, x.shape[-1])
+        ctx.save_for_backward(x2, wq16, wk16, wv16)
+        ctx.shape = x.shape
+        return tuple(torch.addmm(b, x2, w).view(x.shape) for w, b in ((wq16, bq16), (wk16, bk16), (wv16, bv16)))
+
+    @staticmethod
+    def backward(ctx, dq, dk, dv):
+        x2, wq16, wk16, wv16 = ctx.saved_tensors
+        d = [t.reshape(-1, t.shape[-1]) for t in (dq, dk, dv)]
+        d = [t if t.is_contiguous() else t.contiguous() for t in d]
+        dx = torch.mm(d[0], wq16.t())
+        dx.addmm_(d[1], wk16.t())
+        dx.addmm_(d[2], wv16.t())
+        xt = x2.t()
+        grads = []
+        for t in d:
+            grads += [torch.mm(xt, t).float(), _colsum(t)]
+        return (dx.view(ctx.shape), *grads, None, None, None, None, None, None)
+
+
 class _AddLayerNorm(torch.autograd.Function):
     """LayerNorm(x + r) on the fused sm_100a kernel (csrc/forde_norm.cu); gamma / beta are fp32 masters."""
 
@@ -170,15 +225,19 @@ class FORDEDualEncoder:
         B, T, w = x.shape
         pa, pa16 = p["attn"], (p16["attn"] if p16 is not None else None)
 
-        def proj(t, name):
-            return F.linear(t, self._w(pa[name], pa16 and pa16[name], "kernel").t(),
-                            self._w(pa[name], pa16 and pa16[name], "bias"))
+        def mirror(name, leaf):
+            return pa16[name][leaf] if pa16 is not None else pa[name][leaf].to(torch.bfloat16)
 
         # Flax MultiHeadDotProductAttention layout: separate query / key / value / out projections.  Heads are a
         # strided view of the (B, T, w) projections, so nothing is re-packed on the way in or out of the kernel.
-        q, k, v = (proj(x, n).view(B, T, heads, w // heads).transpose(1, 2) for n in ("query", "key", "value"))
+        q, k, v = _QKVDense.apply(x, pa["query"]["kernel"], pa["query"]["bias"], pa["key"]["kernel"], pa["key"]["bias"],
+                                  pa["value"]["kernel"], pa["value"]["bias"], mirror("query", "kernel"),
+                                  mirror("query", "bias"), mirror("key", "kernel"), mirror("key", "bias"),
+                                  mirror("value", "kernel"), mirror("value", "bias"))
+        q, k, v = (t.view(B, T, heads, w // heads).transpose(1, 2) for t in (q, k, v))
         a = F.scaled_dot_product_attention(q, k, v)
-        a = proj(a.transpose(1, 2).reshape(B, T, w), "out")
+        a = _Dense.apply(a.transpose(1, 2).reshape(B, T, w), pa["out"]["kernel"], pa["out"]["bias"],
+                         mirror("out", "kernel"), mirror("out", "bias"))
         x = _AddLayerNorm.apply(x, a, p["ln_1"]["scale"], p["ln_1"]["bias"])
         tower, lname = key.split("/")
         sl_vars = {
