@@ -43,6 +43,15 @@ SIGNATURES = {
     "forde_clip_loss": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp]),
     "forde_clip_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "forde_l2norm_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i]),
+    "forde_moe_capacity_rows": (_i, [_i, _i, _i]),
+    "forde_moe_num_prob_partials": (_i, [_i]),
+    "forde_moe_route": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _f] + [_vp] * 14),
+    "forde_moe_gather": (_i, [_vp, _vp, _vp, _i, _vp, _i, _i]),
+    "forde_moe_scatter": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _i, _i]),
+    "forde_moe_combine": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i]),
+    "forde_moe_gate_grad": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i]),
+    "forde_moe_experts_fwd": (_i, [_vp] * 11 + [_i, _i, _i, _i]),
+    "forde_moe_experts_bwd": (_i, [_vp] * 16 + [_i, _i, _i, _i]),
     "forde_ln_num_partials": (_i, [_i]),
     "forde_add_layernorm_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _f]),
     "forde_add_layernorm_bwd": (_i, [_vp] * 11 + [_i, _i]),

@@ -279,6 +279,71 @@ int gemm_f32(cudaStream_t stream, const GemmArgs& g, float* D, long long ldd, co
   return launch_epi<EPI_F32>(p, g.a_mn, g.b_mn, stream);
 }
 
+// ------------------------------------------------------------------ grouped launches (MoE experts)
+template <bool A_MN, bool B_MN, int EPI>
+static int launch_single(const GemmParams& p, cudaStream_t stream) {
+  return launch_inst<A_MN, B_MN, EPI, false>(p, stream);
+}
+
+int gemm_grouped_m(cudaStream_t stream, const GemmArgs& g, const GroupedM& gm, int mode, void* D, long long ldd,
+                   void* D2, const void* Zin, const float* bias_col) {
+  if (g.a_mn || D == nullptr || gm.m_blocks_dev == nullptr || gm.group_of_mblock == nullptr) return FORDE_EINVAL;
+  GemmParams p;
+  int rc = fill_common(p, g);
+  if (rc != FORDE_OK) return rc;
+  // grouped kernels are single-CTA instantiations (128-row tiles), and B is the expert-STACKED weight array:
+  // rebuild its map with the stacked extents
+  p.pair = 0;
+  p.m_blocks = (g.M + BM - 1) / BM;
+  {
+    const int rows = g.N * (gm.b_n_group_stride ? gm.groups : 1);
+    const int kext = g.K * (gm.b_k_group_stride ? gm.groups : 1);
+    rc = make_operand_map(&p.tmB, g.B, g.b_mn, g.ldb, rows, kext, BN);
+    if (rc != FORDE_OK) return rc;
+  }
+  rc = make_tmap_bf16(&p.tmC0, D, g.N, g.M, ldd, CHUNK, 32);
+  if (rc != FORDE_OK) return rc;
+  p.bias_col = bias_col;
+  p.m_blocks_dev = gm.m_blocks_dev;
+  p.group_of_mblock = gm.group_of_mblock;
+  p.b_k_group_stride = gm.b_k_group_stride;
+  p.b_n_group_stride = gm.b_n_group_stride;
+  p.bias_group_stride = gm.bias_group_stride;
+  p.raster_m_fast = 0;
+  if (mode == 1) {
+    if (D2 == nullptr) return FORDE_EINVAL;
+    rc = make_tmap_bf16(&p.tmC1, D2, g.N, g.M, ldd, CHUNK, 32);
+    if (rc != FORDE_OK) return rc;
+    return g.b_mn ? launch_single<false, true, EPI_MOE_UP>(p, stream) : launch_single<false, false, EPI_MOE_UP>(p, stream);
+  }
+  if (mode == 2) {
+    if (Zin == nullptr) return FORDE_EINVAL;
+    rc = make_tmap_bf16(&p.tmZ, Zin, g.N, g.M, ldd, CHUNK, 32);
+    if (rc != FORDE_OK) return rc;
+    return g.b_mn ? launch_single<false, true, EPI_MOE_DZ>(p, stream) : launch_single<false, false, EPI_MOE_DZ>(p, stream);
+  }
+  return g.b_mn ? launch_single<false, true, EPI_STORE>(p, stream) : launch_single<false, false, EPI_STORE>(p, stream);
+}
+
+int gemm_grouped_k(cudaStream_t stream, const GemmArgs& g, const int* seg_offsets, int groups, float* out,
+                   long long ldo, long long out_group_stride) {
+  if (!g.a_mn || !g.b_mn || out == nullptr || seg_offsets == nullptr || groups <= 0) return FORDE_EINVAL;
+  GemmParams p;
+  int rc = fill_common(p, g);
+  if (rc != FORDE_OK) return rc;
+  if (p.pair) {
+    p.pair = 0;
+    rc = make_operand_map(&p.tmB, g.B, g.b_mn, g.ldb, g.N, g.K, BN);
+    if (rc != FORDE_OK) return rc;
+    p.m_blocks = (g.M + BM - 1) / BM;
+  }
+  p.out_f32 = out; p.ldc = ldo; p.scale = 1.f; p.atomic_out = 0;
+  p.seg_offsets = seg_offsets; p.groups = groups; p.out_group_stride = out_group_stride;
+  // total work = groups * tiles: tell the launcher through split_k so the grid is sized for it
+  p.split_k = groups;
+  return launch_single<true, true, EPI_F32>(p, stream);
+}
+
 }  // namespace forde
 
 using namespace forde;

@@ -33,6 +33,17 @@
 //   EPI_DZ_BWD  : rows are neurons. reads z^T tile, dz = acc * (F_a'(z) + gate_a) (binary_step uses the
 //                 straight-through estimator) -> bf16; per-neuron sum|dz|, sum dz, sum dz^2 -> partials.
 //   EPI_F32     : D * row_scale[m] * col_scale[n] * scale -> fp32, plain store or red.add (split-K dW).
+//   EPI_MOE_UP  : rows are routed token slots (MoE variant of the slot, moe.py:17-29).  z = acc + b_e[col] -> bf16;
+//                 h = gelu_tanh(z) -> bf16.
+//   EPI_MOE_DZ  : dz = acc * gelu_tanh'(z) -> bf16, z tile TMA-prefetched, written in place.
+//
+// Grouped modes for the MoE experts (the rows of A are routed token slots sorted by expert, every expert's
+// segment padded to a multiple of 128 rows; all device-side, no host synchronisation on the routing result):
+//   grouped-M : the number of 128-row blocks comes from device memory (m_blocks_dev) and each block carries its
+//               expert (group_of_mblock); the B operand and the column bias of that expert are selected by
+//               coordinate offsets into the expert-stacked weight / bias arrays.
+//   grouped-K : one work item per (expert, output tile); the reduction runs over that expert's row segment
+//               (seg_offsets) and the fp32 result goes to the expert's slice of the output (dW per expert).
 #pragma once
 #include <cuda.h>
 #include <cuda_runtime.h>
@@ -42,7 +53,7 @@
 
 namespace forde {
 
-enum EpiKind : int { EPI_STORE = 0, EPI_UP_FWD = 1, EPI_DZ_BWD = 2, EPI_F32 = 3 };
+enum EpiKind : int { EPI_STORE = 0, EPI_UP_FWD = 1, EPI_DZ_BWD = 2, EPI_F32 = 3, EPI_MOE_UP = 4, EPI_MOE_DZ = 5 };
 
 constexpr int BM = 128;
 constexpr int BN = 256;
@@ -81,15 +92,22 @@ constexpr int PARTIALS_PER_TILE = BN / CHUNK;
 // EPI_DZ_BWD keeps a per-warp ring of z^T boxes: chunk g is TMA-loaded DZ_DIST chunks ahead into box g % ring,
 // multiplied in place into dz and TMA-stored from there.  ring - DZ_DIST - 1 stores may still be reading smem
 // when a box is refilled, so with ring 4 / distance 2 the refill never waits on the store just issued.
+__host__ __device__ constexpr bool epi_z_ring(int epi) { return epi == EPI_DZ_BWD || epi == EPI_MOE_DZ; }
+__host__ __device__ constexpr bool epi_two_out(int epi) { return epi == EPI_UP_FWD || epi == EPI_MOE_UP; }
+__host__ __device__ constexpr bool epi_col_bias(int epi) { return epi == EPI_STORE || epi == EPI_MOE_UP; }
+__host__ __device__ constexpr bool epi_neuron_rows(int epi) { return epi == EPI_UP_FWD || epi == EPI_DZ_BWD; }
 __host__ __device__ constexpr int dz_ring(bool pair) { return 2; }
 __host__ __device__ constexpr int dz_dist(bool pair) { return 1; }
 // per-warp staging: EPI_STORE [out] ; EPI_UP_FWD [z][h] ; EPI_DZ_BWD [ring of zin/out boxes]
 __host__ __device__ constexpr int epi_warp_staging_bytes(int epi, bool pair) {
-  return epi == EPI_F32 ? 0 : epi == EPI_STORE ? BOX_BYTES : epi == EPI_DZ_BWD ? dz_ring(pair) * BOX_BYTES : 2 * BOX_BYTES;
+  return epi == EPI_F32 ? 0 : epi == EPI_STORE ? BOX_BYTES : epi_z_ring(epi) ? dz_ring(pair) * BOX_BYTES : 2 * BOX_BYTES;
 }
 
 __host__ __device__ constexpr int gemm_stages(int epi, bool pair) {
-  return epi == EPI_UP_FWD ? (pair ? FORDE_UP_STAGES : 3) : epi == EPI_DZ_BWD ? (pair ? FORDE_DZ_STAGES : 3) : (pair ? 6 : 4);
+  return epi == EPI_UP_FWD ? (pair ? FORDE_UP_STAGES : 3)
+         : epi == EPI_DZ_BWD ? (pair ? FORDE_DZ_STAGES : 3)
+         : (epi == EPI_MOE_UP || epi == EPI_MOE_DZ) ? 3
+                                                    : (pair ? 6 : 4);
 }
 __host__ __device__ constexpr int gemm_smem_bytes(int epi, bool pair) {
   // ring + staging + column bias (BN fp32) + barriers/pointers (512 B) + 1 KB alignment slack
@@ -111,6 +129,15 @@ struct GemmParams {
   int split_k, kb_per_split;
   int raster_m_fast;  // 1: consecutive work items walk M first (share the B slab), 0: walk N first
   int pair;           // 1: launched as 2-CTA clusters (256-row tiles, cta_group::2)
+  // grouped modes (MoE experts); all null / 0 otherwise
+  const int* m_blocks_dev;     // grouped-M: number of valid 128-row blocks (device scalar)
+  const int* group_of_mblock;  // grouped-M: expert of each 128-row block
+  int b_k_group_stride;        // grouped-M: B k-coordinate offset per expert (weights stacked along k)
+  int b_n_group_stride;        // grouped-M: B row (n) coordinate offset per expert (weights stacked along n)
+  int bias_group_stride;       // grouped-M: bias_col offset per expert
+  const int* seg_offsets;      // grouped-K: [groups + 1] row offsets (multiples of BK) of the experts' segments
+  int groups;                  // grouped-K: number of experts
+  long long out_group_stride;  // grouped-K: out_f32 offset per expert (elements)
   uint64_t hintA, hintB;
   const float* bias_col;    // [N]  EPI_STORE (may be null)
   const float* bias_row;    // [M]  EPI_UP_FWD (may be null)
@@ -129,27 +156,43 @@ struct GemmParams {
 
 struct WorkItem {
   int m0, n0, nb, kb0, kb1;
+  int group;  // expert (grouped modes), else 0
 };
 
 // `tile_m` = rows of D per work item (128, or 256 for a CTA pair); `m_off` = this CTA's row offset inside it.
-__device__ __forceinline__ WorkItem decode_work(const GemmParams& p, int t, int tile_m, int m_off) {
-  const int n_tiles = p.m_blocks * p.n_blocks;
+// `m_blocks` is passed in because grouped-M kernels read it from device memory.
+__device__ __forceinline__ WorkItem decode_work(const GemmParams& p, int t, int tile_m, int m_off, int m_blocks) {
+  WorkItem w;
+  w.group = 0;
+  if (p.seg_offsets != nullptr) {  // grouped-K: t = group * tiles + tile, the whole segment is one reduction
+    const int n_tiles = m_blocks * p.n_blocks;
+    w.group = t / n_tiles;
+    const int tile = t - w.group * n_tiles;
+    const int nb = tile % p.n_blocks, mb = tile / p.n_blocks;
+    w.m0 = mb * tile_m + m_off;
+    w.n0 = nb * BN;
+    w.nb = nb;
+    w.kb0 = p.seg_offsets[w.group] / BK;
+    w.kb1 = p.seg_offsets[w.group + 1] / BK;
+    return w;
+  }
+  const int n_tiles = m_blocks * p.n_blocks;
   const int tile = t % n_tiles;
   const int ks = t / n_tiles;
   int mb, nb;
   if (p.raster_m_fast) {
-    mb = tile % p.m_blocks;
-    nb = tile / p.m_blocks;
+    mb = tile % m_blocks;
+    nb = tile / m_blocks;
   } else {
     nb = tile % p.n_blocks;
     mb = tile / p.n_blocks;
   }
-  WorkItem w;
   w.m0 = mb * tile_m + m_off;
   w.n0 = nb * BN;
   w.nb = nb;
   w.kb0 = ks * p.kb_per_split;
   w.kb1 = min(w.kb0 + p.kb_per_split, p.k_blocks);
+  if (p.group_of_mblock != nullptr) w.group = p.group_of_mblock[mb];
   return w;
 }
 
@@ -193,7 +236,8 @@ __global__ void __launch_bounds__(num_threads(EPI, PAIR), 1) forde_gemm_kernel(c
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int total_work = p.m_blocks * p.n_blocks * p.split_k;
+  const int m_blocks = (p.m_blocks_dev != nullptr) ? *p.m_blocks_dev : p.m_blocks;
+  const int total_work = (p.seg_offsets != nullptr) ? p.groups * m_blocks * p.n_blocks : m_blocks * p.n_blocks * p.split_k;
   const int cta_rank = PAIR ? static_cast<int>(cluster_ctarank()) : 0;
   const int m_off = cta_rank * BM;
   const int worker = PAIR ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
@@ -203,8 +247,8 @@ __global__ void __launch_bounds__(num_threads(EPI, PAIR), 1) forde_gemm_kernel(c
     tma_prefetch_desc(&p.tmA);
     tma_prefetch_desc(&p.tmB);
     if (EPI != EPI_F32) tma_prefetch_desc(&p.tmC0);
-    if (EPI == EPI_UP_FWD) tma_prefetch_desc(&p.tmC1);
-    if (EPI == EPI_DZ_BWD) tma_prefetch_desc(&p.tmZ);
+    if (epi_two_out(EPI)) tma_prefetch_desc(&p.tmC1);
+    if (epi_z_ring(EPI)) tma_prefetch_desc(&p.tmZ);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
@@ -237,8 +281,10 @@ __global__ void __launch_bounds__(num_threads(EPI, PAIR), 1) forde_gemm_kernel(c
       int stage = 0;
       uint32_t phase = 0;
       for (int t = worker; t < total_work; t += num_workers) {
-        const WorkItem w = decode_work(p, t, TILE_M, m_off);
-        const int nb0 = w.n0 + (PAIR ? cta_rank * BNL : 0);  // first B row (D column) this CTA stages
+        const WorkItem w = decode_work(p, t, TILE_M, m_off, m_blocks);
+        // first B row (D column) this CTA stages (+ the expert's slice of n-stacked weights)
+        const int nb0 = w.n0 + (PAIR ? cta_rank * BNL : 0) + w.group * p.b_n_group_stride;
+        const int kgo = w.group * p.b_k_group_stride;  // expert's slice of k-stacked weights
         for (int kb = w.kb0; kb < w.kb1; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           // pair: both CTAs' bytes are counted on the leader's barrier; only the leader arms it
@@ -258,9 +304,9 @@ __global__ void __launch_bounds__(num_threads(EPI, PAIR), 1) forde_gemm_kernel(c
           }
           if (B_MN) {
 #pragma unroll
-            for (int j = 0; j < BNL / 64; ++j) load(&p.tmB, sb + j * (BK * 128), nb0 + j * 64, k0, p.hintB);
+            for (int j = 0; j < BNL / 64; ++j) load(&p.tmB, sb + j * (BK * 128), nb0 + j * 64, k0 + kgo, p.hintB);
           } else {
-            load(&p.tmB, sb, k0, nb0, p.hintB);
+            load(&p.tmB, sb, k0 + kgo, nb0, p.hintB);
           }
           if (++stage == STAGES) {
             stage = 0;
@@ -282,12 +328,16 @@ __global__ void __launch_bounds__(num_threads(EPI, PAIR), 1) forde_gemm_kernel(c
     int it = 0;
     if (!PAIR || cta_rank == 0) {  // in a pair only the leader issues; its MMAs drive both SMs' tensor cores
       for (int t = worker; t < total_work; t += num_workers, ++it) {
-        const WorkItem w = decode_work(p, t, TILE_M, m_off);
+        const WorkItem w = decode_work(p, t, TILE_M, m_off, m_blocks);
         const int as = it & 1;
         const uint32_t aphase = (it >> 1) & 1;
         mbar_wait(&tempty_bar[as], aphase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + as * BN;
+        if (w.kb0 >= w.kb1 && elect_one()) {  // empty reduction: nothing to wait for, the epilogue writes zeros
+          if (PAIR) umma_commit_pair(&tfull_bar[as]);
+          else umma_commit(&tfull_bar[as]);
+        }
         for (int kb = w.kb0; kb < w.kb1; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
@@ -334,20 +384,20 @@ __global__ void __launch_bounds__(num_threads(EPI, PAIR), 1) forde_gemm_kernel(c
     auto z_prefetch = [&](int gi) {  // lane 0 only
       const int nt = worker + (gi / CPW) * num_workers;
       if (nt < total_work) {
-        const WorkItem wn = decode_work(p, nt, TILE_M, m_off);
+        const WorkItem wn = decode_work(p, nt, TILE_M, m_off, m_blocks);
         const int bi = gi % ZR;
         mbar_expect_tx(&zb[bi], BOX_BYTES);
         tma_load_2d(&p.tmZ, &zb[bi], wst + bi * BOX_BYTES, wn.n0 + (e * CPW + gi % CPW) * CHUNK, wn.m0 + q * 32,
                     kEvictFirst);
       }
     };
-    if (EPI == EPI_DZ_BWD && lane == 0) {
+    if (epi_z_ring(EPI) && lane == 0) {
 #pragma unroll
       for (int i = 0; i < ZD; ++i) z_prefetch(i);
     }
 
     for (int t = worker; t < total_work; t += num_workers, ++it) {
-      const WorkItem w = decode_work(p, t, TILE_M, m_off);
+      const WorkItem w = decode_work(p, t, TILE_M, m_off, m_blocks);
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
       const int row = w.m0 + q * 32 + lane;
@@ -356,7 +406,7 @@ __global__ void __launch_bounds__(num_threads(EPI, PAIR), 1) forde_gemm_kernel(c
       float bias_r = 0.f;
       ActConst act = make_act(0, p.gate_generalist, p.gate_specialist);
       bool warp_has_tanh = false;
-      if (EPI == EPI_UP_FWD || EPI == EPI_DZ_BWD) {
+      if (epi_neuron_rows(EPI)) {
         int a = 0;
         if (row < p.M) {
           a = p.assign[row];
@@ -365,13 +415,13 @@ __global__ void __launch_bounds__(num_threads(EPI, PAIR), 1) forde_gemm_kernel(c
         act = make_act(a, p.gate_generalist, p.gate_specialist);
         warp_has_tanh = __any_sync(0xffffffffu, act.is_tanh);
       }
-      if (EPI == EPI_STORE) {
-        // stage this tile's column bias once for the epilogue warps
+      if (epi_col_bias(EPI)) {
+        // stage this tile's column bias (of this tile's expert in the grouped mode) once for the epilogue warps
         asm volatile("bar.sync 1, %0;" ::"n"(32 * EPI_WARPS) : "memory");  // previous tile's bias no longer read
         const int c = threadIdx.x - 64;
         if (c < BN) {  // 8 epilogue warps = 256 threads = BN
           const int col = w.n0 + c;
-          bias_s[c] = (p.bias_col != nullptr && col < p.N) ? p.bias_col[col] : 0.f;
+          bias_s[c] = (p.bias_col != nullptr && col < p.N) ? p.bias_col[w.group * p.bias_group_stride + col] : 0.f;
         }
         asm volatile("bar.sync 1, %0;" ::"n"(32 * EPI_WARPS) : "memory");
       }
@@ -388,17 +438,17 @@ __global__ void __launch_bounds__(num_threads(EPI, PAIR), 1) forde_gemm_kernel(c
         const bool full = nvalid >= CHUNK;
         float s_abs = 0.f, s_sum = 0.f, s_sq = 0.f;  // this chunk's per-neuron sums (fused epilogues)
 
-        if (EPI == EPI_DZ_BWD && lane == 0) {
+        if (epi_z_ring(EPI) && lane == 0) {
           // refill the box chunk g + ZD will use; the dz store that last read it (chunk g + ZD - ZR) must have drained
           tma_wait_read<ZR - ZD - 1>();
           z_prefetch(g + ZD);
         }
         // single-buffered staging: the previous chunk's TMA stores must have read the boxes (the other epilogue
         // warps of this SM sub-partition cover the wait)
-        if ((EPI == EPI_UP_FWD || EPI == EPI_STORE) && lane == 0) tma_wait_read<0>();
-        if (EPI == EPI_DZ_BWD) mbar_wait(&zb[g % ZR], (g / ZR) & 1);
+        if ((epi_two_out(EPI) || EPI == EPI_STORE) && lane == 0) tma_wait_read<0>();
+        if (epi_z_ring(EPI)) mbar_wait(&zb[g % ZR], (g / ZR) & 1);
         __syncwarp();
-        uint8_t* obuf = (EPI == EPI_DZ_BWD) ? (wst + (g % ZR) * BOX_BYTES) : wst;
+        uint8_t* obuf = epi_z_ring(EPI) ? (wst + (g % ZR) * BOX_BYTES) : wst;
         const uint32_t orow_s = smem_u32(obuf) + lane * 128;
 
         // the 64-column chunk is drained in two 32-column halves to keep the live registers low
@@ -408,12 +458,16 @@ __global__ void __launch_bounds__(num_threads(EPI, PAIR), 1) forde_gemm_kernel(c
           tmem_ld32(taddr + c * CHUNK + half * 32, v);
           tmem_wait_ld();
           const int jbase = half * 32;  // column offset inside the chunk
+          if (EPI == EPI_F32 && w.kb0 >= w.kb1) {  // empty reduction (grouped-K expert without tokens): zeros
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = 0u;
+          }
 
           if (EPI == EPI_F32) {
             if (row < p.M && nvalid > jbase) {
               const float rs = (p.row_scale != nullptr ? p.row_scale[row] : 1.f) * p.scale *
                                (p.scale_dev != nullptr ? *p.scale_dev : 1.f);
-              float* orow = p.out_f32 + static_cast<long long>(row) * p.ldc + col0 + jbase;
+              float* orow = p.out_f32 + w.group * p.out_group_stride + static_cast<long long>(row) * p.ldc + col0 + jbase;
               const bool vec_ok = (nvalid >= jbase + 32) && ((p.ldc & 3) == 0) &&
                                   ((reinterpret_cast<uintptr_t>(p.out_f32) & 15) == 0);
               if (vec_ok) {
@@ -490,6 +544,39 @@ __global__ void __launch_bounds__(num_threads(EPI, PAIR), 1) forde_gemm_kernel(c
               st_shared_v4(orow_s + off, zw[0], zw[1], zw[2], zw[3]);
               st_shared_v4(orow_s + BOX_BYTES + off, hw[0], hw[1], hw[2], hw[3]);
             }
+          } else if (EPI == EPI_MOE_UP) {
+            // z box at wst (tmC0), h = gelu_tanh(z) box at wst + BOX_BYTES (tmC1); flax nn.gelu default (moe.py:27)
+            const float* bsrc = bias_s + c * CHUNK + jbase;
+#pragma unroll
+            for (int j8 = 0; j8 < 4; ++j8) {
+              uint32_t zw[4], hw[4];
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const int j = j8 * 8 + i * 2;
+                const uint32_t zp = pack_bf16x2(__uint_as_float(v[j]) + bsrc[j], __uint_as_float(v[j + 1]) + bsrc[j + 1]);
+                const float z0 = bf16lo_to_f32(zp), z1 = bf16hi_to_f32(zp);
+                zw[i] = zp;
+                hw[i] = pack_bf16x2(gelu_tanh_f(z0), gelu_tanh_f(z1));
+              }
+              const uint32_t off = (static_cast<uint32_t>(half * 4 + j8) ^ sw) << 4;
+              st_shared_v4(orow_s + off, zw[0], zw[1], zw[2], zw[3]);
+              st_shared_v4(orow_s + BOX_BYTES + off, hw[0], hw[1], hw[2], hw[3]);
+            }
+          } else if (EPI == EPI_MOE_DZ) {
+#pragma unroll
+            for (int j8 = 0; j8 < 4; ++j8) {
+              const uint32_t off = (static_cast<uint32_t>(half * 4 + j8) ^ sw) << 4;
+              uint32_t zw[4], dw[4];
+              ld_shared_v4(orow_s + off, zw[0], zw[1], zw[2], zw[3]);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const int j = j8 * 8 + i * 2;
+                const float z0 = bf16lo_to_f32(zw[i]), z1 = bf16hi_to_f32(zw[i]);
+                dw[i] = pack_bf16x2(__uint_as_float(v[j]) * gelu_tanh_grad_f(z0),
+                                    __uint_as_float(v[j + 1]) * gelu_tanh_grad_f(z1));
+              }
+              st_shared_v4(orow_s + off, dw[0], dw[1], dw[2], dw[3]);
+            }
           } else {  // EPI_DZ_BWD: dz over z, in place (same thread, same bytes)
 #pragma unroll
             for (int j8 = 0; j8 < 4; ++j8) {
@@ -531,13 +618,13 @@ __global__ void __launch_bounds__(num_threads(EPI, PAIR), 1) forde_gemm_kernel(c
           __syncwarp();
           if (lane == 0) {
             tma_store_2d(&p.tmC0, obuf, col0, w.m0 + q * 32);
-            if (EPI == EPI_UP_FWD) tma_store_2d(&p.tmC1, obuf + BOX_BYTES, col0, w.m0 + q * 32);
+            if (epi_two_out(EPI)) tma_store_2d(&p.tmC1, obuf + BOX_BYTES, col0, w.m0 + q * 32);
             tma_commit();
           }
         }
-        if (EPI == EPI_DZ_BWD) ++g;
+        if (epi_z_ring(EPI)) ++g;
 
-        if ((EPI == EPI_UP_FWD || EPI == EPI_DZ_BWD) && p.partials != nullptr && row < p.M) {
+        if (epi_neuron_rows(EPI) && p.partials != nullptr && row < p.M) {
           float* dst = p.partials + (static_cast<long long>(w.nb * PARTIALS_PER_TILE + c) * 3) * p.M + row;
           dst[0] = s_abs;
           dst[p.M] = s_sum;

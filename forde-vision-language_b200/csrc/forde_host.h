@@ -28,4 +28,21 @@ int gemm_store_bf16(cudaStream_t stream, const GemmArgs& g, void* D, long long l
 int gemm_f32(cudaStream_t stream, const GemmArgs& g, float* D, long long ldd, const float* row_scale,
              const float* col_scale, float scale, const float* scale_dev, bool accumulate);
 
+// ---- grouped GEMMs for the MoE experts (rows = routed token slots sorted by expert, segments padded to 128) -------
+struct GroupedM {
+  const int* m_blocks_dev;     // device scalar: number of valid 128-row blocks
+  const int* group_of_mblock;  // expert of each 128-row block
+  int b_k_group_stride;        // B stacked along k: k offset per expert (else 0)
+  int b_n_group_stride;        // B stacked along n: row offset per expert (else 0)
+  int bias_group_stride;       // bias_col offset per expert
+  int groups;                  // number of experts stacked in B
+};
+// D (bf16, [M_cap][N]) = A . B_e^T + bias_e ; optional second output / z input select the MoE epilogues:
+//   mode 0: plain store ; mode 1: EPI_MOE_UP (D = z, D2 = gelu(z)) ; mode 2: EPI_MOE_DZ (D = acc * gelu'(Zin))
+int gemm_grouped_m(cudaStream_t stream, const GemmArgs& g, const GroupedM& gm, int mode, void* D, long long ldd,
+                   void* D2, const void* Zin, const float* bias_col);
+// out[e] (fp32 [M][N], plain store) = sum over expert e's row segment of A(m, row) * B(n, row); A and B MN-major.
+int gemm_grouped_k(cudaStream_t stream, const GemmArgs& g, const int* seg_offsets, int groups, float* out,
+                   long long ldo, long long out_group_stride);
+
 }  // namespace forde

@@ -247,6 +247,17 @@ __device__ __forceinline__ float tanh_approx(float x) {
   asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+// gelu, tanh approximation (flax.linen.gelu default approximate=True): 0.5 z (1 + tanh(sqrt(2/pi) (z + 0.044715 z^3)))
+__device__ __forceinline__ float gelu_tanh_f(float z) {
+  const float u = 0.7978845608028654f * fmaf(0.044715f * z * z, z, z);
+  return 0.5f * z * (1.f + tanh_approx(u));
+}
+__device__ __forceinline__ float gelu_tanh_grad_f(float z) {
+  const float z2 = fminf(z * z, 1e8f);  // keeps (1 - t^2) * du finite for absurd |z|
+  const float t = tanh_approx(0.7978845608028654f * fmaf(0.044715f * z2, z, z));
+  const float du = 0.7978845608028654f * fmaf(3.f * 0.044715f, z2, 1.f);
+  return 0.5f * (1.f + t) + 0.5f * z * fmaf(-t, t, 1.f) * du;
+}
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }

@@ -300,3 +300,110 @@ def add_layernorm_bwd(dy, x, r, gamma, mean, rstd):
                                              d_gamma.data_ptr(), d_beta.data_ptr(), rows, cols)
     _lib.check(rc, "forde_add_layernorm_bwd")
     return ds, d_gamma, d_beta
+
+
+# ------------------------------------------------------------------------------------------ MoE variant
+def moe_capacity_rows(M: int, k: int, E: int) -> int:
+    return _lib.load().forde_moe_capacity_rows(M, k, E)
+
+
+def moe_route(x, w_r16, b_r, k: int, aux_weight: float, expert_usage=None, step_count=None):
+    """Router + top-k + histogram + aux loss + routing plan.  Returns a dict of device tensors (the routing state)."""
+    _req(x, torch.bfloat16, "x"); _req(w_r16, torch.bfloat16, "w_r"); _req(b_r, torch.float32, "b_r")
+    M, d = x.shape
+    E = w_r16.shape[1]
+    lib = _lib.load()
+    R = lib.forde_moe_capacity_rows(M, k, E)
+    dev = x.device
+    i32 = dict(dtype=torch.int32, device=dev)
+    f32 = dict(dtype=torch.float32, device=dev)
+    r = {
+        "M": M, "d": d, "E": E, "k": k, "R": R,
+        "logits": torch.empty((M, E), **f32), "probs": torch.empty((M, E), **f32),
+        "topk_idx": torch.empty((M, k), **i32), "topk_w": torch.empty((M, k), **f32),
+        "counts": torch.empty(E, **i32),
+        "prob_partials": torch.empty((lib.forde_moe_num_prob_partials(M), E), **f32),
+        "seg_offsets": torch.empty(E + 1, **i32), "n_blocks": torch.empty(1, **i32),
+        "block_expert": torch.empty(R // 128, **i32), "slot_of": torch.empty(M * k, **i32),
+        "src_of_slot": torch.empty(R, **i32), "aux_loss": torch.empty(1, **f32),
+    }
+    rc = lib.forde_moe_route(_stream(), x.data_ptr(), w_r16.data_ptr(), b_r.data_ptr(), M, d, E, k, float(aux_weight),
+                             r["logits"].data_ptr(), r["probs"].data_ptr(), r["topk_idx"].data_ptr(),
+                             r["topk_w"].data_ptr(), r["counts"].data_ptr(), r["prob_partials"].data_ptr(),
+                             r["seg_offsets"].data_ptr(), r["n_blocks"].data_ptr(), r["block_expert"].data_ptr(),
+                             r["slot_of"].data_ptr(), r["src_of_slot"].data_ptr(), r["aux_loss"].data_ptr(),
+                             _ptr(expert_usage), _ptr(step_count))
+    _lib.check(rc, "forde_moe_route")
+    return r
+
+
+def moe_gather(x, route):
+    xg = torch.empty((route["R"], x.shape[1]), dtype=torch.bfloat16, device=x.device)
+    rc = _lib.load().forde_moe_gather(_stream(), x.data_ptr(), route["src_of_slot"].data_ptr(), route["k"],
+                                      xg.data_ptr(), route["R"], x.shape[1])
+    _lib.check(rc, "forde_moe_gather")
+    return xg
+
+
+def moe_experts_fwd(xg, w_up16, b_up, w_down16, b_down, route):
+    E, d, H = w_up16.shape
+    R = route["R"]
+    _req(w_up16, torch.bfloat16, "w_up_all"); _req(w_down16, torch.bfloat16, "w_down_all")
+    _req(b_up, torch.float32, "b_up_all"); _req(b_down, torch.float32, "b_down_all")
+    zg = torch.empty((R, H), dtype=torch.bfloat16, device=xg.device)
+    hg = torch.empty((R, H), dtype=torch.bfloat16, device=xg.device)
+    yg = torch.empty((R, d), dtype=torch.bfloat16, device=xg.device)
+    rc = _lib.load().forde_moe_experts_fwd(_stream(), xg.data_ptr(), w_up16.data_ptr(), b_up.data_ptr(),
+                                           w_down16.data_ptr(), b_down.data_ptr(), route["n_blocks"].data_ptr(),
+                                           route["block_expert"].data_ptr(), zg.data_ptr(), hg.data_ptr(),
+                                           yg.data_ptr(), R, d, H, E)
+    _lib.check(rc, "forde_moe_experts_fwd")
+    return zg, hg, yg
+
+
+def moe_combine(yg, route, weighted: bool = True):
+    M, k, d = route["M"], route["k"], yg.shape[1]
+    out = torch.empty((M, d), dtype=torch.bfloat16, device=yg.device)
+    rc = _lib.load().forde_moe_combine(_stream(), yg.data_ptr(), route["slot_of"].data_ptr(),
+                                       route["topk_w"].data_ptr() if weighted else 0, out.data_ptr(), M, k, d)
+    _lib.check(rc, "forde_moe_combine")
+    return out
+
+
+def moe_scatter(dout, route):
+    _req(dout, torch.bfloat16, "dout")
+    R, d = route["R"], dout.shape[1]
+    dyg = torch.empty((R, d), dtype=torch.bfloat16, device=dout.device)
+    rc = _lib.load().forde_moe_scatter(_stream(), dout.data_ptr(), route["src_of_slot"].data_ptr(),
+                                       route["topk_w"].data_ptr(), route["k"], dyg.data_ptr(), R, d)
+    _lib.check(rc, "forde_moe_scatter")
+    return dyg
+
+
+def moe_gate_grad(dout, yg, route):
+    M, k = route["M"], route["k"]
+    d_w = torch.empty((M, k), dtype=torch.float32, device=dout.device)
+    rc = _lib.load().forde_moe_gate_grad(_stream(), dout.data_ptr(), yg.data_ptr(), route["slot_of"].data_ptr(),
+                                         d_w.data_ptr(), M, k, dout.shape[1])
+    _lib.check(rc, "forde_moe_gate_grad")
+    return d_w
+
+
+def moe_experts_bwd(xg, dyg, w_up16, w_down16, zg, hg, route):
+    E, d, H = w_up16.shape
+    R = route["R"]
+    dev = xg.device
+    dzg = torch.empty((R, H), dtype=torch.bfloat16, device=dev)
+    dxg = torch.empty((R, d), dtype=torch.bfloat16, device=dev)
+    dw_up = torch.empty((E, d, H), dtype=torch.float32, device=dev)
+    dw_down = torch.empty((E, H, d), dtype=torch.float32, device=dev)
+    db_up = torch.zeros((E, H), dtype=torch.float32, device=dev)
+    db_down = torch.zeros((E, d), dtype=torch.float32, device=dev)
+    rc = _lib.load().forde_moe_experts_bwd(_stream(), xg.data_ptr(), dyg.data_ptr(), w_up16.data_ptr(),
+                                           w_down16.data_ptr(), zg.data_ptr(), hg.data_ptr(),
+                                           route["n_blocks"].data_ptr(), route["block_expert"].data_ptr(),
+                                           route["seg_offsets"].data_ptr(), dzg.data_ptr(), dxg.data_ptr(),
+                                           dw_up.data_ptr(), db_up.data_ptr(), dw_down.data_ptr(), db_down.data_ptr(),
+                                           R, d, H, E)
+    _lib.check(rc, "forde_moe_experts_bwd")
+    return dxg, dw_up, db_up, dw_down, db_down

@@ -135,6 +135,48 @@ int forde_clip_bwd(void* stream, const void* u, const void* v, const float* S, c
 int forde_l2norm_bwd(void* stream, const void* u, const float* inv_norm, const float* dU, float* d_x, int B,
                      int E);
 
+/* ---- MoE variant of the FFN slot (BASELINE config 4) --------------------------------------------------------
+ * Reference: src/forde/moe.py:57-281 (MoELayer / MoEStatefulLayer).  Same result as the reference's "every expert on
+ * every token, then gather the top-k" (moe.py:163,169-185), computed on the routed tokens only.  All routing state
+ * stays on the device (no host synchronisation): the caller allocates
+ *   R = forde_moe_capacity_rows(M, k, E) rows for every "gathered" buffer (xg, zg, hg, yg, dyg, dzg, dxg);
+ *   logits, probs [M][E] f32 ; topk_idx [M][k] i32 ; topk_w [M][k] f32 ; counts [E] i32 ;
+ *   prob_partials [forde_moe_num_prob_partials(M)][E] f32 ; seg_offsets [E+1] i32 ; n_blocks_dev [1] i32 ;
+ *   block_expert [R/128] i32 ; slot_of [M*k] i32 ; src_of_slot [R] i32.
+ * route:   logits = x . w_r + b_r (w_r [d][E] bf16; moe.py:88), probs = softmax (moe.py:90), top-k with
+ *          jax.lax.top_k order (descending, equal values -> lower index; moe.py:130), topk_w = softmax of the k
+ *          logits (moe.py:133), counts = bincount(topk_idx) (moe.py:216, exact), aux_loss[1] = aux_weight * E *
+ *          sum_e counts_e/(M k) * mean_m probs_e (moe.py:212-222), expert_usage[E] += mean_m probs (moe.py:277-278),
+ *          step_count += 1 (moe.py:279); then the routing plan: expert e owns rows seg_offsets[e]..seg_offsets[e+1]
+ *          (128-aligned) of the gathered buffers, entry (token, j) sits in row slot_of[token*k + j], rows keep token
+ *          order inside an expert, src_of_slot is the inverse map (-1 for padding rows).
+ * gather / experts_fwd / combine: xg[slot] = x[token]; zg = xg . w_up[e] + b_up[e]; hg = gelu_tanh(zg)
+ *          (flax nn.gelu default, moe.py:27); yg = hg . w_down[e] + b_down[e]; out[token] = sum_j topk_w * yg[slot].
+ *          Expert weights are stacked: w_up_all [E][d][H], w_down_all [E][H][d] bf16, biases [E][H], [E][d] f32.
+ * backward: scatter (dyg[slot] = topk_w * dout[token]), gate_grad (d_topk_w = <dout[token], yg[slot]>),
+ *          experts_bwd (dzg, dxg, and per expert dw_up_all [E][d][H] (written), dw_down_all [E][H][d] (written),
+ *          db_up_all [E][H] +=, db_down_all [E][d] +=), then combine(dxg, slot_of, NULL) sums the k copies into dx. */
+int forde_moe_capacity_rows(int M, int k, int E);
+int forde_moe_num_prob_partials(int M);
+int forde_moe_route(void* stream, const void* x, const void* w_r, const float* b_r, int M, int d, int E, int k,
+                    float aux_weight, float* logits, float* probs, int* topk_idx, float* topk_w, int* counts,
+                    float* prob_partials, int* seg_offsets, int* n_blocks_dev, int* block_expert, int* slot_of,
+                    int* src_of_slot, float* aux_loss, float* expert_usage, int* step_count);
+int forde_moe_gather(void* stream, const void* x, const int* src_of_slot, int k, void* xg, int rows, int d);
+int forde_moe_scatter(void* stream, const void* dout, const int* src_of_slot, const float* topk_w, int k, void* dyg,
+                      int rows, int d);
+int forde_moe_combine(void* stream, const void* yg, const int* slot_of, const float* topk_w, void* out, int M, int k,
+                      int d);
+int forde_moe_gate_grad(void* stream, const void* dout, const void* yg, const int* slot_of, float* d_topk_w, int M,
+                        int k, int d);
+int forde_moe_experts_fwd(void* stream, const void* xg, const void* w_up_all, const float* b_up_all,
+                          const void* w_down_all, const float* b_down_all, const int* n_blocks_dev,
+                          const int* block_expert, void* zg, void* hg, void* yg, int r_cap, int d, int H, int E);
+int forde_moe_experts_bwd(void* stream, const void* xg, const void* dyg, const void* w_up_all,
+                          const void* w_down_all, const void* zg, const void* hg, const int* n_blocks_dev,
+                          const int* block_expert, const int* seg_offsets, void* dzg, void* dxg, float* dw_up_all,
+                          float* db_up_all, float* dw_down_all, float* db_down_all, int r_cap, int d, int H, int E);
+
 /* ---- fused residual-add + LayerNorm: the `add/norm` either side of the StatefulLayer in a FORDE block
  *      (README.md:42-43; flax nn.LayerNorm, eps 1e-6).  Caller side of the path. -------
  * fwd: out = LayerNorm(x + r) * gamma + beta  (x, r, out bf16 [rows][cols]; r may be NULL; gamma, beta fp32);

@@ -28,6 +28,8 @@ can be compared bit-exactly on the same stored values.
 """
 from __future__ import annotations
 
+import math
+
 import numpy as np
 
 GATE_GENERALIST = 1.0
@@ -324,3 +326,39 @@ def cluster_neurons_gmm(aggregated_stats, num_clusters, seed: int):
 def forde_lite_assignments(stats, threshold=0.8):
     """README.md:58-59 ablation rule: is_spec = grad_gini > 0.8 (specialist = 2, else generalist = 0)."""
     return np.where(np.asarray(stats)[:, 0] > threshold, 2, 0).astype(np.int32)
+
+
+# ----------------------------------------------------------------------------------------------- MoE fwd+bwd (torch)
+def moe_layer_torch(x, w_r, b_r, w_up, b_up, w_down, b_down, k, aux_weight, dout=None, d_aux=1.0):
+    """The reference formulation (moe.py:72-114,137-222) in float64 torch with autograd: EVERY expert on every token,
+    gather the top-k, weighted sum, Switch-style aux loss.  w_up (E,d,H), w_down (E,H,d) stacked.
+    Returns dict(out, aux, probs, idx, counts[, dx, dw_r, db_r, dw_up, db_up, dw_down, db_down])."""
+    import torch
+
+    t = lambda a: torch.tensor(np.asarray(a, np.float64), dtype=torch.float64, requires_grad=True)
+    x_, wr_, br_, wu_, bu_, wd_, bd_ = (t(a) for a in (x, w_r, b_r, w_up, b_up, w_down, b_down))
+    M, E = x_.shape[0], wr_.shape[1]
+    logits = x_ @ wr_ + br_                                                    # moe.py:88
+    probs = torch.softmax(logits, -1)                                          # moe.py:90
+    order = torch.sort(-logits.detach(), dim=-1, stable=True).indices[:, :k]   # lax.top_k order (moe.py:130)
+    top_logits = torch.gather(logits, 1, order)
+    w = torch.softmax(top_logits, -1)                                          # moe.py:133
+
+    def gelu(v):
+        return 0.5 * v * (1.0 + torch.tanh(math.sqrt(2.0 / math.pi) * (v + 0.044715 * v ** 3)))
+
+    all_out = torch.stack([gelu(x_ @ wu_[e] + bu_[e]) @ wd_[e] + bd_[e] for e in range(E)], 0)   # moe.py:163
+    rows = torch.arange(M)
+    out = sum(w[:, j:j + 1] * all_out[order[:, j], rows, :] for j in range(k))                  # moe.py:169-185
+    counts = torch.bincount(order.reshape(-1), minlength=E)                                       # moe.py:216
+    aux = E * torch.sum(counts.double() / (M * k) * probs.mean(0)) * aux_weight                   # moe.py:217-222
+    res = {"out": out.detach().numpy(), "aux": float(aux.detach()), "probs": probs.detach().numpy(),
+           "idx": order.numpy().astype(np.int32), "counts": counts.numpy().astype(np.int32),
+           "logits": logits.detach().numpy()}
+    if dout is not None:
+        loss = (out * torch.tensor(np.asarray(dout, np.float64))).sum() + d_aux * aux
+        loss.backward()
+        for name, v in (("dx", x_), ("dw_r", wr_), ("db_r", br_), ("dw_up", wu_), ("db_up", bu_), ("dw_down", wd_),
+                        ("db_down", bd_)):
+            res[name] = v.grad.numpy()
+    return res

@@ -1,0 +1,155 @@
+"""MoE variant of the FFN slot (BASELINE config 4) against the oracle's restatement of src/forde/moe.py.
+Bit-exact: top-k indices (given the kernel's own logits, jax.lax.top_k order), bincount, the routing plan.
+Tolerances: logits/probs fp32 1e-4; outputs and activation gradients bf16 (rel Frobenius 2e-2); weight gradients
+rel Frobenius 2e-2; aux loss 1e-5."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import forde_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ops():
+    import __graft_entry__ as g
+    g.build()
+    from forde_b200 import ops as _ops
+    return _ops
+
+
+def f32(t):
+    return t.detach().float().cpu().numpy()
+
+
+def rel(a, b):
+    return float(np.linalg.norm(np.asarray(a, np.float64) - b) / (np.linalg.norm(b) + 1e-30))
+
+
+def make(M, d, H, E, seed=0, router_scale=0.5):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    x = torch.randn((M, d), device="cuda", generator=g).bfloat16()
+    w_r = (torch.randn((d, E), device="cuda", generator=g) * router_scale / d ** 0.5).bfloat16()
+    b_r = torch.randn(E, device="cuda", generator=g) * 0.1
+    w_up = (torch.randn((E, d, H), device="cuda", generator=g) / d ** 0.5).bfloat16()
+    b_up = torch.randn((E, H), device="cuda", generator=g) * 0.1
+    w_down = (torch.randn((E, H, d), device="cuda", generator=g) / H ** 0.5).bfloat16()
+    b_down = torch.randn((E, d), device="cuda", generator=g) * 0.1
+    return x, w_r, b_r, w_up, b_up, w_down, b_down
+
+
+@pytest.mark.parametrize("M,d,E,k", [(64, 64, 4, 2), (1000, 128, 8, 2), (8192, 512, 8, 2), (300, 64, 16, 4), (5, 64, 4, 1)])
+def test_router_topk_histogram_and_plan(ops, M, d, E, k):
+    x, w_r, b_r, *_ = make(M, d, 64, E, seed=M)
+    usage = torch.zeros(E, device="cuda"); steps = torch.zeros((), device="cuda", dtype=torch.int32)
+    r = ops.moe_route(x, w_r, b_r, k, 0.01, expert_usage=usage, step_count=steps)
+    torch.cuda.synchronize()
+    logits = f32(r["logits"])
+    ref_logits = f32(x) @ f32(w_r) + f32(b_r)
+    np.testing.assert_allclose(logits, ref_logits, rtol=1e-4, atol=1e-4)
+    # top-k: bit-exact against lax.top_k semantics applied to the kernel's own logits
+    vals, idx = O.top_k(logits, k)
+    np.testing.assert_array_equal(r["topk_idx"].cpu().numpy(), idx)
+    np.testing.assert_allclose(f32(r["topk_w"]), O.softmax(vals), rtol=1e-5, atol=1e-6)
+    probs = f32(r["probs"])
+    np.testing.assert_allclose(probs, O.softmax(logits), rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(probs.sum(-1), 1.0, atol=1e-5)                      # tests/test_moe.py:38
+    # histogram: bit-exact bincount ; aux loss ; usage accumulation
+    aux_ref, counts_ref = O.moe_aux_loss(probs, idx, E, k, 0.01)
+    np.testing.assert_array_equal(r["counts"].cpu().numpy(), counts_ref)
+    assert abs(float(r["aux_loss"].item()) - float(aux_ref)) < 1e-6
+    np.testing.assert_allclose(f32(usage), probs.mean(0), rtol=1e-5, atol=1e-7)
+    assert int(steps.item()) == 1
+    # plan: 128-aligned segments in expert order, stable (token-ordered) slots, inverse map, block -> expert
+    seg = r["seg_offsets"].cpu().numpy()
+    pad = (counts_ref + 127) // 128 * 128
+    np.testing.assert_array_equal(seg, np.concatenate([[0], np.cumsum(pad)]))
+    assert int(r["n_blocks"].item()) == seg[-1] // 128
+    slot_of = r["slot_of"].cpu().numpy(); src = r["src_of_slot"].cpu().numpy()
+    flat = idx.reshape(-1)
+    for e in range(E):
+        entries = np.nonzero(flat == e)[0]                       # ascending entry index = token order
+        np.testing.assert_array_equal(slot_of[entries], seg[e] + np.arange(len(entries)))
+    valid = src >= 0
+    assert valid.sum() == M * k
+    np.testing.assert_array_equal(slot_of[src[valid]], np.nonzero(valid)[0])
+    be = r["block_expert"].cpu().numpy()
+    for e in range(E):
+        assert np.all(be[seg[e] // 128: seg[e + 1] // 128] == e)
+    assert np.all(be[seg[-1] // 128:] == -1)
+
+
+def test_router_tie_rule_matches_lax_top_k(ops):
+    # identical logits everywhere (zero input, zero router weights, equal bias): lower index wins
+    E, k = 8, 2
+    x = torch.zeros((40, 64), device="cuda", dtype=torch.bfloat16)
+    r = ops.moe_route(x, torch.zeros((64, E), device="cuda", dtype=torch.bfloat16), torch.ones(E, device="cuda"), k, 0.01)
+    idx = r["topk_idx"].cpu().numpy()
+    assert np.all(idx[:, 0] == 0) and np.all(idx[:, 1] == 1)
+    # tests/test_moe.py:46-70: hand-made logits [10,2,5,8] -> {0,3}, [1,9,3,4] -> {1,3} (router = identity rows)
+    x2 = torch.zeros((2, 64), device="cuda"); x2[0, :4] = torch.tensor([10., 2., 5., 8.]); x2[1, :4] = torch.tensor([1., 9., 3., 4.])
+    w = torch.zeros((64, 4), device="cuda"); w[:4, :4] = torch.eye(4)
+    r2 = ops.moe_route(x2.bfloat16(), w.bfloat16(), torch.zeros(4, device="cuda"), 2, 0.01)
+    i2 = r2["topk_idx"].cpu().numpy()
+    assert set(i2[0].tolist()) == {0, 3} and set(i2[1].tolist()) == {1, 3}
+    assert i2[0].tolist() == [0, 3] and i2[1].tolist() == [1, 3]          # descending by value
+
+
+@pytest.mark.parametrize("M,d,H,E,k", [(256, 64, 128, 4, 2), (1000, 128, 256, 8, 2), (2048, 512, 2048, 8, 2)])
+def test_moe_layer_forward_backward_parity(ops, M, d, H, E, k):
+    from forde_b200.moe_layer import MoEStatefulLayer
+    x, w_r, b_r, w_up, b_up, w_down, b_down = make(M, d, H, E, seed=1)
+    layer = MoEStatefulLayer(num_experts=E, top_k=k, expert_hidden_dim=H, d_model=d, aux_loss_weight=0.01)
+    v = layer.init(0, x)
+    p = v["params"]
+    p["router"]["router_linear"]["kernel"] = w_r.float().requires_grad_(True)
+    p["router"]["router_linear"]["bias"] = b_r.clone().requires_grad_(True)
+    p["experts"]["up_proj"]["kernel"] = w_up.float().requires_grad_(True)
+    p["experts"]["up_proj"]["bias"] = b_up.clone().requires_grad_(True)
+    p["experts"]["down_proj"]["kernel"] = w_down.float().requires_grad_(True)
+    p["experts"]["down_proj"]["bias"] = b_down.clone().requires_grad_(True)
+    xr = x.clone().requires_grad_(True)
+    (out, aux, routing), upd = layer.apply(v, xr, mutable=["stats_buffer"], return_routing=True)
+    dout = torch.randn(out.shape, device="cuda", generator=torch.Generator(device="cuda").manual_seed(9)).bfloat16()
+    (out.float() * dout.float()).sum().add(aux * 3.0).backward()
+    torch.cuda.synchronize()
+    ref = O.moe_layer_torch(f32(x), f32(w_r), f32(b_r), f32(w_up), f32(b_up), f32(w_down), f32(b_down), k, 0.01,
+                            dout=f32(dout), d_aux=3.0)
+    # routing must agree for the comparison to be meaningful (fp32 vs fp64 logits: no near-ties at these seeds)
+    np.testing.assert_array_equal(routing["top_k_indices"].cpu().numpy(), ref["idx"])
+    np.testing.assert_array_equal(routing["expert_counts"].cpu().numpy(), ref["counts"])
+    assert abs(float(aux.item()) - ref["aux"]) < 1e-5
+    assert rel(f32(out), ref["out"]) < 2e-2
+    assert rel(f32(xr.grad), ref["dx"]) < 2e-2
+    ex = p["experts"]
+    assert rel(f32(ex["up_proj"]["kernel"].grad), ref["dw_up"]) < 2e-2
+    assert rel(f32(ex["down_proj"]["kernel"].grad), ref["dw_down"]) < 2e-2
+    assert rel(f32(ex["up_proj"]["bias"].grad), ref["db_up"]) < 2e-2
+    assert rel(f32(ex["down_proj"]["bias"].grad), ref["db_down"]) < 2e-2
+    assert rel(f32(p["router"]["router_linear"]["kernel"].grad), ref["dw_r"]) < 3e-2
+    assert rel(f32(p["router"]["router_linear"]["bias"].grad), ref["db_r"]) < 3e-2
+    sb = upd["stats_buffer"]
+    assert int(sb["step_count"].item()) == 1
+    np.testing.assert_allclose(f32(sb["expert_usage"]), ref["probs"].mean(0), rtol=1e-4, atol=1e-6)
+
+
+def test_moe_expert_without_tokens_gets_zero_gradient(ops):
+    """An expert nobody routes to: its segment is empty, the grouped-K dW GEMM must write zeros for it."""
+    from forde_b200.moe_layer import MoEStatefulLayer
+    M, d, H, E, k = 200, 64, 128, 4, 1
+    x, w_r, b_r, w_up, b_up, w_down, b_down = make(M, d, H, E, seed=3)
+    b_r = torch.tensor([0.0, 0.0, -1e4, 0.0], device="cuda")        # expert 2 is never selected
+    layer = MoEStatefulLayer(num_experts=E, top_k=k, expert_hidden_dim=H, d_model=d)
+    v = layer.init(0, x)
+    p = v["params"]
+    p["router"]["router_linear"]["kernel"] = w_r.float(); p["router"]["router_linear"]["bias"] = b_r
+    p["experts"]["up_proj"]["kernel"] = w_up.float().requires_grad_(True)
+    p["experts"]["down_proj"]["kernel"] = w_down.float().requires_grad_(True)
+    out, aux, routing = layer.apply(v, x, return_routing=True)
+    out.float().sum().backward()
+    torch.cuda.synchronize()
+    assert int(routing["expert_counts"][2].item()) == 0
+    assert float(p["experts"]["up_proj"]["kernel"].grad[2].abs().max()) == 0.0
+    assert float(p["experts"]["down_proj"]["kernel"].grad[2].abs().max()) == 0.0
+    assert float(p["experts"]["up_proj"]["kernel"].grad[0].abs().max()) > 0.0
