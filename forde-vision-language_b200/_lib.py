@@ -36,6 +36,8 @@ SIGNATURES = {
     "forde_sl_dw_down": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _ll]),
     "forde_colsum_bf16": (_i, [_vp, _vp, _ll, _vp, _i, _i]),
     "forde_sl_bwd": (_i, [_vp] * 15 + [_i, _i, _i, _ll]),
+    "forde_sl_topk_sparsify": (_i, [_vp, _vp, _ll, _i, _i, _i, _vp, _vp, _vp]),
+    "forde_sl_topk_mask": (_i, [_vp, _vp, _ll, _i, _i, _vp, _vp]),
     "forde_stats_finalize": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "forde_stats_from_moments": (_i, [_vp, _vp, _vp, _i, _vp]),
     "forde_clip_fwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i] + [_vp] * 10),

@@ -431,3 +431,163 @@ int forde_l2norm_bwd(void* stream, const void* u, const float* inv_norm, const f
 }
 
 }  // extern "C"
+
+// ------------------------------------------------------------------ top-k activation sparsification
+// Optional (off by default): per token keep the k largest |h| over the H neurons, zero the rest.  hT is neuron-major
+// [H][ld]; a block stages 16 token columns x H neurons in shared memory, one warp per token then
+//   1. finds the k-th largest magnitude by a 15-step bitwise radix search on the bf16 magnitude bits,
+//   2. keeps everything above it and the lowest-indexed ties (jax.lax.top_k tie rule), zeroes the rest of hT in
+//      place and records a kept-bitmask [ceil(H/32)][M] for the backward,
+//   3. writes the kept indices ordered like lax.top_k (|value| descending, equal -> lower index first) and the
+//      per-token Hoyer sparsity of the dense h (sensing.py:5-32 formula over the H axis).
+namespace forde {
+
+constexpr int TK_TOK = 16;  // tokens per block (one warp each)
+
+__global__ void __launch_bounds__(TK_TOK * 32)
+topk_sparsify_kernel(__nv_bfloat16* __restrict__ hT, long long ld, int M, int H, int k, int* __restrict__ idx_out,
+                     float* __restrict__ hoyer_out, uint32_t* __restrict__ keep_bits) {
+  extern __shared__ uint16_t tile[];  // [TK_TOK][H] raw bf16 bits, then [TK_TOK][k] int scratch
+  int* scratch_all = reinterpret_cast<int*>(tile + static_cast<size_t>(TK_TOK) * H);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int m0 = blockIdx.x * TK_TOK;
+  uint16_t* h16 = reinterpret_cast<uint16_t*>(hT);
+  for (int i = threadIdx.x; i < H * TK_TOK; i += blockDim.x) {  // TK_TOK consecutive tokens of every neuron row
+    const int h = i / TK_TOK, t = i - h * TK_TOK;
+    const int m = m0 + t;
+    tile[t * H + h] = (m < M) ? h16[static_cast<size_t>(h) * ld + m] : 0;
+  }
+  __syncthreads();
+  const int m = m0 + warp;
+  if (m >= M) return;
+  const uint16_t* col = tile + warp * H;
+  int* scratch = scratch_all + warp * k;
+  float l1 = 0.f, l2 = 0.f;
+  for (int h = lane; h < H; h += 32) {
+    const float v = __uint_as_float(static_cast<uint32_t>(col[h]) << 16);
+    l1 += fabsf(v);
+    l2 = fmaf(v, v, l2);
+  }
+  l1 = warp_sum(l1);
+  l2 = sqrtf(warp_sum(l2));
+  if (lane == 0 && hoyer_out != nullptr) {
+    const float sn = sqrtf(static_cast<float>(H));
+    hoyer_out[m] = (H == 1 || l2 == 0.f) ? 0.f : (sn - l1 / l2) / (sn - 1.f);
+  }
+  // 1. radix search: after the loop `thr` is the key of the k-th largest magnitude and `need` of the elements equal
+  //    to it are kept
+  uint32_t thr = 0;
+  int need = k;
+  for (int bit = 14; bit >= 0; --bit) {
+    const uint32_t cand = thr | (1u << bit);
+    const uint32_t hi_mask = (~((1u << bit) - 1u)) & 0x7FFFu;
+    int cnt = 0;
+    for (int h = lane; h < H; h += 32) cnt += (((static_cast<uint32_t>(col[h]) & 0x7FFFu) & hi_mask) == cand) ? 1 : 0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    if (cnt >= need) thr = cand;
+    else need -= cnt;
+  }
+  // 2. keep mask, in-place zeroing, unsorted list of kept indices (ascending index) in shared scratch
+  int n_kept = 0, n_tie = 0;
+  for (int h0 = 0; h0 < H; h0 += 32) {
+    const int h = h0 + lane;
+    const uint32_t key = (h < H) ? (static_cast<uint32_t>(col[h]) & 0x7FFFu) : 0u;
+    const bool above = (h < H) && key > thr;
+    const bool tie = (h < H) && key == thr;
+    const unsigned bt = __ballot_sync(0xffffffffu, tie);
+    const bool keep = above || (tie && (n_tie + __popc(bt & ((1u << lane) - 1u))) < need);
+    const unsigned bk = __ballot_sync(0xffffffffu, keep);
+    if (keep) scratch[n_kept + __popc(bk & ((1u << lane) - 1u))] = h;
+    if (h < H && !keep) h16[static_cast<size_t>(h) * ld + m] = 0;
+    if (keep_bits != nullptr && lane == 0) keep_bits[static_cast<size_t>(h0 >> 5) * M + m] = bk;
+    n_kept += __popc(bk);
+    n_tie += __popc(bt);
+  }
+  __syncwarp();
+  // 3. lax.top_k order by counting rank: (|value| descending, index ascending); ranks are a permutation of 0..k-1
+  if (idx_out != nullptr) {
+    for (int a = lane; a < k; a += 32) {
+      const int ia = scratch[a];
+      const uint32_t ka = static_cast<uint32_t>(col[ia]) & 0x7FFFu;
+      int rank = 0;
+      for (int b = 0; b < k; ++b) {
+        const int ib = scratch[b];
+        const uint32_t kb = static_cast<uint32_t>(col[ib]) & 0x7FFFu;
+        rank += (kb > ka || (kb == ka && ib < ia)) ? 1 : 0;
+      }
+      idx_out[static_cast<size_t>(m) * k + rank] = ia;
+    }
+  }
+}
+
+// dzT[h][m] = 0 where the forward dropped h[h][m]; optionally re-takes the per-neuron gradient sums of the MASKED dz
+// in the layout of the GEMM epilogue's partials ([P][3][H], one slot per 64 samples).  One warp per (neuron, 64-sample
+// block), two samples per lane.
+__global__ void topk_mask_kernel(__nv_bfloat16* __restrict__ dzT, long long ld, int M, int H,
+                                 const uint32_t* __restrict__ keep_bits, float* __restrict__ partials) {
+  const int lane = threadIdx.x & 31;
+  const int h = blockIdx.y * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int pb = blockIdx.x;  // 64-sample block
+  if (h >= H) return;
+  float s_abs = 0.f, s_sum = 0.f, s_sq = 0.f;
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const int m = pb * 64 + i * 32 + lane;
+    if (m < M) {
+      const uint32_t w = keep_bits[static_cast<size_t>(h >> 5) * M + m];
+      uint16_t* p = reinterpret_cast<uint16_t*>(dzT) + static_cast<size_t>(h) * ld + m;
+      uint16_t bits = *p;
+      if (((w >> (h & 31)) & 1u) == 0u) {
+        bits = 0;
+        *p = 0;
+      }
+      const float v = __uint_as_float(static_cast<uint32_t>(bits) << 16);
+      s_abs += fabsf(v);
+      s_sum += v;
+      s_sq = fmaf(v, v, s_sq);
+    }
+  }
+  if (partials != nullptr) {
+    s_abs = warp_sum(s_abs);
+    s_sum = warp_sum(s_sum);
+    s_sq = warp_sum(s_sq);
+    if (lane == 0) {
+      float* dst = partials + (static_cast<size_t>(pb) * 3) * H + h;
+      dst[0] = s_abs;
+      dst[H] = s_sum;
+      dst[2 * static_cast<size_t>(H)] = s_sq;
+    }
+  }
+}
+
+}  // namespace forde
+
+extern "C" {
+
+int forde_sl_topk_sparsify(void* stream, void* hT, long long ldz, int M, int H, int k, int* idx_out, float* hoyer_out,
+                           uint32_t* keep_bits) {
+  if (hT == nullptr || M <= 0 || H <= 0 || k <= 0 || k > H || ldz < M) return FORDE_EINVAL;
+  const int smem = forde::TK_TOK * H * 2 + forde::TK_TOK * k * 4;
+  if (smem > 200 * 1024) return FORDE_EINVAL;
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(forde::topk_sparsify_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    attr = true;
+  }
+  forde::topk_sparsify_kernel<<<(M + forde::TK_TOK - 1) / forde::TK_TOK, forde::TK_TOK * 32, smem,
+                                static_cast<cudaStream_t>(stream)>>>(static_cast<__nv_bfloat16*>(hT), ldz, M, H, k,
+                                                                     idx_out, hoyer_out, keep_bits);
+  return forde::check_launch("topk_sparsify_kernel");
+}
+
+int forde_sl_topk_mask(void* stream, void* dzT, long long ldz, int M, int H, const uint32_t* keep_bits,
+                       float* grad_partials) {
+  if (dzT == nullptr || keep_bits == nullptr || M <= 0 || H <= 0 || ldz < M) return FORDE_EINVAL;
+  const int P = forde_sl_num_partials(M);  // 64-sample blocks (trailing ones beyond M get zeros)
+  forde::topk_mask_kernel<<<dim3(P, (H + 7) / 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<__nv_bfloat16*>(dzT), ldz, M, H, keep_bits, grad_partials);
+  return forde::check_launch("topk_mask_kernel");
+}
+
+}  // extern "C"

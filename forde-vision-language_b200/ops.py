@@ -179,6 +179,28 @@ def sl_dw_down(hT, dy, dw_down):
     _lib.check(rc, "forde_sl_dw_down")
 
 
+def sl_topk_sparsify(hT, M: int, k: int, want_indices: bool = True):
+    """In-place per-token top-k of |h| over the neuron axis of hT [H][ld].  Returns (idx (M,k) i32 | None,
+    hoyer (M,) f32, keep_bits (ceil(H/32), M) i32)."""
+    _req(hT, torch.bfloat16, "hT")
+    H = hT.shape[0]
+    dev = hT.device
+    idx = torch.empty((M, k), dtype=torch.int32, device=dev) if want_indices else None
+    hoyer = torch.empty(M, dtype=torch.float32, device=dev)
+    keep = torch.empty(((H + 31) // 32, M), dtype=torch.int32, device=dev)
+    rc = _lib.load().forde_sl_topk_sparsify(_stream(), hT.data_ptr(), hT.stride(0), M, H, k, _ptr(idx), hoyer.data_ptr(),
+                                            keep.data_ptr())
+    _lib.check(rc, "forde_sl_topk_sparsify")
+    return idx, hoyer, keep
+
+
+def sl_topk_mask(dzT, M: int, keep_bits, grad_partials=None):
+    _req(dzT, torch.bfloat16, "dzT")
+    rc = _lib.load().forde_sl_topk_mask(_stream(), dzT.data_ptr(), dzT.stride(0), M, dzT.shape[0], keep_bits.data_ptr(),
+                                        _ptr(grad_partials))
+    _lib.check(rc, "forde_sl_topk_mask")
+
+
 def colsum_bf16(a, out):
     _req(a, torch.bfloat16, "a"); _req(out, torch.float32, "out")
     rc = _lib.load().forde_colsum_bf16(_stream(), a.data_ptr(), a.stride(0), out.data_ptr(), a.shape[0], a.shape[1])

@@ -79,6 +79,9 @@ class _StatefulLayerFn(torch.autograd.Function):
         assign_i8 = layer._assign_i8
         y = torch.empty((M, w_down.shape[1]), dtype=torch.bfloat16, device=x2d.device)
         ops.sl_up_fwd(x2d, w_up16, b_up32, assign_i8, ws.zT, ws.hT, ws.act_partials)
+        ctx.keep_bits = None
+        if layer.top_k is not None:  # D8: keep the k largest |h| per token, zero the rest (in place)
+            layer.last_topk_indices, layer.last_row_hoyer, ctx.keep_bits = ops.sl_topk_sparsify(ws.hT, M, layer.top_k)
         ops.sl_down_fwd(ws.hT, w_down16, b_down32, y, M)
         ctx.save_for_backward(x2d, w_up16, w_down16)
         ctx.layer, ctx.ws, ctx.stats, ctx.assign_i8 = layer, ws, stats, assign_i8
@@ -101,7 +104,11 @@ class _StatefulLayerFn(torch.autograd.Function):
             dy = dy.to(torch.bfloat16)
         dev = x2d.device
         dzT = _dz_scratch(H, ws.ld, dev)
-        ops.sl_dz_bwd(dy, w_down16, ws.zT, assign_i8, dzT, ws.grad_partials)
+        if ctx.keep_bits is None:
+            ops.sl_dz_bwd(dy, w_down16, ws.zT, assign_i8, dzT, ws.grad_partials)
+        else:  # top-k path: dL/dz is zero where h was dropped; the gradient sums are re-taken after masking
+            ops.sl_dz_bwd(dy, w_down16, ws.zT, assign_i8, dzT, None)
+            ops.sl_topk_mask(dzT, M, ctx.keep_bits, ws.grad_partials)
         dx = None
         if ctx.needs_dx:
             dx = torch.empty((M, d), dtype=torch.bfloat16, device=dev)
@@ -138,8 +145,8 @@ class StatefulLayer:
         self._bf16_cache: Dict[str, Tuple[int, int, torch.Tensor]] = {}
         self._assign_i8: Optional[torch.Tensor] = None
         self._assign_src: Optional[Tuple[int, int]] = None
-        if self.top_k is not None:
-            raise NotImplementedError("top_k sparsification is provided by forde_b200.sparsify (LLM variant)")
+        self.last_topk_indices: Optional[torch.Tensor] = None   # (M, k) i32, lax.top_k order (top_k mode)
+        self.last_row_hoyer: Optional[torch.Tensor] = None      # (M,) f32 Hoyer sparsity of each token's dense h
 
     # ------------------------------------------------------------------ Flax-style API
     def init(self, key: Union[int, torch.Generator], x: torch.Tensor) -> Collections:

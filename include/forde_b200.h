@@ -93,6 +93,20 @@ int forde_sl_bwd(void* stream, const void* x, const void* dy, const void* w_up, 
                  float* db_up, float* dw_down, float* db_down, float* grad_partials, int M, int d, int H,
                  long long ldz);
 
+/* ---- optional top-k activation sparsification (nearest reference code: lax.top_k at moe.py:130) ------
+ * sparsify: per token (column of hT) keep the k largest |h| over the H neurons and zero the rest IN PLACE (call it
+ *   between forde_sl_up_fwd and forde_sl_down_fwd).  idx_out [M][k] i32 = kept neuron indices in jax.lax.top_k order of
+ *   |h| (descending, equal values -> lower index first; may be NULL); hoyer_out [M] f32 = Hoyer sparsity of the dense
+ *   h of each token (may be NULL); keep_bits [ceil(H/32)][M] u32 = kept mask for the backward (may be NULL).
+ * mask: dzT[h][m] = 0 where the forward dropped (h, m): call it after forde_sl_dz_bwd (which then gets NULL
+ *   grad_partials) and before dx / dW_up.  grad_partials (may be NULL) receives the per-neuron sums of the MASKED
+ *   dL/dz in the same [P][3][H] layout, so forde_stats_finalize works unchanged.  This is an extra pass over dzT and
+ *   only exists on the optional top-k path. */
+int forde_sl_topk_sparsify(void* stream, void* hT, long long ldz, int M, int H, int k, int* idx_out, float* hoyer_out,
+                           uint32_t* keep_bits);
+int forde_sl_topk_mask(void* stream, void* dzT, long long ldz, int M, int H, const uint32_t* keep_bits,
+                       float* grad_partials);
+
 /* ---- sensing finalisation (sensing.py:5-69) --------------------------------------------------------
  * Reduces the partials in a fixed order and produces this step's (H,5) statistics
  *   [grad_gini, grad_gdp, act_gini, act_gdp, act_variance]   (gini = Hoyer sparsity over the M samples)

@@ -345,3 +345,55 @@ def test_add_layernorm_forward_backward(ops, rows, cols):
     np.testing.assert_allclose(f32(dg), f32(gm.grad), rtol=2e-3, atol=2e-3 * float(gm.grad.abs().mean()) + 1e-4)
     np.testing.assert_allclose(f32(db), f32(bt.grad), rtol=2e-3, atol=2e-3 * float(bt.grad.abs().mean()) + 1e-4)
     np.testing.assert_allclose(f32(mean), f32(s.detach().mean(-1)), rtol=1e-4, atol=1e-5)
+
+
+# ------------------------------------------------------------------------------------------ top-k sparsification (D8)
+@pytest.mark.parametrize("M,H,k", [(100, 256, 16), (513, 3072, 64), (40, 128, 128), (33, 2048, 1)])
+def test_topk_sparsify_matches_lax_top_k_semantics(ops, M, H, k):
+    """Indices bit-exact against the oracle's lax.top_k restatement (incl. ties: bf16 values collide often)."""
+    g = torch.Generator(device="cuda").manual_seed(M)
+    ld = ops.sample_pitch(M)
+    hT = torch.zeros((H, ld), device="cuda", dtype=torch.bfloat16)
+    hT[:, :M] = (torch.randn((H, M), device="cuda", generator=g) * 2).round().div(2).bfloat16()   # many exact ties
+    dense = f32(hT[:, :M].t())                                                                    # (M, H)
+    idx, hoyer, keep = ops.sl_topk_sparsify(hT, M, k)
+    torch.cuda.synchronize()
+    ref_sparse, ref_idx = O.topk_sparsify(dense, k)
+    np.testing.assert_array_equal(idx.cpu().numpy(), ref_idx)
+    np.testing.assert_array_equal(f32(hT[:, :M].t()), ref_sparse)
+    np.testing.assert_allclose(f32(hoyer), O.hoyer_sparsity(dense), rtol=1e-4, atol=1e-6)
+    kb = keep.cpu().numpy().view(np.uint32)
+    kept = ((kb[np.arange(H)[:, None] >> 5, np.arange(M)[None, :]] >> (np.arange(H)[:, None] & 31)) & 1).astype(bool)
+    ref_kept = np.zeros((M, H), bool); np.put_along_axis(ref_kept, ref_idx, True, axis=1)
+    np.testing.assert_array_equal(kept.T, ref_kept)
+
+
+def test_stateful_layer_with_topk_masks_gradients_and_statistics(ops):
+    from forde_b200.stateful_layer import StatefulLayer
+    M, d, H, k = 300, 64, 256, 32
+    layer = StatefulLayer(hidden_dim=H, top_k=k)
+    x = torch.randn((M, d), device="cuda").bfloat16().requires_grad_(True)
+    v = layer.init(2, x)
+    a = np.arange(H) % 3
+    v["neuron_assignments"]["assignments"].copy_(torch.as_tensor(a))
+    ps = [v["params"]["up_proj"]["kernel"], v["params"]["down_proj"]["kernel"]]
+    for p_ in ps:
+        p_.requires_grad_(True)
+    y, upd = layer.apply(v, x, mutable=["stats_buffer"])
+    dy = torch.randn_like(y)
+    y.backward(dy)
+    torch.cuda.synchronize()
+    wu, wd = f32(ps[0].bfloat16()), f32(ps[1].bfloat16())
+    z = O.bf16_round(f32(x) @ wu)
+    h = O.bf16_round(O.gated_residual(z, a))
+    hs, ref_idx = O.topk_sparsify(h, k)
+    np.testing.assert_array_equal(layer.last_topk_indices.cpu().numpy(), ref_idx)
+    assert relerr(f32(y), O.bf16_round(hs @ wd)) < 1e-2
+    mask = np.zeros_like(h, bool); np.put_along_axis(mask, ref_idx, True, axis=1)
+    dz = O.bf16_round((f32(dy) @ wd.T) * (O.multiplex_grad(z, a) + O.gate_of(a)) * mask)
+    assert relerr(f32(x.grad), O.bf16_round(dz @ wu.T)) < 1e-2
+    assert relerr(f32(ps[0].grad), f32(x).T @ dz) < 1e-2
+    st = f32(upd["stats_buffer"]["neuron_stats"])
+    ref = O.calculate_neuron_stats(z, dz)
+    np.testing.assert_allclose(st[:, 1], ref[:, 1], rtol=2e-2, atol=1e-5)      # grad_gdp of the MASKED dL/dz
+    np.testing.assert_allclose(st[:, 3], ref[:, 3], rtol=2e-2, atol=1e-5)
