@@ -257,6 +257,11 @@ def run_gpu(args):
     roofline = None
     sl_ms = sum(r["ms_total"] for r in kt.values())
     sl_flops = sum(r["flops_total"] for r in kt.values())
+    traffic_db = {}
+    tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(tpath):
+        with open(tpath) as f:
+            traffic_db = json.load(f)
     if kt:
         dom = max(kt, key=lambda n: kt[n]["ms_total"])
         r = kt[dom]
@@ -265,7 +270,10 @@ def run_gpu(args):
                     "unit": "TFLOP/s", "frac": round(ach / peaks["sustained"], 4),
                     "peak_kind": f"{peaks['source']} sustained bf16 (kernel timed inside a long step)",
                     "flops_per_launch": r["flops_total"] / r["launches"], "launches": r["launches"],
-                    "us_per_launch": round(1e3 * r["ms_total"] / r["launches"], 2), "traffic": None}
+                    "us_per_launch": round(1e3 * r["ms_total"] / r["launches"], 2),
+                    "traffic": traffic_db.get(dom, {}).get("traffic_bytes"),
+                    "traffic_note": "DRAM read+write bytes per launch from one ncu --set full capture "
+                                    "(profiles/ncu_traffic.json); algorithmic bytes 2(Md+dH+2MH) = 702 MB at C2 vision"}
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,

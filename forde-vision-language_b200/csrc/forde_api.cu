@@ -386,7 +386,7 @@ int forde_gemm_f32(void* stream, const void* A, int a_mn_major, long long lda, c
 
 // zT[H][M] = (x . w_up + b)^T :  A = w_up [d][H] as (m = neuron, k = d) -> MN-major ; B = x [M][d] -> K-major
 int forde_sl_up_fwd(void* stream, const void* x, const void* w_up, const float* b_up, const int8_t* assign,
-                    void* zT, void* hT, float* act_partials, int M, int d, int H, long long ldz) {
+                    void* zT, void* hT, float* act_partials, int M, int d, int H, long long ldz, int save_z) {
   if (assign == nullptr || zT == nullptr || hT == nullptr || ldz < M) return FORDE_EINVAL;
   GemmArgs g{w_up, true, H, x, false, d, H, M, d, /*raster_m_fast=*/true, kEvictLast, kEvictLast};
   GemmParams p;
@@ -399,6 +399,7 @@ int forde_sl_up_fwd(void* stream, const void* x, const void* w_up, const float* 
   p.bias_row = b_up;
   p.assign = assign;
   p.partials = act_partials;
+  p.save_z = save_z;
   return launch_epi<EPI_UP_FWD>(p, true, false, static_cast<cudaStream_t>(stream));
 }
 
@@ -412,16 +413,16 @@ int forde_sl_down_fwd(void* stream, const void* hT, const void* w_down, const fl
 
 int forde_sl_fwd(void* stream, const void* x, const void* w_up, const float* b_up, const void* w_down,
                  const float* b_down, const int8_t* assign, void* zT, void* hT, void* y, float* act_partials,
-                 int M, int d, int H, long long ldz) {
-  int rc = forde_sl_up_fwd(stream, x, w_up, b_up, assign, zT, hT, act_partials, M, d, H, ldz);
+                 int M, int d, int H, long long ldz, int save_z) {
+  int rc = forde_sl_up_fwd(stream, x, w_up, b_up, assign, zT, hT, act_partials, M, d, H, ldz, save_z);
   if (rc != FORDE_OK) return rc;
   return forde_sl_down_fwd(stream, hT, w_down, b_down, y, M, d, H, ldz);
 }
 
 // dzT[H][M] = (dy . w_down^T)^T * (F'(z) + gate) : A = w_down [H][d] (m = neuron, k = d) K-major ; B = dy [M][d] K-major
-int forde_sl_dz_bwd(void* stream, const void* dy, const void* w_down, const void* zT, const int8_t* assign,
-                    void* dzT, float* grad_partials, int M, int d, int H, long long ldz) {
-  if (assign == nullptr || zT == nullptr || dzT == nullptr || ldz < M) return FORDE_EINVAL;
+int forde_sl_dz_bwd(void* stream, const void* dy, const void* w_down, const void* zT, const void* hT,
+                    const int8_t* assign, void* dzT, float* grad_partials, int M, int d, int H, long long ldz) {
+  if (assign == nullptr || zT == nullptr || hT == nullptr || dzT == nullptr || ldz < M) return FORDE_EINVAL;
   GemmArgs g{w_down, false, d, dy, false, d, H, M, d, /*raster_m_fast=*/true, kEvictLast, kEvictLast};
   GemmParams p;
   int rc = fill_common(p, g);
@@ -429,6 +430,8 @@ int forde_sl_dz_bwd(void* stream, const void* dy, const void* w_down, const void
   rc = make_tmap_bf16(&p.tmC0, dzT, M, H, ldz, CHUNK, 32);
   if (rc != FORDE_OK) return rc;
   rc = make_tmap_bf16(&p.tmZ, zT, M, H, ldz, CHUNK, 32);
+  if (rc != FORDE_OK) return rc;
+  rc = make_tmap_bf16(&p.tmH, hT, M, H, ldz, CHUNK, 32);
   if (rc != FORDE_OK) return rc;
   p.assign = assign;
   p.partials = grad_partials;
@@ -463,7 +466,7 @@ int forde_sl_bwd(void* stream, const void* x, const void* dy, const void* w_up, 
                  const void* zT, const void* hT, const int8_t* assign, void* dzT, void* dx, float* dw_up,
                  float* db_up, float* dw_down, float* db_down, float* grad_partials, int M, int d, int H,
                  long long ldz) {
-  int rc = forde_sl_dz_bwd(stream, dy, w_down, zT, assign, dzT, grad_partials, M, d, H, ldz);
+  int rc = forde_sl_dz_bwd(stream, dy, w_down, zT, hT, assign, dzT, grad_partials, M, d, H, ldz);
   if (rc != FORDE_OK) return rc;
   if (dx != nullptr) {
     rc = forde_sl_dx_bwd(stream, dzT, w_up, dx, M, d, H, ldz);

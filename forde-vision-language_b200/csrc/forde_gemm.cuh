@@ -48,6 +48,7 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <cstdint>
+#include <type_traits>
 
 #include "sm100_ptx.cuh"
 
@@ -124,11 +125,13 @@ struct GemmParams {
   CUtensorMap tmC0;  // bf16 output 0 (box 64 x 32): y / dx / z^T / dz^T
   CUtensorMap tmC1;  // bf16 output 1 (box 64 x 32): h^T               (EPI_UP_FWD)
   CUtensorMap tmZ;   // bf16 input z^T (box 64 x 32)                   (EPI_DZ_BWD)
+  CUtensorMap tmH;   // bf16 input h^T (box 64 x 32): stands in for z^T where no neuron of the warp is tanh (EPI_DZ_BWD)
   int M, N, K;       // D is M x N, reduction length K
   int m_blocks, n_blocks, k_blocks;
   int split_k, kb_per_split;
   int raster_m_fast;  // 1: consecutive work items walk M first (share the B slab), 0: walk N first
   int pair;           // 1: launched as 2-CTA clusters (256-row tiles, cta_group::2)
+  int save_z;         // EPI_UP_FWD: 1 = store every z box; 0 = only the boxes the backward needs (warps with tanh neurons)
   // grouped modes (MoE experts); all null / 0 otherwise
   const int* m_blocks_dev;     // grouped-M: number of valid 128-row blocks (device scalar)
   const int* group_of_mblock;  // grouped-M: expert of each 128-row block
@@ -210,6 +213,82 @@ __device__ __forceinline__ ActConst make_act(int a, float g_gen, float g_spec) {
   return c;
 }
 
+// Warp-level specialisation of the fused epilogues.  The multiplex is per NEURON (= per thread), so a warp whose 32
+// neurons share one assignment runs a branch-free body; brain maps are spatially smoothed (smoothing.py:30-91), so
+// that is the common case, and the all-generalist map every layer starts with (D7) is entirely WM_RELU.
+enum WarpMode : int { WM_RELU = 0, WM_STEP = 1, WM_MIXED = 2 };
+
+struct RunningSums {
+  float s_abs, s_sum, s_sq;
+};
+
+// forward, 8 accumulator columns -> 4 packed z words + 4 packed h words; MODE is warp-uniform
+template <int MODE, bool MASKED>
+__device__ __forceinline__ void up_fwd_8(const uint32_t* v, float bias_r, const ActConst& act, bool warp_has_tanh,
+                                         int jcol, int nvalid, uint32_t* zw, uint32_t* hw, RunningSums& rs) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const uint32_t zp = pack_bf16x2(__uint_as_float(v[2 * i]) + bias_r, __uint_as_float(v[2 * i + 1]) + bias_r);
+    const float z0 = bf16lo_to_f32(zp), z1 = bf16hi_to_f32(zp);
+    float h0, h1;
+    if (MODE == WM_RELU) {          // h = relu(z) + 1.0 * z
+      h0 = z0 + fmaxf(z0, 0.f);
+      h1 = z1 + fmaxf(z1, 0.f);
+    } else if (MODE == WM_STEP) {   // h = step(z) + gate * z
+      h0 = fmaf(act.gate, z0, z0 > 0.f ? 1.f : 0.f);
+      h1 = fmaf(act.gate, z1, z1 > 0.f ? 1.f : 0.f);
+    } else {
+      // F_a(z): relu -> z if z>0 ; binary_step -> 1 if z>0 ; else 0.  tanh lanes overwrite.
+      float f0 = (z0 > 0.f) ? (act.is_step ? 1.f : z0) : 0.f;
+      float f1 = (z1 > 0.f) ? (act.is_step ? 1.f : z1) : 0.f;
+      if (warp_has_tanh) {
+        const float t0 = tanh_approx(z0), t1 = tanh_approx(z1);
+        f0 = act.is_tanh ? t0 : f0;
+        f1 = act.is_tanh ? t1 : f1;
+      }
+      h0 = fmaf(act.gate, z0, f0);
+      h1 = fmaf(act.gate, z1, f1);
+    }
+    zw[i] = zp;
+    hw[i] = pack_bf16x2(h0, h1);
+    if (!MASKED) {
+      rs.s_abs += fabsf(z0) + fabsf(z1);
+      rs.s_sum += z0 + z1;
+      rs.s_sq = fmaf(z0, z0, rs.s_sq);
+      rs.s_sq = fmaf(z1, z1, rs.s_sq);
+    } else {  // ragged last chunk: samples beyond N are not counted
+      if (jcol + 2 * i < nvalid) { rs.s_abs += fabsf(z0); rs.s_sum += z0; rs.s_sq = fmaf(z0, z0, rs.s_sq); }
+      if (jcol + 2 * i + 1 < nvalid) { rs.s_abs += fabsf(z1); rs.s_sum += z1; rs.s_sq = fmaf(z1, z1, rs.s_sq); }
+    }
+  }
+}
+
+// backward, 8 columns: dz = acc * (F_a'(z) + gate_a).  Samples beyond N have acc == 0 exactly (TMA zero fill), so
+// they add nothing to the sums and need no masking.  m_pos / m_neg are the per-neuron multipliers for z > 0 / z <= 0:
+// relu (1 + gate, gate), binary step with the straight-through estimator (1 + gate both), tanh computed per element.
+template <bool HAS_TANH>
+__device__ __forceinline__ void dz_bwd_8(const uint32_t* v, const uint32_t* zw, float m_pos, float m_neg,
+                                         const ActConst& act, uint32_t* dw, RunningSums& rs) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float z0 = bf16lo_to_f32(zw[i]), z1 = bf16hi_to_f32(zw[i]);
+    float m0 = z0 > 0.f ? m_pos : m_neg;
+    float m1 = z1 > 0.f ? m_pos : m_neg;
+    if (HAS_TANH) {
+      const float t0 = tanh_approx(z0), t1 = tanh_approx(z1);
+      m0 = act.is_tanh ? (fmaf(-t0, t0, 1.f) + act.gate) : m0;
+      m1 = act.is_tanh ? (fmaf(-t1, t1, 1.f) + act.gate) : m1;
+    }
+    const uint32_t dp = pack_bf16x2(__uint_as_float(v[2 * i]) * m0, __uint_as_float(v[2 * i + 1]) * m1);
+    dw[i] = dp;
+    const float d0 = bf16lo_to_f32(dp), d1 = bf16hi_to_f32(dp);
+    rs.s_abs += fabsf(d0) + fabsf(d1);
+    rs.s_sum += d0 + d1;
+    rs.s_sq = fmaf(d0, d0, rs.s_sq);
+    rs.s_sq = fmaf(d1, d1, rs.s_sq);
+  }
+}
+
 template <bool A_MN, bool B_MN, int EPI, bool PAIR>
 __global__ void __launch_bounds__(num_threads(EPI, PAIR), 1) forde_gemm_kernel(const __grid_constant__ GemmParams p) {
   constexpr int EPI_WARPS = epi_warps(EPI, PAIR);
@@ -249,6 +328,7 @@ __global__ void __launch_bounds__(num_threads(EPI, PAIR), 1) forde_gemm_kernel(c
     if (EPI != EPI_F32) tma_prefetch_desc(&p.tmC0);
     if (epi_two_out(EPI)) tma_prefetch_desc(&p.tmC1);
     if (epi_z_ring(EPI)) tma_prefetch_desc(&p.tmZ);
+    if (EPI == EPI_DZ_BWD) tma_prefetch_desc(&p.tmH);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
@@ -381,19 +461,30 @@ __global__ void __launch_bounds__(num_threads(EPI, PAIR), 1) forde_gemm_kernel(c
     // chunk g lives in box g % ZR and dz is written over it in place.
     int g = 0;
     uint64_t* zb = z_bar + ew * ZR;
-    auto z_prefetch = [&](int gi) {  // lane 0 only
+    // Warp-collective.  The backward only needs z itself for tanh neurons (F' = 1 - tanh^2 z); for relu neurons the
+    // sign of h = z + relu(z) is the sign of z and the straight-through step needs nothing, so a warp without tanh
+    // neurons reads the h^T box (which the forward stores anyway) and the forward never has to write its z^T box.
+    auto z_prefetch = [&](int gi, bool wait_for_store) {
       const int nt = worker + (gi / CPW) * num_workers;
-      if (nt < total_work) {
-        const WorkItem wn = decode_work(p, nt, TILE_M, m_off, m_blocks);
+      if (nt >= total_work) return;
+      const WorkItem wn = decode_work(p, nt, TILE_M, m_off, m_blocks);
+      bool use_z = true;
+      if (EPI == EPI_DZ_BWD) {
+        const int rn = wn.m0 + q * 32 + lane;
+        use_z = __any_sync(0xffffffffu, rn < p.M && p.assign[rn] == 1);
+      }
+      if (lane == 0) {
+        // the dz store that last read this box (chunk gi - ZR) must have drained
+        if (wait_for_store) tma_wait_read<ZR - ZD - 1>();
         const int bi = gi % ZR;
         mbar_expect_tx(&zb[bi], BOX_BYTES);
-        tma_load_2d(&p.tmZ, &zb[bi], wst + bi * BOX_BYTES, wn.n0 + (e * CPW + gi % CPW) * CHUNK, wn.m0 + q * 32,
-                    kEvictFirst);
+        tma_load_2d(use_z ? &p.tmZ : &p.tmH, &zb[bi], wst + bi * BOX_BYTES, wn.n0 + (e * CPW + gi % CPW) * CHUNK,
+                    wn.m0 + q * 32, kEvictFirst);
       }
     };
-    if (epi_z_ring(EPI) && lane == 0) {
+    if (epi_z_ring(EPI)) {
 #pragma unroll
-      for (int i = 0; i < ZD; ++i) z_prefetch(i);
+      for (int i = 0; i < ZD; ++i) z_prefetch(i, false);
     }
 
     for (int t = worker; t < total_work; t += num_workers, ++it) {
@@ -406,6 +497,9 @@ __global__ void __launch_bounds__(num_threads(EPI, PAIR), 1) forde_gemm_kernel(c
       float bias_r = 0.f;
       ActConst act = make_act(0, p.gate_generalist, p.gate_specialist);
       bool warp_has_tanh = false;
+      int wmode = WM_MIXED;
+      bool store_z = true;
+      float m_pos = 0.f, m_neg = 0.f;
       if (epi_neuron_rows(EPI)) {
         int a = 0;
         if (row < p.M) {
@@ -414,6 +508,11 @@ __global__ void __launch_bounds__(num_threads(EPI, PAIR), 1) forde_gemm_kernel(c
         }
         act = make_act(a, p.gate_generalist, p.gate_specialist);
         warp_has_tanh = __any_sync(0xffffffffu, act.is_tanh);
+        const bool relu_row = !act.is_tanh && !act.is_step;
+        wmode = __all_sync(0xffffffffu, relu_row) ? WM_RELU : __all_sync(0xffffffffu, act.is_step) ? WM_STEP : WM_MIXED;
+        store_z = (p.save_z != 0) || warp_has_tanh;  // see z_prefetch: only tanh neurons need z in the backward
+        m_pos = 1.f + act.gate;                      // relu'(z>0) + gate ; STE slope 1 + gate
+        m_neg = act.is_step ? 1.f + act.gate : act.gate;
       }
       if (epi_col_bias(EPI)) {
         // stage this tile's column bias (of this tile's expert in the grouped mode) once for the epilogue warps
@@ -436,13 +535,9 @@ __global__ void __launch_bounds__(num_threads(EPI, PAIR), 1) forde_gemm_kernel(c
         const int col0 = w.n0 + c * CHUNK;
         const int nvalid = p.N - col0;  // valid columns in this chunk (may be <= 0 or >= CHUNK)
         const bool full = nvalid >= CHUNK;
-        float s_abs = 0.f, s_sum = 0.f, s_sq = 0.f;  // this chunk's per-neuron sums (fused epilogues)
+        RunningSums rs{0.f, 0.f, 0.f};  // this chunk's per-neuron sums (fused epilogues)
 
-        if (epi_z_ring(EPI) && lane == 0) {
-          // refill the box chunk g + ZD will use; the dz store that last read it (chunk g + ZD - ZR) must have drained
-          tma_wait_read<ZR - ZD - 1>();
-          z_prefetch(g + ZD);
-        }
+        if (epi_z_ring(EPI)) z_prefetch(g + ZD, true);  // refill the box chunk g + ZD will use
         // single-buffered staging: the previous chunk's TMA stores must have read the boxes (the other epilogue
         // warps of this SM sub-partition cover the wait)
         if ((epi_two_out(EPI) || EPI == EPI_STORE) && lane == 0) tma_wait_read<0>();
@@ -511,39 +606,23 @@ __global__ void __launch_bounds__(num_threads(EPI, PAIR), 1) forde_gemm_kernel(c
             }
           } else if (EPI == EPI_UP_FWD) {
             // z box at wst, h box at wst + BOX_BYTES
+            auto run = [&](auto mode, auto masked) {
 #pragma unroll
-            for (int j8 = 0; j8 < 4; ++j8) {
-              uint32_t zw[4], hw[4];
-#pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                const int j = j8 * 8 + i * 2;
-                const uint32_t zp = pack_bf16x2(__uint_as_float(v[j]) + bias_r, __uint_as_float(v[j + 1]) + bias_r);
-                const float z0 = bf16lo_to_f32(zp), z1 = bf16hi_to_f32(zp);
-                // F_a(z): relu -> z if z>0 ; binary_step -> 1 if z>0 ; else 0.  tanh lanes overwrite below.
-                float f0 = (z0 > 0.f) ? (act.is_step ? 1.f : z0) : 0.f;
-                float f1 = (z1 > 0.f) ? (act.is_step ? 1.f : z1) : 0.f;
-                if (warp_has_tanh) {
-                  const float t0 = tanh_approx(z0), t1 = tanh_approx(z1);
-                  f0 = act.is_tanh ? t0 : f0;
-                  f1 = act.is_tanh ? t1 : f1;
-                }
-                const float h0 = fmaf(act.gate, z0, f0), h1 = fmaf(act.gate, z1, f1);
-                zw[i] = zp;
-                hw[i] = pack_bf16x2(h0, h1);
-                if (full) {
-                  s_abs += fabsf(z0) + fabsf(z1);
-                  s_sum += z0 + z1;
-                  s_sq = fmaf(z0, z0, s_sq);
-                  s_sq = fmaf(z1, z1, s_sq);
-                } else {
-                  if (jbase + j < nvalid) { s_abs += fabsf(z0); s_sum += z0; s_sq = fmaf(z0, z0, s_sq); }
-                  if (jbase + j + 1 < nvalid) { s_abs += fabsf(z1); s_sum += z1; s_sq = fmaf(z1, z1, s_sq); }
-                }
+              for (int j8 = 0; j8 < 4; ++j8) {
+                uint32_t zw[4], hw[4];
+                up_fwd_8<decltype(mode)::value, decltype(masked)::value>(v + j8 * 8, bias_r, act, warp_has_tanh,
+                                                                         jbase + j8 * 8, nvalid, zw, hw, rs);
+                const uint32_t off = (static_cast<uint32_t>(half * 4 + j8) ^ sw) << 4;
+                if (store_z) st_shared_v4(orow_s + off, zw[0], zw[1], zw[2], zw[3]);
+                st_shared_v4(orow_s + BOX_BYTES + off, hw[0], hw[1], hw[2], hw[3]);
               }
-              const uint32_t off = (static_cast<uint32_t>(half * 4 + j8) ^ sw) << 4;
-              st_shared_v4(orow_s + off, zw[0], zw[1], zw[2], zw[3]);
-              st_shared_v4(orow_s + BOX_BYTES + off, hw[0], hw[1], hw[2], hw[3]);
-            }
+            };
+            using T = std::true_type;
+            using F = std::false_type;
+            if (!full) run(std::integral_constant<int, WM_MIXED>{}, T{});
+            else if (wmode == WM_RELU) run(std::integral_constant<int, WM_RELU>{}, F{});
+            else if (wmode == WM_STEP) run(std::integral_constant<int, WM_STEP>{}, F{});
+            else run(std::integral_constant<int, WM_MIXED>{}, F{});
           } else if (EPI == EPI_MOE_UP) {
             // z box at wst (tmC0), h = gelu_tanh(z) box at wst + BOX_BYTES (tmC1); flax nn.gelu default (moe.py:27)
             const float* bsrc = bias_s + c * CHUNK + jbase;
@@ -578,38 +657,18 @@ __global__ void __launch_bounds__(num_threads(EPI, PAIR), 1) forde_gemm_kernel(c
               st_shared_v4(orow_s + off, dw[0], dw[1], dw[2], dw[3]);
             }
           } else {  // EPI_DZ_BWD: dz over z, in place (same thread, same bytes)
+            auto run = [&](auto has_tanh) {
 #pragma unroll
-            for (int j8 = 0; j8 < 4; ++j8) {
-              const uint32_t off = (static_cast<uint32_t>(half * 4 + j8) ^ sw) << 4;
-              uint32_t zw[4], dw[4];
-              ld_shared_v4(orow_s + off, zw[0], zw[1], zw[2], zw[3]);
-#pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                const int j = j8 * 8 + i * 2;
-                const float z0 = bf16lo_to_f32(zw[i]), z1 = bf16hi_to_f32(zw[i]);
-                // F_a'(z) + gate_a : relu 1[z>0] + 1 ; binary_step (STE) 1 + 0.1 ; tanh (1 - t^2) + 1
-                float m0 = act.is_step ? (1.f + act.gate) : ((z0 > 0.f ? 1.f : 0.f) + act.gate);
-                float m1 = act.is_step ? (1.f + act.gate) : ((z1 > 0.f ? 1.f : 0.f) + act.gate);
-                if (warp_has_tanh) {
-                  const float t0 = tanh_approx(z0), t1 = tanh_approx(z1);
-                  m0 = act.is_tanh ? (fmaf(-t0, t0, 1.f) + act.gate) : m0;
-                  m1 = act.is_tanh ? (fmaf(-t1, t1, 1.f) + act.gate) : m1;
-                }
-                const uint32_t dp = pack_bf16x2(__uint_as_float(v[j]) * m0, __uint_as_float(v[j + 1]) * m1);
-                dw[i] = dp;
-                const float d0 = bf16lo_to_f32(dp), d1 = bf16hi_to_f32(dp);
-                if (full) {
-                  s_abs += fabsf(d0) + fabsf(d1);
-                  s_sum += d0 + d1;
-                  s_sq = fmaf(d0, d0, s_sq);
-                  s_sq = fmaf(d1, d1, s_sq);
-                } else {
-                  if (jbase + j < nvalid) { s_abs += fabsf(d0); s_sum += d0; s_sq = fmaf(d0, d0, s_sq); }
-                  if (jbase + j + 1 < nvalid) { s_abs += fabsf(d1); s_sum += d1; s_sq = fmaf(d1, d1, s_sq); }
-                }
+              for (int j8 = 0; j8 < 4; ++j8) {
+                const uint32_t off = (static_cast<uint32_t>(half * 4 + j8) ^ sw) << 4;
+                uint32_t zw[4], dw[4];
+                ld_shared_v4(orow_s + off, zw[0], zw[1], zw[2], zw[3]);
+                dz_bwd_8<decltype(has_tanh)::value>(v + j8 * 8, zw, m_pos, m_neg, act, dw, rs);
+                st_shared_v4(orow_s + off, dw[0], dw[1], dw[2], dw[3]);
               }
-              st_shared_v4(orow_s + off, dw[0], dw[1], dw[2], dw[3]);
-            }
+            };
+            if (warp_has_tanh) run(std::true_type{});
+            else run(std::false_type{});
           }
         }
 
@@ -617,7 +676,7 @@ __global__ void __launch_bounds__(num_threads(EPI, PAIR), 1) forde_gemm_kernel(c
           fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0) {
-            tma_store_2d(&p.tmC0, obuf, col0, w.m0 + q * 32);
+            if (EPI != EPI_UP_FWD || store_z) tma_store_2d(&p.tmC0, obuf, col0, w.m0 + q * 32);
             if (epi_two_out(EPI)) tma_store_2d(&p.tmC1, obuf + BOX_BYTES, col0, w.m0 + q * 32);
             tma_commit();
           }
@@ -626,9 +685,9 @@ __global__ void __launch_bounds__(num_threads(EPI, PAIR), 1) forde_gemm_kernel(c
 
         if (epi_neuron_rows(EPI) && p.partials != nullptr && row < p.M) {
           float* dst = p.partials + (static_cast<long long>(w.nb * PARTIALS_PER_TILE + c) * 3) * p.M + row;
-          dst[0] = s_abs;
-          dst[p.M] = s_sum;
-          dst[2 * static_cast<long long>(p.M)] = s_sq;
+          dst[0] = rs.s_abs;
+          dst[p.M] = rs.s_sum;
+          dst[2 * static_cast<long long>(p.M)] = rs.s_sq;
         }
       }
 

@@ -37,7 +37,7 @@ static ffi::Error SlFwdImpl(cudaStream_t stream, ffi::Buffer<ffi::BF16> x, ffi::
   return status(forde_sl_fwd(stream, x.untyped_data(), w_up.untyped_data(), b_up.typed_data(), w_down.untyped_data(),
                              b_down.typed_data(), reinterpret_cast<const int8_t*>(assign.untyped_data()),
                              zT->untyped_data(), hT->untyped_data(), y->untyped_data(), act_partials->typed_data(), M,
-                             d, H, ldz),
+                             d, H, ldz, /*save_z=*/0),
                 "forde_sl_fwd");
 }
 

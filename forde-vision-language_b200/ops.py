@@ -118,7 +118,7 @@ def gemm_f32(A, B, a_mn_major, b_mn_major, out=None, scale=1.0, accumulate=False
 
 
 # ------------------------------------------------------------------------------------------ StatefulLayer
-def sl_up_fwd(x, w_up, b_up, assign_i8, zT, hT, act_partials):
+def sl_up_fwd(x, w_up, b_up, assign_i8, zT, hT, act_partials, save_z: bool = True):
     M, d = x.shape
     H = w_up.shape[1]
     _req(x, torch.bfloat16, "x"); _req(w_up, torch.bfloat16, "w_up"); _req(assign_i8, torch.int8, "assign")
@@ -127,7 +127,8 @@ def sl_up_fwd(x, w_up, b_up, assign_i8, zT, hT, act_partials):
         _req(b_up, torch.float32, "b_up")
     with _Timed(f"sl_up_fwd[{M}x{d}x{H}]", 2.0 * M * d * H):
         rc = _lib.load().forde_sl_up_fwd(_stream(), x.data_ptr(), w_up.data_ptr(), _ptr(b_up), assign_i8.data_ptr(),
-                                         zT.data_ptr(), hT.data_ptr(), _ptr(act_partials), M, d, H, zT.stride(0))
+                                         zT.data_ptr(), hT.data_ptr(), _ptr(act_partials), M, d, H, zT.stride(0),
+                                         int(save_z))
     _lib.check(rc, "forde_sl_up_fwd")
 
 
@@ -142,12 +143,13 @@ def sl_down_fwd(hT, w_down, b_down, y, M):
     _lib.check(rc, "forde_sl_down_fwd")
 
 
-def sl_dz_bwd(dy, w_down, zT, assign_i8, dzT, grad_partials):
+def sl_dz_bwd(dy, w_down, zT, hT, assign_i8, dzT, grad_partials):
     M, d = dy.shape
     H = w_down.shape[0]
     _req(dy, torch.bfloat16, "dy"); _req(zT, torch.bfloat16, "zT"); _req(dzT, torch.bfloat16, "dzT")
     with _Timed(f"sl_dz_bwd[{M}x{d}x{H}]", 2.0 * M * d * H):
-        rc = _lib.load().forde_sl_dz_bwd(_stream(), dy.data_ptr(), w_down.data_ptr(), zT.data_ptr(), assign_i8.data_ptr(),
+        rc = _lib.load().forde_sl_dz_bwd(_stream(), dy.data_ptr(), w_down.data_ptr(), zT.data_ptr(), hT.data_ptr(),
+                                         assign_i8.data_ptr(),
                                          dzT.data_ptr(), _ptr(grad_partials), M, d, H, zT.stride(0))
     _lib.check(rc, "forde_sl_dz_bwd")
 

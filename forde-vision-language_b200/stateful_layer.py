@@ -78,7 +78,7 @@ class _StatefulLayerFn(torch.autograd.Function):
         b_down32 = b_down.float() if b_down.dtype != torch.float32 else b_down
         assign_i8 = layer._assign_i8
         y = torch.empty((M, w_down.shape[1]), dtype=torch.bfloat16, device=x2d.device)
-        ops.sl_up_fwd(x2d, w_up16, b_up32, assign_i8, ws.zT, ws.hT, ws.act_partials)
+        ops.sl_up_fwd(x2d, w_up16, b_up32, assign_i8, ws.zT, ws.hT, ws.act_partials, save_z=layer.save_z)
         ctx.keep_bits = None
         if layer.top_k is not None:  # D8: keep the k largest |h| per token, zero the rest (in place)
             layer.last_topk_indices, layer.last_row_hoyer, ctx.keep_bits = ops.sl_topk_sparsify(ws.hT, M, layer.top_k)
@@ -105,9 +105,9 @@ class _StatefulLayerFn(torch.autograd.Function):
         dev = x2d.device
         dzT = _dz_scratch(H, ws.ld, dev)
         if ctx.keep_bits is None:
-            ops.sl_dz_bwd(dy, w_down16, ws.zT, assign_i8, dzT, ws.grad_partials)
+            ops.sl_dz_bwd(dy, w_down16, ws.zT, ws.hT, assign_i8, dzT, ws.grad_partials)
         else:  # top-k path: dL/dz is zero where h was dropped; the gradient sums are re-taken after masking
-            ops.sl_dz_bwd(dy, w_down16, ws.zT, assign_i8, dzT, None)
+            ops.sl_dz_bwd(dy, w_down16, ws.zT, ws.hT, assign_i8, dzT, None)
             ops.sl_topk_mask(dzT, M, ctx.keep_bits, ws.grad_partials)
         dx = None
         if ctx.needs_dx:
@@ -138,6 +138,7 @@ class StatefulLayer:
     top_k: Optional[int] = None            # D8 activation sparsification; None = off (vision/text towers)
     param_dtype: torch.dtype = torch.float32
     sense_forward_only: bool = False       # also accumulate activation-only stats in no-grad forwards
+    save_z: bool = False                   # keep all of z^T (debugging); by default only what the backward reads
     name: str = "stateful_layer"
 
     def __post_init__(self):

@@ -163,6 +163,42 @@ class GraphedTrainStep:
         return self.state, self.metrics
 
 
+def fit(state: TrainState, batches, max_steps: int, slow_loop_interval: int = 100, slow_loop_config=None, key: int = 0,
+        use_cuda_graph: bool = True, log=None):
+    """The reference's outer loop (src/training/train.py:320-399): fast steps, and every ``slow_loop_interval`` steps
+    (train.py:219-224 default 100; ``step > 0 and step % interval == 0``, train.py:365-369) the slow loop -- Sense
+    (all-reduced pooled moments) -> Cluster -> Smooth -> Actuate -> Reset -- which rewrites ``neuron_assignments`` in
+    place and zeroes ``stats_buffer`` (train.py:387-399).  ``batches`` is an iterable of batch dicts.
+    Returns (state, history) with history = list of (step, loss) and the slow-loop diagnostics."""
+    from .slow_loop import SlowLoopConfig, slow_loop_step
+
+    cfg = slow_loop_config or SlowLoopConfig()
+    history, diagnostics = [], []
+    step_fn = None
+    it = iter(batches)
+    for step in range(max_steps):
+        try:
+            batch = next(it)
+        except StopIteration:
+            break
+        if use_cuda_graph and state.flat_p32.is_cuda:
+            if step_fn is None:
+                step_fn = GraphedTrainStep(state, batch)
+            _, m = step_fn(batch)
+        else:
+            _, m = train_step(state, batch)
+        if log is not None or step == max_steps - 1 or (step + 1) % slow_loop_interval == 0:
+            history.append((step, float(m["loss"].item())))
+            if log is not None:
+                log(step, history[-1][1])
+        if step > 0 and step % slow_loop_interval == 0:
+            mv = {"stats_buffer": state.variables["stats_buffer"],
+                  "neuron_assignments": state.variables["neuron_assignments"]}
+            _, _, diag = slow_loop_step(state.params, mv, cfg, key=key + step, epoch=0, step=step, group=state.group)
+            diagnostics.append(diag)
+    return state, {"loss": history, "slow_loop": diagnostics}
+
+
 def synthetic_batch(config: DualEncoderConfig, batch: int, seed: int = 42, pinned: bool = True):
     """Synthetic image/caption pairs of the reference's tensor layout (src/data/download_to_drive.py:106-108,
     171-178): image (B,S,S,3) NHWC, input_ids (B,T) int32; fixed-seed ints as src/data/dataset.py:27,39."""

@@ -60,26 +60,32 @@ int forde_gemm_f32(void* stream, const void* A, int a_mn_major, long long lda, c
                    float scale, int accumulate, int M, int N, int K);
 
 /* ---- StatefulLayer forward (README.md:47-56; sensing.py:57-59 for the activation moments) ------------
- * up:   zT = (x . w_up + b_up)^T ; hT = F_assign(zT) + gate_assign * zT ; act_partials (may be NULL)
+ * up:   zT = (x . w_up + b_up)^T ; hT = F_assign(zT) + gate_assign * zT ; act_partials (may be NULL).
+ *       save_z = 1 writes all of zT.  save_z = 0 writes only the 32-neuron x 64-sample boxes whose neuron group
+ *       contains a tanh neuron: the backward needs z itself only there (relu: sign(h) == sign(z); binary step:
+ *       straight-through), reads hT everywhere else, and the forward saves up to half of its HBM writes.  The
+ *       activation statistics are taken from z in registers either way.
  * down: y = h . w_down + b_down */
 int forde_sl_up_fwd(void* stream, const void* x, const void* w_up, const float* b_up, const int8_t* assign,
-                    void* zT, void* hT, float* act_partials, int M, int d, int H, long long ldz);
+                    void* zT, void* hT, float* act_partials, int M, int d, int H, long long ldz, int save_z);
 int forde_sl_down_fwd(void* stream, const void* hT, const void* w_down, const float* b_down, void* y, int M,
                       int d, int H, long long ldz);
 /* both of the above */
 int forde_sl_fwd(void* stream, const void* x, const void* w_up, const float* b_up, const void* w_down,
                  const float* b_down, const int8_t* assign, void* zT, void* hT, void* y, float* act_partials,
-                 int M, int d, int H, long long ldz);
+                 int M, int d, int H, long long ldz, int save_z);
 
 /* ---- StatefulLayer backward (autodiff of the above with the straight-through binary step, README.md:55;
  *      gradient statistics are those of dL/dz, tests/reproduce_grad_sink.py:16-17, sensing.py:62-63) -----
- * dz:      dzT = (dy . w_down^T)^T * (F'(zT) + gate) ; grad_partials (sum|dz|, sum dz (= db_up), sum dz^2)
+ * dz:      dzT = (dy . w_down^T)^T * (F'(zT) + gate) ; grad_partials (sum|dz|, sum dz (= db_up), sum dz^2);
+ *          zT is read only where forde_sl_up_fwd(save_z = 0) would have written it, hT elsewhere; `assign` must be
+ *          the assignment the forward ran with
  * dx:      dx = dz . w_up^T
  * dw_up:   dw_up[d][H]   += x^T . dz      (fp32, accumulated with red.add: caller zeroes or carries grads)
  * dw_down: dw_down[H][d] += h^T . dy
  * db_down: db_down[d]    += sum_m dy */
-int forde_sl_dz_bwd(void* stream, const void* dy, const void* w_down, const void* zT, const int8_t* assign,
-                    void* dzT, float* grad_partials, int M, int d, int H, long long ldz);
+int forde_sl_dz_bwd(void* stream, const void* dy, const void* w_down, const void* zT, const void* hT,
+                    const int8_t* assign, void* dzT, float* grad_partials, int M, int d, int H, long long ldz);
 int forde_sl_dx_bwd(void* stream, const void* dzT, const void* w_up, void* dx, int M, int d, int H,
                     long long ldz);
 int forde_sl_dw_up(void* stream, const void* x, const void* dzT, float* dw_up, int M, int d, int H,

@@ -55,7 +55,7 @@ def check_layer(M, d, H, seed=0):
     db_down = torch.zeros(d, device="cuda"); db_up = torch.zeros(H, device="cuda")
     ops.sl_up_fwd(x, w_up, b_up, assign, zT, hT, actp)
     ops.sl_down_fwd(hT, w_down, b_down, y, M)
-    ops.sl_dz_bwd(dy, w_down, zT, assign, dzT, gradp)
+    ops.sl_dz_bwd(dy, w_down, zT, hT, assign, dzT, gradp)
     ops.sl_dx_bwd(dzT, w_up, dx, M)
     ops.sl_dw_up(x, dzT, dw_up)
     ops.sl_dw_down(hT, dy, dw_down)
@@ -116,7 +116,7 @@ def bench_layer(M, d, H, iters=10):
     steps = {
         "up_fwd": lambda: ops.sl_up_fwd(x, w_up, b_up, assign, zT, hT, actp),
         "down_fwd": lambda: ops.sl_down_fwd(hT, w_down, b_down, y, M),
-        "dz_bwd": lambda: ops.sl_dz_bwd(dy, w_down, zT, assign, dzT, gradp),
+        "dz_bwd": lambda: ops.sl_dz_bwd(dy, w_down, zT, hT, assign, dzT, gradp),
         "dx_bwd": lambda: ops.sl_dx_bwd(dzT, w_up, dx, M),
         "dw_up": lambda: ops.sl_dw_up(x, dzT, dw_up),
         "dw_down": lambda: ops.sl_dw_down(hT, dy, dw_down),

@@ -54,7 +54,7 @@ def test_pure_host_entry_points(lib):
 
 def test_argument_validation_needs_no_gpu(lib):
     # null pointers / bad shapes are rejected on the host before anything touches the device
-    rc = lib.forde_sl_up_fwd(None, None, None, None, None, None, None, None, 16, 16, 16, 16)
+    rc = lib.forde_sl_up_fwd(None, None, None, None, None, None, None, None, 16, 16, 16, 16, 1)
     assert rc == -1
     rc = lib.forde_stats_finalize(None, None, None, 1, 16, 16, None, None, None, None, None, None)
     assert rc == -1

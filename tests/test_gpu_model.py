@@ -100,3 +100,20 @@ def test_cuda_graph_replay_matches_eager_steps(built):
     l2 = float(g(b)[1]["loss"].item())
     assert int(sb_g["step_count"].item()) == 1
     assert abs(l2 - lg[-1]) > 1e-4 and np.isfinite(l2)       # routing changed, so the loss moved
+
+
+def test_fit_runs_fast_and_slow_loops_together(built):
+    """train.py:320-399 cadence: graph-replayed fast steps, slow loop every N steps reading the in-kernel statistics."""
+    from forde_b200 import dual_encoder, train
+
+    cfg = dual_encoder.config_tiny()
+    st = train.create_train_state(cfg, 3, device="cuda")
+    b = {k: v.cuda() for k, v in train.synthetic_batch(cfg, 32, pinned=False).items()}
+    st, hist = train.fit(st, [b] * 7, max_steps=7, slow_loop_interval=3, key=1)
+    assert len(hist["slow_loop"]) == 2                      # steps 3 and 6
+    for diag in hist["slow_loop"]:
+        assert len(diag["layers"]) == 4 and all("census" in d for d in diag["layers"].values())
+    assert np.isfinite(hist["loss"][-1][1])
+    # statistics restarted after the last slow loop (step 6): nothing accumulated since
+    sb = st.variables["stats_buffer"]["vision"]["layer_0"]["stateful_layer"]
+    assert int(sb["step_count"].item()) == 0

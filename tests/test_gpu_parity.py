@@ -87,7 +87,7 @@ def run_layer(ops, M, d, H, assign, seed=0, bias_scale=0.1):
     t["stats"] = torch.zeros((H, 5), device="cuda")
     ops.sl_up_fwd(t["x"], t["w_up"], t["b_up"], t["assign"], t["zT"], t["hT"], t["actp"])
     ops.sl_down_fwd(t["hT"], t["w_down"], t["b_down"], t["y"], M)
-    ops.sl_dz_bwd(t["dy"], t["w_down"], t["zT"], t["assign"], t["dzT"], t["gradp"])
+    ops.sl_dz_bwd(t["dy"], t["w_down"], t["zT"], t["hT"], t["assign"], t["dzT"], t["gradp"])
     ops.sl_dx_bwd(t["dzT"], t["w_up"], t["dx"], M)
     ops.sl_dw_up(t["x"], t["dzT"], t["dw_up"])
     ops.sl_dw_down(t["hT"], t["dy"], t["dw_down"])
@@ -397,3 +397,40 @@ def test_stateful_layer_with_topk_masks_gradients_and_statistics(ops):
     ref = O.calculate_neuron_stats(z, dz)
     np.testing.assert_allclose(st[:, 1], ref[:, 1], rtol=2e-2, atol=1e-5)      # grad_gdp of the MASKED dL/dz
     np.testing.assert_allclose(st[:, 3], ref[:, 3], rtol=2e-2, atol=1e-5)
+
+
+@pytest.mark.parametrize("pattern", ["blocks64", "zeros", "no_tanh_mixed"])
+def test_backward_reads_h_where_z_was_not_saved(ops, pattern):
+    """save_z=0 (the module's default): z^T is only written where a 32-neuron group contains a tanh neuron; elsewhere
+    the backward takes the relu mask from sign(h).  Gradients and statistics must equal the oracle's all the same."""
+    from forde_b200.stateful_layer import StatefulLayer
+    M, d, H = 700, 128, 512
+    a = {"blocks64": (np.arange(H) // 64) % 3, "zeros": np.zeros(H, int),
+         "no_tanh_mixed": np.where(np.arange(H) % 2 == 0, 0, 2)}[pattern]
+    layer = StatefulLayer(hidden_dim=H)
+    assert layer.save_z is False
+    x = torch.randn((M, d), device="cuda").bfloat16().requires_grad_(True)
+    v = layer.init(4, x)
+    v["neuron_assignments"]["assignments"].copy_(torch.as_tensor(a))
+    ps = [v["params"]["up_proj"]["kernel"], v["params"]["up_proj"]["bias"], v["params"]["down_proj"]["kernel"]]
+    ps[1].normal_(0, 0.3)
+    for p_ in ps:
+        p_.requires_grad_(True)
+    # poison the workspace's z^T so a read of an unsaved box cannot go unnoticed
+    y0 = layer.apply(v, x)
+    for ws in layer._ws[(M, H, str(x.device))]:
+        ws.zT.fill_(float("nan"))
+    y, upd = layer.apply(v, x, mutable=["stats_buffer"])
+    dy = torch.randn_like(y)
+    y.backward(dy)
+    torch.cuda.synchronize()
+    wu, wd = f32(ps[0].bfloat16()), f32(ps[2].bfloat16())
+    z = O.bf16_round(f32(x) @ wu + f32(ps[1]))
+    h = O.bf16_round(O.gated_residual(z, a))
+    dz = O.bf16_round((f32(dy) @ wd.T) * (O.multiplex_grad(z, a) + O.gate_of(a)))
+    assert np.isfinite(f32(x.grad)).all()
+    assert relerr(f32(x.grad), O.bf16_round(dz @ wu.T)) < 1e-2
+    assert relerr(f32(ps[0].grad), f32(x).T @ dz) < 1e-2
+    assert relerr(f32(ps[2].grad), h.T @ f32(dy)) < 1e-2
+    st = f32(upd["stats_buffer"]["neuron_stats"])
+    np.testing.assert_allclose(st, O.calculate_neuron_stats(z, dz), rtol=2e-2, atol=2e-4)

@@ -23,6 +23,9 @@ ap.add_argument("--d", type=int, default=768)
 ap.add_argument("--H", type=int, default=3072)
 ap.add_argument("--iters", type=int, default=20)
 ap.add_argument("--once", action="store_true", help="one pass, no timing (for ncu)")
+ap.add_argument("--save-z", type=int, default=0, help="1 = forward writes all of z^T (debug), 0 = only what the backward reads")
+ap.add_argument("--assign", default="mixed", choices=["mixed", "zeros", "blocks"],
+                help="brain map: i.i.d. uniform{0,1,2} | all generalists (init) | contiguous thirds (smoothed map)")
 a = ap.parse_args()
 M, d, H = a.M, a.d, a.H
 g = torch.Generator(device="cuda").manual_seed(0)
@@ -32,6 +35,10 @@ w_down = (torch.randn((H, d), device="cuda", generator=g) / H ** 0.5).bfloat16()
 b_up = torch.randn(H, device="cuda", generator=g) * 0.1
 b_down = torch.randn(d, device="cuda", generator=g) * 0.1
 assign = torch.randint(0, 3, (H,), device="cuda", generator=g).to(torch.int8)
+if a.assign == "zeros":
+    assign.zero_()
+elif a.assign == "blocks":
+    assign = (torch.arange(H, device="cuda") * 3 // H).to(torch.int8)
 dy = torch.randn((M, d), device="cuda", generator=g).bfloat16()
 ld, P = ops.sample_pitch(M), ops.num_partials(M)
 zT = torch.zeros((H, ld), device="cuda", dtype=torch.bfloat16); hT = torch.zeros_like(zT); dzT = torch.zeros_like(zT)
@@ -43,9 +50,9 @@ stats = torch.zeros((H, 5), device="cuda")
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
 
 steps = [
-    ("up_fwd", lambda: ops.sl_up_fwd(x, w_up, b_up, assign, zT, hT, actp)),
+    ("up_fwd", lambda: ops.sl_up_fwd(x, w_up, b_up, assign, zT, hT, actp, save_z=bool(a.save_z))),
     ("down_fwd", lambda: ops.sl_down_fwd(hT, w_down, b_down, y, M)),
-    ("dz_bwd", lambda: ops.sl_dz_bwd(dy, w_down, zT, assign, dzT, gradp)),
+    ("dz_bwd", lambda: ops.sl_dz_bwd(dy, w_down, zT, hT, assign, dzT, gradp)),
     ("dx_bwd", lambda: ops.sl_dx_bwd(dzT, w_up, dx, M)),
     ("dw_up", lambda: ops.sl_dw_up(x, dzT, dw_up)),
     ("dw_down", lambda: ops.sl_dw_down(hT, dy, dw_down)),
@@ -73,7 +80,7 @@ for name, f in steps:
     res[name] = 1e3 * tot / a.iters
 peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {"bf16_tflops": 1590.0, "hbm_gbs": 6650.0}
 fl = 2.0 * M * d * H
-print(f"StatefulLayer M={M} d={d} H={H}  (L2 flushed between launches; peak = {peaks['bf16_tflops']} TF/s burst)")
+print(f"StatefulLayer M={M} d={d} H={H} assignments={a.assign}  (L2 flushed between launches; peak = {peaks['bf16_tflops']} TF/s burst)")
 for name, us in res.items():
     tf = fl / (us * 1e-6) / 1e12 if name not in ("db_down", "finalize") else 0.0
     print(f"  {name:10s} {us:9.1f} us" + (f"  {tf:8.1f} TFLOP/s  {100 * tf / peaks['bf16_tflops']:5.1f}% of burst peak" if tf else ""))
