@@ -37,18 +37,19 @@ __device__ __forceinline__ void stats_from_sums(double a_abs, double a_sum, doub
   out5[4] = static_cast<float>(var);
 }
 
-// block = 32 neurons x FIN_LANES partial-lanes.  Lane y sums partial blocks y, y + FIN_LANES, ... in double,
+// block = FIN_NEUR neurons x FIN_LANES partial-lanes.  Lane y sums partial blocks y, y + FIN_LANES, ... in double,
 // then the lanes are combined in a fixed order: the result does not depend on scheduling (bit-reproducible).
-constexpr int FIN_LANES = 16;
+constexpr int FIN_LANES = 32;
+constexpr int FIN_NEUR = 16;
 
-__global__ void __launch_bounds__(32 * FIN_LANES)
+__global__ void __launch_bounds__(FIN_NEUR * FIN_LANES)
 stats_finalize_kernel(const float* __restrict__ act_p, const float* __restrict__ grad_p, int P, int H, int M,
                       float* __restrict__ step_stats, float* __restrict__ neuron_stats,
                       float* __restrict__ moments, int* sample_count, int* step_count,
                       float* __restrict__ db_up) {
-  __shared__ double red[FIN_LANES][6][33];
+  __shared__ double red[FIN_LANES][6][FIN_NEUR + 1];
   const int tx = threadIdx.x, ty = threadIdx.y;
-  const int h = blockIdx.x * 32 + tx;
+  const int h = blockIdx.x * FIN_NEUR + tx;
   if (blockIdx.x == 0 && tx == 0 && ty == 0) {
     if (sample_count != nullptr) *sample_count += M;
     if (step_count != nullptr) *step_count += 1;
@@ -116,36 +117,41 @@ __global__ void stats_from_moments_kernel(const float* __restrict__ moments, con
 }
 
 // ------------------------------------------------------------------ column sums of a bf16 matrix (db_down)
-// block = 32 x 8 threads: 64 columns (bf16x2 per thread) x 8 row lanes; grid.y splits the rows.
+// block = 32 x 8 threads: a warp covers 256 columns with 16-byte loads, 8 row lanes; grid.y splits the rows.
+// (the scalar tail handles column counts that are not a multiple of 8 or unaligned rows)
 __global__ void colsum_bf16_kernel(const __nv_bfloat16* __restrict__ a, long long lda, float* __restrict__ out,
-                                   int rows, int cols, int rows_per_block) {
-  __shared__ float red[8][64];
+                                   int rows, int cols, int rows_per_block, int vec_ok) {
+  __shared__ float red[8][256 + 8];
   const int tx = threadIdx.x, ty = threadIdx.y;
-  const int c = blockIdx.x * 64 + tx * 2;
+  const int c = blockIdx.x * 256 + tx * 8;
   const int r0 = blockIdx.y * rows_per_block;
   const int r1 = min(rows, r0 + rows_per_block);
-  float s0 = 0.f, s1 = 0.f;
-  if (c + 1 < cols) {
+  float s[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (vec_ok && c + 7 < cols) {
     for (int r = r0 + ty; r < r1; r += 8) {
-      const __nv_bfloat162 v = *reinterpret_cast<const __nv_bfloat162*>(a + static_cast<size_t>(r) * lda + c);
-      s0 += __low2float(v);
-      s1 += __high2float(v);
+      const uint4 q = __ldg(reinterpret_cast<const uint4*>(a + static_cast<size_t>(r) * lda + c));
+      const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        s[2 * i] += __uint_as_float(w[i] << 16);
+        s[2 * i + 1] += __uint_as_float(w[i] & 0xFFFF0000u);
+      }
     }
-  } else if (c < cols) {
-    for (int r = r0 + ty; r < r1; r += 8) s0 += __bfloat162float(a[static_cast<size_t>(r) * lda + c]);
+  } else {
+    for (int r = r0 + ty; r < r1; r += 8) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        if (c + i < cols) s[i] += __bfloat162float(a[static_cast<size_t>(r) * lda + c + i]);
+    }
   }
-  red[ty][tx * 2] = s0;
-  red[ty][tx * 2 + 1] = s1;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) red[ty][tx * 8 + i] = s[i];
   __syncthreads();
-  if (ty == 0) {
+  const int t = ty * 32 + tx;  // 256 threads: one column each
+  float acc = 0.f;
 #pragma unroll
-    for (int k = 0; k < 2; ++k) {
-      float s = 0.f;
-#pragma unroll
-      for (int y = 0; y < 8; ++y) s += red[y][tx * 2 + k];
-      if (c + k < cols) atomicAdd(out + c + k, s);
-    }
-  }
+  for (int y = 0; y < 8; ++y) acc += red[y][t];
+  if (blockIdx.x * 256 + t < cols) atomicAdd(out + blockIdx.x * 256 + t, acc);
 }
 
 // ------------------------------------------------------------------ CLIP loss helpers (README.md:35)
@@ -319,7 +325,7 @@ int forde_stats_finalize(void* stream, const float* act_partials, const float* g
                          int* sample_count, int* step_count, float* db_up) {
   if (H <= 0 || M <= 0 || num_partials <= 0) return FORDE_EINVAL;
   if (act_partials == nullptr && grad_partials == nullptr) return FORDE_EINVAL;
-  stats_finalize_kernel<<<(H + 31) / 32, dim3(32, FIN_LANES), 0, static_cast<cudaStream_t>(stream)>>>(
+  stats_finalize_kernel<<<(H + FIN_NEUR - 1) / FIN_NEUR, dim3(FIN_NEUR, FIN_LANES), 0, static_cast<cudaStream_t>(stream)>>>(
       act_partials, grad_partials, num_partials, H, M, step_stats, neuron_stats, moments, sample_count,
       step_count, db_up);
   return check_launch("stats_finalize_kernel");
@@ -337,7 +343,7 @@ int forde_stats_from_moments(void* stream, const float* moments, const int* samp
 int forde_colsum_bf16(void* stream, const void* a, long long lda, float* out, int rows, int cols) {
   if (a == nullptr || out == nullptr || rows <= 0 || cols <= 0) return FORDE_EINVAL;
   if ((lda & 1) != 0 || (reinterpret_cast<uintptr_t>(a) & 3) != 0) return FORDE_EALIGN;
-  const int col_blocks = (cols + 63) / 64;
+  const int col_blocks = (cols + 255) / 256;
   int sms = sm_count();
   if (sms <= 0) return FORDE_ENODEV;
   int row_blocks = (4 * sms + col_blocks - 1) / col_blocks;
@@ -346,8 +352,9 @@ int forde_colsum_bf16(void* stream, const void* a, long long lda, float* out, in
   if (row_blocks < 1) row_blocks = 1;
   const int rows_per_block = (rows + row_blocks - 1) / row_blocks;
   row_blocks = (rows + rows_per_block - 1) / rows_per_block;
+  const int vec_ok = ((lda & 7) == 0 && (reinterpret_cast<uintptr_t>(a) & 15) == 0) ? 1 : 0;
   colsum_bf16_kernel<<<dim3(col_blocks, row_blocks), dim3(32, 8), 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const __nv_bfloat16*>(a), lda, out, rows, cols, rows_per_block);
+      static_cast<const __nv_bfloat16*>(a), lda, out, rows, cols, rows_per_block, vec_ok);
   return check_launch("colsum_bf16_kernel");
 }
 
