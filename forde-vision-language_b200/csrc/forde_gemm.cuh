@@ -69,19 +69,21 @@ constexpr int TMEM_COLS = 512;
 // Epilogue warps per CTA.  The fused epilogues are instruction/latency heavy (bf16 round trip, multiplex, gate FMA,
 // three running sums per element); 8 warps = 2 per SM sub-partition, 16 = 4 (one 64-column chunk each per tile).
 // More warps cost staging smem, i.e. main-loop stages; the trade-off differs per kernel, see below.
-// Measured at C2 dims (profiles/r1_exp7_variants.txt): up_fwd 8 warps / 5 stages 217 us vs 16 / 3 251 us (its
-// main loop starves with 3 stages); dz_bwd 16 / 3 226 us vs 8 / 5 245 us.  -D overrides are for A/B builds.
+// Measured at C2 dims: with the first (heavier) epilogues dz_bwd preferred 16 warps / 3 stages (226 us vs 245 us,
+// profiles/r1_exp7_variants.txt); after the warp-uniform, branch-free epilogues 8 warps / 5 stages wins for both
+// fused kernels (dz_bwd 192 us vs 221 us, profiles/r1_exp11_dz_variants.txt): the main loop starves with 3 stages.
+// -D overrides are for A/B builds.
 #ifndef FORDE_UP_WARPS
 #define FORDE_UP_WARPS 8
 #endif
 #ifndef FORDE_DZ_WARPS
-#define FORDE_DZ_WARPS 16
+#define FORDE_DZ_WARPS 8
 #endif
 #ifndef FORDE_UP_STAGES
 #define FORDE_UP_STAGES 5
 #endif
 #ifndef FORDE_DZ_STAGES
-#define FORDE_DZ_STAGES 3
+#define FORDE_DZ_STAGES 5
 #endif
 __host__ __device__ constexpr int epi_warps(int epi, bool pair) {
   return !pair ? 8 : epi == EPI_UP_FWD ? FORDE_UP_WARPS : epi == EPI_DZ_BWD ? FORDE_DZ_WARPS : 8;
