@@ -25,7 +25,9 @@ _ALIGN = 64  # elements; keeps every bf16 mirror view 128-byte aligned (TMA need
 
 
 def _leaves(tree, path=()):
-    for k in sorted(tree):
+    # insertion order (vision: embeds, layer_0..L-1, proj; text: ...; log_temp): contiguous layer ranges in the flat
+    # buffers are what the bucketed gradient all-reduce slices
+    for k in tree:
         v = tree[k]
         if isinstance(v, dict):
             yield from _leaves(v, path + (k,))
@@ -37,6 +39,12 @@ def _set(tree, path, value):
     for k in path[:-1]:
         tree = tree[k]
     tree[path[-1]] = value
+
+
+def _get(tree, path):
+    for k in path:
+        tree = tree[k]
+    return tree
 
 
 def _mirror_tree(tree):
@@ -55,6 +63,7 @@ class TrainState:
     opt: torch.optim.Optimizer
     group: Optional["dist.ProcessGroup"] = None
     max_grad_norm: float = 1.0
+    buckets: Optional[list] = None      # gradient all-reduce buckets (see _GradBuckets)
 
     @property
     def params(self):
@@ -91,7 +100,81 @@ def create_train_state(config: DualEncoderConfig, key: int, learning_rate: float
     # optax.adamw(lr, wd) decays every leaf (no mask, train.py:74-77), so one flat parameter is equivalent
     opt = torch.optim.AdamW([flat_p32], lr=learning_rate, weight_decay=weight_decay, betas=(0.9, 0.999), eps=1e-8,
                             fused=dev.type == "cuda", capturable=dev.type == "cuda")
-    return TrainState(0, model, variables, p16_tree, flat_p32, flat_g32, flat_p16, opt, group)
+    state = TrainState(0, model, variables, p16_tree, flat_p32, flat_g32, flat_p16, opt, group)
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        state.buckets = _GradBuckets(leaves, offs, total, flat_g32, group)
+        state.buckets.attach([_get(variables["params"], path) for path, _ in leaves])
+    return state
+
+
+class _GradBuckets:
+    """Bucketed data-parallel gradient exchange overlapped with the backward pass.
+
+    The flat gradient buffer is cut into a few contiguous ranges (groups of transformer layers per tower).  Every
+    parameter has a post-accumulate hook; when the last gradient of a range has been accumulated its SUM all-reduce
+    is issued asynchronously (NCCL's own stream, ordered after the kernels that produced the gradients), so it runs
+    under the rest of the backward.  `finish()` issues whatever did not fire and makes the compute stream wait."""
+
+    def __init__(self, leaves, offs, total, flat_g32, group, layers_per_bucket: int = 4):
+        self.flat, self.group = flat_g32, group
+        ranges = []  # (key, start, end, count)
+        for (path, t), off in zip(leaves, offs):
+            tower = path[0]
+            layer = next((k for k in path if k.startswith("layer_")), None)
+            if layer is not None:
+                idx = int(layer.split("_")[1]) // layers_per_bucket
+            elif len(path) > 1 and ("embed" in path[1] or path[1] == "cls"):
+                idx = -1            # front end of the tower: its gradients arrive last
+            else:
+                idx = 10 ** 6       # projection head / log-temperature: arrive first
+            key = (tower, idx)
+            end = off + (t.numel() + _ALIGN - 1) // _ALIGN * _ALIGN
+            if ranges and ranges[-1][0] == key:
+                ranges[-1][2], ranges[-1][3] = end, ranges[-1][3] + 1
+            else:
+                ranges.append([key, off, end, 1])
+        self.ranges = ranges
+        self.pending = [r[3] for r in ranges]
+        self.works = []
+        self.fired = [False] * len(ranges)
+        self.enabled = False
+
+    def attach(self, params_in_order):
+        """params_in_order: the leaf tensors in the same order as `leaves`."""
+        i = 0
+        for bi, r in enumerate(self.ranges):
+            for _ in range(r[3]):
+                params_in_order[i].register_post_accumulate_grad_hook(self._make_hook(bi))
+                i += 1
+
+    def _make_hook(self, bi):
+        def hook(_param):
+            if not self.enabled:
+                return
+            self.pending[bi] -= 1
+            if self.pending[bi] == 0:
+                self._fire(bi)
+        return hook
+
+    def _fire(self, bi):
+        _, a, b, _ = self.ranges[bi]
+        self.works.append(dist.all_reduce(self.flat[a:b], op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+        self.fired[bi] = True
+
+    def begin(self):
+        self.enabled = True
+        self.pending = [r[3] for r in self.ranges]
+        self.fired = [False] * len(self.ranges)
+        self.works = []
+
+    def finish(self):
+        self.enabled = False
+        for bi in range(len(self.ranges)):
+            if not self.fired[bi]:      # a range whose parameters did not all receive gradients this step
+                self._fire(bi)
+        for w in self.works:
+            w.wait()
+        self.works = []
 
 
 def sync_gradients(flat_g32: torch.Tensor, group=None) -> None:
@@ -115,8 +198,13 @@ def train_step(state: TrainState, batch: Dict[str, torch.Tensor], sense: bool = 
     state.flat_g32.zero_()
     loss, _ = state.model.apply(state.variables, images, ids, mutable=["stats_buffer"] if sense else [],
                                 params_bf16=state.params_bf16, group=state.group)
-    loss.backward()
-    sync_gradients(state.flat_g32, state.group)
+    if state.buckets is not None:
+        state.buckets.begin()
+        loss.backward()
+        state.buckets.finish()          # bucketed SUM all-reduce, overlapped with the backward
+    else:
+        loss.backward()
+        sync_gradients(state.flat_g32, state.group)
     gnorm = state.flat_g32.norm()
     state.flat_g32.mul_(torch.clamp(state.max_grad_norm / (gnorm + 1e-6), max=1.0))   # optax.clip_by_global_norm
     state.opt.step()

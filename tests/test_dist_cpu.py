@@ -156,3 +156,59 @@ def test_two_rank_gradient_sum_and_pooled_moments():
     for rank, g, stats in res:
         np.testing.assert_array_equal(g, np.full(10, 3.0, np.float32))
         np.testing.assert_allclose(stats, ref, rtol=1e-4, atol=1e-6)
+
+
+def _bucket_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import forde_b200  # noqa: F401
+        from forde_b200 import train
+        tree = {"vision": {"patch_embed": {"kernel": torch.ones(70)},
+                           "layer_0": {"w": torch.ones(100)}, "layer_5": {"w": torch.ones(33)},
+                           "proj": {"kernel": torch.ones(10)}},
+                "text": {"token_embed": torch.ones(20), "layer_0": {"w": torch.ones(64)}},
+                "log_temp": torch.ones(())}
+        leaves = list(train._leaves(tree))
+        offs, total = [], 0
+        for _, t in leaves:
+            offs.append(total); total += (t.numel() + 63) // 64 * 64
+        flat_p = torch.zeros(total); flat_g = torch.zeros(total)
+        params = []
+        for (path, t), off in zip(leaves, offs):
+            p = flat_p[off:off + t.numel()].view(t.shape)
+            p.copy_(t); p.requires_grad_(True); p.grad = flat_g[off:off + t.numel()].view(t.shape)
+            params.append(p)
+        b = train._GradBuckets(leaves, offs, total, flat_g, None)
+        b.attach(params)
+        assert [r[0] for r in b.ranges] == [("vision", -1), ("vision", 0), ("vision", 1), ("vision", 10 ** 6),
+                                            ("text", -1), ("text", 0), ("log_temp", 10 ** 6)]
+        for step in range(2):                                   # counters must re-arm every step
+            flat_g.zero_()
+            b.begin()
+            used = params[:-2] + params[-1:]                    # text/layer_0 gets no gradient: finish() must cover it
+            loss = sum(((rank + 1) * (i + 1)) * p.sum() for i, p in enumerate(used))
+            loss.backward()
+            b.finish()
+        q.put((rank, flat_g.clone().numpy(), [(o, t.numel()) for (_, t), o in zip(leaves, offs)]))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_bucketed_gradient_allreduce():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_bucket_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, g, layout in res:
+        used = layout[:-2] + layout[-1:]
+        for i, (off, n) in enumerate(used):
+            np.testing.assert_array_equal(g[off:off + n], np.full(n, 3.0 * (i + 1), np.float32))   # (1 + 2) * (i+1)
+        off, n = layout[-2]
+        np.testing.assert_array_equal(g[off:off + n], np.zeros(n, np.float32))
