@@ -1,6 +1,6 @@
 """Bring-up script (not a pytest file): exercises every kernel family once and prints error metrics.
 
-Run on a B200:  python tests/gpu_debug.py
+Run on a B200:  python tools/gpu_bringup.py
 """
 import os
 import sys
