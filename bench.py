@@ -178,14 +178,17 @@ def run_gpu(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(batches, steps, read_loss, step_fn=None):
+    def timed(batches, steps, read_loss, step_fn=None, prefetch=False):
         step_fn = step_fn or (lambda b: train.train_step(state, b))
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         last = None
         for i in range(steps):
-            _, m = step_fn(batches[i % len(batches)])
+            if prefetch:   # start the NEXT batch's H2D copy on a side stream while this step computes
+                _, m = step_fn(batches[i % len(batches)], prefetch=batches[(i + 1) % len(batches)])
+            else:
+                _, m = step_fn(batches[i % len(batches)])
             if read_loss:
                 last = float(m["loss"].item())      # D2H of the step's result inside the timed region
         e1.record()
@@ -233,7 +236,7 @@ def run_gpu(args):
     # ---- end to end: host (pinned) batches -> public train-step API -> loss on the host, every step
     for i in range(2):
         (step_fn or (lambda b: train.train_step(state, b)))(host[i % 2])
-    ms_e2e, loss = timed(host, args.steps, read_loss=True, step_fn=step_fn)
+    ms_e2e, loss = timed(host, args.steps, read_loss=True, step_fn=step_fn, prefetch=graphed)
     e2e = world * args.batch * args.steps / (ms_e2e * 1e-3)
 
     def finish():

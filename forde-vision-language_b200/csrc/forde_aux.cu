@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdint>
+#include <mutex>
 
 #include "../../include/forde_b200.h"
 #include "forde_host.h"
@@ -577,11 +578,10 @@ int forde_sl_topk_sparsify(void* stream, void* hT, long long ldz, int M, int H, 
   if (hT == nullptr || M <= 0 || H <= 0 || k <= 0 || k > H || ldz < M) return FORDE_EINVAL;
   const int smem = forde::TK_TOK * H * 2 + forde::TK_TOK * k * 4;
   if (smem > 200 * 1024) return FORDE_EINVAL;
-  static bool attr = false;
-  if (!attr) {
+  static std::once_flag once;
+  std::call_once(once, [] {
     cudaFuncSetAttribute(forde::topk_sparsify_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    attr = true;
-  }
+  });
   forde::topk_sparsify_kernel<<<(M + forde::TK_TOK - 1) / forde::TK_TOK, forde::TK_TOK * 32, smem,
                                 static_cast<cudaStream_t>(stream)>>>(static_cast<__nv_bfloat16*>(hT), ldz, M, H, k,
                                                                      idx_out, hoyer_out, keep_bits);

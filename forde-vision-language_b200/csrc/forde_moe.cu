@@ -7,6 +7,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdint>
+#include <mutex>
 
 #include "../../include/forde_b200.h"
 #include "forde_host.h"
@@ -347,11 +348,10 @@ int forde_moe_route(void* stream, const void* x, const void* w_r, const float* b
   cudaMemsetAsync(counts, 0, sizeof(int) * E, st);
 #define FORDE_ROUTER(EE)                                                                                         \
   do {                                                                                                           \
-    static bool attr = false;                                                                                    \
-    if (!attr) {                                                                                                 \
+    static std::once_flag once;                                                                                  \
+    std::call_once(once, [] {                                                                                    \
       cudaFuncSetAttribute(moe_router_kernel<EE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);      \
-      attr = true;                                                                                               \
-    }                                                                                                            \
+    });                                                                                                          \
     moe_router_kernel<EE><<<grid, 256, smem, st>>>(static_cast<const __nv_bfloat16*>(x),                         \
                                                    static_cast<const __nv_bfloat16*>(w_r), b_r, M, d, k, logits, \
                                                    probs, topk_idx, topk_w, counts, prob_partials);              \

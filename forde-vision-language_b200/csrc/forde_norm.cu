@@ -7,6 +7,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdint>
+#include <mutex>
 
 #include "../../include/forde_b200.h"
 #include "forde_host.h"
@@ -268,14 +269,13 @@ int forde_add_layernorm_bwd(void* stream, const void* dy, const void* x, const v
   if (grid <= 0) return FORDE_ENODEV;
   const int smem = LN_WARPS * 2 * cols * static_cast<int>(sizeof(float));
   const int max_smem = LN_WARPS * 2 * 32 * LN_MAXV * 8 * static_cast<int>(sizeof(float));
-  static bool attr_set = false;
-  if (!attr_set) {
+  static std::once_flag once;
+  std::call_once(once, [max_smem] {
     cudaFuncSetAttribute(add_layernorm_bwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
     cudaFuncSetAttribute(add_layernorm_bwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
     cudaFuncSetAttribute(add_layernorm_bwd_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
     cudaFuncSetAttribute(add_layernorm_bwd_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
-    attr_set = true;
-  }
+  });
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int nv = (cols / 8 + 31) / 32;
 #define FORDE_LN_BWD(NV)                                                                                         \

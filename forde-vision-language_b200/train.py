@@ -237,16 +237,40 @@ class GraphedTrainStep:
                 train_step(state, self.static, sense)
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
+        self._staging, self._copy_stream, self._staged_for, self._d2d_done = None, None, None, None
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
             _, self.metrics = train_step(state, self.static, sense)
         torch.cuda.synchronize(dev)
 
-    def __call__(self, batch: Dict[str, torch.Tensor]):
-        for k, v in batch.items():
-            if v.data_ptr() != self.static[k].data_ptr():
-                self.static[k].copy_(v, non_blocking=True)
+    def __call__(self, batch: Dict[str, torch.Tensor], prefetch: Optional[Dict[str, torch.Tensor]] = None):
+        """Run one step on ``batch``.  ``prefetch`` (optional) is the NEXT step's host batch: its host-to-device copy
+        is started on a side stream into a staging buffer so it overlaps this step's compute; pass that same batch
+        object as ``batch`` next time and only a device-to-device move remains on the critical path."""
+        dev = self.state.flat_p32.device
+        cur = torch.cuda.current_stream(dev)
+        if self._staged_for is not None and self._staged_for is batch:
+            cur.wait_stream(self._copy_stream)
+            for k in self.static:
+                self.static[k].copy_(self._staging[k], non_blocking=True)
+            self._d2d_done = torch.cuda.Event()
+            self._d2d_done.record(cur)          # the staging buffers may be refilled once this has passed
+        else:
+            for k, v in batch.items():
+                if v.data_ptr() != self.static[k].data_ptr():
+                    self.static[k].copy_(v, non_blocking=True)
+        self._staged_for = None
         self.graph.replay()
+        if prefetch is not None:
+            if self._staging is None:
+                self._staging = {k: torch.empty_like(v) for k, v in self.static.items()}
+                self._copy_stream = torch.cuda.Stream(device=dev)
+            if self._d2d_done is not None:
+                self._copy_stream.wait_event(self._d2d_done)   # NOT wait_stream(cur): that would wait for this step
+            with torch.cuda.stream(self._copy_stream):
+                for k, v in prefetch.items():
+                    self._staging[k].copy_(v, non_blocking=True)
+            self._staged_for = prefetch
         self.state.step += 1
         return self.state, self.metrics
 

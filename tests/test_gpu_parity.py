@@ -434,3 +434,16 @@ def test_backward_reads_h_where_z_was_not_saved(ops, pattern):
     assert relerr(f32(ps[2].grad), h.T @ f32(dy)) < 1e-2
     st = f32(upd["stats_buffer"]["neuron_stats"])
     np.testing.assert_allclose(st, O.calculate_neuron_stats(z, dz), rtol=2e-2, atol=2e-4)
+
+
+def test_module_edge_cases_empty_batch_and_bad_widths(ops):
+    from forde_b200.stateful_layer import StatefulLayer
+    layer = StatefulLayer(hidden_dim=256)
+    x = torch.zeros((0, 7, 64), device="cuda", dtype=torch.bfloat16)
+    v = layer.init(0, x)
+    y, upd = layer.apply(v, x, mutable=["stats_buffer"])
+    assert y.shape == (0, 7, 64) and int(upd["stats_buffer"]["step_count"].item()) == 0
+    bad = StatefulLayer(hidden_dim=100)
+    xb = torch.zeros((4, 64), device="cuda", dtype=torch.bfloat16)
+    with pytest.raises(ValueError, match="multiples of 8"):
+        bad.apply(bad.init(0, xb), xb)
