@@ -185,7 +185,7 @@ class StatefulLayer:
             x2d = x2d.to(torch.bfloat16)
         x2d = x2d.contiguous()
         if x2d.shape[0] == 0:  # empty batch: nothing to launch, nothing to sense
-            y = x2d.new_zeros((0, p["down_proj"]["kernel"].shape[1])).reshape(*lead, -1)
+            y = x2d.new_zeros((*lead, p["down_proj"]["kernel"].shape[1]))
             return y if (isinstance(mutable, bool) and not mutable) else (y, {k: variables[k] for k in mut if k in variables})
         if x2d.shape[1] % 8 != 0 or self.hidden_dim % 8 != 0:
             raise ValueError("StatefulLayer needs feature sizes that are multiples of 8 (16-byte TMA rows): "
