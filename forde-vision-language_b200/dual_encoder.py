@@ -23,7 +23,7 @@ import torch.nn.functional as F
 
 from . import ops
 from .clip_loss import INIT_LOG_TEMP, clip_contrastive_loss
-from .stateful_layer import StatefulLayer, new_stats_buffer
+from .stateful_layer import StatefulLayer, grad_delivered, grad_sink, new_stats_buffer
 
 
 @dataclass
@@ -85,6 +85,18 @@ def _colsum(dy2d):
     return out
 
 
+def _deliver_dense_grads(w, b, x2t, dy2):
+    """dW = x^T dy and db = colsum(dy) for a Dense whose masters are (w, b).  With gradient sinks attached (train
+    state) they are accumulated in place and (None, None) is returned to autograd; otherwise fresh tensors."""
+    sw, sb = grad_sink(w), grad_sink(b)
+    if sw is not None and sb is not None:
+        sw.add_(torch.mm(x2t, dy2))
+        ops.colsum_bf16(dy2, sb)
+        grad_delivered(w); grad_delivered(b)
+        return None, None
+    return torch.mm(x2t, dy2).float(), _colsum(dy2)
+
+
 class _Dense(torch.autograd.Function):
     """y = x W + b for bf16 activations (cuBLAS GEMMs; the bias gradient is this repository's column-sum kernel
     instead of a generic strided reduction).  `w16` is the bf16 mirror (in, out); gradients go to the fp32 masters."""
@@ -95,6 +107,7 @@ class _Dense(torch.autograd.Function):
         y = torch.addmm(b16, x2, w16)
         ctx.save_for_backward(x2, w16)
         ctx.lead = x.shape[:-1]
+        ctx.masters = (w, b)
         return y.view(*x.shape[:-1], w16.shape[1])
 
     @staticmethod
@@ -104,8 +117,8 @@ class _Dense(torch.autograd.Function):
         if not dy2.is_contiguous():
             dy2 = dy2.contiguous()
         dx = torch.mm(dy2, w16.t()).view(*ctx.lead, w16.shape[0])
-        dw = torch.mm(x2.t(), dy2).float()
-        return dx, dw, _colsum(dy2), None, None
+        dw, db = _deliver_dense_grads(ctx.masters[0], ctx.masters[1], x2.t(), dy2)
+        return dx, dw, db, None, None
 
 
 class _QKVDense(torch.autograd.Function):
@@ -117,6 +130,7 @@ class _QKVDense(torch.autograd.Function):
         x2 = x.reshape(-1, x.shape[-1])
         ctx.save_for_backward(x2, wq16, wk16, wv16)
         ctx.shape = x.shape
+        ctx.masters = ((wq, bq), (wk, bk), (wv, bv))
         return tuple(torch.addmm(b, x2, w).view(x.shape) for w, b in ((wq16, bq16), (wk16, bk16), (wv16, bv16)))
 
     @staticmethod
@@ -129,8 +143,8 @@ class _QKVDense(torch.autograd.Function):
         dx.addmm_(d[2], wv16.t())
         xt = x2.t()
         grads = []
-        for t in d:
-            grads += [torch.mm(xt, t).float(), _colsum(t)]
+        for t, (w, b) in zip(d, ctx.masters):
+            grads += list(_deliver_dense_grads(w, b, xt, t))
         return (dx.view(ctx.shape), *grads, None, None, None, None, None, None)
 
 
@@ -142,12 +156,19 @@ class _AddLayerNorm(torch.autograd.Function):
         x = x.contiguous(); r = r.contiguous()
         out, mean, rstd = ops.add_layernorm_fwd(x, r, gamma, beta, 1e-6)
         ctx.save_for_backward(x, r, gamma, mean, rstd)
+        ctx.masters = (gamma, beta)
         return out
 
     @staticmethod
     def backward(ctx, dy):
         x, r, gamma, mean, rstd = ctx.saved_tensors
-        ds, dg, db = ops.add_layernorm_bwd(dy.contiguous(), x, r, gamma, mean, rstd)
+        sg, sb = grad_sink(ctx.masters[0]), grad_sink(ctx.masters[1])
+        direct = sg is not None and sb is not None
+        ds, dg, db = ops.add_layernorm_bwd(dy.contiguous(), x, r, gamma, mean, rstd, d_gamma=sg if direct else None,
+                                           d_beta=sb if direct else None)
+        if direct:
+            grad_delivered(ctx.masters[0]); grad_delivered(ctx.masters[1])
+            return ds, ds, None, None
         return ds, ds, dg, db
 
 

@@ -309,16 +309,19 @@ def add_layernorm_fwd(x, r, gamma, beta, eps: float = 1e-6):
     return out, mean, rstd
 
 
-def add_layernorm_bwd(dy, x, r, gamma, mean, rstd):
-    """returns (ds, d_gamma, d_beta); ds is the gradient of both x and r."""
+def add_layernorm_bwd(dy, x, r, gamma, mean, rstd, d_gamma=None, d_beta=None):
+    """returns (ds, d_gamma, d_beta); ds is the gradient of both x and r.  d_gamma / d_beta (fp32, accumulated
+    into) may be supplied."""
     _req(dy, torch.bfloat16, "dy")
     cols = x.shape[-1]
     rows = x.numel() // cols
     ds = torch.empty_like(x)
     nb = _lib.load().forde_ln_num_partials(rows)
     partials = torch.empty((nb, 2, cols), dtype=torch.float32, device=x.device)
-    d_gamma = torch.zeros(cols, dtype=torch.float32, device=x.device)
-    d_beta = torch.zeros(cols, dtype=torch.float32, device=x.device)
+    if d_gamma is None:
+        d_gamma = torch.zeros(cols, dtype=torch.float32, device=x.device)
+    if d_beta is None:
+        d_beta = torch.zeros(cols, dtype=torch.float32, device=x.device)
     rc = _lib.load().forde_add_layernorm_bwd(_stream(), dy.data_ptr(), x.data_ptr(), _ptr(r), gamma.data_ptr(),
                                              mean.data_ptr(), rstd.data_ptr(), ds.data_ptr(), partials.data_ptr(),
                                              d_gamma.data_ptr(), d_beta.data_ptr(), rows, cols)

@@ -64,6 +64,21 @@ def _dz_scratch(H: int, ld: int, device) -> torch.Tensor:
     return t
 
 
+def grad_sink(p: torch.Tensor):
+    """A train state may attach to a master parameter the fp32 buffer its gradient must end up in (a view of the flat
+    gradient buffer, ``p._forde_grad``) and a callback to run once it is there (``p._forde_ready``, the bucketed
+    all-reduce trigger).  Kernels that ACCUMULATE (red.add dW GEMMs, column sums, the finalisation's db_up) then
+    write straight into it and the autograd function returns None for that input: no temporary, no zero fill, no
+    AccumulateGrad add."""
+    return getattr(p, "_forde_grad", None)
+
+
+def grad_delivered(p: torch.Tensor) -> None:
+    cb = getattr(p, "_forde_ready", None)
+    if cb is not None:
+        cb(p)
+
+
 class _StatefulLayerFn(torch.autograd.Function):
     """fwd: two GEMM launches (up + fused epilogue, down).  bwd: dz (fused), dx, dW_up, dW_down, db, sensing."""
 
@@ -86,6 +101,7 @@ class _StatefulLayerFn(torch.autograd.Function):
         ctx.save_for_backward(x2d, w_up16, w_down16)
         ctx.layer, ctx.ws, ctx.stats, ctx.assign_i8 = layer, ws, stats, assign_i8
         ctx.param_dtypes = (w_up.dtype, b_up.dtype, w_down.dtype, b_down.dtype)
+        ctx.masters = (w_up, b_up, w_down, b_down)
         ctx.needs_dx = ctx.needs_input_grad[0]
         will_backward = any(ctx.needs_input_grad)
         ws.in_flight = will_backward
@@ -113,11 +129,16 @@ class _StatefulLayerFn(torch.autograd.Function):
         if ctx.needs_dx:
             dx = torch.empty((M, d), dtype=torch.bfloat16, device=dev)
             ops.sl_dx_bwd(dzT, w_up16, dx, M)
-        dw_up = torch.zeros((d, H), dtype=torch.float32, device=dev)
         d_out = dy.shape[1]
-        dw_down = torch.zeros((H, d_out), dtype=torch.float32, device=dev)
-        db_up = torch.zeros(H, dtype=torch.float32, device=dev)
-        db_down = torch.zeros(d_out, dtype=torch.float32, device=dev)
+        sinks = [grad_sink(m) for m in ctx.masters]
+        direct = all(s is not None for s in sinks)      # accumulate straight into the train state's gradient views
+        if direct:
+            dw_up, db_up, dw_down, db_down = sinks
+        else:
+            dw_up = torch.zeros((d, H), dtype=torch.float32, device=dev)
+            dw_down = torch.zeros((H, d_out), dtype=torch.float32, device=dev)
+            db_up = torch.zeros(H, dtype=torch.float32, device=dev)
+            db_down = torch.zeros(d_out, dtype=torch.float32, device=dev)
         ops.sl_dw_up(x2d, dzT, dw_up)
         ops.sl_dw_down(ws.hT, dy, dw_down)
         ops.colsum_bf16(dy, db_down)
@@ -126,6 +147,10 @@ class _StatefulLayerFn(torch.autograd.Function):
         else:
             ops.stats_finalize(None, ws.grad_partials, ws.P, H, M, db_up=db_up)
         ws.in_flight = False
+        if direct:
+            for m in ctx.masters:
+                grad_delivered(m)
+            return dx, None, None, None, None, None, None, None, None
         return dx, dw_up, db_up, dw_down, db_down, None, None, None, None
 
 

@@ -93,6 +93,7 @@ def create_train_state(config: DualEncoderConfig, key: int, learning_rate: float
         flat_p32[off:off + n].copy_(t.reshape(-1))
         p = flat_p32[off:off + n].view(t.shape).requires_grad_(True)
         p.grad = flat_g32[off:off + n].view(t.shape)
+        p._forde_grad = p.grad          # gradient sink for the functions that accumulate in place (grad_sink)
         _set(variables["params"], path, p)
         _set(p16_tree, path, flat_p16[off:off + n].view(t.shape))
     flat_p16.copy_(flat_p32)
@@ -140,11 +141,15 @@ class _GradBuckets:
         self.enabled = False
 
     def attach(self, params_in_order):
-        """params_in_order: the leaf tensors in the same order as `leaves`."""
+        """params_in_order: the leaf tensors in the same order as `leaves`.  The hook fires from autograd's
+        AccumulateGrad, or is called directly (``p._forde_ready``) by the functions that write into the gradient views
+        themselves (stateful_layer.grad_sink)."""
         i = 0
         for bi, r in enumerate(self.ranges):
             for _ in range(r[3]):
-                params_in_order[i].register_post_accumulate_grad_hook(self._make_hook(bi))
+                hook = self._make_hook(bi)
+                params_in_order[i].register_post_accumulate_grad_hook(hook)
+                params_in_order[i]._forde_ready = hook
                 i += 1
 
     def _make_hook(self, bi):
@@ -273,6 +278,43 @@ class GraphedTrainStep:
             self._staged_for = prefetch
         self.state.step += 1
         return self.state, self.metrics
+
+
+def save_checkpoint(state: TrainState, path: str) -> None:
+    """Save params, neuron_assignments, the stat accumulators, the optimizer moments and the step counter (the
+    reference saves the whole TrainState once at the end, src/training/train.py:412-422, and has no restore)."""
+    torch.save({"step": state.step, "config": state.model.cfg, "flat_p32": state.flat_p32.detach().cpu(),
+                "opt": state.opt.state_dict(),
+                "neuron_assignments": _tree_to(state.variables["neuron_assignments"], "cpu"),
+                "stats_buffer": _tree_to(state.variables["stats_buffer"], "cpu")}, path)
+
+
+def restore_checkpoint(state: TrainState, path: str) -> TrainState:
+    """Load a checkpoint written by save_checkpoint into an already created TrainState of the same config, in place
+    (parameter views, bf16 mirror, brain maps and accumulators keep their addresses, so captured CUDA graphs and
+    cached TMA descriptors stay valid)."""
+    ck = torch.load(path, map_location="cpu", weights_only=False)
+    if ck["flat_p32"].numel() != state.flat_p32.numel():
+        raise ValueError("checkpoint does not match this model configuration")
+    state.flat_p32.detach().copy_(ck["flat_p32"])
+    state.flat_p16.copy_(state.flat_p32)
+    state.opt.load_state_dict(ck["opt"])
+    _tree_copy_(state.variables["neuron_assignments"], ck["neuron_assignments"])
+    _tree_copy_(state.variables["stats_buffer"], ck["stats_buffer"])
+    state.step = int(ck["step"])
+    return state
+
+
+def _tree_to(tree, device):
+    return {k: (_tree_to(v, device) if isinstance(v, dict) else v.detach().to(device)) for k, v in tree.items()}
+
+
+def _tree_copy_(dst, src):
+    for k, v in dst.items():
+        if isinstance(v, dict):
+            _tree_copy_(v, src[k])
+        else:
+            v.copy_(src[k])
 
 
 def fit(state: TrainState, batches, max_steps: int, slow_loop_interval: int = 100, slow_loop_config=None, key: int = 0,

@@ -447,3 +447,33 @@ def test_module_edge_cases_empty_batch_and_bad_widths(ops):
     xb = torch.zeros((4, 64), device="cuda", dtype=torch.bfloat16)
     with pytest.raises(ValueError, match="multiples of 8"):
         bad.apply(bad.init(0, xb), xb)
+
+
+def test_clip_loss_row_block_of_a_larger_global_batch(ops):
+    """BASELINE config 3 shape in miniature: one rank's rows (its images x ALL texts) of the global logits; per-rank
+    pieces combined the way clip_loss.py does must equal the oracle on the global batch."""
+    Bg, E, world = 384, 64, 3
+    Bl = Bg // world
+    g = torch.Generator(device="cuda").manual_seed(11)
+    img = torch.randn((Bg, E), device="cuda", generator=g).bfloat16()
+    txt = (torch.randn((Bg, E), device="cuda", generator=g) + 0.7 * img.float()).bfloat16()
+    lt = torch.tensor([1.9], device="cuda")
+    pieces = [ops.clip_fwd(img[r * Bl:(r + 1) * Bl].contiguous(), txt, lt, r * Bl) for r in range(world)]
+    gmax = torch.stack([p["col_max"] for p in pieces]).max(0).values          # all-reduce(MAX)
+    csum = torch.zeros_like(gmax)
+    for p in pieces:
+        ops.clip_col_rescale(p["col_max"], gmax, p["col_sum"])
+        csum += p["col_sum"]                                                   # all-reduce(SUM)
+    loss = sum(ops.clip_loss(p, gmax, csum, r * Bl)[0] for r, p in enumerate(pieces))
+    col_lse = ops.clip_loss(pieces[0], gmax, csum, 0)[1]
+    dV = torch.zeros((Bg, E), device="cuda"); dU = []
+    for r, p in enumerate(pieces):
+        du, dv, _ = ops.clip_bwd(p, col_lse, r * Bl)
+        dU.append(du); dV += dv                                                # reduce-scatter(SUM)
+    torch.cuda.synchronize()
+    ref_loss, S, u, v = O.clip_loss_fwd(f32(img), f32(txt), 1.9)
+    assert abs(float(loss.item()) - float(ref_loss)) < 1e-2
+    _, _, _, dS = O.clip_loss_bwd(f32(img), f32(txt), 1.9)
+    scale = float(np.exp(1.9))
+    assert relerr(f32(torch.cat(dU)), scale * dS @ v) < 3e-2
+    assert relerr(f32(dV), scale * dS.T @ u) < 3e-2

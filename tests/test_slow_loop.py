@@ -88,3 +88,27 @@ def test_forde_lite_rule():
     _, mv2, diag = SL.slow_loop_step({}, mv, cfg, key=0)
     a = mv2["neuron_assignments"]["layer_0"]["stateful_layer"]["assignments"].numpy()
     np.testing.assert_array_equal(a, O.forde_lite_assignments(np.r_[np.full(10, 0.9), np.full(54, 0.5)][:, None]))
+
+
+def test_checkpoint_round_trip_cpu(tmp_path):
+    """params + neuron_assignments + stat accumulators + optimizer state survive save/restore."""
+    from forde_b200 import dual_encoder, train
+    cfg = dual_encoder.config_tiny()
+    a = train.create_train_state(cfg, 0, device="cpu")
+    a.variables["neuron_assignments"]["vision"]["layer_1"]["stateful_layer"]["assignments"].fill_(2)
+    a.variables["stats_buffer"]["text"]["layer_0"]["stateful_layer"]["moments"].add_(1.5)
+    a.flat_g32.normal_()
+    a.opt.step()
+    a.step = 17
+    path = str(tmp_path / "ck.pt")
+    train.save_checkpoint(a, path)
+    b = train.create_train_state(cfg, 99, device="cpu")
+    assert not torch.equal(a.flat_p32, b.flat_p32)
+    ptr = b.variables["params"]["vision"]["proj"]["kernel"].data_ptr()
+    train.restore_checkpoint(b, path)
+    assert b.step == 17 and torch.equal(a.flat_p32, b.flat_p32) and torch.equal(b.flat_p16, b.flat_p32.bfloat16())
+    assert b.variables["params"]["vision"]["proj"]["kernel"].data_ptr() == ptr          # restored in place
+    assert int(b.variables["neuron_assignments"]["vision"]["layer_1"]["stateful_layer"]["assignments"].min()) == 2
+    assert float(b.variables["stats_buffer"]["text"]["layer_0"]["stateful_layer"]["moments"].mean()) == 1.5
+    sa, sb = a.opt.state_dict()["state"][0], b.opt.state_dict()["state"][0]
+    assert torch.equal(sa["exp_avg"], sb["exp_avg"])
