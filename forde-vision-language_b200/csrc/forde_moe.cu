@@ -282,33 +282,38 @@ __global__ void moe_gate_grad_kernel(const __nv_bfloat16* __restrict__ dout, con
   if (lane == 0) d_w[i] = acc;
 }
 
-// out[e][c] += sum of mat[row][c] over expert e's segment; block = 32 x 8, one block per (64 columns, expert)
+// out[e][c] += sum of mat[row][c] over expert e's segment.  block = 32 x 8: a warp covers 256 columns with 16-byte
+// loads, 8 row lanes; grid = (column blocks, experts, SEG_SPLIT row slices), slices combined with fp32 atomics.
+constexpr int SEG_SPLIT = 8;
 __global__ void moe_seg_colsum_kernel(const __nv_bfloat16* __restrict__ mat, const int* __restrict__ seg, int cols,
                                       float* __restrict__ out) {
-  __shared__ float red[8][64];
+  __shared__ float red[8][256 + 8];
   const int tx = threadIdx.x, ty = threadIdx.y, e = blockIdx.y;
-  const int c = blockIdx.x * 64 + tx * 2;
-  float s0 = 0.f, s1 = 0.f;
-  if (c < cols) {
-    for (int r = seg[e] + ty; r < seg[e + 1]; r += 8) {
-      const __nv_bfloat162 v = *reinterpret_cast<const __nv_bfloat162*>(mat + static_cast<size_t>(r) * cols + c);
-      s0 += __low2float(v);
-      s1 += __high2float(v);
-    }
-  }
-  red[ty][tx * 2] = s0;
-  red[ty][tx * 2 + 1] = s1;
-  __syncthreads();
-  if (ty == 0 && c < cols) {
-    float a = 0.f, b = 0.f;
+  const int c = blockIdx.x * 256 + tx * 8;
+  const int s0 = seg[e], s1 = seg[e + 1];
+  const int per = ((s1 - s0) + SEG_SPLIT - 1) / SEG_SPLIT;
+  const int r0 = s0 + blockIdx.z * per, r1 = min(s1, r0 + per);
+  float s[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (c < cols) {  // cols is a multiple of 64 (checked by the caller), rows are 16-byte aligned
+    for (int r = r0 + ty; r < r1; r += 8) {
+      const uint4 q = __ldg(reinterpret_cast<const uint4*>(mat + static_cast<size_t>(r) * cols + c));
+      const uint32_t w[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
-    for (int y = 0; y < 8; ++y) {
-      a += red[y][tx * 2];
-      b += red[y][tx * 2 + 1];
+      for (int i = 0; i < 4; ++i) {
+        s[2 * i] += __uint_as_float(w[i] << 16);
+        s[2 * i + 1] += __uint_as_float(w[i] & 0xFFFF0000u);
+      }
     }
-    out[static_cast<size_t>(e) * cols + c] += a;
-    out[static_cast<size_t>(e) * cols + c + 1] += b;
   }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) red[ty][tx * 8 + i] = s[i];
+  __syncthreads();
+  const int t = ty * 32 + tx;
+  float acc = 0.f;
+#pragma unroll
+  for (int y = 0; y < 8; ++y) acc += red[y][t];
+  const int col = blockIdx.x * 256 + t;
+  if (col < cols && r1 > r0) atomicAdd(out + static_cast<size_t>(e) * cols + col, acc);
 }
 
 }  // namespace forde
@@ -458,9 +463,9 @@ int forde_moe_experts_bwd(void* stream, const void* xg, const void* dyg, const v
   GemmArgs gwd{hg, true, H, dyg, true, d, H, d, r_cap, false, 0x1000000000000000ull, 0x1000000000000000ull};
   rc = gemm_grouped_k(st, gwd, seg_offsets, E, dw_down_all, d, static_cast<long long>(d) * H);
   if (rc != FORDE_OK) return rc;
-  moe_seg_colsum_kernel<<<dim3((H + 63) / 64, E), dim3(32, 8), 0, st>>>(static_cast<const __nv_bfloat16*>(dzg),
+  moe_seg_colsum_kernel<<<dim3((H + 255) / 256, E, SEG_SPLIT), dim3(32, 8), 0, st>>>(static_cast<const __nv_bfloat16*>(dzg),
                                                                        seg_offsets, H, db_up_all);
-  moe_seg_colsum_kernel<<<dim3((d + 63) / 64, E), dim3(32, 8), 0, st>>>(static_cast<const __nv_bfloat16*>(dyg),
+  moe_seg_colsum_kernel<<<dim3((d + 255) / 256, E, SEG_SPLIT), dim3(32, 8), 0, st>>>(static_cast<const __nv_bfloat16*>(dyg),
                                                                        seg_offsets, d, db_down_all);
   return check_launch("moe_seg_colsum_kernel", 2);
 }

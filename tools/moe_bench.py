@@ -64,3 +64,11 @@ for name, f in stages:
     print(f"  {name:36s} {us:8.1f} us")
 fl = 12.0 * M * k * d * H
 print(f"  total fwd+bwd {tot:8.1f} us ; routed-token GEMM work 12*M*k*d*H = {fl / 1e9:.1f} GFLOP -> {fl / (tot * 1e-6) / 1e12:.1f} TFLOP/s")
+
+if "--profile" in sys.argv:
+    from torch.profiler import ProfilerActivity, profile
+    with profile(activities=[ProfilerActivity.CUDA]) as prof:
+        for _ in range(5):
+            run()
+        torch.cuda.synchronize()
+    print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=20, max_name_column_width=70))
