@@ -52,6 +52,7 @@ SIGNATURES = {
     "forde_moe_scatter": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _i, _i]),
     "forde_moe_combine": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i]),
     "forde_moe_gate_grad": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i]),
+    "forde_moe_router_bwd": (_i, [_vp] * 10 + [_f, _i, _i, _i, _i, _vp, _vp, _vp]),
     "forde_moe_experts_fwd": (_i, [_vp] * 11 + [_i, _i, _i, _i]),
     "forde_moe_experts_bwd": (_i, [_vp] * 16 + [_i, _i, _i, _i]),
     "forde_ln_num_partials": (_i, [_i]),

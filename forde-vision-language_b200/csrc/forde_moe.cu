@@ -316,6 +316,80 @@ __global__ void moe_seg_colsum_kernel(const __nv_bfloat16* __restrict__ mat, con
   if (col < cols && r1 > r0) atomicAdd(out + static_cast<size_t>(e) * cols + col, acc);
 }
 
+// ------------------------------------------------------------------ router backward
+// One warp per token.  Gradient of the logits through (a) the top-k softmax weights (moe.py:133) given d_w =
+// dL/d(topk_w), and (b) probs = softmax(logits) given g = dL/d(probs) -- the aux loss contributes
+// d_aux * aux_weight * E / M * counts_e / (M k) per expert (moe.py:212-222; the histogram itself is not
+// differentiable) plus an optional upstream d_probs.  Then dx[token] += dlogits . W_r^T (bf16, in place),
+// db_r / dW_r are reduced per CTA in shared memory and added with fp32 atomics.
+template <int E>
+__global__ void __launch_bounds__(256)
+moe_router_bwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ w_r,
+                      const float* __restrict__ probs, const int* __restrict__ topk_idx,
+                      const float* __restrict__ topk_w, const float* __restrict__ d_topk_w,
+                      const int* __restrict__ counts, const float* __restrict__ d_aux,
+                      const float* __restrict__ d_probs, float aux_weight, int M, int d, int k,
+                      __nv_bfloat16* __restrict__ dx, float* __restrict__ dw_r, float* __restrict__ db_r) {
+  extern __shared__ float sm[];  // [d][E] W_r fp32, then one [d][E] dW_r accumulator PER WARP (lane-owned rows)
+  float* w_s = sm;
+  float* dw_s = sm + d * E * (1 + (threadIdx.x >> 5));
+  __shared__ float db_s[E];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int i = threadIdx.x; i < d * E; i += blockDim.x) w_s[i] = __bfloat162float(w_r[i]);
+  for (int i = threadIdx.x; i < 8 * d * E; i += blockDim.x) sm[d * E + i] = 0.f;
+  if (threadIdx.x < E) db_s[threadIdx.x] = 0.f;
+  __syncthreads();
+  const float aux_scale = (d_aux != nullptr ? *d_aux : 0.f) * aux_weight * static_cast<float>(E) /
+                          static_cast<float>(M) / static_cast<float>(M * k);
+  for (int tok = blockIdx.x * 8 + warp; tok < M; tok += gridDim.x * 8) {
+    float dl[E], pr[E], g[E];
+    float pg = 0.f;
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+      pr[e] = probs[static_cast<size_t>(tok) * E + e];
+      g[e] = aux_scale * static_cast<float>(counts[e]) +
+             (d_probs != nullptr ? d_probs[static_cast<size_t>(tok) * E + e] : 0.f);
+      pg = fmaf(pr[e], g[e], pg);
+    }
+#pragma unroll
+    for (int e = 0; e < E; ++e) dl[e] = pr[e] * (g[e] - pg);
+    float wd = 0.f;
+    for (int j = 0; j < k; ++j)
+      wd = fmaf(topk_w[static_cast<size_t>(tok) * k + j], d_topk_w[static_cast<size_t>(tok) * k + j], wd);
+    for (int j = 0; j < k; ++j) {
+      const int sel = topk_idx[static_cast<size_t>(tok) * k + j];
+      const float v = topk_w[static_cast<size_t>(tok) * k + j] * (d_topk_w[static_cast<size_t>(tok) * k + j] - wd);
+#pragma unroll
+      for (int e = 0; e < E; ++e) dl[e] += (e == sel) ? v : 0.f;
+    }
+    if (lane == 0) {
+#pragma unroll
+      for (int e = 0; e < E; ++e) atomicAdd(&db_s[e], dl[e]);
+    }
+    __nv_bfloat16* dxr = dx + static_cast<size_t>(tok) * d;
+    const __nv_bfloat16* xr = x + static_cast<size_t>(tok) * d;
+    for (int i = lane; i < d; i += 32) {
+      const float* wr = w_s + i * E;
+      float acc = __bfloat162float(dxr[i]);
+      const float xv = __bfloat162float(xr[i]);
+#pragma unroll
+      for (int e = 0; e < E; ++e) {
+        acc = fmaf(dl[e], wr[e], acc);
+        dw_s[i * E + e] = fmaf(xv, dl[e], dw_s[i * E + e]);  // row i of this warp's accumulator belongs to this lane
+      }
+      dxr[i] = __float2bfloat16(acc);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < d * E; i += blockDim.x) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += sm[d * E * (1 + w) + i];
+    atomicAdd(&dw_r[i], t);
+  }
+  if (threadIdx.x < E) atomicAdd(&db_r[threadIdx.x], db_s[threadIdx.x]);
+}
+
 }  // namespace forde
 
 using namespace forde;
@@ -411,6 +485,39 @@ int forde_moe_gate_grad(void* stream, const void* dout, const void* yg, const in
       static_cast<const __nv_bfloat16*>(dout), static_cast<const __nv_bfloat16*>(yg), slot_of, d_topk_w, entries, k,
       d);
   return check_launch("moe_gate_grad_kernel");
+}
+
+int forde_moe_router_bwd(void* stream, const void* x, const void* w_r, const float* probs, const int* topk_idx,
+                         const float* topk_w, const float* d_topk_w, const int* counts, const float* d_aux,
+                         const float* d_probs, float aux_weight, int M, int d, int E, int k, void* dx, float* dw_r,
+                         float* db_r) {
+  if (x == nullptr || w_r == nullptr || probs == nullptr || topk_idx == nullptr || topk_w == nullptr ||
+      d_topk_w == nullptr || counts == nullptr || dx == nullptr || dw_r == nullptr || db_r == nullptr || M <= 0 ||
+      d <= 0)
+    return FORDE_EINVAL;
+  if ((E != 4 && E != 8 && E != 16) || k < 1 || k > MOE_MAX_K) return FORDE_EINVAL;
+  const int smem = 9 * d * E * static_cast<int>(sizeof(float));  // W_r + one dW_r accumulator per warp
+  if (smem > 200 * 1024) return FORDE_EINVAL;                    // d * E <= 5688 (C4: 512 x 8 = 4096)
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int sms = sm_count();
+  if (sms <= 0) return FORDE_ENODEV;
+  const int need = (M + 7) / 8;
+  const int grid = need < sms ? need : sms;
+#define FORDE_ROUTER_BWD(EE)                                                                                     \
+  do {                                                                                                           \
+    static std::once_flag once;                                                                                  \
+    std::call_once(once, [] {                                                                                    \
+      cudaFuncSetAttribute(moe_router_bwd_kernel<EE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);  \
+    });                                                                                                          \
+    moe_router_bwd_kernel<EE><<<grid, 256, smem, st>>>(                                                          \
+        static_cast<const __nv_bfloat16*>(x), static_cast<const __nv_bfloat16*>(w_r), probs, topk_idx, topk_w,   \
+        d_topk_w, counts, d_aux, d_probs, aux_weight, M, d, k, static_cast<__nv_bfloat16*>(dx), dw_r, db_r);     \
+  } while (0)
+  if (E == 4) FORDE_ROUTER_BWD(4);
+  else if (E == 8) FORDE_ROUTER_BWD(8);
+  else FORDE_ROUTER_BWD(16);
+#undef FORDE_ROUTER_BWD
+  return check_launch("moe_router_bwd_kernel");
 }
 
 // experts forward on the gathered rows: zg = xg . W_up[e] + b_up[e]; hg = gelu(zg); yg = hg . W_down[e] + b_down[e]

@@ -15,7 +15,7 @@ gathers (moe.py:163), which is result-equivalent.
 Kernels (csrc/forde_moe.cu + the grouped modes of csrc/forde_gemm.cuh): router / top-k / histogram / aux loss /
 usage statistics / routing plan, gather, grouped up-projection with fused bias + tanh-GELU, grouped down-projection,
 weighted combine; backward: scatter, gate gradient, grouped dz (fused GELU'), dx, per-expert dW (grouped-K) and db.
-The router's own backward (an (M, E) softmax Jacobian and two (M x d x E) products) is a few small torch ops.
+router backward (softmax Jacobians, dx += dlogits W_r^T, dW_r, db_r).
 """
 from __future__ import annotations
 
@@ -58,23 +58,11 @@ class _MoEFn(torch.autograd.Function):
         d_w = ops.moe_gate_grad(dout, yg, r)
         dxg, dw_up, db_up, dw_down, db_down = ops.moe_experts_bwd(xg, dyg, w_up16, w_down16, zg, hg, r)
         dx = ops.moe_combine(dxg, r, weighted=False)
-        # ---- router backward (tiny): top-k softmax Jacobian + the aux-loss path through probs (moe.py:212-222)
-        w = r["topk_w"]
-        d_sel = w * (d_w - (w * d_w).sum(-1, keepdim=True))
-        dlogits = torch.zeros((M, E), dtype=torch.float32, device=dout.device)
-        dlogits.scatter_add_(1, r["topk_idx"].long(), d_sel)
-        probs = r["probs"]
-        g = torch.zeros_like(probs)
-        if d_aux is not None:
-            frac = r["counts"].float() / float(M * k)
-            g = g + d_aux.float() * (ctx.layer.aux_loss_weight * E / M) * frac
-        if d_probs is not None:
-            g = g + d_probs.float()
-        dlogits = dlogits + probs * (g - (probs * g).sum(-1, keepdim=True))
-        xf = x2d.float()
-        dw_r = xf.t() @ dlogits
-        db_r = dlogits.sum(0)
-        dx = (dx.float() + dlogits @ w_r16.float().t()).to(torch.bfloat16)
+        # ---- router backward kernel: top-k softmax Jacobian + the aux-loss path through probs (moe.py:212-222);
+        #      adds dlogits . W_r^T into dx in place
+        da = d_aux.detach().float().reshape(1).contiguous() if d_aux is not None else None
+        dp = d_probs.detach().float().contiguous() if d_probs is not None else None
+        dw_r, db_r = ops.moe_router_bwd(x2d, w_r16, r, d_w, da, dp, ctx.layer.aux_loss_weight, dx)
         dt = ctx.dtypes
         return (dx, dw_r.to(dt[0]), db_r.to(dt[1]), dw_up.to(dt[2]), db_up.to(dt[3]), dw_down.to(dt[4]),
                 db_down.to(dt[5]), None, None)

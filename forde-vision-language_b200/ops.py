@@ -434,3 +434,17 @@ def moe_experts_bwd(xg, dyg, w_up16, w_down16, zg, hg, route):
                                            R, d, H, E)
     _lib.check(rc, "forde_moe_experts_bwd")
     return dxg, dw_up, db_up, dw_down, db_down
+
+
+def moe_router_bwd(x, w_r16, route, d_topk_w, d_aux, d_probs, aux_weight: float, dx):
+    """dx (bf16, in place) += dlogits . w_r^T ; returns (dw_r [d][E], db_r [E]) fp32."""
+    M, d, E, k = route["M"], route["d"], route["E"], route["k"]
+    dw_r = torch.zeros((d, E), dtype=torch.float32, device=x.device)
+    db_r = torch.zeros(E, dtype=torch.float32, device=x.device)
+    rc = _lib.load().forde_moe_router_bwd(_stream(), x.data_ptr(), w_r16.data_ptr(), route["probs"].data_ptr(),
+                                          route["topk_idx"].data_ptr(), route["topk_w"].data_ptr(),
+                                          d_topk_w.data_ptr(), route["counts"].data_ptr(), _ptr(d_aux), _ptr(d_probs),
+                                          float(aux_weight), M, d, E, k, dx.data_ptr(), dw_r.data_ptr(),
+                                          db_r.data_ptr())
+    _lib.check(rc, "forde_moe_router_bwd")
+    return dw_r, db_r

@@ -189,6 +189,13 @@ int forde_moe_combine(void* stream, const void* yg, const int* slot_of, const fl
                       int d);
 int forde_moe_gate_grad(void* stream, const void* dout, const void* yg, const int* slot_of, float* d_topk_w, int M,
                         int k, int d);
+/* router backward: dlogits from d_topk_w (through the top-k softmax) and from d(probs) = d_aux[0] * d(aux)/d(probs)
+ * (+ optional d_probs [M][E]); then dx[M][d] (bf16) += dlogits . w_r^T IN PLACE, dw_r [d][E] += x^T . dlogits,
+ * db_r [E] += sum_m dlogits (fp32 atomics).  d_aux is a device scalar (may be NULL = 0). */
+int forde_moe_router_bwd(void* stream, const void* x, const void* w_r, const float* probs, const int* topk_idx,
+                         const float* topk_w, const float* d_topk_w, const int* counts, const float* d_aux,
+                         const float* d_probs, float aux_weight, int M, int d, int E, int k, void* dx, float* dw_r,
+                         float* db_r);
 int forde_moe_experts_fwd(void* stream, const void* xg, const void* w_up_all, const float* b_up_all,
                           const void* w_down_all, const float* b_down_all, const int* n_blocks_dev,
                           const int* block_expert, void* zg, void* hg, void* yg, int r_cap, int d, int H, int E);
