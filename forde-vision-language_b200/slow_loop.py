@@ -174,3 +174,88 @@ def slow_loop_step(params, mutable_variables, config: SlowLoopConfig, key, epoch
             t.zero_()
     zero(stats_tree)
     return params, mutable_variables, diagnostics
+
+
+# ------------------------------------------------------------------------------------------ MoE variant (config 4)
+def box_smooth_3d(grid: np.ndarray, kernel_size: int = 3, num_clusters: int = 3) -> np.ndarray:
+    """3-D majority smoothing of expert labels (smoothing.py:94-171): per-label k^3 box filter with 'same'
+    convolution, edge padding for grids thinner than the kernel, label of highest density (lowest id on ties)."""
+    from scipy.signal import convolve
+
+    box = np.full((kernel_size,) * 3, 1.0 / kernel_size ** 3, dtype=np.float32)
+    d, h, w = grid.shape
+    pads = [max(0, kernel_size - n) for n in grid.shape]
+    padding = tuple((p // 2, p - p // 2) for p in pads)
+    dens = []
+    for c in range(num_clusters):
+        plane = (grid == c).astype(np.float32)
+        if any(pads):
+            plane = np.pad(plane, padding, "edge")
+        sm = convolve(plane, box, mode="same").astype(np.float32)
+        dens.append(sm[padding[0][0]:padding[0][0] + d, padding[1][0]:padding[1][0] + h, padding[2][0]:padding[2][0] + w])
+    return np.stack(dens, -1).argmax(-1).astype(np.int32)
+
+
+def router_adjustments(assignments: np.ndarray, usage: np.ndarray, target_balance: float = 0.1) -> np.ndarray:
+    """Router-bias nudges (moe_slow_loop.py:211-250): push towards uniform usage, capped at +-0.1, halved for the
+    'specialist' cluster (id 1)."""
+    usage = np.asarray(usage, np.float32)
+    adj = np.clip(-(usage - np.float32(1.0 / usage.shape[0])) * np.float32(target_balance), -0.1, 0.1).astype(np.float32)
+    return np.where(np.asarray(assignments) == 1, adj * np.float32(0.5), adj).astype(np.float32)
+
+
+def _walk_leaves(tree, path=()):
+    if isinstance(tree, dict):
+        for k, v in tree.items():
+            yield from _walk_leaves(v, path + (k,))
+    else:
+        yield path, tree
+
+
+def moe_slow_loop_step(model_params, mutable_variables, config, key, epoch: int = 0, step: int = 0, group=None):
+    """Slow loop of the MoE variant, same contract as src/forde/moe_slow_loop.py:253-464:
+    ``(params, mutable_variables, diagnostics)`` in and out are plain nested dicts; ``config`` needs ``num_layers`` and
+    ``num_experts``.  SENSE: every ``expert_usage`` leaf of ``stats_buffer`` (one per layer, found by name like
+    moe_slow_loop.py:145-170) divided by the largest ``step_count`` (:298); ranks average their usage first.
+    CLUSTER: GMM(3) on (mean, variance over layers) per expert (:314-323).  SMOOTH: labels on a (1, gh, gw) grid,
+    3-D box filter (:337-363).  ANALYSE: load imbalance, relative routing entropy (:372-381).  ACTUATE: add the bias
+    nudges to every ``router_linear/bias`` of matching shape, in place (:418-439).  RESET: zero every leaf of
+    ``stats_buffer`` (:441-449)."""
+    E, L = int(config.num_experts), int(config.num_layers)
+    sb = mutable_variables.get("stats_buffer", {})
+    usages, step_count = [], 0
+    for path, leaf in _walk_leaves(sb):
+        if path[-1] == "expert_usage" and leaf.shape[0] == E:
+            usages.append(leaf)
+        elif path[-1] == "step_count":
+            step_count = max(step_count, int(leaf.item()))
+    if step_count == 0 or not usages:
+        return model_params, mutable_variables, {"skipped": True}
+    world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
+    usage = torch.stack([u.detach().float() for u in usages[:L]] + [torch.zeros_like(usages[0], dtype=torch.float32)] * max(0, L - len(usages)))
+    if world > 1:
+        dist.all_reduce(usage, op=dist.ReduceOp.SUM, group=group)
+        usage = usage / world
+    usage = (usage / step_count).cpu().numpy().astype(np.float32)                     # (L, E)
+    usage_mean, usage_var = usage.mean(0), usage.var(0)
+    labels, gmm_params = gmm_cluster(np.stack([usage_mean, usage_var], -1), 3, _seed_from_key(key))
+    gh = int(np.sqrt(E))
+    while E % gh != 0:
+        gh -= 1
+    smoothed = box_smooth_3d(labels.reshape(1, gh, E // gh), 3, 3).reshape(-1)
+    imbalance = float(np.abs(usage_mean - 1.0 / E).mean())
+    entropy = float(-(usage_mean * np.log(usage_mean + 1e-8)).sum() / np.log(E))
+    adj = router_adjustments(smoothed, usage_mean)
+    updated = 0
+    for path, leaf in _walk_leaves(model_params):
+        if "router_linear" in path and path[-1] == "bias" and tuple(leaf.shape) == adj.shape:
+            with torch.no_grad():
+                leaf.add_(torch.from_numpy(adj).to(leaf.device, leaf.dtype))               # in place: views stay valid
+            updated += 1
+    for _, leaf in _walk_leaves(sb):
+        leaf.zero_()
+    return model_params, mutable_variables, {
+        "expert_usage": usage_mean, "assignments": smoothed, "raw_assignments": labels, "load_imbalance": imbalance,
+        "routing_entropy": entropy, "adjustments": adj, "step_count": step_count, "router_biases_updated": updated,
+        "gmm": gmm_params, "epoch": epoch, "step": step,
+    }

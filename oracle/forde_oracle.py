@@ -362,3 +362,43 @@ def moe_layer_torch(x, w_r, b_r, w_up, b_up, w_down, b_down, k, aux_weight, dout
                         ("db_down", bd_)):
             res[name] = v.grad.numpy()
     return res
+
+
+# ----------------------------------------------------------------------------------------------- MoE slow loop
+def smooth_assignments_3d(assignment_grid, kernel_size=3, num_clusters=3):
+    """smoothing.py:94-171: one-hot -> per-cluster k^3 box filter ('same' convolution; grids smaller than the kernel
+    are edge-padded first and cropped back) -> argmax (first maximum wins)."""
+    from scipy.signal import convolve
+
+    grid = np.asarray(assignment_grid)
+    kernel = np.ones((kernel_size,) * 3, np.float32) / np.float32(kernel_size ** 3)            # :114
+    one_hot = (grid[..., None] == np.arange(num_clusters)).astype(np.float32)                  # :117
+    d, h, w, _ = one_hot.shape
+    chans = []
+    for c in range(num_clusters):
+        ch = one_hot[..., c]
+        pads = [max(0, kernel_size - n) for n in ch.shape]                                     # :133-135
+        padding = tuple((p // 2, p - p // 2) for p in pads)                                    # :139-143
+        padded = np.pad(ch, padding, "edge") if any(pads) else ch                              # :144-146
+        sm = convolve(padded, kernel, mode="same").astype(np.float32)                          # :152
+        if any(pads):
+            sm = sm[padding[0][0]:padding[0][0] + d, padding[1][0]:padding[1][0] + h, padding[2][0]:padding[2][0] + w]
+        chans.append(sm)
+    return np.argmax(np.stack(chans, -1), axis=-1)                                             # :166-169
+
+
+def compute_router_adjustments(expert_assignments, expert_usage, target_balance=0.1):
+    """moe_slow_loop.py:211-250: bias nudge = clip(-(usage - 1/E) * target_balance, +-0.1), halved for cluster 1."""
+    usage = np.asarray(expert_usage, np.float32)
+    uniform = np.float32(1.0 / usage.shape[0])
+    adj = np.clip(-(usage - uniform) * np.float32(target_balance), -0.1, 0.1).astype(np.float32)
+    return np.where(np.asarray(expert_assignments) == 1, adj * np.float32(0.5), adj).astype(np.float32)
+
+
+def moe_usage_diagnostics(usage_mean):
+    """moe_slow_loop.py:372-381: mean |usage - 1/E| and routing entropy relative to log E."""
+    u = np.asarray(usage_mean, np.float32)
+    e = u.shape[0]
+    imbalance = np.abs(u - np.float32(1.0 / e)).mean()
+    entropy = -(u * np.log(u + np.float32(1e-8))).sum() / np.log(np.float32(e))
+    return np.float32(imbalance), np.float32(entropy)

@@ -27,6 +27,28 @@ OUT = os.path.dirname(os.path.abspath(__file__))
 def install_jax_stub():
     import scipy.signal
 
+    class _At:
+        def __init__(self, arr):
+            self.arr = arr
+
+        def __getitem__(self, idx):
+            arr = self.arr
+
+            class _Setter:
+                @staticmethod
+                def set(v):
+                    out = np.array(arr, copy=True).view(_JArr)
+                    out[idx] = v
+                    return out
+            return _Setter
+
+    class _JArr(np.ndarray):
+        """ndarray with jax's functional ``x.at[i].set(v)``."""
+
+        @property
+        def at(self):
+            return _At(self)
+
     class _F32NumPy(types.ModuleType):
         """numpy with float32 defaults for the constructors the reference uses."""
 
@@ -39,7 +61,7 @@ def install_jax_stub():
 
         @staticmethod
         def zeros(shape, dtype=np.float32):
-            return np.zeros(shape, dtype=dtype)
+            return np.zeros(shape, dtype=dtype).view(_JArr)
 
         @staticmethod
         def sqrt(x):
@@ -75,9 +97,45 @@ def install_jax_stub():
     jsp.signal = jsig
     jax.scipy = jsp
     rnd = types.ModuleType("jax.random")
+    rnd.PRNGKey = lambda seed: np.array([0, int(seed)], np.uint32)
+    rnd.split = lambda key, num=2: [np.array([int(key[0]) + i + 1, int(key[1])], np.uint32) for i in range(num)]
+    # clustering.py:25 draws the sklearn seed with jax.random.randint; the stub derives a deterministic int instead
+    # (threefry is not reproduced), so GMM-dependent outputs are pinned only where they do not depend on the seed
+    rnd.randint = lambda key, shape, lo, hi: np.int64((int(key[0]) * 1000003 + int(key[1])) % (hi - lo) + lo)
     jax.random = rnd
+    tree = types.ModuleType("jax.tree")
+
+    def tree_map(fn, t):
+        return {k: tree_map(fn, v) for k, v in t.items()} if isinstance(t, dict) else fn(t)
+    tree.map = tree_map
+    jax.tree = tree
+    flax = types.ModuleType("flax")
+    fcore = types.ModuleType("flax.core")
+    fcore.unfreeze = lambda t: ({k: fcore.unfreeze(v) for k, v in t.items()} if isinstance(t, dict) else t)
+    ftu = types.ModuleType("flax.traverse_util")
+
+    def flatten_dict(t, prefix=()):
+        out = {}
+        for k, v in t.items():
+            if isinstance(v, dict):
+                out.update(flatten_dict(v, prefix + (k,)))
+            else:
+                out[prefix + (k,)] = v
+        return out
+
+    def unflatten_dict(flat):
+        out = {}
+        for path, v in flat.items():
+            d = out
+            for k in path[:-1]:
+                d = d.setdefault(k, {})
+            d[path[-1]] = v
+        return out
+    ftu.flatten_dict, ftu.unflatten_dict = flatten_dict, unflatten_dict
+    flax.core, flax.traverse_util = fcore, ftu
     sys.modules.update({"jax": jax, "jax.numpy": jnp, "jax.nn": nn, "jax.scipy": jsp, "jax.scipy.signal": jsig,
-                        "jax.random": rnd})
+                        "jax.random": rnd, "jax.tree": tree, "flax": flax, "flax.core": fcore,
+                        "flax.traverse_util": ftu})
 
 
 def load_ref(name):
@@ -130,6 +188,41 @@ def main():
         blob[f"params{i}"] = np.array([k, nc], np.int32)
         blob[f"out{i}"] = out.astype(np.int32)
     np.savez(os.path.join(OUT, "smoothing.npz"), **blob)
+
+    # ---- MoE slow loop (moe_slow_loop.py): 3-D smoothing, router adjustments, and one whole step on the pytrees of
+    #      tests/verify_reset.py:17-35 (uniform usage: every expert lands in one GMM cluster whatever the seed)
+    sys.path.insert(0, os.path.join(REF, "src", "forde"))
+    msl = load_ref("moe_slow_loop")
+    blob = {}
+    for i, shape in enumerate([(1, 2, 4), (1, 1, 4), (3, 4, 4), (2, 3, 5)]):
+        grid = rng.randint(0, 3, size=shape).astype(np.int32)
+        blob[f"grid3d_{i}"] = grid
+        blob[f"out3d_{i}"] = np.asarray(smoothing.smooth_assignments_3d(grid, 3, 3)).astype(np.int32)
+    for i in range(3):
+        assign = rng.randint(0, 3, size=8).astype(np.int32)
+        usage = rng.dirichlet(np.ones(8)).astype(np.float32)
+        blob[f"adj_assign_{i}"], blob[f"adj_usage_{i}"] = assign, usage
+        blob[f"adj_out_{i}"] = np.asarray(msl.compute_router_adjustments(assign, usage), np.float32)
+
+    class Cfg:
+        num_layers, num_experts = 1, 4
+    params = {"params": {"layer_0": {"moe": {"router_linear": {"bias": np.zeros(4, np.float32)}}}}}
+    mv = {"stats_buffer": {"layer_0": {"moe": {"expert_usage": np.array([4.0, 3.0, 2.0, 1.0], np.float32),
+                                               "step_count": np.array(10, np.int32)}}}}
+    import contextlib
+    import io
+    with contextlib.redirect_stdout(io.StringIO()):
+        new_p, new_mv, diag = msl.moe_slow_loop_step(params, mv, Cfg, sys.modules["jax.random"].PRNGKey(42), 0, 100)
+    blob["step_usage_in"] = np.array([4.0, 3.0, 2.0, 1.0], np.float32)
+    blob["step_usage_mean"] = np.asarray(diag["expert_usage"], np.float32)
+    blob["step_bias_out"] = np.asarray(new_p["params"]["layer_0"]["moe"]["router_linear"]["bias"], np.float32)
+    blob["step_adjustments"] = np.asarray(diag["adjustments"], np.float32)
+    blob["step_assignments"] = np.asarray(diag["assignments"], np.int32)
+    blob["step_imbalance"] = np.float32(diag["load_imbalance"])
+    blob["step_entropy"] = np.float32(diag["routing_entropy"])
+    blob["step_usage_after"] = np.asarray(new_mv["stats_buffer"]["layer_0"]["moe"]["expert_usage"], np.float32)
+    blob["step_count_after"] = np.asarray(new_mv["stats_buffer"]["layer_0"]["moe"]["step_count"], np.int32)
+    np.savez(os.path.join(OUT, "moe_slow_loop.npz"), **blob)
     print("wrote", sorted(f for f in os.listdir(OUT) if f.endswith(".npz")))
 
 

@@ -153,3 +153,66 @@ def test_moe_expert_without_tokens_gets_zero_gradient(ops):
     assert float(p["experts"]["up_proj"]["kernel"].grad[2].abs().max()) == 0.0
     assert float(p["experts"]["down_proj"]["kernel"].grad[2].abs().max()) == 0.0
     assert float(p["experts"]["up_proj"]["kernel"].grad[0].abs().max()) > 0.0
+
+
+def test_c4_full_size_sampled_tokens(ops):
+    """BASELINE config 4 dims (8 x 1024 tokens, d=512, H=2048, E=8, top-2): the routed-only result for 48 sampled tokens
+    against the reference formulation evaluated per token in float64."""
+    from forde_b200.moe_layer import MoEStatefulLayer
+    M, d, H, E, k = 8192, 512, 2048, 8, 2
+    x, w_r, b_r, w_up, b_up, w_down, b_down = make(M, d, H, E, seed=5)
+    layer = MoEStatefulLayer(num_experts=E, top_k=k, expert_hidden_dim=H, d_model=d)
+    v = layer.init(0, x)
+    p = v["params"]
+    p["router"]["router_linear"]["kernel"] = w_r.float(); p["router"]["router_linear"]["bias"] = b_r
+    p["experts"]["up_proj"]["kernel"] = w_up.float(); p["experts"]["up_proj"]["bias"] = b_up
+    p["experts"]["down_proj"]["kernel"] = w_down.float(); p["experts"]["down_proj"]["bias"] = b_down
+    out, aux, routing = layer.apply(v, x.view(8, 1024, d), return_routing=True)
+    torch.cuda.synchronize()
+    assert out.shape == (8, 1024, d)
+    idx = routing["top_k_indices"].reshape(M, k).cpu().numpy()
+    counts = routing["expert_counts"].cpu().numpy()
+    np.testing.assert_array_equal(counts, np.bincount(idx.reshape(-1), minlength=E))           # histogram exact
+    assert counts.sum() == M * k
+    probs = f32(routing["router_probs"]).reshape(M, E)
+    aux_ref, _ = O.moe_aux_loss(probs, idx, E, k, 0.01)
+    assert abs(float(aux.item()) - float(aux_ref)) < 1e-6
+    xs, wu, wd = f32(x).astype(np.float64), f32(w_up).astype(np.float64), f32(w_down).astype(np.float64)
+    logits = xs @ f32(w_r).astype(np.float64) + f32(b_r)
+    o = f32(out).reshape(M, d)
+    for m in np.random.RandomState(0).choice(M, 48, replace=False):
+        sel = np.argsort(-logits[m], kind="stable")[:k]
+        np.testing.assert_array_equal(idx[m], sel)
+        w = np.exp(logits[m, sel] - logits[m, sel].max()); w /= w.sum()
+        ref = sum(w[j] * (O.gelu_tanh((xs[m] @ wu[e] + f32(b_up)[e]).astype(np.float32)).astype(np.float64) @ wd[e] + f32(b_down)[e])
+                  for j, e in enumerate(sel))
+        assert rel(o[m], ref) < 2e-2
+
+
+def test_moe_slow_loop_closes_the_loop_on_gpu(ops):
+    """Kernel-side expert_usage / step_count feed moe_slow_loop_step; its in-place router-bias nudges are what the next
+    forward routes with (moe_slow_loop.py:418-439), and the statistics restart from zero (:441-449)."""
+    from forde_b200.moe_layer import MoEStatefulLayer
+    from forde_b200 import slow_loop as SL
+    M, d, H, E, k = 512, 64, 128, 4, 2
+    x, *_ = make(M, d, H, E, seed=8)
+    layer = MoEStatefulLayer(num_experts=E, top_k=k, expert_hidden_dim=H, d_model=d)
+    v = layer.init(0, x)
+    v["params"]["router"]["router_linear"]["bias"].copy_(torch.tensor([1.0, 0.0, -0.5, 0.0], device="cuda"))
+    params = {"params": {"layer_0": {"moe": v["params"]["router"]}}}
+    mv = {"stats_buffer": {"layer_0": {"moe": v["stats_buffer"]}}}
+    for _ in range(3):
+        layer.apply(v, x, mutable=["stats_buffer"])
+    torch.cuda.synchronize()
+    assert int(v["stats_buffer"]["step_count"].item()) == 3
+    usage = f32(v["stats_buffer"]["expert_usage"]) / 3
+
+    class Cfg:
+        num_layers, num_experts = 1, E
+    bias_before = v["params"]["router"]["router_linear"]["bias"].clone()
+    _, _, diag = SL.moe_slow_loop_step(params, mv, Cfg, key=3, step=100)
+    np.testing.assert_allclose(diag["expert_usage"], usage, rtol=1e-5)
+    delta = f32(v["params"]["router"]["router_linear"]["bias"] - bias_before)
+    np.testing.assert_allclose(delta, diag["adjustments"], rtol=1e-5, atol=1e-7)
+    assert delta[0] < 0 and delta[2] > 0                       # over-used expert pushed down, under-used pushed up
+    assert int(v["stats_buffer"]["step_count"].item()) == 0 and float(v["stats_buffer"]["expert_usage"].abs().sum()) == 0.0

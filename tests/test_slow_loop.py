@@ -112,3 +112,51 @@ def test_checkpoint_round_trip_cpu(tmp_path):
     assert float(b.variables["stats_buffer"]["text"]["layer_0"]["stateful_layer"]["moments"].mean()) == 1.5
     sa, sb = a.opt.state_dict()["state"][0], b.opt.state_dict()["state"][0]
     assert torch.equal(sa["exp_avg"], sb["exp_avg"])
+
+
+# ------------------------------------------------------------------ MoE variant, pinned by the reference's own code
+def _moe_golden(golden_dir):
+    return np.load(os.path.join(golden_dir, "moe_slow_loop.npz"))
+
+
+@pytest.mark.parametrize("i", range(4))
+def test_smooth_3d_matches_reference_golden(golden_dir, i):
+    z = _moe_golden(golden_dir)
+    np.testing.assert_array_equal(O.smooth_assignments_3d(z[f"grid3d_{i}"], 3, 3), z[f"out3d_{i}"])
+    np.testing.assert_array_equal(SL.box_smooth_3d(z[f"grid3d_{i}"], 3, 3), z[f"out3d_{i}"])
+
+
+@pytest.mark.parametrize("i", range(3))
+def test_router_adjustments_match_reference_golden(golden_dir, i):
+    z = _moe_golden(golden_dir)
+    for fn in (O.compute_router_adjustments, SL.router_adjustments):
+        np.testing.assert_allclose(fn(z[f"adj_assign_{i}"], z[f"adj_usage_{i}"]), z[f"adj_out_{i}"], rtol=1e-6, atol=1e-8)
+
+
+def test_moe_slow_loop_step_matches_reference_run(golden_dir):
+    """The pytrees of tests/verify_reset.py:17-35 through the whole step, against the reference's own
+    moe_slow_loop_step run (tests/golden/make_golden.py).  GMM labels depend on a jax.random-derived seed the stub
+    cannot reproduce, so they are not pinned; everything that follows from them is checked given them."""
+    z = _moe_golden(golden_dir)
+
+    class Cfg:
+        num_layers, num_experts = 1, 4
+    params = {"params": {"layer_0": {"moe": {"router_linear": {"bias": torch.zeros(4)}}}}}
+    mv = {"stats_buffer": {"layer_0": {"moe": {"expert_usage": torch.from_numpy(z["step_usage_in"].copy()),
+                                               "step_count": torch.tensor(10, dtype=torch.int32)}}}}
+    bias = params["params"]["layer_0"]["moe"]["router_linear"]["bias"]
+    p2, mv2, diag = SL.moe_slow_loop_step(params, mv, Cfg, key=42, epoch=0, step=100)
+    np.testing.assert_allclose(diag["expert_usage"], z["step_usage_mean"], rtol=1e-6)
+    assert abs(diag["load_imbalance"] - float(z["step_imbalance"])) < 1e-6
+    assert abs(diag["routing_entropy"] - float(z["step_entropy"])) < 1e-5
+    np.testing.assert_allclose(diag["adjustments"], O.compute_router_adjustments(diag["assignments"], diag["expert_usage"]),
+                               rtol=1e-6)
+    # with the reference's labels the nudges are the reference's
+    np.testing.assert_allclose(SL.router_adjustments(z["step_assignments"], z["step_usage_mean"]), z["step_adjustments"],
+                               rtol=1e-6)
+    np.testing.assert_allclose(bias.numpy(), diag["adjustments"], rtol=1e-6)          # actuated in place
+    assert diag["router_biases_updated"] == 1 and p2 is params
+    leaves = mv2["stats_buffer"]["layer_0"]["moe"]                                      # RESET (verify_reset.py:61-67)
+    assert float(leaves["expert_usage"].abs().sum()) == 0.0 and int(leaves["step_count"]) == 0
+    # nothing accumulated -> skipped (moe_slow_loop.py:293-295)
+    assert SL.moe_slow_loop_step(params, mv2, Cfg, key=1)[2] == {"skipped": True}
