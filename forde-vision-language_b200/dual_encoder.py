@@ -89,22 +89,28 @@ def _deliver_dense_grads(w, b, x2t, dy2):
     """dW = x^T dy and db = colsum(dy) for a Dense whose masters are (w, b).  With gradient sinks attached (train
     state) they are accumulated in place and (None, None) is returned to autograd; otherwise fresh tensors."""
     sw, sb = grad_sink(w), grad_sink(b)
+    x2 = x2t.t()   # (M, in) row-major, the layout the weight-gradient GEMM reads in place
     if sw is not None and sb is not None:
-        sw.add_(torch.mm(x2t, dy2))
+        ops.gemm_f32(x2, dy2, True, True, out=sw, accumulate=True)     # dW += x^T dy, split-K red.add into the sink
         ops.colsum_bf16(dy2, sb)
         grad_delivered(w); grad_delivered(b)
         return None, None
-    return torch.mm(x2t, dy2).float(), _colsum(dy2)
+    dw = torch.zeros(w.shape, dtype=torch.float32, device=dy2.device)
+    ops.gemm_f32(x2, dy2, True, True, out=dw, accumulate=True)
+    return dw, _colsum(dy2)
 
 
 class _Dense(torch.autograd.Function):
-    """y = x W + b for bf16 activations (cuBLAS GEMMs; the bias gradient is this repository's column-sum kernel
-    instead of a generic strided reduction).  `w16` is the bf16 mirror (in, out); gradients go to the fp32 masters."""
+    """y = x W + b for bf16 activations.  Forward and weight gradient run on this repository's tcgen05 GEMM engine
+    (bias fused in the epilogue; dW accumulated in fp32 straight into the gradient sink), the input gradient on
+    cuBLAS, the bias gradient on the column-sum kernel.  `w16` is the bf16 mirror (in, out)."""
 
     @staticmethod
     def forward(ctx, x, w, b, w16, b16):
         x2 = x.reshape(-1, x.shape[-1])
-        y = torch.addmm(b16, x2, w16)
+        if not x2.is_contiguous():
+            x2 = x2.contiguous()
+        y = ops.gemm_bf16(x2, w16, False, True, bias_col=b.detach().float())
         ctx.save_for_backward(x2, w16)
         ctx.lead = x.shape[:-1]
         ctx.masters = (w, b)
@@ -128,10 +134,13 @@ class _QKVDense(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, wq, bq, wk, bk, wv, bv, wq16, bq16, wk16, bk16, wv16, bv16):
         x2 = x.reshape(-1, x.shape[-1])
+        if not x2.is_contiguous():
+            x2 = x2.contiguous()
         ctx.save_for_backward(x2, wq16, wk16, wv16)
         ctx.shape = x.shape
         ctx.masters = ((wq, bq), (wk, bk), (wv, bv))
-        return tuple(torch.addmm(b, x2, w).view(x.shape) for w, b in ((wq16, bq16), (wk16, bk16), (wv16, bv16)))
+        return tuple(ops.gemm_bf16(x2, w16, False, True, bias_col=b.detach().float()).view(x.shape)
+                     for w16, b in ((wq16, bq), (wk16, bk), (wv16, bv)))
 
     @staticmethod
     def backward(ctx, dq, dk, dv):
