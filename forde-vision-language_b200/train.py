@@ -13,6 +13,7 @@ large chunks on a side stream while the remaining backward still runs.
 """
 from __future__ import annotations
 
+import os
 from dataclasses import dataclass
 from typing import Dict, Optional
 
@@ -139,6 +140,9 @@ class _GradBuckets:
         self.works = []
         self.fired = [False] * len(ranges)
         self.enabled = False
+        self.comm_stream = None
+        self.epoch = 0
+        self.mode = os.environ.get("FORDE_BUCKET_MODE", "stream")
 
     def attach(self, params_in_order):
         """params_in_order: the leaf tensors in the same order as `leaves`.  The hook fires from autograd's
@@ -153,9 +157,14 @@ class _GradBuckets:
                 i += 1
 
     def _make_hook(self, bi):
-        def hook(_param):
+        def hook(param):
             if not self.enabled:
                 return
+            # idempotent per step: a parameter whose gradient went through a sink is announced by the function that
+            # wrote it AND (in current PyTorch) by AccumulateGrad's hook, which also runs for a None gradient
+            if getattr(param, "_forde_mark", -1) == self.epoch:
+                return
+            param._forde_mark = self.epoch
             self.pending[bi] -= 1
             if self.pending[bi] == 0:
                 self._fire(bi)
@@ -163,11 +172,22 @@ class _GradBuckets:
 
     def _fire(self, bi):
         _, a, b, _ = self.ranges[bi]
-        self.works.append(dist.all_reduce(self.flat[a:b], op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+        if self.flat.is_cuda and self.mode == "stream":
+            # explicit side stream: it waits for everything enqueued so far on the compute stream (the kernels that
+            # produced this bucket's gradients), the collective is ordered on it, finish() joins it back
+            cur = torch.cuda.current_stream(self.flat.device)
+            if self.comm_stream is None:
+                self.comm_stream = torch.cuda.Stream(device=self.flat.device)
+            self.comm_stream.wait_stream(cur)
+            with torch.cuda.stream(self.comm_stream):
+                dist.all_reduce(self.flat[a:b], op=dist.ReduceOp.SUM, group=self.group)
+        else:
+            self.works.append(dist.all_reduce(self.flat[a:b], op=dist.ReduceOp.SUM, group=self.group, async_op=True))
         self.fired[bi] = True
 
     def begin(self):
         self.enabled = True
+        self.epoch += 1
         self.pending = [r[3] for r in self.ranges]
         self.fired = [False] * len(self.ranges)
         self.works = []
@@ -180,6 +200,8 @@ class _GradBuckets:
         for w in self.works:
             w.wait()
         self.works = []
+        if self.comm_stream is not None:
+            torch.cuda.current_stream(self.flat.device).wait_stream(self.comm_stream)
 
 
 def sync_gradients(flat_g32: torch.Tensor, group=None) -> None:
