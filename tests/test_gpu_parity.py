@@ -477,3 +477,42 @@ def test_clip_loss_row_block_of_a_larger_global_batch(ops):
     scale = float(np.exp(1.9))
     assert relerr(f32(torch.cat(dU)), scale * dS @ v) < 3e-2
     assert relerr(f32(dV), scale * dS.T @ u) < 3e-2
+
+
+def test_composite_abi_entry_points_match_the_stepwise_calls(ops):
+    """forde_sl_fwd / forde_sl_bwd (the two calls an XLA-FFI handler makes) against the per-kernel entry
+    points: bit-identical outputs."""
+    from forde_b200 import _lib
+    lib = _lib.load()
+    M, d, H = 600, 128, 384
+    a = (np.arange(H) // 32) % 3
+    t = run_layer(ops, M, d, H, a)                      # step-wise reference (save_z=1)
+    ld, P = ops.sample_pitch(M), ops.num_partials(M)
+    st = torch.cuda.current_stream().cuda_stream
+    new = lambda like: torch.zeros_like(like)
+    zT, hT, y, actp = new(t["zT"]), new(t["hT"]), new(t["y"]), new(t["actp"])
+    rc = lib.forde_sl_fwd(st, t["x"].data_ptr(), t["w_up"].data_ptr(), t["b_up"].data_ptr(), t["w_down"].data_ptr(),
+                          t["b_down"].data_ptr(), t["assign"].data_ptr(), zT.data_ptr(), hT.data_ptr(), y.data_ptr(),
+                          actp.data_ptr(), M, d, H, ld, 1)
+    assert rc == 0
+    dzT, dx, gradp = new(t["dzT"]), new(t["dx"]), new(t["gradp"])
+    dw_up, db_up, dw_down, db_down = new(t["dw_up"]), new(t["db_up"]), new(t["dw_down"]), new(t["db_down"])
+    rc = lib.forde_sl_bwd(st, t["x"].data_ptr(), t["dy"].data_ptr(), t["w_up"].data_ptr(), t["w_down"].data_ptr(),
+                          zT.data_ptr(), hT.data_ptr(), t["assign"].data_ptr(), dzT.data_ptr(), dx.data_ptr(),
+                          dw_up.data_ptr(), db_up.data_ptr(), dw_down.data_ptr(), db_down.data_ptr(), gradp.data_ptr(),
+                          M, d, H, ld)
+    assert rc == 0
+    torch.cuda.synchronize()
+    for name, got in (("zT", zT), ("hT", hT), ("y", y), ("actp", actp), ("dzT", dzT), ("dx", dx), ("gradp", gradp)):
+        assert torch.equal(got, t[name]), name
+    # split-K red.add order is not fixed: fp32 weight gradients agree to rounding, bias gradients too
+    torch.testing.assert_close(dw_up, t["dw_up"], rtol=1e-5, atol=1e-4)
+    torch.testing.assert_close(dw_down, t["dw_down"], rtol=1e-5, atol=1e-4)
+    torch.testing.assert_close(db_up, t["db_up"], rtol=1e-5, atol=1e-4)
+    torch.testing.assert_close(db_down, t["db_down"], rtol=1e-5, atol=1e-4)
+    # statistics from already pooled moments == per-step finalisation (single step)
+    mom = torch.zeros((H, 5), device="cuda"); cnt = torch.zeros(1, device="cuda", dtype=torch.int32)
+    ops.stats_finalize(actp, gradp, P, H, M, moments=mom, sample_count=cnt)
+    pooled = ops.stats_from_moments(mom, cnt)
+    torch.cuda.synchronize()
+    torch.testing.assert_close(pooled, t["stats"], rtol=1e-4, atol=1e-6)
