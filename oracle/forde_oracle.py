@@ -14,6 +14,10 @@ What is restated, and how firmly it is pinned:
   (tests/golden/smoothing_*.npz).
 * ``cluster_neurons_gmm`` follows src/forde/clustering.py:6-39 (sklearn GaussianMixture; the seed is passed
   as an int because jax.random is unavailable).  Parity unpinned (no reference test pins its labels).
+* ``smooth_assignments_3d`` / ``compute_router_adjustments`` / ``moe_usage_diagnostics`` follow smoothing.py:94-171 and
+  src/forde/moe_slow_loop.py:211-250,372-381.  PINNED: tests/golden/moe_slow_loop.npz holds outputs of the reference's
+  own functions and of one whole ``moe_slow_loop_step`` on the pytrees of tests/verify_reset.py, executed under the
+  same stub (GMM labels excepted: their seed comes from jax.random, which the stub cannot reproduce).
 * ``top_k`` / ``moe_*`` follow src/forde/moe.py:88-93,116-135,163-187,189-222.  Index SETS pinned by
   tests/test_moe.py:46-70 and tests/test_topk_correctness.py:7-23; order/ties follow jax.lax.top_k's
   documented rule (descending, lower index first).
