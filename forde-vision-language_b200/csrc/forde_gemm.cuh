@@ -11,11 +11,11 @@
 //                128 x 256 x 768 tile).
 //   PAIR = false : one CTA per 128 x 256 tile (small problems, where 256-row tiles would leave SMs idle).
 //
-// Roles (320 threads, one CTA per SM):
+// Roles (64 + 32 x epilogue-warps threads, one CTA per SM):
 //   warp 0     : TMA producer  (cp.async.bulk.tensor -> 128B-swizzled smem ring, mbarrier complete_tx)
-//   warp 1     : TMEM allocator + single-thread tcgen05.mma issuer (128 x 256 x 16 per instruction)
-//   warps 2..9 : epilogue: tcgen05.ld the accumulator (TMEM lane quarter = warp % 4, one row per thread; the two
-//                warps of a quarter split the tile's 256 columns in halves), apply the fused epilogue, stage
+//   warp 1     : TMEM allocator + single-thread tcgen05.mma issuer (128 x 256 x 16, or 256 x 256 x 16 for a pair)
+//   warps 2..  : epilogue (8 warps as shipped): tcgen05.ld the accumulator (TMEM lane quarter = warp % 4, one row per
+//                thread; the warps of a quarter split the tile's 256 columns), apply the fused epilogue, stage
 //                through swizzled smem and TMA-store.  Two epilogue warps per SM sub-partition is what hides the
 //                tcgen05.ld / MUFU / st.shared latencies of the fused epilogues (one warp per scheduler left the
 //                tensor pipe 38 % busy; see profiles/).
@@ -28,10 +28,12 @@
 //
 // Epilogues (reference: StatefulLayer spec, /root/reference/README.md:47-56; sensing.py:34-69):
 //   EPI_STORE   : D (+ per-column bias) -> bf16, TMA store.                       (down projection, dx)
-//   EPI_UP_FWD  : rows are neurons. z = acc + b[row] -> bf16; h = F_a(z) + gate_a * z -> bf16;
-//                 per-neuron sum|z|, sum z, sum z^2 over the tile's samples -> partials[nb][3][H].
-//   EPI_DZ_BWD  : rows are neurons. reads z^T tile, dz = acc * (F_a'(z) + gate_a) (binary_step uses the
-//                 straight-through estimator) -> bf16; per-neuron sum|dz|, sum dz, sum dz^2 -> partials.
+//   EPI_UP_FWD  : rows are neurons. z = acc + b[row] -> bf16; h = F_a(z) + gate_a * z -> bf16 (always stored);
+//                 z^T stored only where the backward needs it (save_z / warps with tanh neurons);
+//                 per-neuron sum|z|, sum z, sum z^2 over each 64-sample chunk -> partials[4 nb + c][3][H].
+//   EPI_DZ_BWD  : rows are neurons. TMA-prefetches the z^T box (tanh warps) or the h^T box (sign only),
+//                 dz = acc * (F_a'(z) + gate_a) (binary_step uses the straight-through estimator) -> bf16, written in
+//                 place over that box; per-neuron sum|dz|, sum dz, sum dz^2 -> partials.
 //   EPI_F32     : D * row_scale[m] * col_scale[n] * scale -> fp32, plain store or red.add (split-K dW).
 //   EPI_MOE_UP  : rows are routed token slots (MoE variant of the slot, moe.py:17-29).  z = acc + b_e[col] -> bf16;
 //                 h = gelu_tanh(z) -> bf16.
