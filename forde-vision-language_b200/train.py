@@ -276,6 +276,10 @@ class GraphedTrainStep:
         object as ``batch`` next time and only a device-to-device move remains on the critical path."""
         dev = self.state.flat_p32.device
         cur = torch.cuda.current_stream(dev)
+        for k, v in batch.items():
+            if tuple(v.shape) != tuple(self.static[k].shape) or v.dtype != self.static[k].dtype:
+                raise ValueError(f"GraphedTrainStep was captured for {k} of shape {tuple(self.static[k].shape)} "
+                                 f"{self.static[k].dtype}; got {tuple(v.shape)} {v.dtype} (capture a new one)")
         if self._staged_for is not None and self._staged_for is batch:
             cur.wait_stream(self._copy_stream)
             for k in self.static:
