@@ -15,6 +15,9 @@
 namespace forde {
 
 constexpr int LN_WARPS = 8;
+#ifndef FORDE_LN_BWD_BLOCKS
+#define FORDE_LN_BWD_BLOCKS(NV) ((NV) <= 3 ? 3 : 2)
+#endif
 constexpr int LN_MAXV = 4;  // 16-byte vectors per lane: cols <= 32 * 4 * 8 = 1024
 
 __device__ __forceinline__ float wsum(float v) {
@@ -114,7 +117,7 @@ add_layernorm_fwd_kernel(const uint4* __restrict__ x, const uint4* __restrict__ 
 // pass, and the per-column d_gamma / d_beta accumulate in the warp's own slice of shared memory (each lane owns its
 // columns, so no conflicts and no atomics).
 template <int NV>
-__global__ void __launch_bounds__(LN_WARPS * 32, NV <= 3 ? 3 : 2)
+__global__ void __launch_bounds__(LN_WARPS * 32, FORDE_LN_BWD_BLOCKS(NV))
 add_layernorm_bwd_kernel(const uint4* __restrict__ dy, const uint4* __restrict__ x, const uint4* __restrict__ r,
                          const float* __restrict__ gamma, const float* __restrict__ mean_in,
                          const float* __restrict__ rstd_in, uint4* __restrict__ ds, float* __restrict__ partials,
@@ -207,22 +210,22 @@ add_layernorm_bwd_kernel(const uint4* __restrict__ dy, const uint4* __restrict__
   }
 }
 
-// d_gamma / d_beta from the per-CTA partials: block = 32 columns x 8 lanes over the CTAs, fixed combination order.
+// d_gamma / d_beta from the per-CTA partials: block = 32 columns x 32 lanes over the CTAs, fixed combination order.
 __global__ void ln_param_grad_kernel(const float* __restrict__ partials, int nblocks, int cols,
                                      float* __restrict__ d_gamma, float* __restrict__ d_beta) {
-  __shared__ float red[8][33];
+  __shared__ float red[32][33];
   const int c = blockIdx.x * 32 + threadIdx.x;  // index into [2][cols]
   float t = 0.f;
   if (c < 2 * cols) {
     const int which = c / cols, col = c - which * cols;
-    for (int b = threadIdx.y; b < nblocks; b += 8) t += partials[(static_cast<size_t>(b) * 2 + which) * cols + col];
+    for (int b = threadIdx.y; b < nblocks; b += 32) t += partials[(static_cast<size_t>(b) * 2 + which) * cols + col];
   }
   red[threadIdx.y][threadIdx.x] = t;
   __syncthreads();
   if (threadIdx.y == 0 && c < 2 * cols) {
     float r = 0.f;
 #pragma unroll
-    for (int y = 0; y < 8; ++y) r += red[y][threadIdx.x];
+    for (int y = 0; y < 32; ++y) r += red[y][threadIdx.x];
     const int which = c / cols, col = c - which * cols;
     (which == 0 ? d_gamma : d_beta)[col] += r;
   }
@@ -331,7 +334,7 @@ int forde_add_layernorm_bwd(void* stream, const void* dy, const void* x, const v
   else if (nv == 3) FORDE_LN_BWD(3);
   else FORDE_LN_BWD(4);
 #undef FORDE_LN_BWD
-  ln_param_grad_kernel<<<(2 * cols + 31) / 32, dim3(32, 8), 0, st>>>(partials, grid, cols, d_gamma, d_beta);
+  ln_param_grad_kernel<<<(2 * cols + 31) / 32, dim3(32, 32), 0, st>>>(partials, grid, cols, d_gamma, d_beta);
   return check_launch("add_layernorm_bwd_kernel", 2);
 }
 
