@@ -530,18 +530,17 @@ topk_sparsify_kernel(__nv_bfloat16* __restrict__ hT, long long ld, int M, int H,
 }
 
 // dzT[h][m] = 0 where the forward dropped h[h][m]; optionally re-takes the per-neuron gradient sums of the MASKED dz
-// in the layout of the GEMM epilogue's partials ([P][3][H], one slot per 64 samples).  One warp per (neuron, 64-sample
-// block), two samples per lane.
+// in the layout of the GEMM epilogue's partials ([P][3][H], one slot per `sps` samples).  One warp per (neuron,
+// slot), sps / 32 samples per lane.
 __global__ void topk_mask_kernel(__nv_bfloat16* __restrict__ dzT, long long ld, int M, int H,
-                                 const uint32_t* __restrict__ keep_bits, float* __restrict__ partials) {
+                                 const uint32_t* __restrict__ keep_bits, float* __restrict__ partials, int sps) {
   const int lane = threadIdx.x & 31;
   const int h = blockIdx.y * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  const int pb = blockIdx.x;  // 64-sample block
+  const int pb = blockIdx.x;  // slot (block of sps samples)
   if (h >= H) return;
   float s_abs = 0.f, s_sum = 0.f, s_sq = 0.f;
-#pragma unroll
-  for (int i = 0; i < 2; ++i) {
-    const int m = pb * 64 + i * 32 + lane;
+  for (int i = 0; i < sps / 32; ++i) {
+    const int m = pb * sps + i * 32 + lane;
     if (m < M) {
       const uint32_t w = keep_bits[static_cast<size_t>(h >> 5) * M + m];
       uint16_t* p = reinterpret_cast<uint16_t*>(dzT) + static_cast<size_t>(h) * ld + m;
@@ -591,9 +590,10 @@ int forde_sl_topk_sparsify(void* stream, void* hT, long long ldz, int M, int H, 
 int forde_sl_topk_mask(void* stream, void* dzT, long long ldz, int M, int H, const uint32_t* keep_bits,
                        float* grad_partials) {
   if (dzT == nullptr || keep_bits == nullptr || M <= 0 || H <= 0 || ldz < M) return FORDE_EINVAL;
-  const int P = forde_sl_num_partials(M);  // 64-sample blocks (trailing ones beyond M get zeros)
+  const int P = forde_sl_num_partials(M);             // slots (trailing ones beyond M get zeros)
+  const int sps = 256 / forde_sl_num_partials(256);   // samples per slot: the GEMM epilogues' partials layout
   forde::topk_mask_kernel<<<dim3(P, (H + 7) / 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<__nv_bfloat16*>(dzT), ldz, M, H, keep_bits, grad_partials);
+      static_cast<__nv_bfloat16*>(dzT), ldz, M, H, keep_bits, grad_partials, sps);
   return forde::check_launch("topk_mask_kernel");
 }
 

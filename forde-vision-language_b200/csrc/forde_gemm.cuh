@@ -87,12 +87,16 @@ constexpr int TMEM_COLS = 512;
 #ifndef FORDE_DZ_STAGES
 #define FORDE_DZ_STAGES 5
 #endif
+// Per-neuron partial-sum slots per 256-column tile.  With 8 epilogue warps each warp drains two adjacent 64-column
+// chunks and sums them into ONE slot (2 slots of 128 samples per tile: half the partials traffic and half of what
+// forde_stats_finalize reads); A/B builds with 16 warps keep one slot per chunk.
+constexpr int PARTIALS_PER_TILE = (FORDE_UP_WARPS == 8 && FORDE_DZ_WARPS == 8) ? 2 : 4;
+constexpr int CHUNKS_PER_SLOT = (BN / CHUNK) / PARTIALS_PER_TILE;
 __host__ __device__ constexpr int epi_warps(int epi, bool pair) {
   return !pair ? 8 : epi == EPI_UP_FWD ? FORDE_UP_WARPS : epi == EPI_DZ_BWD ? FORDE_DZ_WARPS : 8;
 }
 __host__ __device__ constexpr int num_threads(int epi, bool pair) { return 64 + 32 * epi_warps(epi, pair); }
-// number of per-neuron partial-sum slots per 256-column tile: always 4 (one per 64-column chunk)
-constexpr int PARTIALS_PER_TILE = BN / CHUNK;
+
 
 // EPI_DZ_BWD keeps a per-warp ring of z^T boxes: chunk g is TMA-loaded DZ_DIST chunks ahead into box g % ring,
 // multiplied in place into dz and TMA-stored from there.  ring - DZ_DIST - 1 stores may still be reading smem
@@ -149,7 +153,7 @@ struct GemmParams {
   const float* bias_col;    // [N]  EPI_STORE (may be null)
   const float* bias_row;    // [M]  EPI_UP_FWD (may be null)
   const int8_t* assign;     // [M]  EPI_UP_FWD / EPI_DZ_BWD: 0 relu, 1 tanh, else binary step
-  float* partials;          // [4 * n_blocks][3][M]  EPI_UP_FWD / EPI_DZ_BWD (may be null): one slot per 64 columns
+  float* partials;          // [PARTIALS_PER_TILE * n_blocks][3][M]  EPI_UP_FWD / EPI_DZ_BWD (may be null)
   float* out_f32;           // EPI_F32
   long long ldc;            // EPI_F32 row pitch in elements
   const float* row_scale;   // EPI_F32 (may be null)
@@ -533,13 +537,14 @@ __global__ void __launch_bounds__(num_threads(EPI, PAIR), 1) forde_gemm_kernel(c
       tc_fence_after();
       const uint32_t taddr = lane_taddr + as * BN;
 
+      static_assert(!epi_neuron_rows(EPI) || CPW % CHUNKS_PER_SLOT == 0, "a partials slot must belong to one warp");
+      RunningSums rs{0.f, 0.f, 0.f};  // per-neuron sums of the current partials slot (fused epilogues)
 #pragma unroll 1
       for (int cc = 0; cc < CPW; ++cc) {
         const int c = e * CPW + cc;
         const int col0 = w.n0 + c * CHUNK;
         const int nvalid = p.N - col0;  // valid columns in this chunk (may be <= 0 or >= CHUNK)
         const bool full = nvalid >= CHUNK;
-        RunningSums rs{0.f, 0.f, 0.f};  // this chunk's per-neuron sums (fused epilogues)
 
         if (epi_z_ring(EPI)) z_prefetch(g + ZD, true);  // refill the box chunk g + ZD will use
         // single-buffered staging: the previous chunk's TMA stores must have read the boxes (the other epilogue
@@ -687,11 +692,14 @@ __global__ void __launch_bounds__(num_threads(EPI, PAIR), 1) forde_gemm_kernel(c
         }
         if (epi_z_ring(EPI)) ++g;
 
-        if (epi_neuron_rows(EPI) && p.partials != nullptr && row < p.M) {
-          float* dst = p.partials + (static_cast<long long>(w.nb * PARTIALS_PER_TILE + c) * 3) * p.M + row;
-          dst[0] = rs.s_abs;
-          dst[p.M] = rs.s_sum;
-          dst[2 * static_cast<long long>(p.M)] = rs.s_sq;
+        if (epi_neuron_rows(EPI) && ((c + 1) % CHUNKS_PER_SLOT) == 0) {  // slot complete
+          if (p.partials != nullptr && row < p.M) {
+            float* dst = p.partials + (static_cast<long long>(w.nb * PARTIALS_PER_TILE + c / CHUNKS_PER_SLOT) * 3) * p.M + row;
+            dst[0] = rs.s_abs;
+            dst[p.M] = rs.s_sum;
+            dst[2 * static_cast<long long>(p.M)] = rs.s_sq;
+          }
+          rs = RunningSums{0.f, 0.f, 0.f};
         }
       }
 

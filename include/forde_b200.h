@@ -20,7 +20,7 @@
  *   zT, hT, dzT  : [H][ldz] bf16, NEURON-major (one row per neuron, samples contiguous), ldz >= M.
  *                  Keeping the per-neuron axis on the TMEM lanes is what lets the sensing statistics be
  *                  accumulated per thread with no cross-lane reduction.
- *   partials     : [P][3][H] fp32 with P = forde_sl_num_partials(M): per 64-sample block the per-neuron
+ *   partials     : [P][3][H] fp32 with P = forde_sl_num_partials(M): per 128-sample block the per-neuron
  *                  sum|v|, sum v, sum v^2 (v = z in the forward, v = dL/dz in the backward).  Written,
  *                  not accumulated: every slot has exactly one writer, so results are deterministic.
  */
@@ -47,8 +47,8 @@ int forde_sm_count(void);
 /* kernels launched by this library in this process so far (bench.py reports the per-step difference) */
 unsigned long long forde_launch_count(void);
 
-/* number of 64-sample partial blocks the forward / backward kernels write for M samples
- * (4 per 256-sample tile column; trailing ones may be empty) */
+/* number of 128-sample partial blocks the forward / backward kernels write for M samples
+ * (2 per 256-sample tile column; the last one may be empty) */
 int forde_sl_num_partials(int M);
 
 /* ---- generic GEMM  D[M][N] = sum_k A(m,k) * B(n,k)  (test + building block) -------------------------

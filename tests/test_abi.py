@@ -46,10 +46,10 @@ def test_pure_host_entry_points(lib):
     assert lib.forde_error_string(0) == b"ok"
     assert b"alignment" in lib.forde_error_string(-2)
     assert lib.forde_sl_num_partials(0) == 0
-    assert lib.forde_sl_num_partials(1) == 4
-    assert lib.forde_sl_num_partials(256) == 4
-    assert lib.forde_sl_num_partials(257) == 8
-    assert lib.forde_sl_num_partials(50432) == 788
+    assert lib.forde_sl_num_partials(1) == 2
+    assert lib.forde_sl_num_partials(256) == 2
+    assert lib.forde_sl_num_partials(257) == 4
+    assert lib.forde_sl_num_partials(50432) == 394
 
 
 def test_argument_validation_needs_no_gpu(lib):
