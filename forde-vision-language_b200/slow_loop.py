@@ -126,20 +126,22 @@ def slow_loop_step(params, mutable_variables, config: SlowLoopConfig, key, epoch
     seed = _seed_from_key(key)
     diagnostics = {"epoch": epoch, "step": step, "layers": {}}
 
+    # SENSE for every layer first (device work + the cross-rank all-reduce, in a fixed order on every rank) ...
+    jobs = []
+
     def walk(st, asg, path):
         if isinstance(st, dict) and "neuron_stats" in st:
-            _update_layer(st, asg, path)
+            jobs.append(("/".join(path), sense_layer(st, config.pooled, group), asg))
             return
         if isinstance(st, dict):
             for k in sorted(st):
                 walk(st[k], asg[k], path + (k,))
 
-    def _update_layer(st, asg, path):
-        stats = sense_layer(st, config.pooled, group)                                   # SENSE
-        name = "/".join(path)
-        if stats is None:
-            diagnostics["layers"][name] = {"skipped": "no statistics accumulated"}
-            return
+    walk(stats_tree, assign_tree, ())
+
+    # ... then CLUSTER + SMOOTH per layer on host threads (scikit-learn / SciPy release the GIL in their kernels; each
+    # layer is independent and seeded, so the result does not depend on the scheduling) ...
+    def cluster_and_smooth(stats):
         H = stats.shape[0]
         k = config.num_clusters
         if config.forde_lite:
@@ -151,6 +153,20 @@ def slow_loop_step(params, mutable_variables, config: SlowLoopConfig, key, epoch
                 labels = _relabel_by_grad_gini(labels, stats, k)
         grid = labels.reshape(default_grid(H))                                          # SMOOTH
         smoothed = box_smooth(grid, config.kernel_size, max(k, 3) if config.forde_lite else k)
+        return labels, smoothed, gmm_params
+
+    from concurrent.futures import ThreadPoolExecutor
+    todo = [(name, stats) for name, stats, _ in jobs if stats is not None]
+    with ThreadPoolExecutor(max_workers=max(1, min(8, len(todo)))) as pool:
+        results = dict(zip([n for n, _ in todo], pool.map(lambda t: cluster_and_smooth(t[1]), todo)))
+
+    # ... and ACTUATE in order
+    k = config.num_clusters
+    for name, stats, asg in jobs:
+        if stats is None:
+            diagnostics["layers"][name] = {"skipped": "no statistics accumulated"}
+            continue
+        labels, smoothed, gmm_params = results[name]
         tgt = asg["assignments"]
         new = torch.from_numpy(smoothed.reshape(-1).astype(np.int32)).to(tgt.device)
         changed = int((new != tgt).sum().item())
@@ -164,7 +180,6 @@ def slow_loop_step(params, mutable_variables, config: SlowLoopConfig, key, epoch
             "gmm": gmm_params,
         }
 
-    walk(stats_tree, assign_tree, ())
     # RESET: zero every leaf of stats_buffer (moe_slow_loop.py:441-449)
     def zero(t):
         if isinstance(t, dict):
