@@ -26,6 +26,7 @@ SIGNATURES = {
     "forde_launch_count": (ctypes.c_ulonglong, []),
     "forde_sl_num_partials": (_i, [_i]),
     "forde_gemm_bf16": (_i, [_vp, _vp, _i, _ll, _vp, _i, _ll, _vp, _ll, _vp, _i, _i, _i]),
+    "forde_gemm_bf16_add": (_i, [_vp, _vp, _i, _ll, _vp, _i, _ll, _vp, _ll, _vp, _vp, _i, _i, _i]),
     "forde_gemm_f32": (_i, [_vp, _vp, _i, _ll, _vp, _i, _ll, _vp, _ll, _vp, _vp, _f, _i, _i, _i, _i]),
     "forde_sl_up_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _ll, _i]),
     "forde_sl_down_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _ll]),

@@ -256,7 +256,8 @@ static void choose_split_k(GemmParams& p) {
   p.split_k = (p.k_blocks + p.kb_per_split - 1) / p.kb_per_split;
 }
 
-int gemm_store_bf16(cudaStream_t stream, const GemmArgs& g, void* D, long long ldd, const float* bias_col) {
+int gemm_store_bf16(cudaStream_t stream, const GemmArgs& g, void* D, long long ldd, const float* bias_col,
+                    const void* Cin) {
   GemmParams p;
   int rc = fill_common(p, g);
   if (rc != FORDE_OK) return rc;
@@ -264,6 +265,11 @@ int gemm_store_bf16(cudaStream_t stream, const GemmArgs& g, void* D, long long l
   rc = make_tmap_bf16(&p.tmC0, D, g.N, g.M, ldd, CHUNK, 32);
   if (rc != FORDE_OK) return rc;
   p.bias_col = bias_col;
+  if (Cin != nullptr) {  // D = A . B^T + bias + Cin (Cin has D's shape and pitch and may be D itself)
+    rc = make_tmap_bf16(&p.tmZ, Cin, g.N, g.M, ldd, CHUNK, 32);
+    if (rc != FORDE_OK) return rc;
+    return launch_epi<EPI_STORE_ADD>(p, g.a_mn, g.b_mn, stream);
+  }
   return launch_epi<EPI_STORE>(p, g.a_mn, g.b_mn, stream);
 }
 
@@ -375,6 +381,14 @@ int forde_gemm_bf16(void* stream, const void* A, int a_mn_major, long long lda, 
                     long long ldb, void* D, long long ldd, const float* bias_col, int M, int N, int K) {
   GemmArgs g{A, a_mn_major != 0, lda, B, b_mn_major != 0, ldb, M, N, K, false, kEvictNormal, kEvictNormal};
   return gemm_store_bf16(static_cast<cudaStream_t>(stream), g, D, ldd, bias_col);
+}
+
+int forde_gemm_bf16_add(void* stream, const void* A, int a_mn_major, long long lda, const void* B, int b_mn_major,
+                        long long ldb, void* D, long long ldd, const void* Cin, const float* bias_col, int M, int N,
+                        int K) {
+  if (Cin == nullptr) return FORDE_EINVAL;
+  GemmArgs g{A, a_mn_major != 0, lda, B, b_mn_major != 0, ldb, M, N, K, false, kEvictNormal, kEvictNormal};
+  return gemm_store_bf16(static_cast<cudaStream_t>(stream), g, D, ldd, bias_col, Cin);
 }
 
 int forde_gemm_f32(void* stream, const void* A, int a_mn_major, long long lda, const void* B, int b_mn_major,

@@ -28,6 +28,8 @@
 //
 // Epilogues (reference: StatefulLayer spec, /root/reference/README.md:47-56; sensing.py:34-69):
 //   EPI_STORE   : D (+ per-column bias) -> bf16, TMA store.                       (down projection, dx)
+//   EPI_STORE_ADD : D (+ bias) + Cin -> bf16: the Cin tile (may be D itself: accumulate) is TMA-prefetched like the
+//                 z tile of EPI_DZ_BWD and overwritten in place.  (input gradients that sum several GEMMs)
 //   EPI_UP_FWD  : rows are neurons. z = acc + b[row] -> bf16; h = F_a(z) + gate_a * z -> bf16 (always stored);
 //                 z^T stored only where the backward needs it (save_z / warps with tanh neurons);
 //                 per-neuron sum|z|, sum z, sum z^2 over each 64-sample chunk -> partials[4 nb + c][3][H].
@@ -56,7 +58,9 @@
 
 namespace forde {
 
-enum EpiKind : int { EPI_STORE = 0, EPI_UP_FWD = 1, EPI_DZ_BWD = 2, EPI_F32 = 3, EPI_MOE_UP = 4, EPI_MOE_DZ = 5 };
+enum EpiKind : int {
+  EPI_STORE = 0, EPI_UP_FWD = 1, EPI_DZ_BWD = 2, EPI_F32 = 3, EPI_MOE_UP = 4, EPI_MOE_DZ = 5, EPI_STORE_ADD = 6
+};
 
 constexpr int BM = 128;
 constexpr int BN = 256;
@@ -101,9 +105,13 @@ __host__ __device__ constexpr int num_threads(int epi, bool pair) { return 64 + 
 // EPI_DZ_BWD keeps a per-warp ring of z^T boxes: chunk g is TMA-loaded DZ_DIST chunks ahead into box g % ring,
 // multiplied in place into dz and TMA-stored from there.  ring - DZ_DIST - 1 stores may still be reading smem
 // when a box is refilled, so with ring 4 / distance 2 the refill never waits on the store just issued.
-__host__ __device__ constexpr bool epi_z_ring(int epi) { return epi == EPI_DZ_BWD || epi == EPI_MOE_DZ; }
+__host__ __device__ constexpr bool epi_z_ring(int epi) {
+  return epi == EPI_DZ_BWD || epi == EPI_MOE_DZ || epi == EPI_STORE_ADD;
+}
 __host__ __device__ constexpr bool epi_two_out(int epi) { return epi == EPI_UP_FWD || epi == EPI_MOE_UP; }
-__host__ __device__ constexpr bool epi_col_bias(int epi) { return epi == EPI_STORE || epi == EPI_MOE_UP; }
+__host__ __device__ constexpr bool epi_col_bias(int epi) {
+  return epi == EPI_STORE || epi == EPI_MOE_UP || epi == EPI_STORE_ADD;
+}
 __host__ __device__ constexpr bool epi_neuron_rows(int epi) { return epi == EPI_UP_FWD || epi == EPI_DZ_BWD; }
 __host__ __device__ constexpr int dz_ring(bool pair) { return 2; }
 __host__ __device__ constexpr int dz_dist(bool pair) { return 1; }
@@ -116,6 +124,7 @@ __host__ __device__ constexpr int gemm_stages(int epi, bool pair) {
   return epi == EPI_UP_FWD ? (pair ? FORDE_UP_STAGES : 3)
          : epi == EPI_DZ_BWD ? (pair ? FORDE_DZ_STAGES : 3)
          : (epi == EPI_MOE_UP || epi == EPI_MOE_DZ) ? 3
+         : epi == EPI_STORE_ADD                     ? (pair ? 5 : 3)
                                                     : (pair ? 6 : 4);
 }
 __host__ __device__ constexpr int gemm_smem_bytes(int epi, bool pair) {
@@ -126,6 +135,7 @@ static_assert(gemm_smem_bytes(EPI_STORE, false) <= 232448 && gemm_smem_bytes(EPI
 static_assert(gemm_smem_bytes(EPI_UP_FWD, false) <= 232448 && gemm_smem_bytes(EPI_UP_FWD, true) <= 232448, "smem");
 static_assert(gemm_smem_bytes(EPI_F32, false) <= 232448 && gemm_smem_bytes(EPI_F32, true) <= 232448, "smem");
 static_assert(gemm_smem_bytes(EPI_DZ_BWD, false) <= 232448 && gemm_smem_bytes(EPI_DZ_BWD, true) <= 232448, "smem");
+static_assert(gemm_smem_bytes(EPI_STORE_ADD, false) <= 232448 && gemm_smem_bytes(EPI_STORE_ADD, true) <= 232448, "smem");
 
 struct GemmParams {
   CUtensorMap tmA;   // operand A   (box 64 x BM for K-major, 64 x 64 for MN-major)
@@ -632,6 +642,21 @@ __global__ void __launch_bounds__(num_threads(EPI, PAIR), 1) forde_gemm_kernel(c
             else if (wmode == WM_RELU) run(std::integral_constant<int, WM_RELU>{}, F{});
             else if (wmode == WM_STEP) run(std::integral_constant<int, WM_STEP>{}, F{});
             else run(std::integral_constant<int, WM_MIXED>{}, F{});
+          } else if (EPI == EPI_STORE_ADD) {
+            const float* bsrc = bias_s + c * CHUNK + jbase;
+#pragma unroll
+            for (int j8 = 0; j8 < 4; ++j8) {
+              const uint32_t off = (static_cast<uint32_t>(half * 4 + j8) ^ sw) << 4;
+              uint32_t cw[4], ow[4];
+              ld_shared_v4(orow_s + off, cw[0], cw[1], cw[2], cw[3]);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const int j = j8 * 8 + i * 2;
+                ow[i] = pack_bf16x2(__uint_as_float(v[j]) + bsrc[j] + bf16lo_to_f32(cw[i]),
+                                    __uint_as_float(v[j + 1]) + bsrc[j + 1] + bf16hi_to_f32(cw[i]));
+              }
+              st_shared_v4(orow_s + off, ow[0], ow[1], ow[2], ow[3]);
+            }
           } else if (EPI == EPI_MOE_UP) {
             // z box at wst (tmC0), h = gelu_tanh(z) box at wst + BOX_BYTES (tmC1); flax nn.gelu default (moe.py:27)
             const float* bsrc = bias_s + c * CHUNK + jbase;

@@ -22,8 +22,9 @@ struct GemmArgs {
   uint64_t hintA, hintB;
 };
 
-// D (bf16) = A . B^T (+ bias_col)
-int gemm_store_bf16(cudaStream_t stream, const GemmArgs& g, void* D, long long ldd, const float* bias_col);
+// D (bf16) = A . B^T (+ bias_col) (+ Cin: same shape / pitch as D, may alias it)
+int gemm_store_bf16(cudaStream_t stream, const GemmArgs& g, void* D, long long ldd, const float* bias_col,
+                    const void* Cin = nullptr);
 // D (fp32) = or += scale * row_scale[m] * col_scale[n] * (A . B^T); accumulate uses split-K + red.add
 int gemm_f32(cudaStream_t stream, const GemmArgs& g, float* D, long long ldd, const float* row_scale,
              const float* col_scale, float scale, const float* scale_dev, bool accumulate);

@@ -101,9 +101,9 @@ def _deliver_dense_grads(w, b, x2t, dy2):
 
 
 class _Dense(torch.autograd.Function):
-    """y = x W + b for bf16 activations.  Forward and weight gradient run on this repository's tcgen05 GEMM engine
-    (bias fused in the epilogue; dW accumulated in fp32 straight into the gradient sink), the input gradient on
-    cuBLAS, the bias gradient on the column-sum kernel.  `w16` is the bf16 mirror (in, out)."""
+    """y = x W + b for bf16 activations.  Forward, input gradient and weight gradient run on this repository's tcgen05
+    GEMM engine (bias fused in the epilogue; dW accumulated in fp32 straight into the gradient sink), the bias
+    gradient on the column-sum kernel.  `w16` is the bf16 mirror (in, out)."""
 
     @staticmethod
     def forward(ctx, x, w, b, w16, b16):
@@ -122,14 +122,14 @@ class _Dense(torch.autograd.Function):
         dy2 = dy.reshape(-1, dy.shape[-1])
         if not dy2.is_contiguous():
             dy2 = dy2.contiguous()
-        dx = torch.mm(dy2, w16.t()).view(*ctx.lead, w16.shape[0])
+        dx = ops.gemm_bf16(dy2, w16, False, False).view(*ctx.lead, w16.shape[0])     # dx = dy W^T
         dw, db = _deliver_dense_grads(ctx.masters[0], ctx.masters[1], x2.t(), dy2)
         return dx, dw, db, None, None
 
 
 class _QKVDense(torch.autograd.Function):
-    """The three attention input projections sharing one input: forward three GEMMs, backward accumulates dx with
-    beta = 1 inside the GEMMs (no separate add passes over the (M, w) gradient)."""
+    """The three attention input projections sharing one input: three forward GEMMs; the backward accumulates dx
+    inside the GEMM epilogues (EPI_STORE_ADD: no separate add passes over the (M, w) gradient)."""
 
     @staticmethod
     def forward(ctx, x, wq, bq, wk, bk, wv, bv, wq16, bq16, wk16, bk16, wv16, bv16):
@@ -147,9 +147,11 @@ class _QKVDense(torch.autograd.Function):
         x2, wq16, wk16, wv16 = ctx.saved_tensors
         d = [t.reshape(-1, t.shape[-1]) for t in (dq, dk, dv)]
         d = [t if t.is_contiguous() else t.contiguous() for t in d]
-        dx = torch.mm(d[0], wq16.t())
-        dx.addmm_(d[1], wk16.t())
-        dx.addmm_(d[2], wv16.t())
+        dx = ops.gemm_bf16(d[0], wq16, False, False)                 # dx = dq Wq^T
+        if not dx.is_contiguous():
+            dx = dx.contiguous()
+        ops.gemm_bf16(d[1], wk16, False, False, add_to=dx)           #    += dk Wk^T  (accumulated in the epilogue)
+        ops.gemm_bf16(d[2], wv16, False, False, add_to=dx)           #    += dv Wv^T
         xt = x2.t()
         grads = []
         for t, (w, b) in zip(d, ctx.masters):

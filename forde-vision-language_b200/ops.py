@@ -86,16 +86,26 @@ def sample_pitch(M: int) -> int:
 
 
 # ------------------------------------------------------------------------------------------ generic GEMM
-def gemm_bf16(A: torch.Tensor, B: torch.Tensor, a_mn_major: bool, b_mn_major: bool, bias_col=None) -> torch.Tensor:
-    """D[M,N] = sum_k A(m,k) B(n,k) -> bf16.  K-major operands are [rows, K]; MN-major operands are [K, rows]."""
+def gemm_bf16(A: torch.Tensor, B: torch.Tensor, a_mn_major: bool, b_mn_major: bool, bias_col=None, add_to=None) -> torch.Tensor:
+    """D[M,N] = sum_k A(m,k) B(n,k) (+ bias_col) -> bf16.  K-major operands are [rows, K]; MN-major operands are
+    [K, rows].  With ``add_to`` (a contiguous bf16 [M, N] tensor, N % 8 == 0) the product is accumulated into it in
+    place and it is returned."""
     _req(A, torch.bfloat16, "A"); _req(B, torch.bfloat16, "B")
     M, K = (A.shape[1], A.shape[0]) if a_mn_major else (A.shape[0], A.shape[1])
     N, Kb = (B.shape[1], B.shape[0]) if b_mn_major else (B.shape[0], B.shape[1])
     assert K == Kb, "reduction extents differ"
-    ldd = round_up(N, 8)
-    D = torch.empty((M, ldd), dtype=torch.bfloat16, device=A.device)
     if bias_col is not None:
         _req(bias_col, torch.float32, "bias_col")
+    if add_to is not None:
+        _req(add_to, torch.bfloat16, "add_to")
+        assert tuple(add_to.shape) == (M, N)
+        rc = _lib.load().forde_gemm_bf16_add(_stream(), A.data_ptr(), int(a_mn_major), A.stride(0), B.data_ptr(),
+                                             int(b_mn_major), B.stride(0), add_to.data_ptr(), add_to.stride(0),
+                                             add_to.data_ptr(), _ptr(bias_col), M, N, K)
+        _lib.check(rc, "forde_gemm_bf16_add")
+        return add_to
+    ldd = round_up(N, 8)
+    D = torch.empty((M, ldd), dtype=torch.bfloat16, device=A.device)
     rc = _lib.load().forde_gemm_bf16(_stream(), A.data_ptr(), int(a_mn_major), A.stride(0), B.data_ptr(),
                                      int(b_mn_major), B.stride(0), D.data_ptr(), ldd, _ptr(bias_col), M, N, K)
     _lib.check(rc, "forde_gemm_bf16")

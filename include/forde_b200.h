@@ -55,6 +55,10 @@ int forde_sl_num_partials(int M);
  * a_mn_major = 0: A stored [M][K] (pitch lda);  1: A stored [K][M] (pitch lda).  Same for B with N. */
 int forde_gemm_bf16(void* stream, const void* A, int a_mn_major, long long lda, const void* B, int b_mn_major,
                     long long ldb, void* D, long long ldd, const float* bias_col, int M, int N, int K);
+/* D = A . B^T + bias_col + Cin, bf16; Cin has D's shape and pitch and may be D itself (accumulate in place) */
+int forde_gemm_bf16_add(void* stream, const void* A, int a_mn_major, long long lda, const void* B, int b_mn_major,
+                        long long ldb, void* D, long long ldd, const void* Cin, const float* bias_col, int M, int N,
+                        int K);
 int forde_gemm_f32(void* stream, const void* A, int a_mn_major, long long lda, const void* B, int b_mn_major,
                    long long ldb, float* D, long long ldd, const float* row_scale, const float* col_scale,
                    float scale, int accumulate, int M, int N, int K);

@@ -516,3 +516,20 @@ def test_composite_abi_entry_points_match_the_stepwise_calls(ops):
     pooled = ops.stats_from_moments(mom, cnt)
     torch.cuda.synchronize()
     torch.testing.assert_close(pooled, t["stats"], rtol=1e-4, atol=1e-6)
+
+
+@pytest.mark.parametrize("shape", [(256, 512, 256), (1000, 264, 72), (50432, 768, 768)])
+def test_gemm_bf16_accumulate_in_place(ops, shape):
+    """EPI_STORE_ADD: D += A B^T + bias with the C tile read and overwritten in the epilogue."""
+    M, N, K = shape
+    g = torch.Generator(device="cuda").manual_seed(7)
+    A = torch.randn((M, K), device="cuda", generator=g).bfloat16()
+    B = torch.randn((N, K), device="cuda", generator=g).bfloat16()
+    C = torch.randn((M, N), device="cuda", generator=g).bfloat16()
+    bias = torch.randn(N, device="cuda", generator=g)
+    ref = (A.float() @ B.float().t() + bias + C.float()).bfloat16()
+    out = ops.gemm_bf16(A, B, False, False, bias_col=bias, add_to=C)
+    torch.cuda.synchronize()
+    assert out.data_ptr() == C.data_ptr()
+    err = (out.float() - ref.float()).norm() / ref.float().norm()
+    assert err.item() < 5e-3
