@@ -2,9 +2,10 @@
 
 This is the benchmark / integration harness around the StatefulLayer, not the product: the towers are the
 plain macro-architecture the README describes (patchify or token embedding -> L x FORDETransformerBlock ->
-[CLS] -> Dense projection), the attention projections and the attention itself go through stock torch ops
-(cuBLAS / cuDNN flash SDPA, "library code" for this task); the FFN slot of every block -- ``StatefulLayer`` --,
-the `add/norm` either side of it and the contrastive loss run on this repository's sm_100a kernels.  FORDE block = self-attention -> add/norm -> StatefulLayer ->
+[CLS] -> Dense projection), the attention core goes through stock torch SDPA (cuDNN flash, "library code" for this
+task) and the front ends / projection heads through torch ops; the FFN slot of every block -- ``StatefulLayer`` --,
+the `add/norm` either side of it, the q/k/v/out projections and the contrastive loss run on this repository's
+sm_100a kernels.  FORDE block = self-attention -> add/norm -> StatefulLayer ->
 add/norm (README.md:42-43).
 
 Variables follow the Flax collection layout the reference's training loop threads through ``train_step``
