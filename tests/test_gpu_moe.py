@@ -216,3 +216,65 @@ def test_moe_slow_loop_closes_the_loop_on_gpu(ops):
     np.testing.assert_allclose(delta, diag["adjustments"], rtol=1e-5, atol=1e-7)
     assert delta[0] < 0 and delta[2] > 0                       # over-used expert pushed down, under-used pushed up
     assert int(v["stats_buffer"]["step_count"].item()) == 0 and float(v["stats_buffer"]["expert_usage"].abs().sum()) == 0.0
+
+
+def test_decoder_lm_with_moe_slot_trains_and_feeds_the_slow_loop(ops):
+    """Config-4 shaped caller in miniature: decoder LM (causal attention + MoEStatefulLayer in the FFN slot), a few
+    AdamW steps on synthetic tokens (src/data/dataset.py:27 style), first-step loss against an fp32 dense-all-experts
+    restatement, then moe_slow_loop_step on the model's own variable trees."""
+    from forde_b200 import llm_harness as LM, slow_loop as SL
+    cfg = LM.LLMConfig(vocab_size=512, d_model=64, num_layers=2, num_heads=2, head_dim=32, max_seq_len=64,
+                       num_experts=4, top_k_experts=2, expert_hidden_dim=128)
+    model = LM.FORDEDecoderLM(cfg)
+    v = model.init(0, "cuda")
+    ids = torch.from_numpy(np.random.RandomState(42).randint(0, cfg.vocab_size, (4, 64)).astype(np.int32)).cuda()
+    leaves = list(LM.param_leaves(v["params"]))
+    opt = torch.optim.AdamW(leaves, lr=3e-3)
+
+    # fp32 restatement of the same forward (every expert on every token, moe.py:163) for the first-step loss
+    def ref_loss():
+        p = v["params"]
+        f = lambda t: t.detach().float()
+        B, S = ids.shape
+        x = torch.nn.functional.embedding(ids.long(), f(p["token_embed"])) + f(p["pos_embed"])[:S]
+        aux_t = 0.0
+        for i in range(cfg.num_layers):
+            lp = p[f"layer_{i}"]
+            h = torch.nn.functional.layer_norm(x, (64,), f(lp["attn_norm"]["scale"]), f(lp["attn_norm"]["bias"]), 1e-6)
+            q, k, vv = (h @ f(lp["attn"]["qkv"])).view(B, S, 3, 2, 32).permute(2, 0, 3, 1, 4)
+            a = torch.nn.functional.scaled_dot_product_attention(q, k, vv, is_causal=True).transpose(1, 2).reshape(B, S, -1)
+            x = x + a @ f(lp["attn"]["out"])
+            h = torch.nn.functional.layer_norm(x, (64,), f(lp["ffn_norm"]["scale"]), f(lp["ffn_norm"]["bias"]), 1e-6)
+            mp = lp["moe"]
+            r = O.moe_layer_torch(h.reshape(-1, 64).cpu().numpy(), f(mp["router"]["router_linear"]["kernel"]).cpu().numpy(),
+                                  f(mp["router"]["router_linear"]["bias"]).cpu().numpy(), f(mp["experts"]["up_proj"]["kernel"]).cpu().numpy(),
+                                  f(mp["experts"]["up_proj"]["bias"]).cpu().numpy(), f(mp["experts"]["down_proj"]["kernel"]).cpu().numpy(),
+                                  f(mp["experts"]["down_proj"]["bias"]).cpu().numpy(), 2, 0.01)
+            x = x + torch.from_numpy(r["out"]).float().cuda().view(B, S, 64)
+            aux_t += r["aux"]
+        x = torch.nn.functional.layer_norm(x, (64,), f(p["final_norm"]["scale"]), f(p["final_norm"]["bias"]), 1e-6)
+        logits = x @ f(p["lm_head"]["kernel"]) + f(p["lm_head"]["bias"])
+        return float(LM.lm_loss(logits, ids, aux_t)[0])
+
+    expected = ref_loss()
+    losses = []
+    for step in range(6):
+        (logits, aux), _ = model.apply(v, ids, mutable=["stats_buffer"])
+        loss, lm = LM.lm_loss(logits, ids, aux)
+        opt.zero_grad(set_to_none=True)
+        loss.backward()
+        opt.step()
+        losses.append(float(loss.item()))
+    assert abs(losses[0] - expected) < 5e-2, (losses[0], expected)
+    assert losses[-1] < losses[0] - 0.3                                        # it learns the fixed batch
+    sb = v["stats_buffer"]["layer_1"]["moe"]
+    assert int(sb["step_count"].item()) == 6 and abs(float(sb["expert_usage"].sum().item()) - 6.0) < 1e-3
+
+    class Cfg:
+        num_layers, num_experts = cfg.num_layers, cfg.num_experts
+    bias0 = v["params"]["layer_0"]["moe"]["router"]["router_linear"]["bias"].detach().clone()
+    _, _, diag = SL.moe_slow_loop_step({"params": v["params"]}, {"stats_buffer": v["stats_buffer"]}, Cfg, key=1, step=6)
+    assert diag["router_biases_updated"] == cfg.num_layers and diag["step_count"] == 6
+    assert int(sb["step_count"].item()) == 0
+    delta = v["params"]["layer_0"]["moe"]["router"]["router_linear"]["bias"].detach() - bias0
+    np.testing.assert_allclose(delta.cpu().numpy(), diag["adjustments"], rtol=1e-5, atol=1e-7)
