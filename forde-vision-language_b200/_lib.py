@@ -33,6 +33,7 @@ SIGNATURES = {
     "forde_sl_fwd": (_i, [_vp] * 11 + [_i, _i, _i, _ll, _i]),
     "forde_sl_dz_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _ll]),
     "forde_sl_dx_bwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _ll]),
+    "forde_sl_dx_bwd_add": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _ll]),
     "forde_sl_dw_up": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _ll]),
     "forde_sl_dw_down": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _ll]),
     "forde_colsum_bf16": (_i, [_vp, _vp, _ll, _vp, _i, _i]),

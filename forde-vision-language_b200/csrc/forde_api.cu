@@ -460,6 +460,14 @@ int forde_sl_dx_bwd(void* stream, const void* dzT, const void* w_up, void* dx, i
   return gemm_store_bf16(static_cast<cudaStream_t>(stream), g, dx, d, nullptr);
 }
 
+// dx = dz . w_up^T + residual : the FORDE block's `x + StatefulLayer(x)` skip path joins its gradient here
+int forde_sl_dx_bwd_add(void* stream, const void* dzT, const void* w_up, const void* residual, void* dx, int M, int d,
+                        int H, long long ldz) {
+  if (ldz < M || residual == nullptr) return FORDE_EINVAL;
+  GemmArgs g{dzT, true, ldz, w_up, false, H, M, d, H, /*raster_m_fast=*/false, kEvictFirst, kEvictLast};
+  return gemm_store_bf16(static_cast<cudaStream_t>(stream), g, dx, d, nullptr, residual);
+}
+
 // dw_up[d][H] += x^T . dz : A = x [M][d] (m = d, k = sample) MN-major ; B = dzT [H][M] (n = neuron, k = sample) K-major
 int forde_sl_dw_up(void* stream, const void* x, const void* dzT, float* dw_up, int M, int d, int H,
                    long long ldz) {

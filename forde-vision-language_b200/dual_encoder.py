@@ -281,11 +281,12 @@ class FORDEDualEncoder:
         if p16 is not None:
             sl_vars["params_bf16"] = p16["stateful_layer"]
         layer = self.layers[key]
+        # second half of the FORDE block in one call: LayerNorm(x + StatefulLayer(x))
         if sense:
-            m, _ = layer.apply(sl_vars, x, mutable=["stats_buffer"])
+            out, _ = layer.apply(sl_vars, x, mutable=["stats_buffer"], post_norm=p["ln_2"])
         else:
-            m = layer.apply(sl_vars, x)
-        return _AddLayerNorm.apply(x, m, p["ln_2"]["scale"], p["ln_2"]["bias"])
+            out = layer.apply(sl_vars, x, post_norm=p["ln_2"])
+        return out
 
     def encode_image(self, variables, images, sense=True, params_bf16=None):
         """images (B, S, S, 3) NHWC (src/data/download_to_drive.py:173), any float dtype."""

@@ -164,11 +164,18 @@ def sl_dz_bwd(dy, w_down, zT, hT, assign_i8, dzT, grad_partials):
     _lib.check(rc, "forde_sl_dz_bwd")
 
 
-def sl_dx_bwd(dzT, w_up, dx, M):
+def sl_dx_bwd(dzT, w_up, dx, M, residual=None):
+    """dx = dz . w_up^T (+ residual, which may be dx itself)."""
     d, H = w_up.shape
     _req(dzT, torch.bfloat16, "dzT"); _req(dx, torch.bfloat16, "dx")
     with _Timed(f"sl_dx_bwd[{M}x{d}x{H}]", 2.0 * M * d * H):
-        rc = _lib.load().forde_sl_dx_bwd(_stream(), dzT.data_ptr(), w_up.data_ptr(), dx.data_ptr(), M, d, H, dzT.stride(0))
+        if residual is None:
+            rc = _lib.load().forde_sl_dx_bwd(_stream(), dzT.data_ptr(), w_up.data_ptr(), dx.data_ptr(), M, d, H,
+                                             dzT.stride(0))
+        else:
+            _req(residual, torch.bfloat16, "residual")
+            rc = _lib.load().forde_sl_dx_bwd_add(_stream(), dzT.data_ptr(), w_up.data_ptr(), residual.data_ptr(),
+                                                 dx.data_ptr(), M, d, H, dzT.stride(0))
     _lib.check(rc, "forde_sl_dx_bwd")
 
 

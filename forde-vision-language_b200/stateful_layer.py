@@ -80,10 +80,13 @@ def grad_delivered(p: torch.Tensor) -> None:
 
 
 class _StatefulLayerFn(torch.autograd.Function):
-    """fwd: two GEMM launches (up + fused epilogue, down).  bwd: dz (fused), dx, dW_up, dW_down, db, sensing."""
+    """fwd: two GEMM launches (up + fused epilogue, down).  bwd: dz (fused), dx, dW_up, dW_down, db, sensing.
+    With LayerNorm parameters (ln_g, ln_b) the function is the second half of a FORDE block, LayerNorm(x + layer(x))
+    (README.md:43): the add/norm kernels run inside, and in the backward the skip path's gradient is added in the dx
+    GEMM's epilogue instead of by autograd."""
 
     @staticmethod
-    def forward(ctx, x2d, w_up, b_up, w_down, b_down, layer, stats, w_up16, w_down16):
+    def forward(ctx, x2d, w_up, b_up, w_down, b_down, ln_g, ln_b, layer, stats, w_up16, w_down16):
         M, d = x2d.shape
         H = w_up.shape[1]
         ws = layer._workspace(M, H, x2d.device)
@@ -98,7 +101,14 @@ class _StatefulLayerFn(torch.autograd.Function):
         if layer.top_k is not None:  # D8: keep the k largest |h| per token, zero the rest (in place)
             layer.last_topk_indices, layer.last_row_hoyer, ctx.keep_bits = ops.sl_topk_sparsify(ws.hT, M, layer.top_k)
         ops.sl_down_fwd(ws.hT, w_down16, b_down32, y, M)
-        ctx.save_for_backward(x2d, w_up16, w_down16)
+        ctx.with_norm = ln_g is not None
+        if ctx.with_norm:
+            out, mean, rstd = ops.add_layernorm_fwd(x2d, y, ln_g, ln_b, 1e-6)
+            ctx.save_for_backward(x2d, w_up16, w_down16, y, ln_g, mean, rstd)
+            ctx.ln_masters = (ln_g, ln_b)
+        else:
+            out = y
+            ctx.save_for_backward(x2d, w_up16, w_down16)
         ctx.layer, ctx.ws, ctx.stats, ctx.assign_i8 = layer, ws, stats, assign_i8
         ctx.param_dtypes = (w_up.dtype, b_up.dtype, w_down.dtype, b_down.dtype)
         ctx.masters = (w_up, b_up, w_down, b_down)
@@ -107,17 +117,32 @@ class _StatefulLayerFn(torch.autograd.Function):
         ws.in_flight = will_backward
         if stats is not None and not will_backward and layer.sense_forward_only:
             layer._finalize(ws, stats, with_grad=False)
-        return y
+        return out
 
     @staticmethod
     def backward(ctx, dy):
-        x2d, w_up16, w_down16 = ctx.saved_tensors
         layer, ws, stats, assign_i8 = ctx.layer, ctx.ws, ctx.stats, ctx.assign_i8
-        M, d = x2d.shape
-        H = ws.H
         dy = dy.contiguous()
         if dy.dtype != torch.bfloat16:
             dy = dy.to(torch.bfloat16)
+        d_ln = (None, None)
+        skip = None
+        if ctx.with_norm:
+            x2d, w_up16, w_down16, y, ln_g, mean, rstd = ctx.saved_tensors
+            sg, sb = grad_sink(ctx.ln_masters[0]), grad_sink(ctx.ln_masters[1])
+            direct_ln = sg is not None and sb is not None
+            # d(x + y): the gradient of the layer's output AND of the skip path
+            dy, dg, db = ops.add_layernorm_bwd(dy, x2d, y, ln_g, mean, rstd, d_gamma=sg if direct_ln else None,
+                                               d_beta=sb if direct_ln else None)
+            skip = dy
+            if direct_ln:
+                grad_delivered(ctx.ln_masters[0]); grad_delivered(ctx.ln_masters[1])
+            else:
+                d_ln = (dg, db)
+        else:
+            x2d, w_up16, w_down16 = ctx.saved_tensors
+        M, d = x2d.shape
+        H = ws.H
         dev = x2d.device
         dzT = _dz_scratch(H, ws.ld, dev)
         if ctx.keep_bits is None:
@@ -125,10 +150,6 @@ class _StatefulLayerFn(torch.autograd.Function):
         else:  # top-k path: dL/dz is zero where h was dropped; the gradient sums are re-taken after masking
             ops.sl_dz_bwd(dy, w_down16, ws.zT, ws.hT, assign_i8, dzT, None)
             ops.sl_topk_mask(dzT, M, ctx.keep_bits, ws.grad_partials)
-        dx = None
-        if ctx.needs_dx:
-            dx = torch.empty((M, d), dtype=torch.bfloat16, device=dev)
-            ops.sl_dx_bwd(dzT, w_up16, dx, M)
         d_out = dy.shape[1]
         sinks = [grad_sink(m) for m in ctx.masters]
         direct = all(s is not None for s in sinks)      # accumulate straight into the train state's gradient views
@@ -146,12 +167,22 @@ class _StatefulLayerFn(torch.autograd.Function):
             layer._finalize(ws, stats, with_grad=True, db_up=db_up)
         else:
             ops.stats_finalize(None, ws.grad_partials, ws.P, H, M, db_up=db_up)
+        # dx last: with the fused add/norm it is accumulated over the skip gradient IN PLACE, i.e. over `dy`, which the
+        # dW_down GEMM and the db_down column sum above still had to read
+        dx = None
+        if ctx.needs_dx:
+            if skip is not None:
+                dx = skip
+                ops.sl_dx_bwd(dzT, w_up16, dx, M, residual=skip)
+            else:
+                dx = torch.empty((M, d), dtype=torch.bfloat16, device=dev)
+                ops.sl_dx_bwd(dzT, w_up16, dx, M)
         ws.in_flight = False
         if direct:
             for m in ctx.masters:
                 grad_delivered(m)
-            return dx, None, None, None, None, None, None, None, None
-        return dx, dw_up, db_up, dw_down, db_down, None, None, None, None
+            return dx, None, None, None, None, d_ln[0], d_ln[1], None, None, None, None
+        return dx, dw_up, db_up, dw_down, db_down, d_ln[0], d_ln[1], None, None, None, None
 
 
 @dataclass
@@ -197,9 +228,12 @@ class StatefulLayer:
             "stats_buffer": new_stats_buffer(H, dev),
         }
 
-    def apply(self, variables: Collections, x: torch.Tensor, mutable: Union[bool, Iterable[str]] = False):
+    def apply(self, variables: Collections, x: torch.Tensor, mutable: Union[bool, Iterable[str]] = False,
+              post_norm: Optional[Dict[str, torch.Tensor]] = None):
         """Forward pass.  With ``mutable=["stats_buffer"]`` returns ``(y, {"stats_buffer": ...})`` and the
-        sensing statistics of this step are accumulated into those leaves (see module docstring)."""
+        sensing statistics of this step are accumulated into those leaves (see module docstring).
+        ``post_norm={"scale": ..., "bias": ...}`` (fp32) makes the call the whole second half of a FORDE block,
+        ``LayerNorm(x + layer(x))`` (README.md:43), with the add/norm fused around the layer."""
         p = variables["params"]
         mut = set(mutable) if not isinstance(mutable, bool) else (set(variables) - {"params"} if mutable else set())
         stats = variables.get("stats_buffer") if "stats_buffer" in mut else None
@@ -220,8 +254,12 @@ class StatefulLayer:
         p16 = variables.get("params_bf16")
         w_up16 = p16["up_proj"]["kernel"] if p16 is not None else None
         w_down16 = p16["down_proj"]["kernel"] if p16 is not None else None
+        ln_g = post_norm["scale"] if post_norm is not None else None
+        ln_b = post_norm["bias"] if post_norm is not None else None
+        if post_norm is not None and p["down_proj"]["kernel"].shape[1] != x2d.shape[1]:
+            raise ValueError("post_norm needs out_dim == input width (residual connection)")
         y = _StatefulLayerFn.apply(x2d, p["up_proj"]["kernel"], p["up_proj"]["bias"], p["down_proj"]["kernel"],
-                                   p["down_proj"]["bias"], self, stats, w_up16, w_down16)
+                                   p["down_proj"]["bias"], ln_g, ln_b, self, stats, w_up16, w_down16)
         y = y.reshape(*lead, y.shape[-1])
         if isinstance(mutable, bool) and not mutable:
             return y

@@ -92,6 +92,10 @@ int forde_sl_dz_bwd(void* stream, const void* dy, const void* w_down, const void
                     const int8_t* assign, void* dzT, float* grad_partials, int M, int d, int H, long long ldz);
 int forde_sl_dx_bwd(void* stream, const void* dzT, const void* w_up, void* dx, int M, int d, int H,
                     long long ldz);
+/* dx = dz . w_up^T + residual ([M][d] bf16; may be dx itself): when the layer sits in `x + StatefulLayer(x)` (README.md:43)
+ * the skip path's gradient is added in the GEMM epilogue instead of by a separate pass */
+int forde_sl_dx_bwd_add(void* stream, const void* dzT, const void* w_up, const void* residual, void* dx, int M, int d,
+                        int H, long long ldz);
 int forde_sl_dw_up(void* stream, const void* x, const void* dzT, float* dw_up, int M, int d, int H,
                    long long ldz);
 int forde_sl_dw_down(void* stream, const void* hT, const void* dy, float* dw_down, int M, int d, int H,

@@ -533,3 +533,33 @@ def test_gemm_bf16_accumulate_in_place(ops, shape):
     assert out.data_ptr() == C.data_ptr()
     err = (out.float() - ref.float()).norm() / ref.float().norm()
     assert err.item() < 5e-3
+
+
+def test_fused_block_half_equals_layer_then_add_norm(ops):
+    """apply(..., post_norm=ln) == LayerNorm(x + apply(x)) with autograd doing the skip-path add: same outputs and
+    gradients (the fused form adds the skip gradient in the dx GEMM's epilogue)."""
+    from forde_b200.stateful_layer import StatefulLayer
+    M, d, H = 520, 128, 384
+    a = (np.arange(H) // 48) % 3
+    xs, res = [], []
+    for fused in (False, True):
+        layer = StatefulLayer(hidden_dim=H)
+        x = torch.randn((M, d), device="cuda", generator=torch.Generator(device="cuda").manual_seed(3)).bfloat16().requires_grad_(True)
+        v = layer.init(5, x)
+        v["neuron_assignments"]["assignments"].copy_(torch.as_tensor(a))
+        ps = [v["params"]["up_proj"]["kernel"], v["params"]["down_proj"]["kernel"], v["params"]["down_proj"]["bias"]]
+        ln = {"scale": (torch.rand(d, device="cuda", generator=torch.Generator(device="cuda").manual_seed(4)) + 0.5).requires_grad_(True),
+              "bias": torch.zeros(d, device="cuda").requires_grad_(True)}
+        for p_ in ps:
+            p_.requires_grad_(True)
+        if fused:
+            out = layer.apply(v, x, post_norm=ln)
+        else:
+            y = layer.apply(v, x)
+            out = torch.nn.functional.layer_norm(x.float() + y.float(), (d,), ln["scale"], ln["bias"], 1e-6).bfloat16()
+        dout = torch.randn(out.shape, device="cuda", generator=torch.Generator(device="cuda").manual_seed(6)).bfloat16()
+        out.backward(dout)
+        torch.cuda.synchronize()
+        res.append([f32(out), f32(x.grad), f32(ps[0].grad), f32(ps[1].grad), f32(ps[2].grad), f32(ln["scale"].grad)])
+    for name, r0, r1 in zip(("out", "dx", "dw_up", "dw_down", "db_down", "d_gamma"), *res):
+        assert relerr(r1, r0) < 1.5e-2, name
