@@ -133,7 +133,8 @@ class _QKVDense(torch.autograd.Function):
     inside the GEMM epilogues (EPI_STORE_ADD: no separate add passes over the (M, w) gradient)."""
 
     @staticmethod
-    def forward(ctx, x, wq, bq, wk, bk, wv, bv, wq16, bq16, wk16, bk16, wv16, bv16):
+    def forward(ctx, x, wq, bq, wk, bk, wv, bv, wq16, bq16, wk16, bk16, wv16, bv16, skip_holder=None):
+        ctx.skip_holder = skip_holder
         x2 = x.reshape(-1, x.shape[-1])
         if not x2.is_contiguous():
             x2 = x2.contiguous()
@@ -148,23 +149,33 @@ class _QKVDense(torch.autograd.Function):
         x2, wq16, wk16, wv16 = ctx.saved_tensors
         d = [t.reshape(-1, t.shape[-1]) for t in (dq, dk, dv)]
         d = [t if t.is_contiguous() else t.contiguous() for t in d]
-        dx = ops.gemm_bf16(d[0], wq16, False, False)                 # dx = dq Wq^T
-        if not dx.is_contiguous():
-            dx = dx.contiguous()
+        base = ctx.skip_holder.pop("ds", None) if ctx.skip_holder is not None else None
+        if base is not None:
+            # the block's skip path (x -> add/norm) left its gradient here: dx = d(skip) + dq Wq^T + dk Wk^T + dv Wv^T
+            dx = base.reshape(-1, base.shape[-1])
+            ops.gemm_bf16(d[0], wq16, False, False, add_to=dx)
+        else:
+            dx = ops.gemm_bf16(d[0], wq16, False, False)             # dx = dq Wq^T
+            if not dx.is_contiguous():
+                dx = dx.contiguous()
         ops.gemm_bf16(d[1], wk16, False, False, add_to=dx)           #    += dk Wk^T  (accumulated in the epilogue)
         ops.gemm_bf16(d[2], wv16, False, False, add_to=dx)           #    += dv Wv^T
         xt = x2.t()
         grads = []
         for t, (w, b) in zip(d, ctx.masters):
             grads += list(_deliver_dense_grads(w, b, xt, t))
-        return (dx.view(ctx.shape), *grads, None, None, None, None, None, None)
+        return (dx.view(ctx.shape), *grads, None, None, None, None, None, None, None)
 
 
 class _AddLayerNorm(torch.autograd.Function):
     """LayerNorm(x + r) on the fused sm_100a kernel (csrc/forde_norm.cu); gamma / beta are fp32 masters."""
 
     @staticmethod
-    def forward(ctx, x, r, gamma, beta):
+    def forward(ctx, x, r, gamma, beta, skip_holder=None):
+        # skip_holder: a dict shared with the _QKVDense of the same block.  The gradient of the skip input x is then
+        # not returned to autograd (which would add it to the projections' input gradient with a separate pass) but
+        # left in the holder, and _QKVDense.backward accumulates its GEMMs on top of it.
+        ctx.skip_holder = skip_holder
         x = x.contiguous(); r = r.contiguous()
         out, mean, rstd = ops.add_layernorm_fwd(x, r, gamma, beta, 1e-6)
         ctx.save_for_backward(x, r, gamma, mean, rstd)
@@ -178,10 +189,14 @@ class _AddLayerNorm(torch.autograd.Function):
         direct = sg is not None and sb is not None
         ds, dg, db = ops.add_layernorm_bwd(dy.contiguous(), x, r, gamma, mean, rstd, d_gamma=sg if direct else None,
                                            d_beta=sb if direct else None)
+        dx_skip = ds
+        if ctx.skip_holder is not None:
+            ctx.skip_holder["ds"] = ds
+            dx_skip = None
         if direct:
             grad_delivered(ctx.masters[0]); grad_delivered(ctx.masters[1])
-            return ds, ds, None, None
-        return ds, ds, dg, db
+            return dx_skip, ds, None, None, None
+        return dx_skip, ds, dg, db, None
 
 
 def _flatten(tree, prefix=""):
@@ -263,15 +278,16 @@ class FORDEDualEncoder:
 
         # Flax MultiHeadDotProductAttention layout: separate query / key / value / out projections.  Heads are a
         # strided view of the (B, T, w) projections, so nothing is re-packed on the way in or out of the kernel.
+        holder = {} if x.requires_grad else None      # carries d(skip) from the add/norm to the q/k/v input gradient
         q, k, v = _QKVDense.apply(x, pa["query"]["kernel"], pa["query"]["bias"], pa["key"]["kernel"], pa["key"]["bias"],
                                   pa["value"]["kernel"], pa["value"]["bias"], mirror("query", "kernel"),
                                   mirror("query", "bias"), mirror("key", "kernel"), mirror("key", "bias"),
-                                  mirror("value", "kernel"), mirror("value", "bias"))
+                                  mirror("value", "kernel"), mirror("value", "bias"), holder)
         q, k, v = (t.view(B, T, heads, w // heads).transpose(1, 2) for t in (q, k, v))
         a = F.scaled_dot_product_attention(q, k, v)
         a = _Dense.apply(a.transpose(1, 2).reshape(B, T, w), pa["out"]["kernel"], pa["out"]["bias"],
                          mirror("out", "kernel"), mirror("out", "bias"))
-        x = _AddLayerNorm.apply(x, a, p["ln_1"]["scale"], p["ln_1"]["bias"])
+        x = _AddLayerNorm.apply(x, a, p["ln_1"]["scale"], p["ln_1"]["bias"], holder)
         tower, lname = key.split("/")
         sl_vars = {
             "params": p["stateful_layer"],
