@@ -344,12 +344,15 @@ def _tree_copy_(dst, src):
 
 
 def fit(state: TrainState, batches, max_steps: int, slow_loop_interval: int = 100, slow_loop_config=None, key: int = 0,
-        use_cuda_graph: bool = True, log=None):
+        use_cuda_graph: bool = True, log=None, plot_dir: Optional[str] = None):
     """The reference's outer loop (src/training/train.py:320-399): fast steps, and every ``slow_loop_interval`` steps
     (train.py:219-224 default 100; ``step > 0 and step % interval == 0``, train.py:365-369) the slow loop -- Sense
     (all-reduced pooled moments) -> Cluster -> Smooth -> Actuate -> Reset -- which rewrites ``neuron_assignments`` in
     place and zeroes ``stats_buffer`` (train.py:387-399).  ``batches`` is an iterable of batch dicts.
+    With ``plot_dir`` rank 0 also writes each layer's brain scan and feature-space scatter after every slow loop
+    (the reference's plot_brain_scan / plot_feature_space, src/utils/logging.py:7-52), into one sub-directory per layer.
     Returns (state, history) with history = list of (step, loss) and the slow-loop diagnostics."""
+    from .brain_scan import plot_brain_scan, plot_feature_space
     from .slow_loop import SlowLoopConfig, slow_loop_step
 
     cfg = slow_loop_config or SlowLoopConfig()
@@ -376,6 +379,14 @@ def fit(state: TrainState, batches, max_steps: int, slow_loop_interval: int = 10
                   "neuron_assignments": state.variables["neuron_assignments"]}
             _, _, diag = slow_loop_step(state.params, mv, cfg, key=key + step, epoch=0, step=step, group=state.group)
             diagnostics.append(diag)
+            if plot_dir is not None and (not dist.is_initialized() or dist.get_rank(state.group) == 0):
+                for name, d in diag["layers"].items():
+                    if "brain_scan" not in d:
+                        continue
+                    sub = os.path.join(plot_dir, name.replace("/", "_"))
+                    os.makedirs(sub, exist_ok=True)
+                    plot_brain_scan(d["brain_scan"], step, 0, out_dir=sub)
+                    plot_feature_space(d["features"], d["brain_scan"].reshape(-1), step, 0, out_dir=sub)
     return state, {"loss": history, "slow_loop": diagnostics}
 
 

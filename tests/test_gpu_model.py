@@ -102,15 +102,18 @@ def test_cuda_graph_replay_matches_eager_steps(built):
     assert abs(l2 - lg[-1]) > 1e-4 and np.isfinite(l2)       # routing changed, so the loss moved
 
 
-def test_fit_runs_fast_and_slow_loops_together(built):
+def test_fit_runs_fast_and_slow_loops_together(built, tmp_path):
     """train.py:320-399 cadence: graph-replayed fast steps, slow loop every N steps reading the in-kernel statistics."""
     from forde_b200 import dual_encoder, train
 
     cfg = dual_encoder.config_tiny()
     st = train.create_train_state(cfg, 3, device="cuda")
     b = {k: v.cuda() for k, v in train.synthetic_batch(cfg, 32, pinned=False).items()}
-    st, hist = train.fit(st, [b] * 7, max_steps=7, slow_loop_interval=3, key=1)
+    st, hist = train.fit(st, [b] * 7, max_steps=7, slow_loop_interval=3, key=1, plot_dir=str(tmp_path))
     assert len(hist["slow_loop"]) == 2                      # steps 3 and 6
+    import glob, os
+    assert len(glob.glob(os.path.join(str(tmp_path), "*", "brain_scan_epoch0_step*.png"))) == 8   # 4 layers x 2 loops
+    assert len(glob.glob(os.path.join(str(tmp_path), "*", "feature_space_epoch0_step*.png"))) == 8
     for diag in hist["slow_loop"]:
         assert len(diag["layers"]) == 4 and all("census" in d for d in diag["layers"].values())
     assert np.isfinite(hist["loss"][-1][1])

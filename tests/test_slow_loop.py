@@ -160,3 +160,46 @@ def test_moe_slow_loop_step_matches_reference_run(golden_dir):
     assert float(leaves["expert_usage"].abs().sum()) == 0.0 and int(leaves["step_count"]) == 0
     # nothing accumulated -> skipped (moe_slow_loop.py:293-295)
     assert SL.moe_slow_loop_step(params, mv2, Cfg, key=1)[2] == {"skipped": True}
+
+
+def _read_png(path):
+    import struct, zlib
+    b = open(path, "rb").read()
+    assert b[:8] == b"\x89PNG\r\n\x1a\n"
+    pos, idat, w, h = 8, b"", 0, 0
+    while pos < len(b):
+        n, tag = struct.unpack(">I", b[pos:pos + 4])[0], b[pos + 4:pos + 8]
+        data = b[pos + 8:pos + 8 + n]
+        assert struct.unpack(">I", b[pos + 8 + n:pos + 12 + n])[0] == (zlib.crc32(tag + data) & 0xFFFFFFFF)
+        if tag == b"IHDR":
+            w, h = struct.unpack(">II", data[:8])
+        if tag == b"IDAT":
+            idat += data
+        pos += 12 + n
+    rows = np.frombuffer(zlib.decompress(idat), np.uint8).reshape(h, 1 + 3 * w)
+    assert (rows[:, 0] == 0).all()
+    return rows[:, 1:].reshape(h, w, 3)
+
+
+def test_brain_scan_and_feature_space_files(tmp_path):
+    """utils/logging.py:7-52: same call signatures and output file names; one colour per cluster id."""
+    from forde_b200 import brain_scan as BS
+    grid = np.arange(12).reshape(3, 4) % 3
+    p = BS.plot_brain_scan(grid, step=7, epoch=2, out_dir=str(tmp_path), cell=4)
+    assert os.path.basename(p) == "brain_scan_epoch2_step7.png"
+    img = _read_png(p)
+    assert img.shape == (12, 16, 3)
+    ids = {tuple(img[4 * r, 4 * c]) for r in range(3) for c in range(4)}
+    assert len(ids) == 3
+    for r in range(3):
+        for c in range(4):
+            assert (img[4 * r:4 * r + 4, 4 * c:4 * c + 4] == img[4 * r, 4 * c]).all()
+            assert (tuple(img[4 * r, 4 * c]) == tuple(img[0, 0])) == (grid[r, c] == grid[0, 0])
+    rng = np.random.RandomState(0)
+    stats = rng.rand(50, 5).astype(np.float32)
+    q = BS.plot_feature_space(stats, rng.randint(0, 3, 50), step=7, epoch=2, out_dir=str(tmp_path), size=64)
+    assert os.path.basename(q) == "feature_space_epoch2_step7.png"
+    assert _read_png(q).shape == (64, 64, 3)
+    assert BS.plot_feature_space(stats[:, :1], np.zeros(50), 0, 0, out_dir=str(tmp_path)) is None
+    with pytest.raises(ValueError):
+        BS.plot_brain_scan(np.zeros(5), 0, 0, out_dir=str(tmp_path))
