@@ -91,6 +91,25 @@ constexpr int TMEM_COLS = 512;
 #ifndef FORDE_DZ_STAGES
 #define FORDE_DZ_STAGES 5
 #endif
+// Software pipelining of the accumulator reads (tcgen05.ld) in the fused epilogues: 0 = load a 32-column half, use
+// it, load the next; 1 = the chunk's second half is in flight while the first is processed; 2 = additionally the next
+// chunk's first half is requested before the second half is processed (64 more live registers, still no spills).
+// Measured at C2 vision dims (profiles/r1_exp12_tmem_pipe.txt): up_fwd 164.9 -> 161.9 us (all-generalist map),
+// 215.6 -> 210.8 us (i.i.d. map) with 2; dz_bwd unchanged within noise -- the epilogues are not bound by the TMEM
+// read latency.  -D FORDE_TMEM_PIPE=n sets both for A/B builds.
+#ifdef FORDE_TMEM_PIPE
+#define FORDE_TMEM_PIPE_UP FORDE_TMEM_PIPE
+#define FORDE_TMEM_PIPE_DZ FORDE_TMEM_PIPE
+#endif
+#ifndef FORDE_TMEM_PIPE_UP
+#define FORDE_TMEM_PIPE_UP 2
+#endif
+#ifndef FORDE_TMEM_PIPE_DZ
+#define FORDE_TMEM_PIPE_DZ 0
+#endif
+__host__ __device__ constexpr int tmem_pipe(int epi) {
+  return epi == 1 /*EPI_UP_FWD*/ ? FORDE_TMEM_PIPE_UP : epi == 2 /*EPI_DZ_BWD*/ ? FORDE_TMEM_PIPE_DZ : 0;
+}
 // Per-neuron partial-sum slots per 256-column tile.  With 8 epilogue warps each warp drains two adjacent 64-column
 // chunks and sums them into ONE slot (2 slots of 128 samples per tile: half the partials traffic and half of what
 // forde_stats_finalize reads); A/B builds with 16 warps keep one slot per chunk.
@@ -549,6 +568,7 @@ __global__ void __launch_bounds__(num_threads(EPI, PAIR), 1) forde_gemm_kernel(c
 
       static_assert(!epi_neuron_rows(EPI) || CPW % CHUNKS_PER_SLOT == 0, "a partials slot must belong to one warp");
       RunningSums rs{0.f, 0.f, 0.f};  // per-neuron sums of the current partials slot (fused epilogues)
+      uint32_t va_next[32];           // tmem_pipe == 2: first half of the next chunk, in flight
 #pragma unroll 1
       for (int cc = 0; cc < CPW; ++cc) {
         const int c = e * CPW + cc;
@@ -566,11 +586,10 @@ __global__ void __launch_bounds__(num_threads(EPI, PAIR), 1) forde_gemm_kernel(c
         const uint32_t orow_s = smem_u32(obuf) + lane * 128;
 
         // the 64-column chunk is drained in two 32-column halves to keep the live registers low
-#pragma unroll
-        for (int half = 0; half < 2; ++half) {
+        auto drain_half = [&](const uint32_t* v_in, const int half) {
           uint32_t v[32];
-          tmem_ld32(taddr + c * CHUNK + half * 32, v);
-          tmem_wait_ld();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = v_in[j];
           const int jbase = half * 32;  // column offset inside the chunk
           if (EPI == EPI_F32 && w.kb0 >= w.kb1) {  // empty reduction (grouped-K expert without tokens): zeros
 #pragma unroll
@@ -703,6 +722,34 @@ __global__ void __launch_bounds__(num_threads(EPI, PAIR), 1) forde_gemm_kernel(c
             };
             if (warp_has_tanh) run(std::true_type{});
             else run(std::false_type{});
+          }
+        };
+        if (tmem_pipe(EPI) == 2) {
+          // as below, and the next chunk's first half is requested before this chunk's second half is processed
+          uint32_t vb[32];
+          if (cc == 0) tmem_ld32(taddr + c * CHUNK, va_next);
+          tmem_ld32(taddr + c * CHUNK + 32, vb);
+          tmem_wait_ld();  // (a no-op in SASS: consumers wait on the LDTM scoreboards, so vb stays in flight)
+          drain_half(va_next, 0);
+          if (cc + 1 < CPW) tmem_ld32(taddr + (c + 1) * CHUNK, va_next);
+          tmem_wait_ld();
+          drain_half(vb, 1);
+        } else if (tmem_pipe(EPI) == 1) {
+          // fused epilogues: the second half's tcgen05.ld is in flight while the first half is processed
+          uint32_t va[32], vb[32];
+          tmem_ld32(taddr + c * CHUNK, va);
+          tmem_wait_ld();
+          tmem_ld32(taddr + c * CHUNK + 32, vb);
+          drain_half(va, 0);
+          tmem_wait_ld();
+          drain_half(vb, 1);
+        } else {
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {
+            uint32_t vh[32];
+            tmem_ld32(taddr + c * CHUNK + half * 32, vh);
+            tmem_wait_ld();
+            drain_half(vh, half);
           }
         }
 
