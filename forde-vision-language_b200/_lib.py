@@ -25,6 +25,9 @@ SIGNATURES = {
     "forde_sm_count": (_i, []),
     "forde_launch_count": (ctypes.c_ulonglong, []),
     "forde_sl_num_partials": (_i, [_i]),
+    "forde_sl_sign_words": (_i, [_i]),
+    "forde_sl_up_fwd_signs": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _ll]),
+    "forde_sl_dz_bwd_signs": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _ll]),
     "forde_gemm_bf16": (_i, [_vp, _vp, _i, _ll, _vp, _i, _ll, _vp, _ll, _vp, _i, _i, _i]),
     "forde_gemm_bf16_add": (_i, [_vp, _vp, _i, _ll, _vp, _i, _ll, _vp, _ll, _vp, _vp, _i, _i, _i]),
     "forde_gemm_f32": (_i, [_vp, _vp, _i, _ll, _vp, _i, _ll, _vp, _ll, _vp, _vp, _f, _i, _i, _i, _i]),

@@ -375,6 +375,8 @@ int forde_sm_count(void) { return sm_count(); }
 
 unsigned long long forde_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
+int forde_sl_sign_words(int M) { return M <= 0 ? 0 : 8 * ((M + BN - 1) / BN); }
+
 int forde_sl_num_partials(int M) { return M <= 0 ? 0 : PARTIALS_PER_TILE * ((M + BN - 1) / BN); }
 
 int forde_gemm_bf16(void* stream, const void* A, int a_mn_major, long long lda, const void* B, int b_mn_major,
@@ -399,9 +401,11 @@ int forde_gemm_f32(void* stream, const void* A, int a_mn_major, long long lda, c
 }
 
 // zT[H][M] = (x . w_up + b)^T :  A = w_up [d][H] as (m = neuron, k = d) -> MN-major ; B = x [M][d] -> K-major
-int forde_sl_up_fwd(void* stream, const void* x, const void* w_up, const float* b_up, const int8_t* assign,
-                    void* zT, void* hT, float* act_partials, int M, int d, int H, long long ldz, int save_z) {
+static int sl_up_fwd_impl(void* stream, const void* x, const void* w_up, const float* b_up, const int8_t* assign,
+                          void* zT, void* hT, uint32_t* sign_bits, float* act_partials, int M, int d, int H,
+                          long long ldz, int save_z) {
   if (assign == nullptr || zT == nullptr || hT == nullptr || ldz < M) return FORDE_EINVAL;
+  if (sign_bits != nullptr && (reinterpret_cast<uintptr_t>(sign_bits) & 15) != 0) return FORDE_EALIGN;
   GemmArgs g{w_up, true, H, x, false, d, H, M, d, /*raster_m_fast=*/true, kEvictLast, kEvictLast};
   GemmParams p;
   int rc = fill_common(p, g);
@@ -414,7 +418,21 @@ int forde_sl_up_fwd(void* stream, const void* x, const void* w_up, const float* 
   p.assign = assign;
   p.partials = act_partials;
   p.save_z = save_z;
+  p.sign_bits = sign_bits;
+  p.sign_ld = forde_sl_sign_words(M);
   return launch_epi<EPI_UP_FWD>(p, true, false, static_cast<cudaStream_t>(stream));
+}
+
+int forde_sl_up_fwd(void* stream, const void* x, const void* w_up, const float* b_up, const int8_t* assign,
+                    void* zT, void* hT, float* act_partials, int M, int d, int H, long long ldz, int save_z) {
+  return sl_up_fwd_impl(stream, x, w_up, b_up, assign, zT, hT, nullptr, act_partials, M, d, H, ldz, save_z);
+}
+
+int forde_sl_up_fwd_signs(void* stream, const void* x, const void* w_up, const float* b_up, const int8_t* assign,
+                          void* zT, void* hT, uint32_t* sign_bits, float* act_partials, int M, int d, int H,
+                          long long ldz) {
+  if (sign_bits == nullptr) return FORDE_EINVAL;
+  return sl_up_fwd_impl(stream, x, w_up, b_up, assign, zT, hT, sign_bits, act_partials, M, d, H, ldz, /*save_z=*/0);
 }
 
 // y[M][d] = h . w_down + b :  A = hT [H][M] as (m = sample, k = neuron) -> MN-major ; B = w_down [H][d] -> MN-major
@@ -434,9 +452,13 @@ int forde_sl_fwd(void* stream, const void* x, const void* w_up, const float* b_u
 }
 
 // dzT[H][M] = (dy . w_down^T)^T * (F'(z) + gate) : A = w_down [H][d] (m = neuron, k = d) K-major ; B = dy [M][d] K-major
-int forde_sl_dz_bwd(void* stream, const void* dy, const void* w_down, const void* zT, const void* hT,
-                    const int8_t* assign, void* dzT, float* grad_partials, int M, int d, int H, long long ldz) {
-  if (assign == nullptr || zT == nullptr || hT == nullptr || dzT == nullptr || ldz < M) return FORDE_EINVAL;
+static int sl_dz_bwd_impl(void* stream, const void* dy, const void* w_down, const void* zT, const void* hT,
+                          const uint32_t* sign_bits, const int8_t* assign, void* dzT, float* grad_partials, int M,
+                          int d, int H, long long ldz) {
+  if (assign == nullptr || zT == nullptr || dzT == nullptr || ldz < M) return FORDE_EINVAL;
+  if (hT == nullptr && sign_bits == nullptr) return FORDE_EINVAL;
+  if (sign_bits != nullptr && (reinterpret_cast<uintptr_t>(sign_bits) & 15) != 0) return FORDE_EALIGN;
+  if (hT == nullptr) hT = zT;  // sign-bit mode never loads through this map; it only has to encode
   GemmArgs g{w_down, false, d, dy, false, d, H, M, d, /*raster_m_fast=*/true, kEvictLast, kEvictLast};
   GemmParams p;
   int rc = fill_common(p, g);
@@ -449,7 +471,22 @@ int forde_sl_dz_bwd(void* stream, const void* dy, const void* w_down, const void
   if (rc != FORDE_OK) return rc;
   p.assign = assign;
   p.partials = grad_partials;
+  p.sign_bits = const_cast<uint32_t*>(sign_bits);
+  p.sign_ld = forde_sl_sign_words(M);
   return launch_epi<EPI_DZ_BWD>(p, false, false, static_cast<cudaStream_t>(stream));
+}
+
+int forde_sl_dz_bwd(void* stream, const void* dy, const void* w_down, const void* zT, const void* hT,
+                    const int8_t* assign, void* dzT, float* grad_partials, int M, int d, int H, long long ldz) {
+  if (hT == nullptr) return FORDE_EINVAL;
+  return sl_dz_bwd_impl(stream, dy, w_down, zT, hT, nullptr, assign, dzT, grad_partials, M, d, H, ldz);
+}
+
+int forde_sl_dz_bwd_signs(void* stream, const void* dy, const void* w_down, const void* zT,
+                          const uint32_t* sign_bits, const int8_t* assign, void* dzT, float* grad_partials, int M,
+                          int d, int H, long long ldz) {
+  if (sign_bits == nullptr) return FORDE_EINVAL;
+  return sl_dz_bwd_impl(stream, dy, w_down, zT, nullptr, sign_bits, assign, dzT, grad_partials, M, d, H, ldz);
 }
 
 // dx[M][d] = dz . w_up^T : A = dzT [H][M] (m = sample, k = neuron) MN-major ; B = w_up [d][H] (n = d, k = neuron) K-major

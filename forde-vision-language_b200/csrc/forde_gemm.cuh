@@ -169,6 +169,11 @@ struct GemmParams {
   int raster_m_fast;  // 1: consecutive work items walk M first (share the B slab), 0: walk N first
   int pair;           // 1: launched as 2-CTA clusters (256-row tiles, cta_group::2)
   int save_z;         // EPI_UP_FWD: 1 = store every z box; 0 = only the boxes the backward needs (warps with tanh neurons)
+  // Optional sign bits of z, [M rows = neurons][sign_ld] u32, bit j of word w = (z[neuron][32 w + j] > 0).
+  // EPI_UP_FWD writes them for the 32-neuron groups whose z box it does not store; EPI_DZ_BWD then reads 8 bytes
+  // per neuron and 64-sample chunk instead of TMA-loading the h^T box (1/16 of the bytes).  Null = off.
+  uint32_t* sign_bits;
+  int sign_ld;        // row pitch in u32 words: 8 * ceil(N / 256)
   // grouped modes (MoE experts); all null / 0 otherwise
   const int* m_blocks_dev;     // grouped-M: number of valid 128-row blocks (device scalar)
   const int* group_of_mblock;  // grouped-M: expert of each 128-row block
@@ -260,13 +265,19 @@ struct RunningSums {
 };
 
 // forward, 8 accumulator columns -> 4 packed z words + 4 packed h words; MODE is warp-uniform
-template <int MODE, bool MASKED>
+// SIGNS: also collect (z > 0) into `bits`, bit (jcol % 32) + 2 i (+ 1) for the pair's two columns.
+template <int MODE, bool MASKED, bool SIGNS>
 __device__ __forceinline__ void up_fwd_8(const uint32_t* v, float bias_r, const ActConst& act, bool warp_has_tanh,
-                                         int jcol, int nvalid, uint32_t* zw, uint32_t* hw, RunningSums& rs) {
+                                         int jcol, int nvalid, uint32_t* zw, uint32_t* hw, RunningSums& rs,
+                                         uint32_t& bits) {
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const uint32_t zp = pack_bf16x2(__uint_as_float(v[2 * i]) + bias_r, __uint_as_float(v[2 * i + 1]) + bias_r);
     const float z0 = bf16lo_to_f32(zp), z1 = bf16hi_to_f32(zp);
+    if (SIGNS) {
+      if (z0 > 0.f) bits |= 1u << ((jcol & 31) + 2 * i);
+      if (z1 > 0.f) bits |= 1u << ((jcol & 31) + 2 * i + 1);
+    }
     float h0, h1;
     if (MODE == WM_RELU) {          // h = relu(z) + 1.0 * z
       h0 = z0 + fmaxf(z0, 0.f);
@@ -316,6 +327,23 @@ __device__ __forceinline__ void dz_bwd_8(const uint32_t* v, const uint32_t* zw, 
       m0 = act.is_tanh ? (fmaf(-t0, t0, 1.f) + act.gate) : m0;
       m1 = act.is_tanh ? (fmaf(-t1, t1, 1.f) + act.gate) : m1;
     }
+    const uint32_t dp = pack_bf16x2(__uint_as_float(v[2 * i]) * m0, __uint_as_float(v[2 * i + 1]) * m1);
+    dw[i] = dp;
+    const float d0 = bf16lo_to_f32(dp), d1 = bf16hi_to_f32(dp);
+    rs.s_abs += fabsf(d0) + fabsf(d1);
+    rs.s_sum += d0 + d1;
+    rs.s_sq = fmaf(d0, d0, rs.s_sq);
+    rs.s_sq = fmaf(d1, d1, rs.s_sq);
+  }
+}
+
+// backward from the sign bits (no tanh neuron in the warp): bit i of `bits8` = (z > 0) for column i of these 8
+__device__ __forceinline__ void dz_bwd_8_bits(const uint32_t* v, uint32_t bits8, float m_pos, float m_neg,
+                                              uint32_t* dw, RunningSums& rs) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float m0 = (bits8 & (1u << (2 * i))) ? m_pos : m_neg;
+    const float m1 = (bits8 & (1u << (2 * i + 1))) ? m_pos : m_neg;
     const uint32_t dp = pack_bf16x2(__uint_as_float(v[2 * i]) * m0, __uint_as_float(v[2 * i + 1]) * m1);
     dw[i] = dp;
     const float d0 = bf16lo_to_f32(dp), d1 = bf16hi_to_f32(dp);
@@ -497,6 +525,7 @@ __global__ void __launch_bounds__(num_threads(EPI, PAIR), 1) forde_gemm_kernel(c
     // z^T prefetch state (EPI_DZ_BWD): g = running chunk index of this warp (tile g / CPW, chunk g % CPW);
     // chunk g lives in box g % ZR and dz is written over it in place.
     int g = 0;
+    uint32_t zph = 0;  // phase bit per box: a box's barrier advances only when a load into it has been consumed
     uint64_t* zb = z_bar + ew * ZR;
     // Warp-collective.  The backward only needs z itself for tanh neurons (F' = 1 - tanh^2 z); for relu neurons the
     // sign of h = z + relu(z) is the sign of z and the straight-through step needs nothing, so a warp without tanh
@@ -509,6 +538,7 @@ __global__ void __launch_bounds__(num_threads(EPI, PAIR), 1) forde_gemm_kernel(c
       if (EPI == EPI_DZ_BWD) {
         const int rn = wn.m0 + q * 32 + lane;
         use_z = __any_sync(0xffffffffu, rn < p.M && p.assign[rn] == 1);
+        if (!use_z && p.sign_bits != nullptr) return;  // sign-bit path: this chunk loads nothing into its box
       }
       if (lane == 0) {
         // the dz store that last read this box (chunk gi - ZR) must have drained
@@ -551,6 +581,20 @@ __global__ void __launch_bounds__(num_threads(EPI, PAIR), 1) forde_gemm_kernel(c
         m_pos = 1.f + act.gate;                      // relu'(z>0) + gate ; STE slope 1 + gate
         m_neg = act.is_step ? 1.f + act.gate : act.gate;
       }
+      // sign-bit paths (warp-uniform per tile): the forward writes bits instead of the z box, the backward reads them
+      const bool want_bits = (EPI == EPI_UP_FWD) && !store_z && p.sign_bits != nullptr;
+      const bool bits_path = (EPI == EPI_DZ_BWD) && !warp_has_tanh && p.sign_bits != nullptr;
+      uint32_t mw[4] = {0u, 0u, 0u, 0u};  // this warp's sign words of the tile: [chunk][half]
+      static_assert(EPI != EPI_DZ_BWD || CPW <= 2, "sign words per tile");
+      if (bits_path && row < p.M) {
+        const uint32_t* src = p.sign_bits + static_cast<long long>(row) * p.sign_ld + (w.n0 + e * CPW * CHUNK) / 32;
+#pragma unroll
+        for (int i = 0; i < CPW; ++i) {
+          const uint2 t2 = __ldg(reinterpret_cast<const uint2*>(src) + i);
+          mw[2 * i] = t2.x;
+          mw[2 * i + 1] = t2.y;
+        }
+      }
       if (epi_col_bias(EPI)) {
         // stage this tile's column bias (of this tile's expert in the grouped mode) once for the epilogue warps
         asm volatile("bar.sync 1, %0;" ::"n"(32 * EPI_WARPS) : "memory");  // previous tile's bias no longer read
@@ -580,7 +624,14 @@ __global__ void __launch_bounds__(num_threads(EPI, PAIR), 1) forde_gemm_kernel(c
         // single-buffered staging: the previous chunk's TMA stores must have read the boxes (the other epilogue
         // warps of this SM sub-partition cover the wait)
         if ((epi_two_out(EPI) || EPI == EPI_STORE) && lane == 0) tma_wait_read<0>();
-        if (epi_z_ring(EPI)) mbar_wait(&zb[g % ZR], (g / ZR) & 1);
+        if (epi_z_ring(EPI)) {
+          if (bits_path) {  // no load to wait for; the store that last read this box (chunk g - ZR) must have drained
+            if (lane == 0) tma_wait_read<ZR - 1>();
+          } else {
+            mbar_wait(&zb[g % ZR], (zph >> (g % ZR)) & 1u);
+            zph ^= 1u << (g % ZR);
+          }
+        }
         __syncwarp();
         uint8_t* obuf = epi_z_ring(EPI) ? (wst + (g % ZR) * BOX_BYTES) : wst;
         const uint32_t orow_s = smem_u32(obuf) + lane * 128;
@@ -644,12 +695,13 @@ __global__ void __launch_bounds__(num_threads(EPI, PAIR), 1) forde_gemm_kernel(c
             }
           } else if (EPI == EPI_UP_FWD) {
             // z box at wst, h box at wst + BOX_BYTES
-            auto run = [&](auto mode, auto masked) {
+            uint32_t sbits = 0u;  // (z > 0) of this half's 32 samples
+            auto run = [&](auto mode, auto masked, auto signs) {
 #pragma unroll
               for (int j8 = 0; j8 < 4; ++j8) {
                 uint32_t zw[4], hw[4];
-                up_fwd_8<decltype(mode)::value, decltype(masked)::value>(v + j8 * 8, bias_r, act, warp_has_tanh,
-                                                                         jbase + j8 * 8, nvalid, zw, hw, rs);
+                up_fwd_8<decltype(mode)::value, decltype(masked)::value, decltype(signs)::value>(
+                    v + j8 * 8, bias_r, act, warp_has_tanh, jbase + j8 * 8, nvalid, zw, hw, rs, sbits);
                 const uint32_t off = (static_cast<uint32_t>(half * 4 + j8) ^ sw) << 4;
                 if (store_z) st_shared_v4(orow_s + off, zw[0], zw[1], zw[2], zw[3]);
                 st_shared_v4(orow_s + BOX_BYTES + off, hw[0], hw[1], hw[2], hw[3]);
@@ -657,10 +709,18 @@ __global__ void __launch_bounds__(num_threads(EPI, PAIR), 1) forde_gemm_kernel(c
             };
             using T = std::true_type;
             using F = std::false_type;
-            if (!full) run(std::integral_constant<int, WM_MIXED>{}, T{});
-            else if (wmode == WM_RELU) run(std::integral_constant<int, WM_RELU>{}, F{});
-            else if (wmode == WM_STEP) run(std::integral_constant<int, WM_STEP>{}, F{});
-            else run(std::integral_constant<int, WM_MIXED>{}, F{});
+            auto dispatch = [&](auto signs) {
+              if (!full) run(std::integral_constant<int, WM_MIXED>{}, T{}, signs);
+              else if (wmode == WM_RELU) run(std::integral_constant<int, WM_RELU>{}, F{}, signs);
+              else if (wmode == WM_STEP) run(std::integral_constant<int, WM_STEP>{}, F{}, signs);
+              else run(std::integral_constant<int, WM_MIXED>{}, F{}, signs);
+            };
+            if (want_bits) {
+              dispatch(T{});
+              if (row < p.M) p.sign_bits[static_cast<long long>(row) * p.sign_ld + col0 / 32 + half] = sbits;
+            } else {
+              dispatch(F{});
+            }
           } else if (EPI == EPI_STORE_ADD) {
             const float* bsrc = bias_s + c * CHUNK + jbase;
 #pragma unroll
@@ -720,8 +780,20 @@ __global__ void __launch_bounds__(num_threads(EPI, PAIR), 1) forde_gemm_kernel(c
                 st_shared_v4(orow_s + off, dw[0], dw[1], dw[2], dw[3]);
               }
             };
-            if (warp_has_tanh) run(std::true_type{});
-            else run(std::false_type{});
+            if (bits_path) {
+              uint32_t word = mw[half];
+              if (CPW > 1 && cc == 1) word = mw[2 + half];
+#pragma unroll
+              for (int j8 = 0; j8 < 4; ++j8) {
+                uint32_t dw[4];
+                dz_bwd_8_bits(v + j8 * 8, word >> (j8 * 8), m_pos, m_neg, dw, rs);
+                st_shared_v4(orow_s + ((static_cast<uint32_t>(half * 4 + j8) ^ sw) << 4), dw[0], dw[1], dw[2], dw[3]);
+              }
+            } else if (warp_has_tanh) {
+              run(std::true_type{});
+            } else {
+              run(std::false_type{});
+            }
           }
         };
         if (tmem_pipe(EPI) == 2) {

@@ -80,6 +80,11 @@ def num_partials(M: int) -> int:
     return _lib.load().forde_sl_num_partials(M)
 
 
+def sign_words(M: int) -> int:
+    """Row pitch (u32 words) of the optional sign-bit buffer [H][sign_words(M)] for M samples."""
+    return _lib.load().forde_sl_sign_words(M)
+
+
 def sample_pitch(M: int) -> int:
     """Row pitch (in elements) of the neuron-major zT / hT / dzT buffers for M samples."""
     return round_up(M, 8)
@@ -128,13 +133,25 @@ def gemm_f32(A, B, a_mn_major, b_mn_major, out=None, scale=1.0, accumulate=False
 
 
 # ------------------------------------------------------------------------------------------ StatefulLayer
-def sl_up_fwd(x, w_up, b_up, assign_i8, zT, hT, act_partials, save_z: bool = True):
+def sl_up_fwd(x, w_up, b_up, assign_i8, zT, hT, act_partials, save_z: bool = True, sign_bits=None):
+    """With ``sign_bits`` (int32 [H, sign_words(M)]) the save_z = 0 forward also records (z > 0) wherever it does not
+    store the z box, for ``sl_dz_bwd(..., sign_bits=...)``."""
     M, d = x.shape
     H = w_up.shape[1]
     _req(x, torch.bfloat16, "x"); _req(w_up, torch.bfloat16, "w_up"); _req(assign_i8, torch.int8, "assign")
     _req(zT, torch.bfloat16, "zT"); _req(hT, torch.bfloat16, "hT")
     if b_up is not None:
         _req(b_up, torch.float32, "b_up")
+    if sign_bits is not None:
+        _req(sign_bits, torch.int32, "sign_bits")
+        assert not save_z, "sign bits replace the z boxes the save_z = 0 forward skips"
+        assert tuple(sign_bits.shape) == (H, sign_words(M)) and sign_bits.is_contiguous()
+        with _Timed(f"sl_up_fwd[{M}x{d}x{H}]", 2.0 * M * d * H):
+            rc = _lib.load().forde_sl_up_fwd_signs(_stream(), x.data_ptr(), w_up.data_ptr(), _ptr(b_up),
+                                                   assign_i8.data_ptr(), zT.data_ptr(), hT.data_ptr(),
+                                                   sign_bits.data_ptr(), _ptr(act_partials), M, d, H, zT.stride(0))
+        _lib.check(rc, "forde_sl_up_fwd_signs")
+        return
     with _Timed(f"sl_up_fwd[{M}x{d}x{H}]", 2.0 * M * d * H):
         rc = _lib.load().forde_sl_up_fwd(_stream(), x.data_ptr(), w_up.data_ptr(), _ptr(b_up), assign_i8.data_ptr(),
                                          zT.data_ptr(), hT.data_ptr(), _ptr(act_partials), M, d, H, zT.stride(0),
@@ -153,10 +170,20 @@ def sl_down_fwd(hT, w_down, b_down, y, M):
     _lib.check(rc, "forde_sl_down_fwd")
 
 
-def sl_dz_bwd(dy, w_down, zT, hT, assign_i8, dzT, grad_partials):
+def sl_dz_bwd(dy, w_down, zT, hT, assign_i8, dzT, grad_partials, sign_bits=None):
+    """With ``sign_bits`` (written by ``sl_up_fwd(..., sign_bits=...)``) h^T is not read and may be None."""
     M, d = dy.shape
     H = w_down.shape[0]
     _req(dy, torch.bfloat16, "dy"); _req(zT, torch.bfloat16, "zT"); _req(dzT, torch.bfloat16, "dzT")
+    if sign_bits is not None:
+        _req(sign_bits, torch.int32, "sign_bits")
+        assert tuple(sign_bits.shape) == (H, sign_words(M)) and sign_bits.is_contiguous()
+        with _Timed(f"sl_dz_bwd[{M}x{d}x{H}]", 2.0 * M * d * H):
+            rc = _lib.load().forde_sl_dz_bwd_signs(_stream(), dy.data_ptr(), w_down.data_ptr(), zT.data_ptr(),
+                                                   sign_bits.data_ptr(), assign_i8.data_ptr(), dzT.data_ptr(),
+                                                   _ptr(grad_partials), M, d, H, zT.stride(0))
+        _lib.check(rc, "forde_sl_dz_bwd_signs")
+        return
     with _Timed(f"sl_dz_bwd[{M}x{d}x{H}]", 2.0 * M * d * H):
         rc = _lib.load().forde_sl_dz_bwd(_stream(), dy.data_ptr(), w_down.data_ptr(), zT.data_ptr(), hT.data_ptr(),
                                          assign_i8.data_ptr(),

@@ -25,7 +25,8 @@ updated IN PLACE when the backward pass of that call finishes (forward-only call
 from __future__ import annotations
 
 import math
-from dataclasses import dataclass
+import os
+from dataclasses import dataclass, field
 from typing import Dict, Iterable, Optional, Tuple, Union
 
 import torch
@@ -40,7 +41,7 @@ STAT_NAMES = ("grad_gini", "grad_gdp", "act_gini", "act_gdp", "act_variance")  #
 class _Workspace:
     """Per-(M, H, device) scratch that is reused every step: the neuron-major residual buffers and partials."""
 
-    def __init__(self, M: int, H: int, device):
+    def __init__(self, M: int, H: int, device, sign_bits: bool = False):
         ld = ops.sample_pitch(M)
         P = ops.num_partials(M)
         self.M, self.H, self.ld, self.P = M, H, ld, P
@@ -48,6 +49,8 @@ class _Workspace:
         self.hT = torch.empty((H, ld), dtype=torch.bfloat16, device=device)
         self.act_partials = torch.empty((P, 3, H), dtype=torch.float32, device=device)
         self.grad_partials = torch.empty((P, 3, H), dtype=torch.float32, device=device)
+        # (z > 0) bit per neuron and sample for the neuron groups whose z box the forward does not store
+        self.signs = torch.empty((H, ops.sign_words(M)), dtype=torch.int32, device=device) if sign_bits else None
         self.in_flight = False  # forward done, backward pending: zT / hT must not be overwritten
 
 
@@ -96,7 +99,8 @@ class _StatefulLayerFn(torch.autograd.Function):
         b_down32 = b_down.float() if b_down.dtype != torch.float32 else b_down
         assign_i8 = layer._assign_i8
         y = torch.empty((M, w_down.shape[1]), dtype=torch.bfloat16, device=x2d.device)
-        ops.sl_up_fwd(x2d, w_up16, b_up32, assign_i8, ws.zT, ws.hT, ws.act_partials, save_z=layer.save_z)
+        ops.sl_up_fwd(x2d, w_up16, b_up32, assign_i8, ws.zT, ws.hT, ws.act_partials, save_z=layer.save_z,
+                      sign_bits=ws.signs)
         ctx.keep_bits = None
         if layer.top_k is not None:  # D8: keep the k largest |h| per token, zero the rest (in place)
             layer.last_topk_indices, layer.last_row_hoyer, ctx.keep_bits = ops.sl_topk_sparsify(ws.hT, M, layer.top_k)
@@ -146,9 +150,9 @@ class _StatefulLayerFn(torch.autograd.Function):
         dev = x2d.device
         dzT = _dz_scratch(H, ws.ld, dev)
         if ctx.keep_bits is None:
-            ops.sl_dz_bwd(dy, w_down16, ws.zT, ws.hT, assign_i8, dzT, ws.grad_partials)
+            ops.sl_dz_bwd(dy, w_down16, ws.zT, ws.hT, assign_i8, dzT, ws.grad_partials, sign_bits=ws.signs)
         else:  # top-k path: dL/dz is zero where h was dropped; the gradient sums are re-taken after masking
-            ops.sl_dz_bwd(dy, w_down16, ws.zT, ws.hT, assign_i8, dzT, None)
+            ops.sl_dz_bwd(dy, w_down16, ws.zT, ws.hT, assign_i8, dzT, None, sign_bits=ws.signs)
             ops.sl_topk_mask(dzT, M, ctx.keep_bits, ws.grad_partials)
         d_out = dy.shape[1]
         sinks = [grad_sink(m) for m in ctx.masters]
@@ -195,6 +199,9 @@ class StatefulLayer:
     param_dtype: torch.dtype = torch.float32
     sense_forward_only: bool = False       # also accumulate activation-only stats in no-grad forwards
     save_z: bool = False                   # keep all of z^T (debugging); by default only what the backward reads
+    # record (z > 0) bits where z is not stored and let the backward read those instead of h^T (1/16 of the bytes);
+    # same results bit for bit.  Off unless FORDE_SIGN_BITS=1 (or set explicitly); ignored with save_z.
+    sign_bits: bool = field(default_factory=lambda: os.environ.get("FORDE_SIGN_BITS", "0") == "1")
     name: str = "stateful_layer"
 
     def __post_init__(self):
@@ -273,7 +280,7 @@ class StatefulLayer:
         for ws in pool:
             if not ws.in_flight:
                 return ws
-        ws = _Workspace(M, H, device)  # the module is applied again before its previous backward ran
+        ws = _Workspace(M, H, device, sign_bits=self.sign_bits and not self.save_z)  # the module is applied again before its previous backward ran
         pool.append(ws)
         return ws
 

@@ -74,6 +74,14 @@ int forde_sl_up_fwd(void* stream, const void* x, const void* w_up, const float* 
                     void* zT, void* hT, float* act_partials, int M, int d, int H, long long ldz, int save_z);
 int forde_sl_down_fwd(void* stream, const void* hT, const void* w_down, const float* b_down, void* y, int M,
                       int d, int H, long long ldz);
+/* Sign-bit variant of the save_z = 0 forward.  Where the z box is not written the kernel also records (z > 0), one
+ * bit per neuron and sample: sign_bits[H][forde_sl_sign_words(M)] u32 (16-byte aligned), bit j of word w of a row =
+ * sample 32 w + j.  forde_sl_dz_bwd_signs then reads these 1/16 as many bytes instead of the hT box.  Same results
+ * as the hT path bit for bit (relu'(z) needs only the sign of z; the straight-through step needs nothing). */
+int forde_sl_sign_words(int M);
+int forde_sl_up_fwd_signs(void* stream, const void* x, const void* w_up, const float* b_up, const int8_t* assign,
+                          void* zT, void* hT, uint32_t* sign_bits, float* act_partials, int M, int d, int H,
+                          long long ldz);
 /* both of the above */
 int forde_sl_fwd(void* stream, const void* x, const void* w_up, const float* b_up, const void* w_down,
                  const float* b_down, const int8_t* assign, void* zT, void* hT, void* y, float* act_partials,
@@ -90,6 +98,10 @@ int forde_sl_fwd(void* stream, const void* x, const void* w_up, const float* b_u
  * db_down: db_down[d]    += sum_m dy */
 int forde_sl_dz_bwd(void* stream, const void* dy, const void* w_down, const void* zT, const void* hT,
                     const int8_t* assign, void* dzT, float* grad_partials, int M, int d, int H, long long ldz);
+/* backward of forde_sl_up_fwd_signs: zT where a neuron group has a tanh neuron, sign_bits elsewhere */
+int forde_sl_dz_bwd_signs(void* stream, const void* dy, const void* w_down, const void* zT,
+                          const uint32_t* sign_bits, const int8_t* assign, void* dzT, float* grad_partials, int M,
+                          int d, int H, long long ldz);
 int forde_sl_dx_bwd(void* stream, const void* dzT, const void* w_up, void* dx, int M, int d, int H,
                     long long ldz);
 /* dx = dz . w_up^T + residual ([M][d] bf16; may be dx itself): when the layer sits in `x + StatefulLayer(x)` (README.md:43)

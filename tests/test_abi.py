@@ -50,11 +50,19 @@ def test_pure_host_entry_points(lib):
     assert lib.forde_sl_num_partials(256) == 2
     assert lib.forde_sl_num_partials(257) == 4
     assert lib.forde_sl_num_partials(50432) == 394
+    assert lib.forde_sl_sign_words(0) == 0
+    assert lib.forde_sl_sign_words(1) == 8
+    assert lib.forde_sl_sign_words(257) == 16
+    assert lib.forde_sl_sign_words(50432) == 1576          # = M / 32: one bit per sample
 
 
 def test_argument_validation_needs_no_gpu(lib):
     # null pointers / bad shapes are rejected on the host before anything touches the device
     rc = lib.forde_sl_up_fwd(None, None, None, None, None, None, None, None, 16, 16, 16, 16, 1)
+    assert rc == -1
+    rc = lib.forde_sl_up_fwd_signs(None, None, None, None, None, None, None, None, None, 16, 16, 16, 16)
+    assert rc == -1
+    rc = lib.forde_sl_dz_bwd_signs(None, None, None, None, None, None, None, None, 16, 16, 16, 16)
     assert rc == -1
     rc = lib.forde_stats_finalize(None, None, None, 1, 16, 16, None, None, None, None, None, None)
     assert rc == -1

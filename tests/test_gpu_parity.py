@@ -436,6 +436,75 @@ def test_backward_reads_h_where_z_was_not_saved(ops, pattern):
     np.testing.assert_allclose(st, O.calculate_neuron_stats(z, dz), rtol=2e-2, atol=2e-4)
 
 
+def _pack_sign_bits(zT_bool: torch.Tensor, words: int) -> torch.Tensor:
+    """[H, M] bool -> [H, words] int32, bit j of word w = sample 32 w + j."""
+    H, M = zT_bool.shape
+    pad = torch.zeros((H, words * 32), dtype=torch.int64, device=zT_bool.device)
+    pad[:, :M] = zT_bool.to(torch.int64)
+    w = (pad.view(H, words, 32) << torch.arange(32, device=pad.device)).sum(-1)
+    return torch.where(w >= 2 ** 31, w - 2 ** 32, w).to(torch.int32)
+
+
+@pytest.mark.parametrize("shape", [(160, 128, 512), (1000, 256, 640), (7, 64, 136), (2048, 768, 3072), (2500, 256, 3000)])
+@pytest.mark.parametrize("pattern", ["zeros", "blocks", "mixed", "no_tanh_mixed"])
+def test_sign_bit_path_is_bit_identical_to_the_h_path(ops, shape, pattern):
+    """forde_sl_up_fwd_signs / forde_sl_dz_bwd_signs: where z is not stored the forward records (z > 0) bits and the
+    backward reads those instead of h^T.  Integer/bit work: the bits equal (z > 0) of the stored-z run exactly, and
+    h^T, dz^T and both partial-sum buffers are bit-identical to the default path (single-CTA and CTA-pair tiles,
+    ragged M and H, neuron groups with and without tanh neurons)."""
+    M, d, H = shape
+    a = {"zeros": np.zeros(H, int), "blocks": np.arange(H) * 3 // H, "mixed": np.random.RandomState(3).randint(0, 3, H),
+         "no_tanh_mixed": np.where(np.arange(H) % 2 == 0, 0, 2)}[pattern]
+    t = run_layer(ops, M, d, H, a, seed=5, bias_scale=0.3)     # default path, every z box stored
+    words = ops.sign_words(M)
+    assert words == 8 * ((M + 255) // 256)
+    zT2 = torch.full_like(t["zT"], float("nan")); hT2 = torch.zeros_like(t["hT"])
+    signs = torch.full((H, words), 0x5A5A5A5A, device="cuda", dtype=torch.int32)
+    actp2 = torch.zeros_like(t["actp"]); gradp2 = torch.zeros_like(t["gradp"]); dzT2 = torch.zeros_like(t["dzT"])
+    ops.sl_up_fwd(t["x"], t["w_up"], t["b_up"], t["assign"], zT2, hT2, actp2, save_z=False, sign_bits=signs)
+    ops.sl_dz_bwd(t["dy"], t["w_down"], zT2, None, t["assign"], dzT2, gradp2, sign_bits=signs)
+    torch.cuda.synchronize()
+    assert torch.equal(hT2[:, :M], t["hT"][:, :M]) and torch.equal(actp2, t["actp"])
+    has_tanh = torch.as_tensor(a == 1, device="cuda")
+    grp = torch.arange(H, device="cuda") // 32
+    grp_tanh = torch.zeros(int(grp.max()) + 1, dtype=torch.bool, device="cuda").index_put_((grp,), has_tanh, accumulate=True)[grp]
+    want = _pack_sign_bits(t["zT"][:, :M] > 0, words)
+    valid = torch.zeros((H, words * 32), dtype=torch.bool, device="cuda"); valid[:, :M] = True
+    vmask = _pack_sign_bits(valid, words)                                 # samples beyond M carry no meaning
+    rows = ~grp_tanh
+    assert torch.equal(signs[rows] & vmask[rows], want[rows]), "sign bits differ from (z > 0)"
+    if bool(grp_tanh.any()):                                              # tanh groups: z box stored, bits untouched
+        assert torch.equal(zT2[grp_tanh][:, :M], t["zT"][grp_tanh][:, :M])
+        assert bool((signs[grp_tanh] == 0x5A5A5A5A).all())
+    assert torch.equal(dzT2[:, :M], t["dzT"][:, :M]), "dz differs between the sign-bit and h^T paths"
+    assert torch.equal(gradp2, t["gradp"])
+
+
+def test_module_with_sign_bits_matches_default_module(ops):
+    """StatefulLayer(sign_bits=True) end to end through autograd: same outputs, gradients and statistics, bit for bit."""
+    from forde_b200.stateful_layer import StatefulLayer
+    M, d, H = 700, 128, 512
+    a = (np.arange(H) // 64) % 3
+    outs = []
+    for sb in (False, True):
+        layer = StatefulLayer(hidden_dim=H, sign_bits=sb)
+        x = torch.randn((M, d), device="cuda", generator=torch.Generator(device="cuda").manual_seed(9)).bfloat16().requires_grad_(True)
+        v = layer.init(4, x)
+        v["neuron_assignments"]["assignments"].copy_(torch.as_tensor(a))
+        ps = [v["params"]["up_proj"]["kernel"], v["params"]["up_proj"]["bias"], v["params"]["down_proj"]["kernel"]]
+        ps[1].copy_(torch.linspace(-0.5, 0.5, H, device="cuda"))
+        for p_ in ps:
+            p_.requires_grad_(True)
+        y, upd = layer.apply(v, x, mutable=["stats_buffer"])
+        y.backward(torch.ones_like(y))
+        torch.cuda.synchronize()
+        ws = layer._ws[(M, H, str(x.device))][0]
+        assert (ws.signs is not None) == sb
+        outs.append([y.detach(), x.grad, ps[0].grad, ps[1].grad, ps[2].grad, upd["stats_buffer"]["neuron_stats"]])
+    for p0, p1 in zip(*outs):
+        assert torch.equal(p0, p1)
+
+
 def test_module_edge_cases_empty_batch_and_bad_widths(ops):
     from forde_b200.stateful_layer import StatefulLayer
     layer = StatefulLayer(hidden_dim=256)

@@ -24,6 +24,7 @@ ap.add_argument("--H", type=int, default=3072)
 ap.add_argument("--iters", type=int, default=20)
 ap.add_argument("--once", action="store_true", help="one pass, no timing (for ncu)")
 ap.add_argument("--save-z", type=int, default=0, help="1 = forward writes all of z^T (debug), 0 = only what the backward reads")
+ap.add_argument("--sign-bits", type=int, default=0, help="1 = forward records (z > 0) bits, backward reads them instead of h^T")
 ap.add_argument("--assign", default="mixed", choices=["mixed", "zeros", "blocks"],
                 help="brain map: i.i.d. uniform{0,1,2} | all generalists (init) | contiguous thirds (smoothed map)")
 a = ap.parse_args()
@@ -47,12 +48,13 @@ y = torch.zeros((M, d), device="cuda", dtype=torch.bfloat16); dx = torch.zeros_l
 dw_up = torch.zeros((d, H), device="cuda"); dw_down = torch.zeros((H, d), device="cuda")
 db_up = torch.zeros(H, device="cuda"); db_down = torch.zeros(d, device="cuda")
 stats = torch.zeros((H, 5), device="cuda")
+signs = torch.zeros((H, ops.sign_words(M)), device="cuda", dtype=torch.int32) if a.sign_bits else None
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
 
 steps = [
-    ("up_fwd", lambda: ops.sl_up_fwd(x, w_up, b_up, assign, zT, hT, actp, save_z=bool(a.save_z))),
+    ("up_fwd", lambda: ops.sl_up_fwd(x, w_up, b_up, assign, zT, hT, actp, save_z=bool(a.save_z), sign_bits=signs)),
     ("down_fwd", lambda: ops.sl_down_fwd(hT, w_down, b_down, y, M)),
-    ("dz_bwd", lambda: ops.sl_dz_bwd(dy, w_down, zT, hT, assign, dzT, gradp)),
+    ("dz_bwd", lambda: ops.sl_dz_bwd(dy, w_down, zT, hT, assign, dzT, gradp, sign_bits=signs)),
     ("dx_bwd", lambda: ops.sl_dx_bwd(dzT, w_up, dx, M)),
     ("dw_up", lambda: ops.sl_dw_up(x, dzT, dw_up)),
     ("dw_down", lambda: ops.sl_dw_down(hT, dy, dw_down)),
