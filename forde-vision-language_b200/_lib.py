@@ -26,6 +26,7 @@ SIGNATURES = {
     "forde_launch_count": (ctypes.c_ulonglong, []),
     "forde_sl_num_partials": (_i, [_i]),
     "forde_sl_sign_words": (_i, [_i]),
+    "forde_sl_sign_layout": (_i, []),
     "forde_sl_up_fwd_signs": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _ll]),
     "forde_sl_dz_bwd_signs": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _ll]),
     "forde_gemm_bf16": (_i, [_vp, _vp, _i, _ll, _vp, _i, _ll, _vp, _ll, _vp, _i, _i, _i]),

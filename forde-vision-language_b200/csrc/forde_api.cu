@@ -375,6 +375,8 @@ int forde_sm_count(void) { return sm_count(); }
 
 unsigned long long forde_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
+int forde_sl_sign_layout(void) { return (FORDE_UP_PACKED ? 1 : 0) | (FORDE_SIGN_WORD_MAJOR ? 2 : 0); }
+
 int forde_sl_sign_words(int M) { return M <= 0 ? 0 : 8 * ((M + BN - 1) / BN); }
 
 int forde_sl_num_partials(int M) { return M <= 0 ? 0 : PARTIALS_PER_TILE * ((M + BN - 1) / BN); }

@@ -107,6 +107,23 @@ constexpr int TMEM_COLS = 512;
 #ifndef FORDE_TMEM_PIPE_DZ
 #define FORDE_TMEM_PIPE_DZ 0
 #endif
+// 1: packed bf16x2 arithmetic in the forward epilogue (A/B, not yet the default): h = z + max(z, 0) of the all-relu
+// warp mode as HMNMX2 + HFMA2 on the packed word, and the sign bits from one HSET2 per pair.  The packed compare
+// yields the pair's two bits 16 apart, so the sign words then use the INTERLEAVED layout: within a 32-sample word,
+// sample 2k -> bit k, sample 2k + 1 -> bit 16 + k (forde_sl_sign_layout() reports which layout the build uses).
+#ifndef FORDE_UP_PACKED
+#define FORDE_UP_PACKED 0
+#endif
+// 1: word-major sign buffer [sign_ld words][M neurons] instead of [M neurons][sign_ld words] (A/B, not yet the
+// default).  A warp's 32 lanes are 32 consecutive neurons, so in the word-major buffer each of its sign stores and
+// loads touches one 128-byte line instead of 32 lines a row pitch apart: exp13 measured the forward paying ~12 us
+// for the neuron-major stores although they are only 6 % of its bytes (they are 50 % more L2 write transactions).
+#ifndef FORDE_SIGN_WORD_MAJOR
+#define FORDE_SIGN_WORD_MAJOR 0
+#endif
+__device__ __forceinline__ long long sign_index(long long row, long long word, int rows, int sign_ld) {
+  return FORDE_SIGN_WORD_MAJOR ? word * rows + row : row * sign_ld + word;
+}
 __host__ __device__ constexpr int tmem_pipe(int epi) {
   return epi == 1 /*EPI_UP_FWD*/ ? FORDE_TMEM_PIPE_UP : epi == 2 /*EPI_DZ_BWD*/ ? FORDE_TMEM_PIPE_DZ : 0;
 }
@@ -169,7 +186,8 @@ struct GemmParams {
   int raster_m_fast;  // 1: consecutive work items walk M first (share the B slab), 0: walk N first
   int pair;           // 1: launched as 2-CTA clusters (256-row tiles, cta_group::2)
   int save_z;         // EPI_UP_FWD: 1 = store every z box; 0 = only the boxes the backward needs (warps with tanh neurons)
-  // Optional sign bits of z, [M rows = neurons][sign_ld] u32, bit j of word w = (z[neuron][32 w + j] > 0).
+  // Optional sign bits of z, [M rows = neurons][sign_ld] u32, bit j of word w = (z[neuron][32 w + j] > 0)
+  // ([sign_ld][M] with FORDE_SIGN_WORD_MAJOR, interleaved bit order with FORDE_UP_PACKED; forde_sl_sign_layout()).
   // EPI_UP_FWD writes them for the 32-neuron groups whose z box it does not store; EPI_DZ_BWD then reads 8 bytes
   // per neuron and 64-sample chunk instead of TMA-loading the h^T box (1/16 of the bytes).  Null = off.
   uint32_t* sign_bits;
@@ -275,13 +293,19 @@ __device__ __forceinline__ void up_fwd_8(const uint32_t* v, float bias_r, const 
     const uint32_t zp = pack_bf16x2(__uint_as_float(v[2 * i]) + bias_r, __uint_as_float(v[2 * i + 1]) + bias_r);
     const float z0 = bf16lo_to_f32(zp), z1 = bf16hi_to_f32(zp);
     if (SIGNS) {
-      if (z0 > 0.f) bits |= 1u << ((jcol & 31) + 2 * i);
-      if (z1 > 0.f) bits |= 1u << ((jcol & 31) + 2 * i + 1);
+      if (FORDE_UP_PACKED) {
+        bits |= (bf16x2_gt_zero_mask(zp) & 0x00010001u) << (((jcol & 31) >> 1) + i);
+      } else {
+        if (z0 > 0.f) bits |= 1u << ((jcol & 31) + 2 * i);
+        if (z1 > 0.f) bits |= 1u << ((jcol & 31) + 2 * i + 1);
+      }
     }
-    float h0, h1;
+    float h0 = 0.f, h1 = 0.f;
     if (MODE == WM_RELU) {          // h = relu(z) + 1.0 * z
-      h0 = z0 + fmaxf(z0, 0.f);
-      h1 = z1 + fmaxf(z1, 0.f);
+      if (!FORDE_UP_PACKED) {
+        h0 = z0 + fmaxf(z0, 0.f);
+        h1 = z1 + fmaxf(z1, 0.f);
+      }
     } else if (MODE == WM_STEP) {   // h = step(z) + gate * z
       h0 = fmaf(act.gate, z0, z0 > 0.f ? 1.f : 0.f);
       h1 = fmaf(act.gate, z1, z1 > 0.f ? 1.f : 0.f);
@@ -298,7 +322,7 @@ __device__ __forceinline__ void up_fwd_8(const uint32_t* v, float bias_r, const 
       h1 = fmaf(act.gate, z1, f1);
     }
     zw[i] = zp;
-    hw[i] = pack_bf16x2(h0, h1);
+    hw[i] = (FORDE_UP_PACKED && MODE == WM_RELU) ? bf16x2_relu_plus_self(zp) : pack_bf16x2(h0, h1);
     if (!MASKED) {
       rs.s_abs += fabsf(z0) + fabsf(z1);
       rs.s_sum += z0 + z1;
@@ -338,12 +362,13 @@ __device__ __forceinline__ void dz_bwd_8(const uint32_t* v, const uint32_t* zw, 
 }
 
 // backward from the sign bits (no tanh neuron in the warp): bit i of `bits8` = (z > 0) for column i of these 8
+// (interleaved layout: bits i and 16 + i for columns 2 i and 2 i + 1)
 __device__ __forceinline__ void dz_bwd_8_bits(const uint32_t* v, uint32_t bits8, float m_pos, float m_neg,
                                               uint32_t* dw, RunningSums& rs) {
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    const float m0 = (bits8 & (1u << (2 * i))) ? m_pos : m_neg;
-    const float m1 = (bits8 & (1u << (2 * i + 1))) ? m_pos : m_neg;
+    const float m0 = (bits8 & (FORDE_UP_PACKED ? (1u << i) : (1u << (2 * i)))) ? m_pos : m_neg;
+    const float m1 = (bits8 & (FORDE_UP_PACKED ? (1u << (16 + i)) : (1u << (2 * i + 1)))) ? m_pos : m_neg;
     const uint32_t dp = pack_bf16x2(__uint_as_float(v[2 * i]) * m0, __uint_as_float(v[2 * i + 1]) * m1);
     dw[i] = dp;
     const float d0 = bf16lo_to_f32(dp), d1 = bf16hi_to_f32(dp);
@@ -587,12 +612,18 @@ __global__ void __launch_bounds__(num_threads(EPI, PAIR), 1) forde_gemm_kernel(c
       uint32_t mw[4] = {0u, 0u, 0u, 0u};  // this warp's sign words of the tile: [chunk][half]
       static_assert(EPI != EPI_DZ_BWD || CPW <= 2, "sign words per tile");
       if (bits_path && row < p.M) {
-        const uint32_t* src = p.sign_bits + static_cast<long long>(row) * p.sign_ld + (w.n0 + e * CPW * CHUNK) / 32;
+        const int w0 = (w.n0 + e * CPW * CHUNK) / 32;  // first sign word of this warp's columns
+        if (FORDE_SIGN_WORD_MAJOR) {
 #pragma unroll
-        for (int i = 0; i < CPW; ++i) {
-          const uint2 t2 = __ldg(reinterpret_cast<const uint2*>(src) + i);
-          mw[2 * i] = t2.x;
-          mw[2 * i + 1] = t2.y;
+          for (int i = 0; i < 2 * CPW; ++i) mw[i] = __ldg(p.sign_bits + sign_index(row, w0 + i, p.M, p.sign_ld));
+        } else {
+          const uint32_t* src = p.sign_bits + sign_index(row, w0, p.M, p.sign_ld);
+#pragma unroll
+          for (int i = 0; i < CPW; ++i) {
+            const uint2 t2 = __ldg(reinterpret_cast<const uint2*>(src) + i);
+            mw[2 * i] = t2.x;
+            mw[2 * i + 1] = t2.y;
+          }
         }
       }
       if (epi_col_bias(EPI)) {
@@ -717,7 +748,7 @@ __global__ void __launch_bounds__(num_threads(EPI, PAIR), 1) forde_gemm_kernel(c
             };
             if (want_bits) {
               dispatch(T{});
-              if (row < p.M) p.sign_bits[static_cast<long long>(row) * p.sign_ld + col0 / 32 + half] = sbits;
+              if (row < p.M) p.sign_bits[sign_index(row, col0 / 32 + half, p.M, p.sign_ld)] = sbits;
             } else {
               dispatch(F{});
             }
@@ -786,7 +817,7 @@ __global__ void __launch_bounds__(num_threads(EPI, PAIR), 1) forde_gemm_kernel(c
 #pragma unroll
               for (int j8 = 0; j8 < 4; ++j8) {
                 uint32_t dw[4];
-                dz_bwd_8_bits(v + j8 * 8, word >> (j8 * 8), m_pos, m_neg, dw, rs);
+                dz_bwd_8_bits(v + j8 * 8, word >> (FORDE_UP_PACKED ? j8 * 4 : j8 * 8), m_pos, m_neg, dw, rs);
                 st_shared_v4(orow_s + ((static_cast<uint32_t>(half * 4 + j8) ^ sw) << 4), dw[0], dw[1], dw[2], dw[3]);
               }
             } else if (warp_has_tanh) {

@@ -240,6 +240,17 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
   return r;
 }
+// packed bf16x2 arithmetic (sm_90+): both halves in one instruction, one rounding of the exact result
+__device__ __forceinline__ uint32_t bf16x2_relu_plus_self(uint32_t z) {  // z + max(z, 0)
+  uint32_t h;
+  asm("{\n\t.reg .b32 t;\n\tmax.bf16x2 t, %1, %2;\n\tadd.rn.bf16x2 %0, %1, t;\n\t}" : "=r"(h) : "r"(z), "r"(0u));
+  return h;
+}
+__device__ __forceinline__ uint32_t bf16x2_gt_zero_mask(uint32_t z) {  // 0xFFFF per half where z > 0
+  uint32_t m;
+  asm("set.gt.u32.bf16x2 %0, %1, %2;" : "=r"(m) : "r"(z), "r"(0u));
+  return m;
+}
 __device__ __forceinline__ float bf16lo_to_f32(uint32_t p) { return __uint_as_float(p << 16); }
 __device__ __forceinline__ float bf16hi_to_f32(uint32_t p) { return __uint_as_float(p & 0xFFFF0000u); }
 __device__ __forceinline__ float tanh_approx(float x) {

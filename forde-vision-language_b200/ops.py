@@ -85,6 +85,17 @@ def sign_words(M: int) -> int:
     return _lib.load().forde_sl_sign_words(M)
 
 
+def sign_layout() -> int:
+    """Bit mask.  Bit 0: 0 = bit j of a sign word is sample 32 w + j, 1 = interleaved (sample 2k -> bit k, 2k + 1 ->
+    bit 16 + k).  Bit 1: 0 = buffer is [H, words], 1 = [words, H].  The shipped build returns 0."""
+    return _lib.load().forde_sl_sign_layout()
+
+
+def sign_shape(M: int, H: int):
+    """Shape of the int32 sign-bit buffer for M samples and H neurons in this build."""
+    return (sign_words(M), H) if sign_layout() & 2 else (H, sign_words(M))
+
+
 def sample_pitch(M: int) -> int:
     """Row pitch (in elements) of the neuron-major zT / hT / dzT buffers for M samples."""
     return round_up(M, 8)
@@ -134,7 +145,7 @@ def gemm_f32(A, B, a_mn_major, b_mn_major, out=None, scale=1.0, accumulate=False
 
 # ------------------------------------------------------------------------------------------ StatefulLayer
 def sl_up_fwd(x, w_up, b_up, assign_i8, zT, hT, act_partials, save_z: bool = True, sign_bits=None):
-    """With ``sign_bits`` (int32 [H, sign_words(M)]) the save_z = 0 forward also records (z > 0) wherever it does not
+    """With ``sign_bits`` (int32, ``sign_shape(M, H)``) the save_z = 0 forward also records (z > 0) wherever it does not
     store the z box, for ``sl_dz_bwd(..., sign_bits=...)``."""
     M, d = x.shape
     H = w_up.shape[1]
@@ -145,7 +156,7 @@ def sl_up_fwd(x, w_up, b_up, assign_i8, zT, hT, act_partials, save_z: bool = Tru
     if sign_bits is not None:
         _req(sign_bits, torch.int32, "sign_bits")
         assert not save_z, "sign bits replace the z boxes the save_z = 0 forward skips"
-        assert tuple(sign_bits.shape) == (H, sign_words(M)) and sign_bits.is_contiguous()
+        assert tuple(sign_bits.shape) == sign_shape(M, H) and sign_bits.is_contiguous()
         with _Timed(f"sl_up_fwd[{M}x{d}x{H}]", 2.0 * M * d * H):
             rc = _lib.load().forde_sl_up_fwd_signs(_stream(), x.data_ptr(), w_up.data_ptr(), _ptr(b_up),
                                                    assign_i8.data_ptr(), zT.data_ptr(), hT.data_ptr(),
@@ -177,7 +188,7 @@ def sl_dz_bwd(dy, w_down, zT, hT, assign_i8, dzT, grad_partials, sign_bits=None)
     _req(dy, torch.bfloat16, "dy"); _req(zT, torch.bfloat16, "zT"); _req(dzT, torch.bfloat16, "dzT")
     if sign_bits is not None:
         _req(sign_bits, torch.int32, "sign_bits")
-        assert tuple(sign_bits.shape) == (H, sign_words(M)) and sign_bits.is_contiguous()
+        assert tuple(sign_bits.shape) == sign_shape(M, H) and sign_bits.is_contiguous()
         with _Timed(f"sl_dz_bwd[{M}x{d}x{H}]", 2.0 * M * d * H):
             rc = _lib.load().forde_sl_dz_bwd_signs(_stream(), dy.data_ptr(), w_down.data_ptr(), zT.data_ptr(),
                                                    sign_bits.data_ptr(), assign_i8.data_ptr(), dzT.data_ptr(),

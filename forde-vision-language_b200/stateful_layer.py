@@ -50,7 +50,7 @@ class _Workspace:
         self.act_partials = torch.empty((P, 3, H), dtype=torch.float32, device=device)
         self.grad_partials = torch.empty((P, 3, H), dtype=torch.float32, device=device)
         # (z > 0) bit per neuron and sample for the neuron groups whose z box the forward does not store
-        self.signs = torch.empty((H, ops.sign_words(M)), dtype=torch.int32, device=device) if sign_bits else None
+        self.signs = torch.empty(ops.sign_shape(M, H), dtype=torch.int32, device=device) if sign_bits else None
         self.in_flight = False  # forward done, backward pending: zT / hT must not be overwritten
 
 

@@ -79,6 +79,12 @@ int forde_sl_down_fwd(void* stream, const void* hT, const void* w_down, const fl
  * sample 32 w + j.  forde_sl_dz_bwd_signs then reads these 1/16 as many bytes instead of the hT box.  Same results
  * as the hT path bit for bit (relu'(z) needs only the sign of z; the straight-through step needs nothing). */
 int forde_sl_sign_words(int M);
+/* Layout of sign_bits in this build, a bit mask (the shipped build returns 0).  Bit 0: bit order inside a 32-sample
+ * word, 0 = sample order (bit j = sample 32 w + j), 1 = interleaved (sample 2k -> bit k, sample 2k + 1 -> bit 16 + k;
+ * -DFORDE_UP_PACKED=1).  Bit 1: 0 = neuron-major [H][words], 1 = word-major [words][H] (-DFORDE_SIGN_WORD_MAJOR=1).
+ * The buffer is a private residual between the two kernels and always H * forde_sl_sign_words(M) words; only tools
+ * that inspect it need this. */
+int forde_sl_sign_layout(void);
 int forde_sl_up_fwd_signs(void* stream, const void* x, const void* w_up, const float* b_up, const int8_t* assign,
                           void* zT, void* hT, uint32_t* sign_bits, float* act_partials, int M, int d, int H,
                           long long ldz);

@@ -436,12 +436,15 @@ def test_backward_reads_h_where_z_was_not_saved(ops, pattern):
     np.testing.assert_allclose(st, O.calculate_neuron_stats(z, dz), rtol=2e-2, atol=2e-4)
 
 
-def _pack_sign_bits(zT_bool: torch.Tensor, words: int) -> torch.Tensor:
-    """[H, M] bool -> [H, words] int32, bit j of word w = sample 32 w + j."""
+def _pack_sign_bits(zT_bool: torch.Tensor, words: int, layout: int = 0) -> torch.Tensor:
+    """[H, M] bool -> [H, words] int32; layout 0: bit j of word w = sample 32 w + j; layout 1 (builds with packed
+    bf16x2 epilogues): sample 2k -> bit k, sample 2k + 1 -> bit 16 + k."""
     H, M = zT_bool.shape
     pad = torch.zeros((H, words * 32), dtype=torch.int64, device=zT_bool.device)
     pad[:, :M] = zT_bool.to(torch.int64)
-    w = (pad.view(H, words, 32) << torch.arange(32, device=pad.device)).sum(-1)
+    j = torch.arange(32, device=pad.device)
+    pos = j if layout == 0 else (j >> 1) + 16 * (j & 1)
+    w = (pad.view(H, words, 32) << pos).sum(-1)
     return torch.where(w >= 2 ** 31, w - 2 ** 32, w).to(torch.int32)
 
 
@@ -459,18 +462,20 @@ def test_sign_bit_path_is_bit_identical_to_the_h_path(ops, shape, pattern):
     words = ops.sign_words(M)
     assert words == 8 * ((M + 255) // 256)
     zT2 = torch.full_like(t["zT"], float("nan")); hT2 = torch.zeros_like(t["hT"])
-    signs = torch.full((H, words), 0x5A5A5A5A, device="cuda", dtype=torch.int32)
+    layout = ops.sign_layout()
+    signs_buf = torch.full(ops.sign_shape(M, H), 0x5A5A5A5A, device="cuda", dtype=torch.int32)
+    signs = signs_buf.t() if layout & 2 else signs_buf          # [H, words] view either way
     actp2 = torch.zeros_like(t["actp"]); gradp2 = torch.zeros_like(t["gradp"]); dzT2 = torch.zeros_like(t["dzT"])
-    ops.sl_up_fwd(t["x"], t["w_up"], t["b_up"], t["assign"], zT2, hT2, actp2, save_z=False, sign_bits=signs)
-    ops.sl_dz_bwd(t["dy"], t["w_down"], zT2, None, t["assign"], dzT2, gradp2, sign_bits=signs)
+    ops.sl_up_fwd(t["x"], t["w_up"], t["b_up"], t["assign"], zT2, hT2, actp2, save_z=False, sign_bits=signs_buf)
+    ops.sl_dz_bwd(t["dy"], t["w_down"], zT2, None, t["assign"], dzT2, gradp2, sign_bits=signs_buf)
     torch.cuda.synchronize()
     assert torch.equal(hT2[:, :M], t["hT"][:, :M]) and torch.equal(actp2, t["actp"])
     has_tanh = torch.as_tensor(a == 1, device="cuda")
     grp = torch.arange(H, device="cuda") // 32
     grp_tanh = torch.zeros(int(grp.max()) + 1, dtype=torch.bool, device="cuda").index_put_((grp,), has_tanh, accumulate=True)[grp]
-    want = _pack_sign_bits(t["zT"][:, :M] > 0, words)
+    want = _pack_sign_bits(t["zT"][:, :M] > 0, words, layout & 1)
     valid = torch.zeros((H, words * 32), dtype=torch.bool, device="cuda"); valid[:, :M] = True
-    vmask = _pack_sign_bits(valid, words)                                 # samples beyond M carry no meaning
+    vmask = _pack_sign_bits(valid, words, layout & 1)                                 # samples beyond M carry no meaning
     rows = ~grp_tanh
     assert torch.equal(signs[rows] & vmask[rows], want[rows]), "sign bits differ from (z > 0)"
     if bool(grp_tanh.any()):                                              # tanh groups: z box stored, bits untouched

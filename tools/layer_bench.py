@@ -48,7 +48,7 @@ y = torch.zeros((M, d), device="cuda", dtype=torch.bfloat16); dx = torch.zeros_l
 dw_up = torch.zeros((d, H), device="cuda"); dw_down = torch.zeros((H, d), device="cuda")
 db_up = torch.zeros(H, device="cuda"); db_down = torch.zeros(d, device="cuda")
 stats = torch.zeros((H, 5), device="cuda")
-signs = torch.zeros((H, ops.sign_words(M)), device="cuda", dtype=torch.int32) if a.sign_bits else None
+signs = torch.zeros(ops.sign_shape(M, H), device="cuda", dtype=torch.int32) if a.sign_bits else None
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
 
 steps = [
