@@ -308,23 +308,43 @@ class GraphedTrainStep:
 
 def save_checkpoint(state: TrainState, path: str) -> None:
     """Save params, neuron_assignments, the stat accumulators, the optimizer moments and the step counter (the
-    reference saves the whole TrainState once at the end, src/training/train.py:412-422, and has no restore)."""
-    torch.save({"step": state.step, "config": state.model.cfg, "flat_p32": state.flat_p32.detach().cpu(),
+    reference saves the whole TrainState once at the end, src/training/train.py:412-422, and has no restore).
+    Only tensors, numbers and strings are written, so the file loads with ``weights_only=True``."""
+    import dataclasses
+    cfg = state.model.cfg
+    cfg_dict = {k: (dataclasses.asdict(v) if dataclasses.is_dataclass(v) else v)
+                for k, v in (dataclasses.asdict(cfg) if dataclasses.is_dataclass(cfg) else dict(vars(cfg))).items()}
+    torch.save({"step": state.step, "config": cfg_dict, "flat_p32": state.flat_p32.detach().cpu(),
                 "opt": state.opt.state_dict(),
                 "neuron_assignments": _tree_to(state.variables["neuron_assignments"], "cpu"),
                 "stats_buffer": _tree_to(state.variables["stats_buffer"], "cpu")}, path)
 
 
 def restore_checkpoint(state: TrainState, path: str) -> TrainState:
-    """Load a checkpoint written by save_checkpoint into an already created TrainState of the same config, in place
-    (parameter views, bf16 mirror, brain maps and accumulators keep their addresses, so captured CUDA graphs and
-    cached TMA descriptors stay valid)."""
-    ck = torch.load(path, map_location="cpu", weights_only=False)
+    """Load a checkpoint written by save_checkpoint into an already created TrainState of the same config, in place:
+    parameter views, bf16 mirror, brain maps, accumulators AND the optimizer moments keep their addresses, so captured
+    CUDA graphs and cached TMA descriptors stay valid."""
+    ck = torch.load(path, map_location="cpu", weights_only=True)
     if ck["flat_p32"].numel() != state.flat_p32.numel():
         raise ValueError("checkpoint does not match this model configuration")
     state.flat_p32.detach().copy_(ck["flat_p32"])
     state.flat_p16.copy_(state.flat_p32)
-    state.opt.load_state_dict(ck["opt"])
+    saved = ck["opt"]["state"]
+    live = state.opt.state.get(state.flat_p32)
+    if live and saved and all(k in live for k in saved[0]):
+        # the optimizer has stepped already (e.g. inside a captured graph): overwrite its moment tensors in place,
+        # Optimizer.load_state_dict would replace them with new tensors the graph does not know about
+        for k, v in saved[0].items():
+            if torch.is_tensor(live[k]):
+                live[k].copy_(torch.as_tensor(v))
+            else:
+                live[k] = v
+        for g_live, g_saved in zip(state.opt.param_groups, ck["opt"]["param_groups"]):
+            for k, v in g_saved.items():
+                if k != "params" and not torch.is_tensor(g_live.get(k)):
+                    g_live[k] = v
+    else:
+        state.opt.load_state_dict(ck["opt"])
     _tree_copy_(state.variables["neuron_assignments"], ck["neuron_assignments"])
     _tree_copy_(state.variables["stats_buffer"], ck["stats_buffer"])
     state.step = int(ck["step"])

@@ -112,6 +112,17 @@ def test_checkpoint_round_trip_cpu(tmp_path):
     assert float(b.variables["stats_buffer"]["text"]["layer_0"]["stateful_layer"]["moments"].mean()) == 1.5
     sa, sb = a.opt.state_dict()["state"][0], b.opt.state_dict()["state"][0]
     assert torch.equal(sa["exp_avg"], sb["exp_avg"])
+    # a state whose optimizer has already stepped (as under a captured CUDA graph) is restored IN PLACE
+    b.flat_g32.normal_()
+    b.opt.step()
+    m_ptr = b.opt.state[b.flat_p32]["exp_avg"].data_ptr()
+    assert not torch.equal(b.opt.state[b.flat_p32]["exp_avg"], sa["exp_avg"])
+    train.restore_checkpoint(b, path)
+    st = b.opt.state[b.flat_p32]
+    assert st["exp_avg"].data_ptr() == m_ptr
+    assert torch.equal(st["exp_avg"], sa["exp_avg"]) and torch.equal(st["exp_avg_sq"], sa["exp_avg_sq"])
+    assert float(torch.as_tensor(st["step"])) == float(torch.as_tensor(sa["step"]))
+    assert torch.equal(a.flat_p32, b.flat_p32)
 
 
 # ------------------------------------------------------------------ MoE variant, pinned by the reference's own code
