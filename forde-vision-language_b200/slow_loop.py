@@ -20,6 +20,7 @@ deterministic slow loop with the same seed, which keeps ``neuron_assignments`` r
 from __future__ import annotations
 
 from dataclasses import dataclass
+import os
 from typing import Dict, Optional, Tuple
 
 import numpy as np
@@ -64,6 +65,14 @@ def box_smooth(grid: np.ndarray, kernel_size: int, num_clusters: int) -> np.ndar
         plane = np.pad((grid == c).astype(np.float32), ((top, ph - top), (left, pw - left)))
         dens[:, :, c] = convolve2d(plane, box, mode="same")[top:top + h, left:left + w]
     return dens.argmax(axis=-1).astype(np.int32)
+
+
+def warm_up() -> None:
+    """Import scikit-learn / SciPy and run one tiny fit so the first slow loop does not pay ~4 s of imports.
+    ``train.fit`` calls this on a background thread while the first fast steps run."""
+    rng = np.random.RandomState(0)
+    gmm_cluster(rng.rand(32, 5).astype(np.float32), 3, 0)
+    box_smooth(np.zeros((4, 8), np.int32), 3, 3)
 
 
 def gmm_cluster(stats: np.ndarray, num_clusters: int, seed: int):
@@ -156,8 +165,16 @@ def slow_loop_step(params, mutable_variables, config: SlowLoopConfig, key, epoch
         return labels, smoothed, gmm_params
 
     from concurrent.futures import ThreadPoolExecutor
+    from contextlib import nullcontext
+    try:    # (H, 5) problems are far too small for multi-threaded BLAS / OpenMP: with the library pools left on,
+        # one GaussianMixture.fit takes 23 ms instead of 8 ms and 8 of them at once fight over the cores
+        from threadpoolctl import threadpool_limits
+        one_thread_kernels = threadpool_limits(limits=1)
+    except ImportError:
+        one_thread_kernels = nullcontext()
     todo = [(name, stats) for name, stats, _ in jobs if stats is not None]
-    with ThreadPoolExecutor(max_workers=max(1, min(8, len(todo)))) as pool:
+    workers = max(1, min(os.cpu_count() or 1, 16, len(todo)))
+    with one_thread_kernels, ThreadPoolExecutor(max_workers=workers) as pool:
         results = dict(zip([n for n, _ in todo], pool.map(lambda t: cluster_and_smooth(t[1]), todo)))
 
     # ... and ACTUATE in order

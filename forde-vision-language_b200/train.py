@@ -376,6 +376,12 @@ def fit(state: TrainState, batches, max_steps: int, slow_loop_interval: int = 10
     from .slow_loop import SlowLoopConfig, slow_loop_step
 
     cfg = slow_loop_config or SlowLoopConfig()
+    warm = None
+    if max_steps > slow_loop_interval:   # a slow loop will run: pay its imports now, under the first fast steps
+        import threading
+        from .slow_loop import warm_up
+        warm = threading.Thread(target=warm_up, daemon=True)
+        warm.start()
     history, diagnostics = [], []
     step_fn = None
     it = iter(batches)
@@ -395,6 +401,9 @@ def fit(state: TrainState, batches, max_steps: int, slow_loop_interval: int = 10
             if log is not None:
                 log(step, history[-1][1])
         if step > 0 and step % slow_loop_interval == 0:
+            if warm is not None:
+                warm.join()
+                warm = None
             mv = {"stats_buffer": state.variables["stats_buffer"],
                   "neuron_assignments": state.variables["neuron_assignments"]}
             _, _, diag = slow_loop_step(state.params, mv, cfg, key=key + step, epoch=0, step=step, group=state.group)
