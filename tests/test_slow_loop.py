@@ -214,3 +214,45 @@ def test_brain_scan_and_feature_space_files(tmp_path):
     assert BS.plot_feature_space(stats[:, :1], np.zeros(50), 0, 0, out_dir=str(tmp_path)) is None
     with pytest.raises(ValueError):
         BS.plot_brain_scan(np.zeros(5), 0, 0, out_dir=str(tmp_path))
+
+
+def test_fit_cadence_with_a_stubbed_fast_step(tmp_path, monkeypatch):
+    """train.fit's outer loop on CPU (train.py:320-399 cadence) with the fast step replaced by a stub that only
+    accumulates statistics: slow loop at steps N, 2N, ..., statistics reset afterwards, brain scans written, the
+    import warm-up thread joined before the first slow loop."""
+    from forde_b200 import dual_encoder, train
+    cfg = dual_encoder.config_tiny()
+    st = train.create_train_state(cfg, 0, device="cpu")
+    rng = np.random.RandomState(0)
+    calls = []
+
+    def stub_step(state, batch, sense=True):
+        calls.append(state.step)
+        for tower in state.variables["stats_buffer"].values():
+            for name, layer in tower.items():
+                if not name.startswith("layer_"):
+                    continue
+                sb = layer["stateful_layer"]
+                H = sb["neuron_stats"].shape[0]
+                s = rng.rand(H, 5).astype(np.float32)
+                s[: H // 2, 0] += 2.0
+                sb["neuron_stats"].add_(torch.from_numpy(s))
+                sb["step_count"].add_(1)
+        state.step += 1
+        return state, {"loss": torch.tensor(1.0 / (state.step + 1)), "grad_norm": torch.tensor(1.0)}
+
+    monkeypatch.setattr(train, "train_step", stub_step)
+    b = train.synthetic_batch(cfg, 4, pinned=False)
+    st, hist = train.fit(st, [b] * 10, max_steps=10, slow_loop_interval=4, key=1, use_cuda_graph=False,
+                         slow_loop_config=SL.SlowLoopConfig(pooled=False), plot_dir=str(tmp_path))
+    assert calls == list(range(10))
+    assert [d["step"] for d in hist["slow_loop"]] == [4, 8]
+    n_layers = cfg.vision.layers + cfg.text.layers
+    for d in hist["slow_loop"]:
+        assert len(d["layers"]) == n_layers
+        assert all(sum(v["census"]) == v["brain_scan"].size for v in d["layers"].values())
+    import glob
+    assert len(glob.glob(os.path.join(str(tmp_path), "*", "brain_scan_epoch0_step*.png"))) == 2 * n_layers
+    sb = st.variables["stats_buffer"]["vision"]["layer_0"]["stateful_layer"]
+    assert int(sb["step_count"]) == 1                      # one fast step (step 9) since the reset at step 8
+    assert hist["loss"][-1][0] == 9
