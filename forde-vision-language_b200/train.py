@@ -364,16 +364,20 @@ def _tree_copy_(dst, src):
 
 
 def fit(state: TrainState, batches, max_steps: int, slow_loop_interval: int = 100, slow_loop_config=None, key: int = 0,
-        use_cuda_graph: bool = True, log=None, plot_dir: Optional[str] = None):
+        use_cuda_graph: bool = True, log=None, plot_dir: Optional[str] = None, slow_loop_overlap_steps: int = 0):
     """The reference's outer loop (src/training/train.py:320-399): fast steps, and every ``slow_loop_interval`` steps
     (train.py:219-224 default 100; ``step > 0 and step % interval == 0``, train.py:365-369) the slow loop -- Sense
     (all-reduced pooled moments) -> Cluster -> Smooth -> Actuate -> Reset -- which rewrites ``neuron_assignments`` in
     place and zeroes ``stats_buffer`` (train.py:387-399).  ``batches`` is an iterable of batch dicts.
     With ``plot_dir`` rank 0 also writes each layer's brain scan and feature-space scatter after every slow loop
     (the reference's plot_brain_scan / plot_feature_space, src/utils/logging.py:7-52), into one sub-directory per layer.
+    ``slow_loop_overlap_steps`` = k > 0 takes the slow loop's host work (GMM + smoothing, ~0.2 s per update at
+    ViT-B/16 sizes = 5 fast steps) off the training thread: statistics are sensed and reset at the slow-loop step,
+    clustered on a worker thread while fast steps continue, and the new maps take effect exactly k steps later on
+    every rank (slow_loop.OverlappedSlowLoop).  0 = the reference's synchronous update.
     Returns (state, history) with history = list of (step, loss) and the slow-loop diagnostics."""
     from .brain_scan import plot_brain_scan, plot_feature_space
-    from .slow_loop import SlowLoopConfig, slow_loop_step
+    from .slow_loop import OverlappedSlowLoop, SlowLoopConfig, slow_loop_step
 
     cfg = slow_loop_config or SlowLoopConfig()
     warm = None
@@ -383,6 +387,21 @@ def fit(state: TrainState, batches, max_steps: int, slow_loop_interval: int = 10
         warm = threading.Thread(target=warm_up, daemon=True)
         warm.start()
     history, diagnostics = [], []
+    overlapped = OverlappedSlowLoop(cfg, slow_loop_overlap_steps, state.group) if slow_loop_overlap_steps > 0 else None
+
+    def record(diag):
+        if diag is None:
+            return
+        diagnostics.append(diag)
+        if plot_dir is not None and (not dist.is_initialized() or dist.get_rank(state.group) == 0):
+            for name, d in diag["layers"].items():
+                if "brain_scan" not in d:
+                    continue
+                sub = os.path.join(plot_dir, name.replace("/", "_"))
+                os.makedirs(sub, exist_ok=True)
+                plot_brain_scan(d["brain_scan"], diag["step"], 0, out_dir=sub)
+                plot_feature_space(d["features"], d["brain_scan"].reshape(-1), diag["step"], 0, out_dir=sub)
+
     step_fn = None
     it = iter(batches)
     for step in range(max_steps):
@@ -390,6 +409,8 @@ def fit(state: TrainState, batches, max_steps: int, slow_loop_interval: int = 10
             batch = next(it)
         except StopIteration:
             break
+        if overlapped is not None:
+            record(overlapped.poll(step))      # a background update that is due takes effect before this step
         if use_cuda_graph and state.flat_p32.is_cuda:
             if step_fn is None:
                 step_fn = GraphedTrainStep(state, batch)
@@ -406,16 +427,14 @@ def fit(state: TrainState, batches, max_steps: int, slow_loop_interval: int = 10
                 warm = None
             mv = {"stats_buffer": state.variables["stats_buffer"],
                   "neuron_assignments": state.variables["neuron_assignments"]}
-            _, _, diag = slow_loop_step(state.params, mv, cfg, key=key + step, epoch=0, step=step, group=state.group)
-            diagnostics.append(diag)
-            if plot_dir is not None and (not dist.is_initialized() or dist.get_rank(state.group) == 0):
-                for name, d in diag["layers"].items():
-                    if "brain_scan" not in d:
-                        continue
-                    sub = os.path.join(plot_dir, name.replace("/", "_"))
-                    os.makedirs(sub, exist_ok=True)
-                    plot_brain_scan(d["brain_scan"], step, 0, out_dir=sub)
-                    plot_feature_space(d["features"], d["brain_scan"].reshape(-1), step, 0, out_dir=sub)
+            if overlapped is not None:
+                record(overlapped.start(mv, key=key + step, epoch=0, step=step))
+            else:
+                _, _, diag = slow_loop_step(state.params, mv, cfg, key=key + step, epoch=0, step=step, group=state.group)
+                record(diag)
+    if overlapped is not None:
+        record(overlapped.flush())
+        overlapped.close()
     return state, {"loss": history, "slow_loop": diagnostics}
 
 

@@ -256,3 +256,55 @@ def test_fit_cadence_with_a_stubbed_fast_step(tmp_path, monkeypatch):
     sb = st.variables["stats_buffer"]["vision"]["layer_0"]["stateful_layer"]
     assert int(sb["step_count"]) == 1                      # one fast step (step 9) since the reset at step 8
     assert hist["loss"][-1][0] == 9
+
+
+def test_overlapped_slow_loop_actuates_after_a_fixed_delay(monkeypatch):
+    """fit(slow_loop_overlap_steps=k): Sense + Reset at the slow-loop step, Cluster + Smooth on a worker thread, the new
+    maps in force exactly k steps later; same maps as the synchronous update computes from the same statistics."""
+    from forde_b200 import dual_encoder, train
+    cfg = dual_encoder.config_tiny()
+    b = train.synthetic_batch(cfg, 4, pinned=False)
+
+    def run(overlap):
+        st = train.create_train_state(cfg, 0, device="cpu")
+        rng = np.random.RandomState(0)
+        seen = []       # per fast step: a fingerprint of the brain maps it ran under
+
+        def stub_step(state, batch, sense=True):
+            seen.append(sum(int(l["stateful_layer"]["assignments"].sum())
+                            for t in state.variables["neuron_assignments"].values() for l in t.values()))
+            for tower in state.variables["stats_buffer"].values():
+                for name, layer in tower.items():
+                    sb = layer["stateful_layer"]
+                    H = sb["neuron_stats"].shape[0]
+                    s = rng.rand(H, 5).astype(np.float32)
+                    s[: H // 2, 0] += 2.0
+                    sb["neuron_stats"].add_(torch.from_numpy(s))
+                    sb["step_count"].add_(1)
+            state.step += 1
+            return state, {"loss": torch.tensor(1.0), "grad_norm": torch.tensor(1.0)}
+
+        monkeypatch.setattr(train, "train_step", stub_step)
+        st, hist = train.fit(st, [b] * 12, max_steps=12, slow_loop_interval=4, key=1, use_cuda_graph=False,
+                             slow_loop_config=SL.SlowLoopConfig(pooled=False), slow_loop_overlap_steps=overlap)
+        maps = [l["stateful_layer"]["assignments"].clone()
+                for t in st.variables["neuron_assignments"].values() for l in t.values()]
+        return seen, hist, maps, st
+
+    seen0, hist0, maps0, _ = run(0)
+    seen3, hist3, maps3, st3 = run(3)
+    assert [d["step"] for d in hist3["slow_loop"]] == [4, 8] == [d["step"] for d in hist0["slow_loop"]]
+    assert [d["actuated_at_step"] for d in hist3["slow_loop"]] == [7, 11]
+    assert all(torch.equal(a, c) for a, c in zip(maps0, maps3))              # same statistics -> same maps
+    assert seen0[0] == seen3[0] == 0
+    assert seen0[5] != 0 and seen0[4] == 0            # synchronous: the update after step 4 is in force at step 5
+    assert seen3[5] == 0 and seen3[6] == 0            # overlapped by 3: steps 5 and 6 still run under the old maps
+    assert seen3[7] == seen0[5]                       # ... and step 7 under the maps the synchronous run had at step 5
+    assert seen3[11] == seen0[9]
+    sb = st3.variables["stats_buffer"]["vision"]["layer_0"]["stateful_layer"]
+    assert int(sb["step_count"]) == 3                 # steps 9, 10, 11 since the reset at step 8
+
+
+def test_overlapped_slow_loop_rejects_zero_delay():
+    with pytest.raises(ValueError):
+        SL.OverlappedSlowLoop(SL.SlowLoopConfig(), 0)
