@@ -114,6 +114,12 @@ constexpr int TMEM_COLS = 512;
 #ifndef FORDE_UP_PACKED
 #define FORDE_UP_PACKED 0
 #endif
+// 1: when the forward does not store a warp's z box (save_z = 0, no tanh neuron in the group) the idle z staging box
+// double-buffers the h box: chunk g's TMA store may still be reading its box while chunk g + 1 is written into the
+// other one (wait_group.read 1 instead of 0).  A/B, not yet the default; exp9 showed up_fwd bound by its store path.
+#ifndef FORDE_UP_DBL_H
+#define FORDE_UP_DBL_H 0
+#endif
 // 1: word-major sign buffer [sign_ld words][M neurons] instead of [M neurons][sign_ld words] (A/B, not yet the
 // default).  A warp's 32 lanes are 32 consecutive neurons, so in the word-major buffer each of its sign stores and
 // loads touches one 128-byte line instead of 32 lines a row pitch apart: exp13 measured the forward paying ~12 us
@@ -546,6 +552,10 @@ __global__ void __launch_bounds__(num_threads(EPI, PAIR), 1) forde_gemm_kernel(c
     const uint32_t lane_taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
     const uint32_t sw = static_cast<uint32_t>(lane & 7);
     int it = 0;
+#if FORDE_UP_DBL_H
+    bool prev_dbl = false;  // the previous chunk used only one of the two staging boxes
+    uint32_t hsel = 0;      // which box this chunk's h goes to (alternates while double-buffering)
+#endif
 
     // z^T prefetch state (EPI_DZ_BWD): g = running chunk index of this warp (tile g / CPW, chunk g % CPW);
     // chunk g lives in box g % ZR and dz is written over it in place.
@@ -654,7 +664,22 @@ __global__ void __launch_bounds__(num_threads(EPI, PAIR), 1) forde_gemm_kernel(c
         if (epi_z_ring(EPI)) z_prefetch(g + ZD, true);  // refill the box chunk g + ZD will use
         // single-buffered staging: the previous chunk's TMA stores must have read the boxes (the other epilogue
         // warps of this SM sub-partition cover the wait)
+#if FORDE_UP_DBL_H
+        const bool dbl_h = (EPI == EPI_UP_FWD) && !store_z;  // warp-uniform
+        if ((epi_two_out(EPI) || EPI == EPI_STORE) && lane == 0) {
+          // double-buffered h: only the store two chunks back (same box) must have drained, and only if the previous
+          // chunk did not use both boxes
+          if (dbl_h && prev_dbl) tma_wait_read<1>();
+          else tma_wait_read<0>();
+        }
+        // h box of this chunk: the second box, or alternately the idle z box while double-buffering
+        hsel = dbl_h ? (hsel ^ 1u) : 1u;
+        prev_dbl = dbl_h;
+        const uint32_t hoff = hsel * BOX_BYTES;
+#else
         if ((epi_two_out(EPI) || EPI == EPI_STORE) && lane == 0) tma_wait_read<0>();
+        constexpr uint32_t hoff = BOX_BYTES;
+#endif
         if (epi_z_ring(EPI)) {
           if (bits_path) {  // no load to wait for; the store that last read this box (chunk g - ZR) must have drained
             if (lane == 0) tma_wait_read<ZR - 1>();
@@ -735,7 +760,7 @@ __global__ void __launch_bounds__(num_threads(EPI, PAIR), 1) forde_gemm_kernel(c
                     v + j8 * 8, bias_r, act, warp_has_tanh, jbase + j8 * 8, nvalid, zw, hw, rs, sbits);
                 const uint32_t off = (static_cast<uint32_t>(half * 4 + j8) ^ sw) << 4;
                 if (store_z) st_shared_v4(orow_s + off, zw[0], zw[1], zw[2], zw[3]);
-                st_shared_v4(orow_s + BOX_BYTES + off, hw[0], hw[1], hw[2], hw[3]);
+                st_shared_v4(orow_s + hoff + off, hw[0], hw[1], hw[2], hw[3]);
               }
             };
             using T = std::true_type;
@@ -861,7 +886,7 @@ __global__ void __launch_bounds__(num_threads(EPI, PAIR), 1) forde_gemm_kernel(c
           __syncwarp();
           if (lane == 0) {
             if (EPI != EPI_UP_FWD || store_z) tma_store_2d(&p.tmC0, obuf, col0, w.m0 + q * 32);
-            if (epi_two_out(EPI)) tma_store_2d(&p.tmC1, obuf + BOX_BYTES, col0, w.m0 + q * 32);
+            if (epi_two_out(EPI)) tma_store_2d(&p.tmC1, obuf + (EPI == EPI_UP_FWD ? hoff : BOX_BYTES), col0, w.m0 + q * 32);
             tma_commit();
           }
         }

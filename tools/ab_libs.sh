@@ -4,7 +4,7 @@
 # SIGN_BITS=1 runs everything with the opt-in sign-bit backward (layer_bench --sign-bits 1, FORDE_SIGN_BITS=1).
 # Example (the round-2 candidate of DESIGN.md section 7, built in-tree so it travels to the GPU box):
 #   mkdir -p build && (cd forde-vision-language_b200 && nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a \
-#     -lineinfo -Xcompiler -fPIC -shared --threads 4 -DFORDE_UP_PACKED=1 -DFORDE_SIGN_WORD_MAJOR=1 \
+#     -lineinfo -Xcompiler -fPIC -shared --threads 4 -DFORDE_UP_PACKED=1 -DFORDE_SIGN_WORD_MAJOR=1 -DFORDE_UP_DBL_H=1 \
 #     -o ../build/libforde_r2.so csrc/forde_api.cu csrc/forde_aux.cu csrc/forde_norm.cu csrc/forde_moe.cu -lcuda)
 #   gpurun -- 'SIGN_BITS=1 tools/ab_libs.sh gpurun_out/ab.log build/libforde_r2.so'
 out=$1; shift
