@@ -20,7 +20,9 @@ What is restated, and how firmly it is pinned:
   same stub (GMM labels excepted: their seed comes from jax.random, which the stub cannot reproduce).
 * ``top_k`` / ``moe_*`` follow src/forde/moe.py:88-93,116-135,163-187,189-222.  Index SETS pinned by
   tests/test_moe.py:46-70 and tests/test_topk_correctness.py:7-23; order/ties follow jax.lax.top_k's
-  documented rule (descending, lower index first).
+  documented rule (descending, lower index first).  PINNED: tests/golden/moe_layer.npz holds outputs of the
+  reference's own MoELayer._top_k_gating / _compute_expert_outputs / _load_balancing_loss (renormalised gates, the
+  gather + weighted combine, the load-balancing loss) executed under the same stub.
 * ``stateful_layer_*`` and ``clip_loss_*`` restate /root/reference/README.md:47-56 and :35 under the
   decisions D1-D9 of SURVEY.md section 8a.  **PARITY UNPINNED**: the reference snapshot contains no
   StatefulLayer / contrastive-loss code and no test vectors for them; the gradient-capture point is pinned
@@ -245,12 +247,20 @@ def moe_layer_fwd(x, w_r, b_r, experts, k, aux_weight=0.01):
     x = np.asarray(x, np.float32)
     probs, idx, w = moe_router(x, w_r, b_r, k)
     outs = np.stack([gelu_tanh(x @ wu + bu) @ wd + bd for (wu, bu, wd, bd) in experts], axis=0)  # (E,M,d)
-    out = np.zeros_like(x)
-    rows = np.arange(x.shape[0])
-    for j in range(k):
-        out = out + w[:, j:j + 1] * outs[idx[:, j], rows, :]
+    out = moe_combine(outs, idx, w)
     aux, counts = moe_aux_loss(probs, idx, len(experts), k, aux_weight)
     return out, aux, probs, idx, counts
+
+
+def moe_combine(expert_outs, idx, w):
+    """moe.py:163-187: out[m] = sum_j w[m, j] * expert_outs[idx[m, j], m].  expert_outs (E, M, d); idx, w (M, k).
+    Pinned by tests/golden/moe_layer.npz (the reference's own _compute_expert_outputs)."""
+    expert_outs = np.asarray(expert_outs, np.float32)
+    out = np.zeros(expert_outs.shape[1:], np.float32)
+    rows = np.arange(expert_outs.shape[1])
+    for j in range(idx.shape[1]):
+        out = out + w[:, j:j + 1] * expert_outs[idx[:, j], rows, :]
+    return out
 
 
 # ----------------------------------------------------------------------------------------------- CLIP loss

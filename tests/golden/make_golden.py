@@ -89,7 +89,23 @@ def install_jax_stub():
     jax.vmap = lambda f: (lambda xs: np.stack([f(x) for x in xs]))
     nn = types.ModuleType("jax.nn")
     nn.one_hot = lambda x, n: (np.asarray(x)[..., None] == np.arange(n)).astype(np.float32)
+
+    def softmax(x, axis=-1):
+        x = np.asarray(x, np.float32)
+        e = np.exp(x - x.max(axis=axis, keepdims=True))
+        return (e / e.sum(axis=axis, keepdims=True)).astype(np.float32)
+    nn.softmax = softmax
     jax.nn = nn
+    lax = types.ModuleType("jax.lax")
+
+    def lax_top_k(x, k):
+        # jax.lax.top_k: values descending, equal values keep the lower index first (stable)
+        idx = np.argsort(-np.asarray(x), axis=-1, kind="stable")[..., :k]
+        return np.take_along_axis(np.asarray(x), idx, axis=-1), idx.astype(np.int32)
+    lax.top_k = lax_top_k
+    jax.lax = lax
+    jnp.bincount = lambda x, length=None, minlength=0: np.bincount(
+        np.asarray(x).reshape(-1), minlength=length or minlength)[: length or None]
     jsp = types.ModuleType("jax.scipy")
     jsig = types.ModuleType("jax.scipy.signal")
     jsig.convolve2d = lambda a, k, mode="full": scipy.signal.convolve2d(a, k, mode=mode).astype(np.float32)
@@ -133,6 +149,18 @@ def install_jax_stub():
         return out
     ftu.flatten_dict, ftu.unflatten_dict = flatten_dict, unflatten_dict
     flax.core, flax.traverse_util = fcore, ftu
+    # flax.linen: just enough for `src/forde/moe.py` to IMPORT (class bodies, decorators).  Its array-only helper
+    # methods (_top_k_gating, _compute_expert_outputs, _load_balancing_loss) are then called unbound; nothing here
+    # emulates flax's module system.
+    linen = types.ModuleType("flax.linen")
+
+    class _Module:
+        pass
+    linen.Module = _Module
+    linen.compact = lambda f: f
+    flax.linen = linen
+    sys.modules["flax.linen"] = linen
+    sys.modules["jax.lax"] = lax
     sys.modules.update({"jax": jax, "jax.numpy": jnp, "jax.nn": nn, "jax.scipy": jsp, "jax.scipy.signal": jsig,
                         "jax.random": rnd, "jax.tree": tree, "flax": flax, "flax.core": fcore,
                         "flax.traverse_util": ftu})
@@ -226,5 +254,39 @@ def main():
     print("wrote", sorted(f for f in os.listdir(OUT) if f.endswith(".npz")))
 
 
+def moe_layer_golden():
+    """MoE layer routing math from the reference's own `src/forde/moe.py` (its array-only helper methods called
+    unbound with a plain namespace as `self`): top-k gating + renormalisation (moe.py:116-135), the gather /
+    weighted combine (moe.py:137-187) on given per-expert outputs, and the load-balancing loss (moe.py:189-222).
+    `jax.lax.top_k`, `jax.nn.softmax` and `jnp.bincount` come from the stub above (jax's documented semantics);
+    what is pinned is how the reference composes them."""
+    install_jax_stub()
+    moe = load_ref("moe")
+    rng = np.random.RandomState(4321)
+    blob = {}
+    for i, (B, S, d, E, k) in enumerate([(2, 5, 8, 4, 2), (1, 7, 16, 8, 2), (3, 4, 8, 8, 1), (2, 3, 4, 4, 4)]):
+        ns = types.SimpleNamespace(num_experts=E, top_k=k, aux_loss_weight=0.01)
+        logits = rng.randn(B, S, E).astype(np.float32)
+        if i == 1:
+            logits[0, 0, :] = np.array([1, 3, 3, 2, 3, 0, -1, 3], np.float32)      # ties
+        x = rng.randn(B, S, d).astype(np.float32)
+        expert_out = rng.randn(E, B, S, d).astype(np.float32)                      # what expert e returns for x
+        experts = [(lambda xx, e=e: expert_out[e]) for e in range(E)]
+        idx, w = moe.MoELayer._top_k_gating(ns, logits)
+        out = moe.MoELayer._compute_expert_outputs(ns, x, experts, idx, w)
+        probs = sys.modules["jax.nn"].softmax(logits, axis=-1)
+        aux = moe.MoELayer._load_balancing_loss(ns, probs, idx)
+        blob.update({f"logits{i}": logits, f"x{i}": x, f"expert_out{i}": expert_out,
+                     f"cfg{i}": np.array([E, k], np.int32), f"idx{i}": np.asarray(idx, np.int32),
+                     f"w{i}": np.asarray(w, np.float32), f"out{i}": np.asarray(out, np.float32),
+                     f"probs{i}": np.asarray(probs, np.float32), f"aux{i}": np.float32(aux)})
+    np.savez(os.path.join(OUT, "moe_layer.npz"), **blob)
+    print("wrote moe_layer.npz")
+
+
 if __name__ == "__main__":
-    main()
+    if "--moe-layer-only" in sys.argv:      # adds moe_layer.npz without rewriting the other fixtures
+        moe_layer_golden()
+    else:
+        main()
+        moe_layer_golden()

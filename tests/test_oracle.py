@@ -212,3 +212,27 @@ def test_clip_loss_perfect_alignment_is_small():
     e = np.eye(8, 16, dtype=np.float32)
     loss, s, _, _ = O.clip_loss_fwd(e, e, np.log(100.0))
     assert loss < 1e-3 and abs(s[0, 0] - 100.0) < 1e-3
+
+
+@pytest.mark.parametrize("i", range(4))
+def test_moe_routing_math_matches_the_reference_golden(golden_dir, i):
+    """tests/golden/moe_layer.npz: outputs of the reference's own MoELayer._top_k_gating / _compute_expert_outputs /
+    _load_balancing_loss (src/forde/moe.py:116-222), executed by tests/golden/make_golden.py.  Indices bit-exact."""
+    z = np.load(os.path.join(golden_dir, "moe_layer.npz"))
+    E, k = (int(v) for v in z[f"cfg{i}"])
+    logits = z[f"logits{i}"]
+    B, S, _ = logits.shape
+    vals, idx = O.top_k(logits.reshape(B * S, E), k)
+    np.testing.assert_array_equal(idx, z[f"idx{i}"].reshape(B * S, k))
+    w = O.softmax(vals)
+    np.testing.assert_allclose(w, z[f"w{i}"].reshape(B * S, k), rtol=1e-6, atol=1e-7)
+    probs = O.softmax(logits.reshape(B * S, E))
+    np.testing.assert_allclose(probs, z[f"probs{i}"].reshape(B * S, E), rtol=1e-6, atol=1e-7)
+    eo = z[f"expert_out{i}"]
+    out = O.moe_combine(eo.reshape(E, B * S, -1), idx, w)
+    np.testing.assert_allclose(out, z[f"out{i}"].reshape(B * S, -1), rtol=1e-5, atol=1e-6)
+    aux, counts = O.moe_aux_loss(probs, idx, E, k, 0.01)
+    np.testing.assert_allclose(aux, z[f"aux{i}"], rtol=1e-5)
+    assert int(counts.sum()) == B * S * k
+    if i == 1:   # the tie row [1,3,3,2,3,0,-1,3]: lower index first
+        np.testing.assert_array_equal(idx[0], [1, 2])
