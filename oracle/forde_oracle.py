@@ -13,7 +13,9 @@ What is restated, and how firmly it is pinned:
 * ``smooth_assignments`` / ``assignments_to_grid`` follow src/forde/smoothing.py:14-91.  PINNED the same way
   (tests/golden/smoothing_*.npz).
 * ``cluster_neurons_gmm`` follows src/forde/clustering.py:6-39 (sklearn GaussianMixture; the seed is passed
-  as an int because jax.random is unavailable).  Parity unpinned (no reference test pins its labels).
+  as an int because jax.random is unavailable).  PINNED for a given seed: tests/golden/clustering.npz holds the
+  partition and GMM parameters the reference's own function returns (scikit-learn is installed, the function runs
+  unchanged under the stub); the jax PRNG step that turns a key into that seed is not reproduced.
 * ``smooth_assignments_3d`` / ``compute_router_adjustments`` / ``moe_usage_diagnostics`` follow smoothing.py:94-171 and
   src/forde/moe_slow_loop.py:211-250,372-381.  PINNED: tests/golden/moe_slow_loop.npz holds outputs of the reference's
   own functions and of one whole ``moe_slow_loop_step`` on the pytrees of tests/verify_reset.py, executed under the

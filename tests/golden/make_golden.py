@@ -284,9 +284,39 @@ def moe_layer_golden():
     print("wrote moe_layer.npz")
 
 
+def clustering_golden():
+    """`src/forde/clustering.py:6-39` run as it is (scikit-learn is installed).  The sklearn seed it derives with
+    jax.random.randint comes from the stub's deterministic stand-in and is recorded, so what is pinned is the call
+    sequence (GaussianMixture(n_components, random_state=seed).fit(stats).predict(stats), label dtype, the returned
+    parameter dict) for a GIVEN seed -- not jax's PRNG."""
+    install_jax_stub()
+    clustering = load_ref("clustering")
+    rnd = sys.modules["jax.random"]
+    rng = np.random.RandomState(77)
+    blob = {}
+    for i, (H, k, key_seed) in enumerate([(192, 3, 0), (512, 3, 42), (96, 4, 7)]):
+        centres = rng.randn(k, 5) * 3
+        stats = (centres[rng.randint(0, k, H)] + 0.3 * rng.randn(H, 5)).astype(np.float32)
+        key = rnd.PRNGKey(key_seed)
+        labels, params = clustering.cluster_neurons_gmm(stats, k, key)
+        blob[f"stats{i}"] = stats
+        blob[f"k{i}"] = np.int32(k)
+        blob[f"seed{i}"] = np.int64(rnd.randint(key, (), 0, 2 ** 31 - 1))
+        blob[f"labels{i}"] = np.asarray(labels, np.int32)
+        blob[f"means{i}"] = np.asarray(params["means"], np.float64)
+        blob[f"weights{i}"] = np.asarray(params["weights"], np.float64)
+    import sklearn
+    blob["sklearn_version"] = np.array(sklearn.__version__)
+    np.savez(os.path.join(OUT, "clustering.npz"), **blob)
+    print("wrote clustering.npz")
+
+
 if __name__ == "__main__":
     if "--moe-layer-only" in sys.argv:      # adds moe_layer.npz without rewriting the other fixtures
         moe_layer_golden()
+    elif "--clustering-only" in sys.argv:
+        clustering_golden()
     else:
         main()
         moe_layer_golden()
+        clustering_golden()

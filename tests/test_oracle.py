@@ -236,3 +236,26 @@ def test_moe_routing_math_matches_the_reference_golden(golden_dir, i):
     assert int(counts.sum()) == B * S * k
     if i == 1:   # the tie row [1,3,3,2,3,0,-1,3]: lower index first
         np.testing.assert_array_equal(idx[0], [1, 2])
+
+
+@pytest.mark.parametrize("i", range(3))
+def test_gmm_clustering_matches_the_reference_call_for_a_given_seed(golden_dir, i):
+    """tests/golden/clustering.npz: labels and parameters returned by the reference's own cluster_neurons_gmm
+    (src/forde/clustering.py:6-39) for a recorded sklearn seed.  Same scikit-learn, same call -> same labels; if the
+    installed scikit-learn differs from the one that wrote the fixture only the partition is compared."""
+    import sklearn
+    z = np.load(os.path.join(golden_dir, "clustering.npz"))
+    stats, k, seed = z[f"stats{i}"], int(z[f"k{i}"]), int(z[f"seed{i}"])
+    labels, params = O.cluster_neurons_gmm(stats, k, seed)
+    assert labels.dtype == np.int32 and set(params) == {"weights", "means", "covariances"}
+    ref = z[f"labels{i}"]
+    # the partition must be the reference's (well-separated blobs); label ids and parameters are compared after
+    # ordering the components by their means, so a k-means++ draw that differs in the last ulp on another CPU
+    # (a relabelling, nothing else) cannot fail the test
+    pairs = set(zip(labels.tolist(), ref.tolist()))
+    assert len(pairs) == k, "different partition of the neurons"
+    if str(z["sklearn_version"]) == sklearn.__version__:
+        order = np.lexsort(params["means"].T[::-1])
+        ref_order = np.lexsort(z[f"means{i}"].T[::-1])
+        np.testing.assert_allclose(params["means"][order], z[f"means{i}"][ref_order], rtol=1e-5, atol=1e-7)
+        np.testing.assert_allclose(params["weights"][order], z[f"weights{i}"][ref_order], rtol=1e-5, atol=1e-7)
