@@ -5,6 +5,8 @@ hand-written sm_100a kernels in csrc/.  Tensors must live on a CUDA device; noth
 """
 from __future__ import annotations
 
+import os
+
 import torch
 
 from . import _lib
@@ -101,6 +103,34 @@ def sample_pitch(M: int) -> int:
     return round_up(M, 8)
 
 
+# ---- experimental (FORDE_TAIL_SPLIT=1, default off; not yet timed on the GPU): tail split of sample-row GEMMs ----
+# A GEMM whose output rows are samples runs as ceil(M/256) x ceil(N/256) pair tiles on sm/2 persistent CTA pairs.
+# When the last wave is nearly empty (text tower at C2: 154 tiles on 74 pairs = 2 full waves + 6 tiles, 69 %
+# efficiency, tools/wave_report.py) the rows of the full waves are launched first and the few remaining rows as a
+# second, small launch (which the library tiles with single CTAs): ~2.5 tile times instead of 3.
+_TAIL_SPLIT = os.environ.get("FORDE_TAIL_SPLIT", "0") == "1"
+
+
+def tail_split_rows(M: int, N: int, workers: int):
+    """Row at which to cut a samples-by-N output into a full-waves part and a tail part, or None."""
+    mt, nt = (M + 255) // 256, (N + 255) // 256
+    tiles = mt * nt
+    if workers <= 0 or tiles < workers:
+        return None
+    full = (tiles // workers) * workers
+    rem = tiles - full
+    if rem == 0 or rem > workers // 4 or full % nt != 0:   # (the first launch must itself be whole waves)
+        return None
+    rows = (full // nt) * 256          # whole 256-row blocks covered by the full waves
+    return rows if 0 < rows < M else None
+
+
+def _split_rows(M: int, N: int):
+    if not _TAIL_SPLIT:
+        return None
+    return tail_split_rows(M, N, _lib.load().forde_sm_count() // 2)
+
+
 # ------------------------------------------------------------------------------------------ generic GEMM
 def gemm_bf16(A: torch.Tensor, B: torch.Tensor, a_mn_major: bool, b_mn_major: bool, bias_col=None, add_to=None) -> torch.Tensor:
     """D[M,N] = sum_k A(m,k) B(n,k) (+ bias_col) -> bf16.  K-major operands are [rows, K]; MN-major operands are
@@ -175,9 +205,17 @@ def sl_down_fwd(hT, w_down, b_down, y, M):
     _req(hT, torch.bfloat16, "hT"); _req(w_down, torch.bfloat16, "w_down"); _req(y, torch.bfloat16, "y")
     if b_down is not None:
         _req(b_down, torch.float32, "b_down")
+    cut = _split_rows(M, d)
     with _Timed(f"sl_down_fwd[{M}x{d}x{H}]", 2.0 * M * d * H):
-        rc = _lib.load().forde_sl_down_fwd(_stream(), hT.data_ptr(), w_down.data_ptr(), _ptr(b_down), y.data_ptr(), M, d,
-                                           H, hT.stride(0))
+        if cut is None:
+            rc = _lib.load().forde_sl_down_fwd(_stream(), hT.data_ptr(), w_down.data_ptr(), _ptr(b_down), y.data_ptr(),
+                                               M, d, H, hT.stride(0))
+        else:   # samples [0, cut) then [cut, M): h^T columns and y rows offset by `cut`
+            rc = _lib.load().forde_sl_down_fwd(_stream(), hT.data_ptr(), w_down.data_ptr(), _ptr(b_down), y.data_ptr(),
+                                               cut, d, H, hT.stride(0))
+            if rc == 0:
+                rc = _lib.load().forde_sl_down_fwd(_stream(), hT.data_ptr() + 2 * cut, w_down.data_ptr(), _ptr(b_down),
+                                                   y.data_ptr() + 2 * cut * y.stride(0), M - cut, d, H, hT.stride(0))
     _lib.check(rc, "forde_sl_down_fwd")
 
 
@@ -206,14 +244,22 @@ def sl_dx_bwd(dzT, w_up, dx, M, residual=None):
     """dx = dz . w_up^T (+ residual, which may be dx itself)."""
     d, H = w_up.shape
     _req(dzT, torch.bfloat16, "dzT"); _req(dx, torch.bfloat16, "dx")
+    if residual is not None:
+        _req(residual, torch.bfloat16, "residual")
+    cut = _split_rows(M, d)
+    parts = [(0, M)] if cut is None else [(0, cut), (cut, M - cut)]
+    rc = 0
     with _Timed(f"sl_dx_bwd[{M}x{d}x{H}]", 2.0 * M * d * H):
-        if residual is None:
-            rc = _lib.load().forde_sl_dx_bwd(_stream(), dzT.data_ptr(), w_up.data_ptr(), dx.data_ptr(), M, d, H,
-                                             dzT.stride(0))
-        else:
-            _req(residual, torch.bfloat16, "residual")
-            rc = _lib.load().forde_sl_dx_bwd_add(_stream(), dzT.data_ptr(), w_up.data_ptr(), residual.data_ptr(),
-                                                 dx.data_ptr(), M, d, H, dzT.stride(0))
+        for r0, rows in parts:      # one launch, or full waves + tail (dz^T columns and dx rows offset by r0)
+            if rc != 0:
+                break
+            if residual is None:
+                rc = _lib.load().forde_sl_dx_bwd(_stream(), dzT.data_ptr() + 2 * r0, w_up.data_ptr(),
+                                                 dx.data_ptr() + 2 * r0 * dx.stride(0), rows, d, H, dzT.stride(0))
+            else:
+                rc = _lib.load().forde_sl_dx_bwd_add(_stream(), dzT.data_ptr() + 2 * r0, w_up.data_ptr(),
+                                                     residual.data_ptr() + 2 * r0 * residual.stride(0),
+                                                     dx.data_ptr() + 2 * r0 * dx.stride(0), rows, d, H, dzT.stride(0))
     _lib.check(rc, "forde_sl_dx_bwd")
 
 

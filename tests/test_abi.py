@@ -84,3 +84,20 @@ def test_ops_refuse_cpu_tensors(lib):
     x = torch.zeros((8, 8), dtype=torch.bfloat16)
     with pytest.raises(_lib.FordeError, match="CUDA tensor"):
         ops.gemm_bf16(x, x, False, False)
+
+
+def test_tail_split_planner_is_off_by_default_and_cuts_at_a_wave_boundary():
+    """ops.tail_split_rows (experimental, FORDE_TAIL_SPLIT=1): host arithmetic only."""
+    from forde_b200 import ops
+    assert ops._TAIL_SPLIT is False and ops._split_rows(19712, 512) is None
+    # text tower at C2: 77 x 2 = 154 pair tiles on 74 pairs -> 2 full waves (74 row blocks) + 6 tiles
+    assert ops.tail_split_rows(19712, 512, 74) == 74 * 256
+    assert ops.tail_split_rows(19712, 768, 74) == 74 * 256           # 231 tiles = 3 full waves + 9
+    assert ops.tail_split_rows(50432, 768, 74) is None               # 591 tiles = 7.99 waves: nothing to gain
+    assert ops.tail_split_rows(100, 512, 74) is None                 # less than one wave
+    assert ops.tail_split_rows(19712, 512, 0) is None
+    for M, N in [(19712, 512), (19712, 768), (30000, 1024)]:
+        cut = ops.tail_split_rows(M, N, 74)
+        if cut is not None:
+            assert cut % 256 == 0 and 0 < cut < M
+            assert ((cut // 256) * ((N + 255) // 256)) % 74 == 0     # the first launch is whole waves
