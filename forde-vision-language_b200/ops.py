@@ -215,7 +215,7 @@ def sl_down_fwd(hT, w_down, b_down, y, M):
                                                cut, d, H, hT.stride(0))
             if rc == 0:
                 rc = _lib.load().forde_sl_down_fwd(_stream(), hT.data_ptr() + 2 * cut, w_down.data_ptr(), _ptr(b_down),
-                                                   y.data_ptr() + 2 * cut * y.stride(0), M - cut, d, H, hT.stride(0))
+                                                   y.data_ptr() + 2 * cut * d, M - cut, d, H, hT.stride(0))
     _lib.check(rc, "forde_sl_down_fwd")
 
 
@@ -255,11 +255,11 @@ def sl_dx_bwd(dzT, w_up, dx, M, residual=None):
                 break
             if residual is None:
                 rc = _lib.load().forde_sl_dx_bwd(_stream(), dzT.data_ptr() + 2 * r0, w_up.data_ptr(),
-                                                 dx.data_ptr() + 2 * r0 * dx.stride(0), rows, d, H, dzT.stride(0))
+                                                 dx.data_ptr() + 2 * r0 * d, rows, d, H, dzT.stride(0))
             else:
                 rc = _lib.load().forde_sl_dx_bwd_add(_stream(), dzT.data_ptr() + 2 * r0, w_up.data_ptr(),
-                                                     residual.data_ptr() + 2 * r0 * residual.stride(0),
-                                                     dx.data_ptr() + 2 * r0 * dx.stride(0), rows, d, H, dzT.stride(0))
+                                                     residual.data_ptr() + 2 * r0 * d,
+                                                     dx.data_ptr() + 2 * r0 * d, rows, d, H, dzT.stride(0))
     _lib.check(rc, "forde_sl_dx_bwd")
 
 
