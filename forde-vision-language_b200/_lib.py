@@ -44,7 +44,7 @@ SIGNATURES = {
     "forde_sl_bwd": (_i, [_vp] * 15 + [_i, _i, _i, _ll]),
     "forde_sl_topk_sparsify": (_i, [_vp, _vp, _ll, _i, _i, _i, _vp, _vp, _vp]),
     "forde_sl_topk_mask": (_i, [_vp, _vp, _ll, _i, _i, _vp, _vp]),
-    "forde_stats_finalize": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "forde_stats_finalize": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "forde_stats_from_moments": (_i, [_vp, _vp, _vp, _i, _vp]),
     "forde_clip_fwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i] + [_vp] * 10),
     "forde_clip_col_rescale": (_i, [_vp, _vp, _vp, _vp, _i]),
@@ -64,6 +64,10 @@ SIGNATURES = {
     "forde_ln_num_partials": (_i, [_i]),
     "forde_add_layernorm_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _f]),
     "forde_add_layernorm_bwd": (_i, [_vp] * 11 + [_i, _i]),
+    "forde_optim_num_partials": (_i, [_ll]),
+    "forde_grad_sqnorm": (_i, [_vp, _vp, _vp, _ll, _vp, _vp]),
+    "forde_adamw_clip_step": (_i, [_vp] * 7 + [_ll, _vp, _i, _f, _f, _f, _f, _f, _f, _vp, _vp]),
+    "forde_cast_f32_bf16": (_i, [_vp, _vp, _vp, _ll]),
 }
 
 

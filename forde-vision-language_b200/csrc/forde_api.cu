@@ -375,7 +375,7 @@ int forde_sm_count(void) { return sm_count(); }
 
 unsigned long long forde_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
-int forde_sl_sign_layout(void) { return (FORDE_UP_PACKED ? 1 : 0) | (FORDE_SIGN_WORD_MAJOR ? 2 : 0); }
+int forde_sl_sign_layout(void) { return 3; }  // bit 0: interleaved bit order ; bit 1: word-major buffer
 
 int forde_sl_sign_words(int M) { return M <= 0 ? 0 : 8 * ((M + BN - 1) / BN); }
 
@@ -547,7 +547,7 @@ int forde_sl_bwd(void* stream, const void* x, const void* dy, const void* w_up, 
   }
   if (db_up != nullptr && grad_partials != nullptr) {
     rc = forde_stats_finalize(stream, nullptr, grad_partials, forde_sl_num_partials(M), H, M, nullptr, nullptr,
-                              nullptr, nullptr, nullptr, db_up);
+                              nullptr, nullptr, nullptr, nullptr, db_up);
     if (rc != FORDE_OK) return rc;
   }
   return FORDE_OK;

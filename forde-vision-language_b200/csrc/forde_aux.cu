@@ -46,8 +46,8 @@ constexpr int FIN_NEUR = 16;
 __global__ void __launch_bounds__(FIN_NEUR * FIN_LANES)
 stats_finalize_kernel(const float* __restrict__ act_p, const float* __restrict__ grad_p, int P, int H, int M,
                       float* __restrict__ step_stats, float* __restrict__ neuron_stats,
-                      float* __restrict__ moments, int* sample_count, int* step_count,
-                      float* __restrict__ db_up) {
+                      float* __restrict__ moments, float* __restrict__ moments_lo, int* sample_count,
+                      int* step_count, float* __restrict__ db_up) {
   __shared__ double red[FIN_LANES][6][FIN_NEUR + 1];
   const int tx = threadIdx.x, ty = threadIdx.y;
   const int h = blockIdx.x * FIN_NEUR + tx;
@@ -95,15 +95,23 @@ stats_finalize_kernel(const float* __restrict__ act_p, const float* __restrict__
     for (int k = 0; k < 5; ++k) neuron_stats[h * 5 + k] += s[k];
   }
   if (moments != nullptr) {
-    moments[h * 5 + 0] += static_cast<float>(a_abs);
-    moments[h * 5 + 1] += static_cast<float>(a_sum);
-    moments[h * 5 + 2] += static_cast<float>(a_sq);
-    moments[h * 5 + 3] += static_cast<float>(g_abs);
-    moments[h * 5 + 4] += static_cast<float>(g_sq);
+    // The pooled variance is sum z^2 / n - mean^2 over a whole slow-loop interval (100 steps x 50k samples x ranks):
+    // an fp32 running sum would lose it to cancellation for bias-dominated neurons (|mean| >> std).  The accumulator
+    // is therefore a double-single pair of fp32 leaves (moments = high part, moments_lo = the rounding residue,
+    // ~48 significant bits together); both stay ordinary fp32 arrays for the Flax-style collection.
+    const double inc[5] = {a_abs, a_sum, a_sq, g_abs, g_sq};
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+      const double t = static_cast<double>(moments[h * 5 + k]) +
+                       (moments_lo != nullptr ? static_cast<double>(moments_lo[h * 5 + k]) : 0.0) + inc[k];
+      const float hi = static_cast<float>(t);
+      moments[h * 5 + k] = hi;
+      if (moments_lo != nullptr) moments_lo[h * 5 + k] = static_cast<float>(t - static_cast<double>(hi));
+    }
   }
 }
 
-__global__ void stats_from_moments_kernel(const float* __restrict__ moments, const int* __restrict__ sample_count,
+__global__ void stats_from_moments_kernel(const double* __restrict__ moments, const int* __restrict__ sample_count,
                                           int H, float* __restrict__ out) {
   const int h = blockIdx.x * blockDim.x + threadIdx.x;
   if (h >= H) return;
@@ -322,17 +330,17 @@ using namespace forde;
 extern "C" {
 
 int forde_stats_finalize(void* stream, const float* act_partials, const float* grad_partials, int num_partials,
-                         int H, int M, float* step_stats, float* neuron_stats, float* moments,
+                         int H, int M, float* step_stats, float* neuron_stats, float* moments, float* moments_lo,
                          int* sample_count, int* step_count, float* db_up) {
   if (H <= 0 || M <= 0 || num_partials <= 0) return FORDE_EINVAL;
   if (act_partials == nullptr && grad_partials == nullptr) return FORDE_EINVAL;
   stats_finalize_kernel<<<(H + FIN_NEUR - 1) / FIN_NEUR, dim3(FIN_NEUR, FIN_LANES), 0, static_cast<cudaStream_t>(stream)>>>(
-      act_partials, grad_partials, num_partials, H, M, step_stats, neuron_stats, moments, sample_count,
+      act_partials, grad_partials, num_partials, H, M, step_stats, neuron_stats, moments, moments_lo, sample_count,
       step_count, db_up);
   return check_launch("stats_finalize_kernel");
 }
 
-int forde_stats_from_moments(void* stream, const float* moments, const int* sample_count, int H,
+int forde_stats_from_moments(void* stream, const double* moments, const int* sample_count, int H,
                              float* stats_out) {
   if (moments == nullptr || sample_count == nullptr || stats_out == nullptr || H <= 0) return FORDE_EINVAL;
   const int threads = 128;

@@ -107,29 +107,16 @@ constexpr int TMEM_COLS = 512;
 #ifndef FORDE_TMEM_PIPE_DZ
 #define FORDE_TMEM_PIPE_DZ 0
 #endif
-// 1: packed bf16x2 arithmetic in the forward epilogue (A/B, not yet the default): h = z + max(z, 0) of the all-relu
-// warp mode as HMNMX2 + HFMA2 on the packed word, and the sign bits from one HSET2 per pair.  The packed compare
-// yields the pair's two bits 16 apart, so the sign words then use the INTERLEAVED layout: within a 32-sample word,
-// sample 2k -> bit k, sample 2k + 1 -> bit 16 + k (forde_sl_sign_layout() reports which layout the build uses).
-#ifndef FORDE_UP_PACKED
-#define FORDE_UP_PACKED 0
-#endif
-// 1: when the forward does not store a warp's z box (save_z = 0, no tanh neuron in the group) the idle z staging box
-// double-buffers the h box: chunk g's TMA store may still be reading its box while chunk g + 1 is written into the
-// other one (wait_group.read 1 instead of 0).  A/B, not yet the default; exp9 showed up_fwd bound by its store path.
-#ifndef FORDE_UP_DBL_H
-#define FORDE_UP_DBL_H 0
-#endif
-// 1: word-major sign buffer [sign_ld words][M neurons] instead of [M neurons][sign_ld words] (A/B, not yet the
-// default).  A warp's 32 lanes are 32 consecutive neurons, so in the word-major buffer each of its sign stores and
-// loads touches one 128-byte line instead of 32 lines a row pitch apart: exp13 measured the forward paying ~12 us
-// for the neuron-major stores although they are only 6 % of its bytes (they are 50 % more L2 write transactions).
-#ifndef FORDE_SIGN_WORD_MAJOR
-#define FORDE_SIGN_WORD_MAJOR 0
-#endif
-__device__ __forceinline__ long long sign_index(long long row, long long word, int rows, int sign_ld) {
-  return FORDE_SIGN_WORD_MAJOR ? word * rows + row : row * sign_ld + word;
-}
+// Forward epilogue arithmetic and the sign-bit buffer (adopted after the round-2 A/B, profiles/r2_ab1_sign_bits.txt:
+// up_fwd 163.8 us / dz_bwd 162.9 us against 163.2 / 191.0 us for the h^T-reading backward at C2 vision dims):
+//  * packed bf16x2 arithmetic: h = z + max(z, 0) of the all-relu warp mode is HMNMX2 + HFMA2 on the packed word and
+//    the sign bits come from one HSET2 per pair.  The packed compare yields the pair's two bits 16 apart, so a sign
+//    word is INTERLEAVED: within a 32-sample word, sample 2k -> bit k, sample 2k + 1 -> bit 16 + k.
+//  * the sign buffer is word-major, [sign_ld words][M neurons]: a warp's 32 lanes are 32 consecutive neurons, so each
+//    of its sign stores and loads touches one 128-byte line (the neuron-major layout cost the forward ~12 us: 32
+//    lines a row pitch apart per store instruction, +50 % L2 write transactions for 6 % of the bytes).
+// forde_sl_sign_layout() reports both properties (= 3) to callers that inspect the bits.
+__device__ __forceinline__ long long sign_index(long long row, long long word, int rows) { return word * rows + row; }
 __host__ __device__ constexpr int tmem_pipe(int epi) {
   return epi == 1 /*EPI_UP_FWD*/ ? FORDE_TMEM_PIPE_UP : epi == 2 /*EPI_DZ_BWD*/ ? FORDE_TMEM_PIPE_DZ : 0;
 }
@@ -192,8 +179,8 @@ struct GemmParams {
   int raster_m_fast;  // 1: consecutive work items walk M first (share the B slab), 0: walk N first
   int pair;           // 1: launched as 2-CTA clusters (256-row tiles, cta_group::2)
   int save_z;         // EPI_UP_FWD: 1 = store every z box; 0 = only the boxes the backward needs (warps with tanh neurons)
-  // Optional sign bits of z, [M rows = neurons][sign_ld] u32, bit j of word w = (z[neuron][32 w + j] > 0)
-  // ([sign_ld][M] with FORDE_SIGN_WORD_MAJOR, interleaved bit order with FORDE_UP_PACKED; forde_sl_sign_layout()).
+  // Optional sign bits of z, word-major [sign_ld words][M rows = neurons] u32; word w of a neuron covers samples
+  // 32 w .. 32 w + 31 in the interleaved bit order described at sign_index() (forde_sl_sign_layout() == 3).
   // EPI_UP_FWD writes them for the 32-neuron groups whose z box it does not store; EPI_DZ_BWD then reads 8 bytes
   // per neuron and 64-sample chunk instead of TMA-loading the h^T box (1/16 of the bytes).  Null = off.
   uint32_t* sign_bits;
@@ -289,7 +276,7 @@ struct RunningSums {
 };
 
 // forward, 8 accumulator columns -> 4 packed z words + 4 packed h words; MODE is warp-uniform
-// SIGNS: also collect (z > 0) into `bits`, bit (jcol % 32) + 2 i (+ 1) for the pair's two columns.
+// SIGNS: also collect (z > 0) into `bits` (interleaved: the pair's two columns land 16 bits apart).
 template <int MODE, bool MASKED, bool SIGNS>
 __device__ __forceinline__ void up_fwd_8(const uint32_t* v, float bias_r, const ActConst& act, bool warp_has_tanh,
                                          int jcol, int nvalid, uint32_t* zw, uint32_t* hw, RunningSums& rs,
@@ -298,20 +285,9 @@ __device__ __forceinline__ void up_fwd_8(const uint32_t* v, float bias_r, const 
   for (int i = 0; i < 4; ++i) {
     const uint32_t zp = pack_bf16x2(__uint_as_float(v[2 * i]) + bias_r, __uint_as_float(v[2 * i + 1]) + bias_r);
     const float z0 = bf16lo_to_f32(zp), z1 = bf16hi_to_f32(zp);
-    if (SIGNS) {
-      if (FORDE_UP_PACKED) {
-        bits |= (bf16x2_gt_zero_mask(zp) & 0x00010001u) << (((jcol & 31) >> 1) + i);
-      } else {
-        if (z0 > 0.f) bits |= 1u << ((jcol & 31) + 2 * i);
-        if (z1 > 0.f) bits |= 1u << ((jcol & 31) + 2 * i + 1);
-      }
-    }
+    if (SIGNS) bits |= (bf16x2_gt_zero_mask(zp) & 0x00010001u) << (((jcol & 31) >> 1) + i);
     float h0 = 0.f, h1 = 0.f;
-    if (MODE == WM_RELU) {          // h = relu(z) + 1.0 * z
-      if (!FORDE_UP_PACKED) {
-        h0 = z0 + fmaxf(z0, 0.f);
-        h1 = z1 + fmaxf(z1, 0.f);
-      }
+    if (MODE == WM_RELU) {          // h = relu(z) + 1.0 * z: packed, below
     } else if (MODE == WM_STEP) {   // h = step(z) + gate * z
       h0 = fmaf(act.gate, z0, z0 > 0.f ? 1.f : 0.f);
       h1 = fmaf(act.gate, z1, z1 > 0.f ? 1.f : 0.f);
@@ -328,7 +304,7 @@ __device__ __forceinline__ void up_fwd_8(const uint32_t* v, float bias_r, const 
       h1 = fmaf(act.gate, z1, f1);
     }
     zw[i] = zp;
-    hw[i] = (FORDE_UP_PACKED && MODE == WM_RELU) ? bf16x2_relu_plus_self(zp) : pack_bf16x2(h0, h1);
+    hw[i] = (MODE == WM_RELU) ? bf16x2_relu_plus_self(zp) : pack_bf16x2(h0, h1);
     if (!MASKED) {
       rs.s_abs += fabsf(z0) + fabsf(z1);
       rs.s_sum += z0 + z1;
@@ -373,8 +349,8 @@ __device__ __forceinline__ void dz_bwd_8_bits(const uint32_t* v, uint32_t bits8,
                                               uint32_t* dw, RunningSums& rs) {
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    const float m0 = (bits8 & (FORDE_UP_PACKED ? (1u << i) : (1u << (2 * i)))) ? m_pos : m_neg;
-    const float m1 = (bits8 & (FORDE_UP_PACKED ? (1u << (16 + i)) : (1u << (2 * i + 1)))) ? m_pos : m_neg;
+    const float m0 = (bits8 & (1u << i)) ? m_pos : m_neg;
+    const float m1 = (bits8 & (1u << (16 + i))) ? m_pos : m_neg;
     const uint32_t dp = pack_bf16x2(__uint_as_float(v[2 * i]) * m0, __uint_as_float(v[2 * i + 1]) * m1);
     dw[i] = dp;
     const float d0 = bf16lo_to_f32(dp), d1 = bf16hi_to_f32(dp);
@@ -552,10 +528,6 @@ __global__ void __launch_bounds__(num_threads(EPI, PAIR), 1) forde_gemm_kernel(c
     const uint32_t lane_taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
     const uint32_t sw = static_cast<uint32_t>(lane & 7);
     int it = 0;
-#if FORDE_UP_DBL_H
-    bool prev_dbl = false;  // the previous chunk used only one of the two staging boxes
-    uint32_t hsel = 0;      // which box this chunk's h goes to (alternates while double-buffering)
-#endif
 
     // z^T prefetch state (EPI_DZ_BWD): g = running chunk index of this warp (tile g / CPW, chunk g % CPW);
     // chunk g lives in box g % ZR and dz is written over it in place.
@@ -623,18 +595,8 @@ __global__ void __launch_bounds__(num_threads(EPI, PAIR), 1) forde_gemm_kernel(c
       static_assert(EPI != EPI_DZ_BWD || CPW <= 2, "sign words per tile");
       if (bits_path && row < p.M) {
         const int w0 = (w.n0 + e * CPW * CHUNK) / 32;  // first sign word of this warp's columns
-        if (FORDE_SIGN_WORD_MAJOR) {
 #pragma unroll
-          for (int i = 0; i < 2 * CPW; ++i) mw[i] = __ldg(p.sign_bits + sign_index(row, w0 + i, p.M, p.sign_ld));
-        } else {
-          const uint32_t* src = p.sign_bits + sign_index(row, w0, p.M, p.sign_ld);
-#pragma unroll
-          for (int i = 0; i < CPW; ++i) {
-            const uint2 t2 = __ldg(reinterpret_cast<const uint2*>(src) + i);
-            mw[2 * i] = t2.x;
-            mw[2 * i + 1] = t2.y;
-          }
-        }
+        for (int i = 0; i < 2 * CPW; ++i) mw[i] = __ldg(p.sign_bits + sign_index(row, w0 + i, p.M));
       }
       if (epi_col_bias(EPI)) {
         // stage this tile's column bias (of this tile's expert in the grouped mode) once for the epilogue warps
@@ -664,22 +626,8 @@ __global__ void __launch_bounds__(num_threads(EPI, PAIR), 1) forde_gemm_kernel(c
         if (epi_z_ring(EPI)) z_prefetch(g + ZD, true);  // refill the box chunk g + ZD will use
         // single-buffered staging: the previous chunk's TMA stores must have read the boxes (the other epilogue
         // warps of this SM sub-partition cover the wait)
-#if FORDE_UP_DBL_H
-        const bool dbl_h = (EPI == EPI_UP_FWD) && !store_z;  // warp-uniform
-        if ((epi_two_out(EPI) || EPI == EPI_STORE) && lane == 0) {
-          // double-buffered h: only the store two chunks back (same box) must have drained, and only if the previous
-          // chunk did not use both boxes
-          if (dbl_h && prev_dbl) tma_wait_read<1>();
-          else tma_wait_read<0>();
-        }
-        // h box of this chunk: the second box, or alternately the idle z box while double-buffering
-        hsel = dbl_h ? (hsel ^ 1u) : 1u;
-        prev_dbl = dbl_h;
-        const uint32_t hoff = hsel * BOX_BYTES;
-#else
         if ((epi_two_out(EPI) || EPI == EPI_STORE) && lane == 0) tma_wait_read<0>();
         constexpr uint32_t hoff = BOX_BYTES;
-#endif
         if (epi_z_ring(EPI)) {
           if (bits_path) {  // no load to wait for; the store that last read this box (chunk g - ZR) must have drained
             if (lane == 0) tma_wait_read<ZR - 1>();
@@ -773,7 +721,7 @@ __global__ void __launch_bounds__(num_threads(EPI, PAIR), 1) forde_gemm_kernel(c
             };
             if (want_bits) {
               dispatch(T{});
-              if (row < p.M) p.sign_bits[sign_index(row, col0 / 32 + half, p.M, p.sign_ld)] = sbits;
+              if (row < p.M) p.sign_bits[sign_index(row, col0 / 32 + half, p.M)] = sbits;
             } else {
               dispatch(F{});
             }
@@ -842,7 +790,7 @@ __global__ void __launch_bounds__(num_threads(EPI, PAIR), 1) forde_gemm_kernel(c
 #pragma unroll
               for (int j8 = 0; j8 < 4; ++j8) {
                 uint32_t dw[4];
-                dz_bwd_8_bits(v + j8 * 8, word >> (FORDE_UP_PACKED ? j8 * 4 : j8 * 8), m_pos, m_neg, dw, rs);
+                dz_bwd_8_bits(v + j8 * 8, word >> (j8 * 4), m_pos, m_neg, dw, rs);
                 st_shared_v4(orow_s + ((static_cast<uint32_t>(half * 4 + j8) ^ sw) << 4), dw[0], dw[1], dw[2], dw[3]);
               }
             } else if (warp_has_tanh) {

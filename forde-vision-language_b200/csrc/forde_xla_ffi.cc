@@ -2,17 +2,23 @@
 // jax.ffi.register_ffi_target(name, capsule, platform="CUDA") and call through jax.ffi.ffi_call inside a
 // jax.custom_vjp.
 //
-// COMPILE-GATED AND UNTESTED IN THIS IMAGE: jaxlib (and with it xla/ffi/api/ffi.h) is not installed and cannot
-// be installed here (no network), so this file is not part of libforde_b200.so and __graft_entry__.build() skips
-// it.  Build it where jaxlib exists:
+// COMPILE-GATED IN THIS IMAGE: jaxlib (and with it xla/ffi/api/ffi.h) is not installed and cannot be installed here
+// (no network), so this file is not part of libforde_b200.so and __graft_entry__.build() skips it.  What IS checked
+// here: tests/test_abi.py compiles it with -fsyntax-only against a minimal stub of the FFI types
+// (tests/stubs/xla/ffi/api/ffi.h), which verifies the includes, the C-ABI call signatures and that every handler's
+// parameter list matches its binding.  It has never run against a real jaxlib.  Build it where jaxlib exists:
 //   g++ -O2 -fPIC -shared -DFORDE_WITH_XLA_FFI -I$(python -c "import jax.ffi; print(jax.ffi.include_dir())") \
-//       -I include forde-vision-language_b200/csrc/forde_xla_ffi.cc -L forde-vision-language_b200 -lforde_b200 \
+//       -I include -I /usr/local/cuda/include forde-vision-language_b200/csrc/forde_xla_ffi.cc \
+//       -L forde-vision-language_b200 -lforde_b200 -L /usr/local/cuda/lib64 -lcudart \
 //       -o forde-vision-language_b200/libforde_xla_ffi.so
 // It contains no kernel code: every handler forwards plain pointers and sizes to the C ABI of
 // include/forde_b200.h, on XLA's compute stream, with buffers XLA allocated.
 #ifdef FORDE_WITH_XLA_FFI
 
+#include <cuda_runtime.h>
+
 #include <cstdint>
+#include <string>
 
 #include "forde_b200.h"
 #include "xla/ffi/api/ffi.h"
@@ -52,10 +58,15 @@ static ffi::Error SlBwdImpl(cudaStream_t stream, ffi::Buffer<ffi::BF16> x, ffi::
   const int M = static_cast<int>(x.dimensions()[0]), d = static_cast<int>(x.dimensions()[1]);
   const int H = static_cast<int>(w_up.dimensions()[1]);
   const long long ldz = zT.dimensions()[1];
-  cudaMemsetAsync(dw_up->typed_data(), 0, sizeof(float) * d * H, stream);
-  cudaMemsetAsync(dw_down->typed_data(), 0, sizeof(float) * d * H, stream);
-  cudaMemsetAsync(db_up->typed_data(), 0, sizeof(float) * H, stream);
-  cudaMemsetAsync(db_down->typed_data(), 0, sizeof(float) * d, stream);
+  const cudaError_t zero[4] = {
+      cudaMemsetAsync(dw_up->typed_data(), 0, sizeof(float) * d * H, stream),
+      cudaMemsetAsync(dw_down->typed_data(), 0, sizeof(float) * d * H, stream),
+      cudaMemsetAsync(db_up->typed_data(), 0, sizeof(float) * H, stream),
+      cudaMemsetAsync(db_down->typed_data(), 0, sizeof(float) * d, stream)};
+  for (cudaError_t e : zero) {
+    if (e != cudaSuccess)
+      return ffi::Error(ffi::ErrorCode::kInternal, std::string("cudaMemsetAsync: ") + cudaGetErrorString(e));
+  }
   return status(forde_sl_bwd(stream, x.untyped_data(), dy.untyped_data(), w_up.untyped_data(), w_down.untyped_data(),
                              zT.untyped_data(), hT.untyped_data(),
                              reinterpret_cast<const int8_t*>(assign.untyped_data()), dzT->untyped_data(),
@@ -70,7 +81,7 @@ static ffi::Error StatsImpl(cudaStream_t stream, ffi::Buffer<ffi::F32> act_parti
   const int P = static_cast<int>(act_partials.dimensions()[0]);
   const int H = static_cast<int>(act_partials.dimensions()[2]);
   return status(forde_stats_finalize(stream, act_partials.typed_data(), grad_partials.typed_data(), P, H, M,
-                                     step_stats->typed_data(), nullptr, nullptr, nullptr, nullptr, nullptr),
+                                     step_stats->typed_data(), nullptr, nullptr, nullptr, nullptr, nullptr, nullptr),
                 "forde_stats_finalize");
 }
 

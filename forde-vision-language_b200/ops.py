@@ -89,7 +89,7 @@ def sign_words(M: int) -> int:
 
 def sign_layout() -> int:
     """Bit mask.  Bit 0: 0 = bit j of a sign word is sample 32 w + j, 1 = interleaved (sample 2k -> bit k, 2k + 1 ->
-    bit 16 + k).  Bit 1: 0 = buffer is [H, words], 1 = [words, H].  The shipped build returns 0."""
+    bit 16 + k).  Bit 1: 0 = buffer is [H, words], 1 = [words, H].  This build returns 3."""
     return _lib.load().forde_sl_sign_layout()
 
 
@@ -101,34 +101,6 @@ def sign_shape(M: int, H: int):
 def sample_pitch(M: int) -> int:
     """Row pitch (in elements) of the neuron-major zT / hT / dzT buffers for M samples."""
     return round_up(M, 8)
-
-
-# ---- experimental (FORDE_TAIL_SPLIT=1, default off; not yet timed on the GPU): tail split of sample-row GEMMs ----
-# A GEMM whose output rows are samples runs as ceil(M/256) x ceil(N/256) pair tiles on sm/2 persistent CTA pairs.
-# When the last wave is nearly empty (text tower at C2: 154 tiles on 74 pairs = 2 full waves + 6 tiles, 69 %
-# efficiency, tools/wave_report.py) the rows of the full waves are launched first and the few remaining rows as a
-# second, small launch (which the library tiles with single CTAs): ~2.5 tile times instead of 3.
-_TAIL_SPLIT = os.environ.get("FORDE_TAIL_SPLIT", "0") == "1"
-
-
-def tail_split_rows(M: int, N: int, workers: int):
-    """Row at which to cut a samples-by-N output into a full-waves part and a tail part, or None."""
-    mt, nt = (M + 255) // 256, (N + 255) // 256
-    tiles = mt * nt
-    if workers <= 0 or tiles < workers:
-        return None
-    full = (tiles // workers) * workers
-    rem = tiles - full
-    if rem == 0 or rem > workers // 4 or full % nt != 0:   # (the first launch must itself be whole waves)
-        return None
-    rows = (full // nt) * 256          # whole 256-row blocks covered by the full waves
-    return rows if 0 < rows < M else None
-
-
-def _split_rows(M: int, N: int):
-    if not _TAIL_SPLIT:
-        return None
-    return tail_split_rows(M, N, _lib.load().forde_sm_count() // 2)
 
 
 # ------------------------------------------------------------------------------------------ generic GEMM
@@ -205,17 +177,9 @@ def sl_down_fwd(hT, w_down, b_down, y, M):
     _req(hT, torch.bfloat16, "hT"); _req(w_down, torch.bfloat16, "w_down"); _req(y, torch.bfloat16, "y")
     if b_down is not None:
         _req(b_down, torch.float32, "b_down")
-    cut = _split_rows(M, d)
     with _Timed(f"sl_down_fwd[{M}x{d}x{H}]", 2.0 * M * d * H):
-        if cut is None:
-            rc = _lib.load().forde_sl_down_fwd(_stream(), hT.data_ptr(), w_down.data_ptr(), _ptr(b_down), y.data_ptr(),
-                                               M, d, H, hT.stride(0))
-        else:   # samples [0, cut) then [cut, M): h^T columns and y rows offset by `cut`
-            rc = _lib.load().forde_sl_down_fwd(_stream(), hT.data_ptr(), w_down.data_ptr(), _ptr(b_down), y.data_ptr(),
-                                               cut, d, H, hT.stride(0))
-            if rc == 0:
-                rc = _lib.load().forde_sl_down_fwd(_stream(), hT.data_ptr() + 2 * cut, w_down.data_ptr(), _ptr(b_down),
-                                                   y.data_ptr() + 2 * cut * d, M - cut, d, H, hT.stride(0))
+        rc = _lib.load().forde_sl_down_fwd(_stream(), hT.data_ptr(), w_down.data_ptr(), _ptr(b_down), y.data_ptr(),
+                                           M, d, H, hT.stride(0))
     _lib.check(rc, "forde_sl_down_fwd")
 
 
@@ -246,20 +210,13 @@ def sl_dx_bwd(dzT, w_up, dx, M, residual=None):
     _req(dzT, torch.bfloat16, "dzT"); _req(dx, torch.bfloat16, "dx")
     if residual is not None:
         _req(residual, torch.bfloat16, "residual")
-    cut = _split_rows(M, d)
-    parts = [(0, M)] if cut is None else [(0, cut), (cut, M - cut)]
-    rc = 0
     with _Timed(f"sl_dx_bwd[{M}x{d}x{H}]", 2.0 * M * d * H):
-        for r0, rows in parts:      # one launch, or full waves + tail (dz^T columns and dx rows offset by r0)
-            if rc != 0:
-                break
-            if residual is None:
-                rc = _lib.load().forde_sl_dx_bwd(_stream(), dzT.data_ptr() + 2 * r0, w_up.data_ptr(),
-                                                 dx.data_ptr() + 2 * r0 * d, rows, d, H, dzT.stride(0))
-            else:
-                rc = _lib.load().forde_sl_dx_bwd_add(_stream(), dzT.data_ptr() + 2 * r0, w_up.data_ptr(),
-                                                     residual.data_ptr() + 2 * r0 * d,
-                                                     dx.data_ptr() + 2 * r0 * d, rows, d, H, dzT.stride(0))
+        if residual is None:
+            rc = _lib.load().forde_sl_dx_bwd(_stream(), dzT.data_ptr(), w_up.data_ptr(), dx.data_ptr(), M, d, H,
+                                             dzT.stride(0))
+        else:
+            rc = _lib.load().forde_sl_dx_bwd_add(_stream(), dzT.data_ptr(), w_up.data_ptr(), residual.data_ptr(),
+                                                 dx.data_ptr(), M, d, H, dzT.stride(0))
     _lib.check(rc, "forde_sl_dx_bwd")
 
 
@@ -311,21 +268,75 @@ def colsum_bf16(a, out):
 
 
 def stats_finalize(act_partials, grad_partials, P, H, M, step_stats=None, neuron_stats=None, moments=None,
-                   sample_count=None, step_count=None, db_up=None):
+                   sample_count=None, step_count=None, db_up=None, moments_lo=None):
+    """``moments`` (+ optional ``moments_lo``, the double-single residue) accumulate the raw sums."""
     rc = _lib.load().forde_stats_finalize(_stream(), _ptr(act_partials), _ptr(grad_partials), P, H, M,
-                                          _ptr(step_stats), _ptr(neuron_stats), _ptr(moments), _ptr(sample_count),
-                                          _ptr(step_count), _ptr(db_up))
+                                          _ptr(step_stats), _ptr(neuron_stats), _ptr(moments), _ptr(moments_lo),
+                                          _ptr(sample_count), _ptr(step_count), _ptr(db_up))
     _lib.check(rc, "forde_stats_finalize")
 
 
+def pooled_moments(stats_leaf) -> torch.Tensor:
+    """fp64 value of a stats_buffer leaf's raw-moment accumulator (high + low fp32 parts)."""
+    m = stats_leaf["moments"].double()
+    lo = stats_leaf.get("moments_lo")
+    return m + lo.double() if lo is not None else m
+
+
 def stats_from_moments(moments, sample_count, out=None):
-    _req(moments, torch.float32, "moments"); _req(sample_count, torch.int32, "sample_count")
+    """(H,5) statistics from pooled raw moments (fp64, see ``pooled_moments``; fp32 input is widened)."""
+    if moments.dtype == torch.float32:
+        moments = moments.double()
+    _req(moments, torch.float64, "moments"); _req(sample_count, torch.int32, "sample_count")
     H = moments.shape[0]
     if out is None:
         out = torch.empty((H, 5), dtype=torch.float32, device=moments.device)
     rc = _lib.load().forde_stats_from_moments(_stream(), moments.data_ptr(), sample_count.data_ptr(), H, out.data_ptr())
     _lib.check(rc, "forde_stats_from_moments")
     return out
+
+
+# ------------------------------------------------------------------------------------------ optimizer step
+def optim_num_partials(n: int) -> int:
+    return _lib.load().forde_optim_num_partials(n)
+
+
+def grad_sqnorm(grads, partials, step_count=None):
+    """partials[blocks] = per-block sums of g^2 over the flat gradient buffer (fp32 or bf16); step_count += 1."""
+    if grads.dtype == torch.float32:
+        _req(grads, torch.float32, "grads"); g32, g16 = grads.data_ptr(), 0
+    else:
+        _req(grads, torch.bfloat16, "grads"); g32, g16 = 0, grads.data_ptr()
+    _req(partials, torch.float32, "partials")
+    rc = _lib.load().forde_grad_sqnorm(_stream(), g32, g16, grads.numel(), partials.data_ptr(), _ptr(step_count))
+    _lib.check(rc, "forde_grad_sqnorm")
+
+
+def adamw_clip_step(p32, grads, mu, nu, p16, partials, step_count, grad_norm_out, max_norm, lr, b1, b2, eps, wd):
+    """optax.chain(clip_by_global_norm(max_norm), adamw(lr, b1, b2, eps, weight_decay=wd)) over flat buffers, plus the
+    bf16 mirror refresh; grads fp32 or bf16.  Call grad_sqnorm first (it also advances step_count)."""
+    _req(p32, torch.float32, "p32"); _req(mu, torch.float32, "mu"); _req(nu, torch.float32, "nu")
+    if grads.dtype == torch.float32:
+        _req(grads, torch.float32, "grads"); g32, g16 = grads.data_ptr(), 0
+    else:
+        _req(grads, torch.bfloat16, "grads"); g32, g16 = 0, grads.data_ptr()
+    if p16 is not None:
+        _req(p16, torch.bfloat16, "p16")
+    _req(step_count, torch.int32, "step_count")
+    n = p32.numel()
+    assert grads.numel() == n and mu.numel() == n and nu.numel() == n
+    rc = _lib.load().forde_adamw_clip_step(_stream(), p32.data_ptr(), g32, g16, mu.data_ptr(), nu.data_ptr(), _ptr(p16),
+                                           n, partials.data_ptr(), partials.numel(), float(max_norm), float(lr),
+                                           float(b1), float(b2), float(eps), float(wd), step_count.data_ptr(),
+                                           _ptr(grad_norm_out))
+    _lib.check(rc, "forde_adamw_clip_step")
+
+
+def cast_f32_bf16(src, dst):
+    _req(src, torch.float32, "src"); _req(dst, torch.bfloat16, "dst")
+    assert src.numel() == dst.numel()
+    rc = _lib.load().forde_cast_f32_bf16(_stream(), src.data_ptr(), dst.data_ptr(), src.numel())
+    _lib.check(rc, "forde_cast_f32_bf16")
 
 
 # ------------------------------------------------------------------------------------------ CLIP loss

@@ -106,9 +106,10 @@ def sense_layer(stats_leaf: Dict[str, torch.Tensor], pooled: bool, group=None) -
     accumulated.  With `pooled`, the raw moments are all-reduced across ranks first."""
     world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
     if pooled:
-        moments, count = stats_leaf["moments"], stats_leaf["sample_count"]
+        # fp64 = high + low fp32 parts of the double-single accumulator; the cross-rank SUM runs in fp64 too
+        moments, count = ops.pooled_moments(stats_leaf), stats_leaf["sample_count"]
         if world > 1:
-            moments = moments.clone(); count = count.clone()
+            count = count.clone()
             dist.all_reduce(moments, op=dist.ReduceOp.SUM, group=group)
             dist.all_reduce(count, op=dist.ReduceOp.SUM, group=group)
         if int(count.item()) == 0:

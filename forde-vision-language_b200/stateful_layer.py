@@ -8,7 +8,8 @@ Reference interface this keeps:
       params/{up_proj,down_proj}/{kernel,bias}      Flax Dense layout, kernel is (in, out)
       neuron_assignments/assignments                (H,) int32, read in the fast loop, written by the slow loop
                                                     (README.md:15,20,50); initialised to 0 = generalist (D7)
-      stats_buffer/{neuron_stats (H,5) f32, moments (H,5) f32, sample_count i32, step_count i32}
+      stats_buffer/{neuron_stats (H,5) f32, moments (H,5) f32, moments_lo (H,5) f32, sample_count i32,
+                    step_count i32}
                                                     (pattern of moe.py:265-279; D6)
   * the per-step statistics leave through the mutable collection, not the return value (moe.py:281).
 
@@ -200,8 +201,9 @@ class StatefulLayer:
     sense_forward_only: bool = False       # also accumulate activation-only stats in no-grad forwards
     save_z: bool = False                   # keep all of z^T (debugging); by default only what the backward reads
     # record (z > 0) bits where z is not stored and let the backward read those instead of h^T (1/16 of the bytes);
-    # same results bit for bit.  Off unless FORDE_SIGN_BITS=1 (or set explicitly); ignored with save_z.
-    sign_bits: bool = field(default_factory=lambda: os.environ.get("FORDE_SIGN_BITS", "0") == "1")
+    # same results bit for bit, dz_bwd 191 -> 163 us at C2 vision dims.  On unless FORDE_SIGN_BITS=0 (or set
+    # explicitly); ignored with save_z.
+    sign_bits: bool = field(default_factory=lambda: os.environ.get("FORDE_SIGN_BITS", "1") == "1")
     name: str = "stateful_layer"
 
     def __post_init__(self):
@@ -310,8 +312,8 @@ class StatefulLayer:
     def _finalize(self, ws: _Workspace, stats: Dict[str, torch.Tensor], with_grad: bool, db_up=None) -> None:
         ops.stats_finalize(ws.act_partials, ws.grad_partials if with_grad else None, ws.P, ws.H, ws.M,
                            step_stats=stats.get("last_step_stats"), neuron_stats=stats["neuron_stats"],
-                           moments=stats["moments"], sample_count=stats["sample_count"],
-                           step_count=stats["step_count"], db_up=db_up)
+                           moments=stats["moments"], moments_lo=stats.get("moments_lo"),
+                           sample_count=stats["sample_count"], step_count=stats["step_count"], db_up=db_up)
 
 
 def new_stats_buffer(H: int, device) -> Dict[str, torch.Tensor]:
@@ -320,6 +322,8 @@ def new_stats_buffer(H: int, device) -> Dict[str, torch.Tensor]:
     return {
         "neuron_stats": torch.zeros((H, 5), dtype=torch.float32, device=device),
         "moments": torch.zeros((H, 5), dtype=torch.float32, device=device),
+        # rounding residue of `moments` (double-single accumulation over a slow-loop interval, forde_stats_finalize)
+        "moments_lo": torch.zeros((H, 5), dtype=torch.float32, device=device),
         "sample_count": torch.zeros((), dtype=torch.int32, device=device),
         "step_count": torch.zeros((), dtype=torch.int32, device=device),
     }

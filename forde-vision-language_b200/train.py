@@ -20,6 +20,7 @@ from typing import Dict, Optional
 import torch
 import torch.distributed as dist
 
+from . import ops
 from .dual_encoder import DualEncoderConfig, FORDEDualEncoder
 
 _ALIGN = 64  # elements; keeps every bf16 mirror view 128-byte aligned (TMA needs 16 B)
@@ -61,7 +62,11 @@ class TrainState:
     flat_p32: torch.Tensor
     flat_g32: torch.Tensor
     flat_p16: torch.Tensor
-    opt: torch.optim.Optimizer
+    opt_state: Dict[str, torch.Tensor]  # optax.adamw state over the flat buffer: mu, nu (fp32), count (i32 scalar)
+    hyper: Dict[str, float]             # learning_rate, weight_decay, b1, b2, eps
+    norm_partials: torch.Tensor         # scratch of the two-pass global-norm reduction
+    grad_norm: torch.Tensor             # [1] fp32, the step's pre-clip global gradient norm (train.py:168)
+    flat_g16: Optional[torch.Tensor] = None   # bf16 gradient exchange buffer (world > 1, grad_comm_dtype="bf16")
     group: Optional["dist.ProcessGroup"] = None
     max_grad_norm: float = 1.0
     buckets: Optional[list] = None      # gradient all-reduce buckets (see _GradBuckets)
@@ -76,7 +81,10 @@ class TrainState:
 
 
 def create_train_state(config: DualEncoderConfig, key: int, learning_rate: float = 1e-4, weight_decay: float = 0.01,
-                       device="cuda", group=None) -> TrainState:
+                       device="cuda", group=None, grad_comm_dtype: Optional[str] = None) -> TrainState:
+    """``grad_comm_dtype``: "bf16" (default, or env FORDE_GRAD_COMM) exchanges gradients between ranks as bf16 (half
+    the NVLink bytes and half the time NCCL's CTAs take SMs from the backward GEMMs; each rank still accumulates its
+    local gradient in fp32 and AdamW's moments stay fp32), "fp32" exchanges the fp32 buffer itself."""
     model = FORDEDualEncoder(config)
     variables = model.init(key, device)
     leaves = list(_leaves(variables["params"]))
@@ -99,14 +107,39 @@ def create_train_state(config: DualEncoderConfig, key: int, learning_rate: float
         _set(p16_tree, path, flat_p16[off:off + n].view(t.shape))
     flat_p16.copy_(flat_p32)
     flat_p32.grad = flat_g32
-    # optax.adamw(lr, wd) decays every leaf (no mask, train.py:74-77), so one flat parameter is equivalent
-    opt = torch.optim.AdamW([flat_p32], lr=learning_rate, weight_decay=weight_decay, betas=(0.9, 0.999), eps=1e-8,
-                            fused=dev.type == "cuda", capturable=dev.type == "cuda")
-    state = TrainState(0, model, variables, p16_tree, flat_p32, flat_g32, flat_p16, opt, group)
+    # optax.adamw(lr, wd) decays every leaf (no mask, train.py:74-77), so one flat parameter is equivalent; the
+    # state is optax's ScaleByAdamState (count, mu, nu) over the flat buffer, stepped by the fused kernels of
+    # csrc/forde_optim.cu (apply_gradients below)
+    opt_state = {"mu": torch.zeros_like(flat_p32), "nu": torch.zeros_like(flat_p32),
+                 "count": torch.zeros((), dtype=torch.int32, device=dev)}
+    hyper = {"learning_rate": float(learning_rate), "weight_decay": float(weight_decay), "b1": 0.9, "b2": 0.999,
+             "eps": 1e-8}
+    n_part = ops.optim_num_partials(total) if dev.type == "cuda" else 1
+    state = TrainState(0, model, variables, p16_tree, flat_p32, flat_g32, flat_p16, opt_state, hyper,
+                       torch.zeros(n_part, dtype=torch.float32, device=dev),
+                       torch.zeros(1, dtype=torch.float32, device=dev), None, group)
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
-        state.buckets = _GradBuckets(leaves, offs, total, flat_g32, group)
+        comm = grad_comm_dtype or os.environ.get("FORDE_GRAD_COMM", "bf16")
+        if comm not in ("bf16", "fp32"):
+            raise ValueError(f"grad_comm_dtype must be 'bf16' or 'fp32', got {comm!r}")
+        if comm == "bf16" and dev.type == "cuda":
+            state.flat_g16 = torch.zeros(total, dtype=torch.bfloat16, device=dev)
+        state.buckets = _GradBuckets(leaves, offs, total, flat_g32, group, flat_g16=state.flat_g16)
         state.buckets.attach([_get(variables["params"], path) for path, _ in leaves])
     return state
+
+
+def apply_gradients(state: TrainState) -> torch.Tensor:
+    """optax.chain(clip_by_global_norm(max_grad_norm), adamw) on the flat buffers + bf16 mirror refresh: two streaming
+    kernels (state.apply_gradients of the reference, src/training/train.py:162).  Reads the exchanged bf16 gradients
+    when the data-parallel exchange ran in bf16.  Returns the pre-clip global gradient norm ([1], device)."""
+    g = state.flat_g16 if state.flat_g16 is not None else state.flat_g32
+    h = state.hyper
+    ops.grad_sqnorm(g, state.norm_partials, state.opt_state["count"])
+    ops.adamw_clip_step(state.flat_p32.detach(), g, state.opt_state["mu"], state.opt_state["nu"], state.flat_p16,
+                        state.norm_partials, state.opt_state["count"], state.grad_norm, state.max_grad_norm,
+                        h["learning_rate"], h["b1"], h["b2"], h["eps"], h["weight_decay"])
+    return state.grad_norm
 
 
 class _GradBuckets:
@@ -117,8 +150,9 @@ class _GradBuckets:
     is issued asynchronously (NCCL's own stream, ordered after the kernels that produced the gradients), so it runs
     under the rest of the backward.  `finish()` issues whatever did not fire and makes the compute stream wait."""
 
-    def __init__(self, leaves, offs, total, flat_g32, group, layers_per_bucket: int = 4):
+    def __init__(self, leaves, offs, total, flat_g32, group, layers_per_bucket: int = 4, flat_g16=None):
         self.flat, self.group = flat_g32, group
+        self.flat16 = flat_g16      # when set, a bucket is cast to bf16 on the side stream and exchanged as bf16
         ranges = []  # (key, start, end, count)
         for (path, t), off in zip(leaves, offs):
             tower = path[0]
@@ -180,9 +214,17 @@ class _GradBuckets:
                 self.comm_stream = torch.cuda.Stream(device=self.flat.device)
             self.comm_stream.wait_stream(cur)
             with torch.cuda.stream(self.comm_stream):
-                dist.all_reduce(self.flat[a:b], op=dist.ReduceOp.SUM, group=self.group)
+                if self.flat16 is not None:
+                    ops.cast_f32_bf16(self.flat[a:b], self.flat16[a:b])
+                    dist.all_reduce(self.flat16[a:b], op=dist.ReduceOp.SUM, group=self.group)
+                else:
+                    dist.all_reduce(self.flat[a:b], op=dist.ReduceOp.SUM, group=self.group)
         else:
-            self.works.append(dist.all_reduce(self.flat[a:b], op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+            buf = self.flat
+            if self.flat16 is not None:
+                ops.cast_f32_bf16(self.flat[a:b], self.flat16[a:b])
+                buf = self.flat16
+            self.works.append(dist.all_reduce(buf[a:b], op=dist.ReduceOp.SUM, group=self.group, async_op=True))
         self.fired[bi] = True
 
     def begin(self):
@@ -232,12 +274,9 @@ def train_step(state: TrainState, batch: Dict[str, torch.Tensor], sense: bool = 
     else:
         loss.backward()
         sync_gradients(state.flat_g32, state.group)
-    gnorm = state.flat_g32.norm()
-    state.flat_g32.mul_(torch.clamp(state.max_grad_norm / (gnorm + 1e-6), max=1.0))   # optax.clip_by_global_norm
-    state.opt.step()
-    state.flat_p16.copy_(state.flat_p32)
+    gnorm = apply_gradients(state)      # clip_by_global_norm(1.0) -> AdamW -> bf16 mirror, two fused passes
     state.step += 1
-    return state, {"loss": loss.detach(), "grad_norm": gnorm}
+    return state, {"loss": loss.detach(), "grad_norm": gnorm.reshape(())}
 
 
 class GraphedTrainStep:
@@ -257,6 +296,11 @@ class GraphedTrainStep:
         self.static = {k: torch.empty_like(v, device=dev) for k, v in example_batch.items()}
         for k, v in example_batch.items():
             self.static[k].copy_(v, non_blocking=True)
+        # The warm-up runs are real train steps (they size workspaces, prime cuBLAS/cuDNN/NCCL and the TMA descriptor
+        # cache).  Everything they mutate is snapshotted here and restored IN PLACE after the capture (addresses stay
+        # valid for the graph), so building the graph trains on nothing: one optimizer update per replayed batch, as
+        # in the reference's loop (src/training/train.py:320-343).
+        snap = _snapshot_mutable(state)
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(side):
@@ -268,6 +312,8 @@ class GraphedTrainStep:
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
             _, self.metrics = train_step(state, self.static, sense)
+        torch.cuda.synchronize(dev)
+        _restore_mutable(state, snap)
         torch.cuda.synchronize(dev)
 
     def __call__(self, batch: Dict[str, torch.Tensor], prefetch: Optional[Dict[str, torch.Tensor]] = None):
@@ -306,6 +352,30 @@ class GraphedTrainStep:
         return self.state, self.metrics
 
 
+def _stat_leaves(tree):
+    for v in tree.values():
+        if isinstance(v, dict):
+            yield from _stat_leaves(v)
+        else:
+            yield v
+
+
+def _snapshot_mutable(state: TrainState):
+    """Clones of everything a train step mutates: parameters, optimizer state, stats_buffer leaves, step counter."""
+    return {"p32": state.flat_p32.detach().clone(), "opt": {k: v.clone() for k, v in state.opt_state.items()},
+            "stats": [t.clone() for t in _stat_leaves(state.variables["stats_buffer"])], "step": state.step}
+
+
+def _restore_mutable(state: TrainState, snap) -> None:
+    state.flat_p32.detach().copy_(snap["p32"])
+    state.flat_p16.copy_(state.flat_p32)
+    for k, v in state.opt_state.items():
+        v.copy_(snap["opt"][k])
+    for t, s in zip(_stat_leaves(state.variables["stats_buffer"]), snap["stats"]):
+        t.copy_(s)
+    state.step = snap["step"]
+
+
 def save_checkpoint(state: TrainState, path: str) -> None:
     """Save params, neuron_assignments, the stat accumulators, the optimizer moments and the step counter (the
     reference saves the whole TrainState once at the end, src/training/train.py:412-422, and has no restore).
@@ -315,7 +385,7 @@ def save_checkpoint(state: TrainState, path: str) -> None:
     cfg_dict = {k: (dataclasses.asdict(v) if dataclasses.is_dataclass(v) else v)
                 for k, v in (dataclasses.asdict(cfg) if dataclasses.is_dataclass(cfg) else dict(vars(cfg))).items()}
     torch.save({"step": state.step, "config": cfg_dict, "flat_p32": state.flat_p32.detach().cpu(),
-                "opt": state.opt.state_dict(),
+                "opt_state": {k: v.detach().cpu() for k, v in state.opt_state.items()}, "hyper": dict(state.hyper),
                 "neuron_assignments": _tree_to(state.variables["neuron_assignments"], "cpu"),
                 "stats_buffer": _tree_to(state.variables["stats_buffer"], "cpu")}, path)
 
@@ -329,22 +399,9 @@ def restore_checkpoint(state: TrainState, path: str) -> TrainState:
         raise ValueError("checkpoint does not match this model configuration")
     state.flat_p32.detach().copy_(ck["flat_p32"])
     state.flat_p16.copy_(state.flat_p32)
-    saved = ck["opt"]["state"]
-    live = state.opt.state.get(state.flat_p32)
-    if live and saved and all(k in live for k in saved[0]):
-        # the optimizer has stepped already (e.g. inside a captured graph): overwrite its moment tensors in place,
-        # Optimizer.load_state_dict would replace them with new tensors the graph does not know about
-        for k, v in saved[0].items():
-            if torch.is_tensor(live[k]):
-                live[k].copy_(torch.as_tensor(v))
-            else:
-                live[k] = v
-        for g_live, g_saved in zip(state.opt.param_groups, ck["opt"]["param_groups"]):
-            for k, v in g_saved.items():
-                if k != "params" and not torch.is_tensor(g_live.get(k)):
-                    g_live[k] = v
-    else:
-        state.opt.load_state_dict(ck["opt"])
+    for k, v in state.opt_state.items():          # optimizer moments and count, in place
+        v.copy_(ck["opt_state"][k])
+    state.hyper.update(ck.get("hyper", {}))
     _tree_copy_(state.variables["neuron_assignments"], ck["neuron_assignments"])
     _tree_copy_(state.variables["stats_buffer"], ck["stats_buffer"])
     state.step = int(ck["step"])

@@ -74,16 +74,17 @@ int forde_sl_up_fwd(void* stream, const void* x, const void* w_up, const float* 
                     void* zT, void* hT, float* act_partials, int M, int d, int H, long long ldz, int save_z);
 int forde_sl_down_fwd(void* stream, const void* hT, const void* w_down, const float* b_down, void* y, int M,
                       int d, int H, long long ldz);
-/* Sign-bit variant of the save_z = 0 forward.  Where the z box is not written the kernel also records (z > 0), one
- * bit per neuron and sample: sign_bits[H][forde_sl_sign_words(M)] u32 (16-byte aligned), bit j of word w of a row =
- * sample 32 w + j.  forde_sl_dz_bwd_signs then reads these 1/16 as many bytes instead of the hT box.  Same results
- * as the hT path bit for bit (relu'(z) needs only the sign of z; the straight-through step needs nothing). */
+/* Sign-bit variant of the save_z = 0 forward (what the module uses by default).  Where the z box is not written the
+ * kernel also records (z > 0), one bit per neuron and sample, in sign_bits: H * forde_sl_sign_words(M) u32 words,
+ * 16-byte aligned, word-major [forde_sl_sign_words(M)][H] so that a warp (32 consecutive neurons) touches one
+ * 128-byte line per access.  forde_sl_dz_bwd_signs then reads these 1/16 as many bytes instead of the hT box.  Same
+ * results as the hT path bit for bit (relu'(z) needs only the sign of z; the straight-through step needs nothing).
+ * Measured at C2 vision dims: dz_bwd 191 -> 163 us at no cost to the forward (profiles/r2_ab1_sign_bits.txt). */
 int forde_sl_sign_words(int M);
-/* Layout of sign_bits in this build, a bit mask (the shipped build returns 0).  Bit 0: bit order inside a 32-sample
- * word, 0 = sample order (bit j = sample 32 w + j), 1 = interleaved (sample 2k -> bit k, sample 2k + 1 -> bit 16 + k;
- * -DFORDE_UP_PACKED=1).  Bit 1: 0 = neuron-major [H][words], 1 = word-major [words][H] (-DFORDE_SIGN_WORD_MAJOR=1).
- * The buffer is a private residual between the two kernels and always H * forde_sl_sign_words(M) words; only tools
- * that inspect it need this. */
+/* Layout of sign_bits, a bit mask (this build returns 3).  Bit 0: bit order inside a 32-sample word, 1 = interleaved
+ * (sample 2k -> bit k, sample 2k + 1 -> bit 16 + k: the packed bf16x2 compare yields a pair's bits 16 apart).
+ * Bit 1: 1 = word-major [words][H].  The buffer is a private residual between the two kernels; only tools that
+ * inspect it need this. */
 int forde_sl_sign_layout(void);
 int forde_sl_up_fwd_signs(void* stream, const void* x, const void* w_up, const float* b_up, const int8_t* assign,
                           void* zT, void* hT, uint32_t* sign_bits, float* act_partials, int M, int d, int H,
@@ -144,12 +145,16 @@ int forde_sl_topk_mask(void* stream, void* dzT, long long ldz, int M, int H, con
  *   [grad_gini, grad_gdp, act_gini, act_gdp, act_variance]   (gini = Hoyer sparsity over the M samples)
  * then accumulates the stats_buffer leaves (moe.py:265-279 pattern): neuron_stats (H,5) += step stats,
  * moments (H,5) += [sum|z|, sum z, sum z^2, sum|g|, sum g^2], sample_count += M, step_count += 1.
+ * moments_lo (H,5; may be NULL) makes the accumulator a double-single pair: moments holds the fp32 high part,
+ * moments_lo the rounding residue, so sums over a whole slow-loop interval keep ~48 bits (the pooled variance
+ * sum z^2 / n - mean^2 cancels catastrophically in plain fp32 when |mean| >> std).  Both remain fp32 leaves.
  * step_stats / neuron_stats / moments / counters may each be NULL.  db_up (may be NULL) += sum g. */
 int forde_stats_finalize(void* stream, const float* act_partials, const float* grad_partials, int num_partials,
-                         int H, int M, float* step_stats, float* neuron_stats, float* moments,
+                         int H, int M, float* step_stats, float* neuron_stats, float* moments, float* moments_lo,
                          int* sample_count, int* step_count, float* db_up);
-/* stats from already pooled moments (used after the cross-rank all-reduce of the accumulators) */
-int forde_stats_from_moments(void* stream, const float* moments, const int* sample_count, int H,
+/* stats from already pooled moments, given in fp64 = double(moments) + double(moments_lo), summed over ranks
+ * (used after the cross-rank all-reduce of the accumulators) */
+int forde_stats_from_moments(void* stream, const double* moments, const int* sample_count, int H,
                              float* stats_out);
 
 /* ---- CLIP contrastive loss (README.md:35) ------------------------------------------------
@@ -242,6 +247,27 @@ int forde_add_layernorm_fwd(void* stream, const void* x, const void* r, const fl
 int forde_add_layernorm_bwd(void* stream, const void* dy, const void* x, const void* r, const float* gamma,
                             const float* mean, const float* rstd, void* ds, float* partials, float* d_gamma,
                             float* d_beta, int rows, int cols);
+
+/* ---- optimizer step of the fast loop ---------------------------------------------------------
+ * Reference: optax.chain(optax.clip_by_global_norm(1.0), optax.adamw(lr, weight_decay)) built at
+ * src/training/train.py:74-77 and applied by state.apply_gradients at :162; the monitored grad_norm of :168.
+ * All parameters / gradients / moments live in flat, 64-element-padded fp32 buffers of n elements (n % 4 == 0,
+ * 16-byte aligned); pad elements are zero and stay zero.  Exactly one of g32 / g16 is non-NULL: fp32 gradients, or
+ * the bf16 gradients that come back from a bf16 all-reduce.
+ *   forde_grad_sqnorm     : partials[forde_optim_num_partials(n)] = per-block sums of g^2 (fixed order, so the
+ *                           norm is bit-reproducible); *step_count += 1 (the optax count; may be NULL).
+ *   forde_adamw_clip_step : norm = sqrt(sum partials); g *= (norm < max_norm ? 1 : max_norm / norm)   [no epsilon,
+ *                           optax.clip_by_global_norm]; mu = b1 mu + (1-b1) g; nu = b2 nu + (1-b2) g^2;
+ *                           p -= lr * (mu/(1-b1^t) / (sqrt(nu/(1-b2^t)) + eps) + wd * p), t = *step_count (already
+ *                           incremented by forde_grad_sqnorm); p16 (may be NULL) = bf16(p), the compute mirror;
+ *                           grad_norm_out[1] (may be NULL) = the pre-clip norm.  max_norm <= 0 disables clipping.
+ *   forde_cast_f32_bf16   : dst = bf16(src) (gradient buckets before a bf16 all-reduce). */
+int forde_optim_num_partials(long long n);
+int forde_grad_sqnorm(void* stream, const float* g32, const void* g16, long long n, float* partials, int* step_count);
+int forde_adamw_clip_step(void* stream, float* p32, const float* g32, const void* g16, float* mu, float* nu, void* p16,
+                          long long n, const float* partials, int num_partials, float max_norm, float lr, float b1,
+                          float b2, float eps, float wd, const int* step_count, float* grad_norm_out);
+int forde_cast_f32_bf16(void* stream, const float* src, void* dst, long long n);
 
 #ifdef __cplusplus
 }

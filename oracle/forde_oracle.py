@@ -303,6 +303,27 @@ def clip_loss_bwd(img, txt, log_temp):
     return dimg.astype(np.float32), dtxt.astype(np.float32), np.float32(dlog_temp), ds.astype(np.float32)
 
 
+# ----------------------------------------------------------------------------------------------- optimizer
+def optax_clip_adamw_step(params, grads, mu, nu, count, lr, wd, max_norm=1.0, b1=0.9, b2=0.999, eps=1e-8):
+    """One update of optax.chain(optax.clip_by_global_norm(max_norm), optax.adamw(lr, weight_decay=wd)), the
+    optimizer the reference builds at src/training/train.py:74-77 (optax 0.2.6 is not installable here; this restates
+    its published update rules in fp32): clip_by_global_norm scales by max_norm / norm only when norm >= max_norm (no
+    epsilon); scale_by_adam keeps mu, nu, count with bias correction 1 - b^count and eps OUTSIDE the square root
+    (eps_root = 0); add_decayed_weights(wd) adds wd * p; the update is -lr times that.
+    Returns (params, mu, nu, count, global_norm) -- global_norm is the pre-clip norm train.py:168 logs."""
+    p = np.asarray(params, np.float32); g = np.asarray(grads, np.float32)
+    norm = np.float32(np.sqrt(np.sum(g.astype(np.float64) ** 2)))
+    if norm >= np.float32(max_norm):
+        g = (g / norm) * np.float32(max_norm)
+    count = int(count) + 1
+    mu = (np.float32(b1) * mu + np.float32(1 - b1) * g).astype(np.float32)
+    nu = (np.float32(b2) * nu + np.float32(1 - b2) * g * g).astype(np.float32)
+    mu_hat = mu / np.float32(1 - b1 ** count)
+    nu_hat = nu / np.float32(1 - b2 ** count)
+    upd = mu_hat / (np.sqrt(nu_hat) + np.float32(eps)) + np.float32(wd) * p
+    return (p - np.float32(lr) * upd).astype(np.float32), mu, nu, count, norm
+
+
 # ----------------------------------------------------------------------------------------------- slow loop
 def assignments_to_grid(assignments, grid_size):
     """smoothing.py:14-27."""

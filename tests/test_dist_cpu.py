@@ -65,7 +65,12 @@ class _FakeOps:
         return inv_norm[:, None] * (dU - u * (u * dU).sum(1, keepdim=True))
 
     @staticmethod
+    def pooled_moments(stats_leaf):
+        return stats_leaf["moments"].double() + stats_leaf["moments_lo"].double()
+
+    @staticmethod
     def stats_from_moments(moments, sample_count, out=None):
+        assert moments.dtype == torch.float64          # the cross-rank SUM of the accumulators runs in fp64
         return torch.from_numpy(O.stats_from_moments(moments.numpy(), int(sample_count.reshape(-1)[0])))
 
 
@@ -132,7 +137,9 @@ def _grad_and_moments_worker(rank, world, port, q):
         sl = slice(rank * 32, (rank + 1) * 32)                   # each rank sensed its own half of the samples
         m, n = O.raw_moments(a[sl], gr[sl])
         sb = new_stats_buffer(8, "cpu")
-        sb["moments"] += torch.from_numpy(m.astype(np.float32)); sb["sample_count"] += n; sb["step_count"] += 1
+        hi = m.astype(np.float32)                                # double-single accumulator: high part + residue
+        sb["moments"] += torch.from_numpy(hi); sb["moments_lo"] += torch.from_numpy((m - hi).astype(np.float32))
+        sb["sample_count"] += n; sb["step_count"] += 1
         stats = SL.sense_layer(sb, pooled=True)
         q.put((rank, g.numpy(), stats))
     finally:

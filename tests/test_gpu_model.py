@@ -82,11 +82,16 @@ def test_cuda_graph_replay_matches_eager_steps(built):
     eager = train.create_train_state(cfg, 5, device="cuda")
     le = [float(train.train_step(eager, b)[1]["loss"].item()) for _ in range(warm + 3)]
     gs = train.create_train_state(cfg, 5, device="cuda")
-    g = train.GraphedTrainStep(gs, b, warmup=warm)          # warm-up (3 eager) + capture (not a step)
-    lg = [float(g(b)[1]["loss"].item()) for _ in range(3)]
-    np.testing.assert_allclose(lg, le[warm:warm + 3], rtol=2e-3, atol=2e-3)
-    sb_e = eager.variables["stats_buffer"]["text"]["layer_1"]["stateful_layer"]
+    p0 = gs.flat_p32.detach().clone()
+    g = train.GraphedTrainStep(gs, b, warmup=warm)          # warm-up + capture train on NOTHING (state restored)
+    assert gs.step == 0 and torch.equal(gs.flat_p32.detach(), p0) and int(gs.opt_state["count"].item()) == 0
+    assert float(gs.opt_state["mu"].abs().sum()) == 0.0
     sb_g = gs.variables["stats_buffer"]["text"]["layer_1"]["stateful_layer"]
+    assert int(sb_g["step_count"].item()) == 0 and float(sb_g["moments"].abs().sum()) == 0.0
+    lg = [float(g(b)[1]["loss"].item()) for _ in range(warm + 3)]
+    assert gs.step == warm + 3
+    np.testing.assert_allclose(lg, le, rtol=2e-3, atol=2e-3)     # one optimizer update per replayed batch
+    sb_e = eager.variables["stats_buffer"]["text"]["layer_1"]["stateful_layer"]
     assert int(sb_g["step_count"].item()) == int(sb_e["step_count"].item()) == warm + 3
     np.testing.assert_allclose(sb_g["moments"].cpu().numpy(), sb_e["moments"].cpu().numpy(), rtol=2e-2, atol=1e-3)
     # slow-loop side effects between replays: new brain map + zeroed statistics

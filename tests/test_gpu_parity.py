@@ -209,7 +209,7 @@ def test_module_contract_and_in_place_statistics(ops):
     assert v["params"]["up_proj"]["kernel"].shape == (128, 512)       # Flax Dense kernel is (in, out)
     assert v["neuron_assignments"]["assignments"].dtype == torch.int32
     assert int(v["neuron_assignments"]["assignments"].abs().sum()) == 0  # D7: all generalists at init
-    assert set(v["stats_buffer"]) == {"neuron_stats", "moments", "sample_count", "step_count"}
+    assert set(v["stats_buffer"]) == {"neuron_stats", "moments", "moments_lo", "sample_count", "step_count"}
     for grp in v["params"].values():
         for p in grp.values():
             p.requires_grad_(True)

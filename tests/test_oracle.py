@@ -259,3 +259,23 @@ def test_gmm_clustering_matches_the_reference_call_for_a_given_seed(golden_dir, 
         ref_order = np.lexsort(z[f"means{i}"].T[::-1])
         np.testing.assert_allclose(params["means"][order], z[f"means{i}"][ref_order], rtol=1e-5, atol=1e-7)
         np.testing.assert_allclose(params["weights"][order], z[f"weights{i}"][ref_order], rtol=1e-5, atol=1e-7)
+
+
+def test_optax_clip_adamw_restatement_known_answers():
+    """Hand-computed first AdamW step (bias correction makes |update| = lr for every nonzero gradient) and the
+    clip_by_global_norm trigger (strictly-below-threshold gradients pass unchanged, no epsilon)."""
+    p = np.array([1.0, -2.0, 0.5, 0.0], np.float32)
+    g = np.array([3.0, -4.0, 0.0, 0.0], np.float32)               # norm 5 -> clipped to norm 1: (0.6, -0.8, 0, 0)
+    z = np.zeros(4, np.float32)
+    p1, mu, nu, count, norm = O.optax_clip_adamw_step(p, g, z, z, 0, lr=0.1, wd=0.0)
+    assert count == 1 and abs(float(norm) - 5.0) < 1e-6
+    np.testing.assert_allclose(mu, 0.1 * np.array([0.6, -0.8, 0, 0]), rtol=1e-6)
+    np.testing.assert_allclose(nu, 0.001 * np.array([0.36, 0.64, 0, 0]), rtol=1e-5)
+    np.testing.assert_allclose(p1, p - 0.1 * np.array([1, -1, 0, 0]), rtol=1e-5, atol=1e-6)   # mu_hat/sqrt(nu_hat) = sign(g)
+    # weight decay is decoupled: with zero gradients the step is p * (1 - lr * wd)
+    p2, *_ = O.optax_clip_adamw_step(p, z, z, z, 0, lr=0.1, wd=0.5)
+    np.testing.assert_allclose(p2, p * 0.95, rtol=1e-6)
+    # below the threshold nothing is scaled
+    _, mu3, _, _, n3 = O.optax_clip_adamw_step(p, 0.1 * g, z, z, 0, lr=0.1, wd=0.0)
+    np.testing.assert_allclose(mu3, 0.1 * 0.1 * g, rtol=1e-6)
+    assert abs(float(n3) - 0.5) < 1e-6

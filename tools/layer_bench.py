@@ -24,7 +24,7 @@ ap.add_argument("--H", type=int, default=3072)
 ap.add_argument("--iters", type=int, default=20)
 ap.add_argument("--once", action="store_true", help="one pass, no timing (for ncu)")
 ap.add_argument("--save-z", type=int, default=0, help="1 = forward writes all of z^T (debug), 0 = only what the backward reads")
-ap.add_argument("--sign-bits", type=int, default=0, help="1 = forward records (z > 0) bits, backward reads them instead of h^T")
+ap.add_argument("--sign-bits", type=int, default=1, help="1 = forward records (z > 0) bits, backward reads them instead of h^T")
 ap.add_argument("--assign", default="mixed", choices=["mixed", "zeros", "blocks"],
                 help="brain map: i.i.d. uniform{0,1,2} | all generalists (init) | contiguous thirds (smoothed map)")
 a = ap.parse_args()
