@@ -53,6 +53,23 @@ class _Workspace:
         # (z > 0) bit per neuron and sample for the neuron groups whose z box the forward does not store
         self.signs = torch.empty(ops.sign_shape(M, H), dtype=torch.int32, device=device) if sign_bits else None
         self.in_flight = False  # forward done, backward pending: zT / hT must not be overwritten
+        self.generation = 0     # bumped by every forward that takes this workspace (stale-backward detection)
+
+
+class _WorkspaceLease:
+    """Lives on the autograd ctx of one forward.  When that ctx dies without its backward having run (a grad-enabled
+    forward used for evaluation, a skipped step, an exception) the workspace is handed back instead of staying
+    in flight forever."""
+
+    __slots__ = ("ws", "generation")
+
+    def __init__(self, ws: "_Workspace"):
+        self.ws, self.generation = ws, ws.generation
+
+    def __del__(self):
+        ws = self.ws
+        if ws.in_flight and ws.generation == self.generation:
+            ws.in_flight = False
 
 
 _DZ_POOL: Dict[Tuple[int, int, str], torch.Tensor] = {}
@@ -119,7 +136,9 @@ class _StatefulLayerFn(torch.autograd.Function):
         ctx.masters = (w_up, b_up, w_down, b_down)
         ctx.needs_dx = ctx.needs_input_grad[0]
         will_backward = any(ctx.needs_input_grad)
+        ws.generation += 1
         ws.in_flight = will_backward
+        ctx.lease = _WorkspaceLease(ws) if will_backward else None
         if stats is not None and not will_backward and layer.sense_forward_only:
             layer._finalize(ws, stats, with_grad=False)
         return out
@@ -127,6 +146,11 @@ class _StatefulLayerFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dy):
         layer, ws, stats, assign_i8 = ctx.layer, ctx.ws, ctx.stats, ctx.assign_i8
+        if ctx.lease is None or ctx.lease.generation != ws.generation:
+            raise RuntimeError(
+                "StatefulLayer backward: the saved z^T / h^T of this forward were overwritten by a later forward of the "
+                "same layer (a second backward through a retained graph after the workspace was released); run the "
+                "backward before the next forward, or use separate layer objects")
         dy = dy.contiguous()
         if dy.dtype != torch.bfloat16:
             dy = dy.to(torch.bfloat16)
@@ -205,6 +229,7 @@ class StatefulLayer:
     # explicitly); ignored with save_z.
     sign_bits: bool = field(default_factory=lambda: os.environ.get("FORDE_SIGN_BITS", "1") == "1")
     name: str = "stateful_layer"
+    max_workspaces: int = 4                # forwards of one shape that may await their backward at the same time
 
     def __post_init__(self):
         self._ws: Dict[Tuple[int, int, str], list] = {}
@@ -282,6 +307,11 @@ class StatefulLayer:
         for ws in pool:
             if not ws.in_flight:
                 return ws
+        if len(pool) >= self.max_workspaces:
+            raise RuntimeError(
+                f"StatefulLayer {self.name!r}: {len(pool)} forwards of shape M={M}, H={H} are waiting for their backward "
+                f"(each holds z^T and h^T, {2 * 2 * H * ops.sample_pitch(M) / 2 ** 20:.0f} MiB).  Run inference under "
+                "torch.no_grad(), or raise max_workspaces if the module really is applied that often per step")
         ws = _Workspace(M, H, device, sign_bits=self.sign_bits and not self.save_z)  # the module is applied again before its previous backward ran
         pool.append(ws)
         return ws

@@ -187,9 +187,10 @@ def test_pooled_moments_over_a_100_step_interval_with_bias_dominated_neurons(ops
     got = f32(ops.stats_from_moments(ops.pooled_moments(sb), sb["sample_count"].reshape(1)))
     np.testing.assert_allclose(got[:, 4], ref_var, rtol=1e-3, atol=1e-6)
     np.testing.assert_allclose(got[:, :4], ref[:, :4], rtol=1e-3, atol=1e-5)
-    # the raw sums themselves agree with fp64 sums to ~1e-9 relative (double-single), far beyond one fp32 leaf
+    # the raw sums agree with fp64 sums to the rounding of the per-slot fp32 partials (128 samples each, ~1e-7
+    # relative, not growing with the number of steps): accumulation over the interval adds nothing to it
     mom_ref, n = O.raw_moments(z_all, dz_all)
-    np.testing.assert_allclose(ops.pooled_moments(sb).cpu().numpy(), mom_ref, rtol=1e-7)
+    np.testing.assert_allclose(ops.pooled_moments(sb).cpu().numpy(), mom_ref, rtol=2e-6)
     err_plain = np.abs(f32(ops.stats_from_moments(plain, sb["sample_count"].reshape(1)))[:, 4] - ref_var) / ref_var
     print(f"pooled variance: max rel err double-single {np.abs(got[:, 4] - ref_var).max():.2e} abs; "
           f"a plain fp32 accumulator would be off by up to {err_plain.max():.2e} relative")
