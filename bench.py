@@ -43,6 +43,28 @@ def measured_peaks():
     return {"burst": 1590.0, "sustained": 1400.0, "hbm": 6650.0, "source": "fallback"}
 
 
+def workload_config(cfg, batch, world):
+    """`config` of the JSON line: the workload only, identical for the B200 arm and the reference arm."""
+    return {"workload": f"FORDE {cfg.name} dual-encoder train step: ViT {cfg.image_size}px/p{cfg.patch_size} "
+                        f"d={cfg.vision.width} H={cfg.vision.hidden} L={cfg.vision.layers} + text S={cfg.text_len} "
+                        f"d={cfg.text.width} H={cfg.text.hidden} L={cfg.text.layers}, embed {cfg.embed_dim}; forward, "
+                        "contrastive loss, backward, in-kernel sensing, clip_by_global_norm(1.0) + AdamW",
+            "batch_per_gpu": batch, "global_batch": batch * world, "parallelism": f"dp{world}",
+            "optimizer": "clip_by_global_norm(1.0)+AdamW fp32 master, bf16 compute",
+            "l2": "per-step working set (activations + weights, several GB) exceeds the 126 MB L2; no flush"}
+
+
+def lib_sha16():
+    """First 16 hex digits of the SHA-256 of the shared library the run loads (evidence is tied to a build)."""
+    import hashlib
+    path = os.environ.get("FORDE_LIB", os.path.join(ROOT, "forde-vision-language_b200", "libforde_b200.so"))
+    try:
+        with open(path, "rb") as f:
+            return hashlib.sha256(f.read()).hexdigest()[:16]
+    except OSError:
+        return None
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
 
@@ -133,12 +155,12 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"FORDE {cfg.name} dual-encoder train step (fwd+bwd+sensing+AdamW), CPU port, "
-                               f"{sample} pairs per step", "image": cfg.image_size, "text_len": cfg.text_len},
+        "config": workload_config(cfg, args.batch, args.gpus),
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": f"{sample} synthetic pairs per step of the {cfg.name} workload "
-                                   f"(the GPU arm runs {args.batch} per GPU per step); torch CPU fp32, "
-                                   "restated reference (not JAX/XLA: not installable here)"},
+                         "sample": f"each step = {sample} synthetic pairs of the {cfg.name} workload (a bounded sample "
+                                   f"of the {args.batch} pairs per GPU per step the B200 arm runs); "
+                                   f"{1e3 * dt / args.steps / sample:.1f} ms per pair; torch CPU fp32 port of the "
+                                   "restated reference on all host cores (JAX/XLA not installable here)"},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
@@ -239,6 +261,51 @@ def run_gpu(args):
     ms_e2e, loss = timed(host, args.steps, read_loss=True, step_fn=step_fn, prefetch=graphed)
     e2e = world * args.batch * args.steps / (ms_e2e * 1e-3)
 
+    # ---- the same step on a post-slow-loop brain map: contiguous thirds of relu / tanh / step neurons in every layer
+    #      (spatially smoothed maps are contiguous, smoothing.py:30-91).  tanh groups make the forward store z^T and
+    #      the backward read it; the all-generalist map above is the cheapest case.  The graph sees the in-place rewrite.
+    smoothed = None
+    if not args.no_smoothed_map:
+        for tower in state.variables["neuron_assignments"].values():
+            for l in tower.values():
+                a_ = l["stateful_layer"]["assignments"]
+                a_.copy_((torch.arange(a_.numel(), device=dev) * 3 // a_.numel()).to(a_.dtype))
+        for i in range(2):
+            (step_fn or (lambda b: train.train_step(state, b)))(devb[i % 2])
+        ms_s, _ = timed(devb, args.steps, read_loss=False, step_fn=step_fn)
+        ops.enable_timing(True)
+        timed(devb, min(args.steps, 3), read_loss=False)
+        kt_s = ops.timing_summary()
+        ops.enable_timing(False)
+        smoothed = {"map": "contiguous thirds of relu / tanh / binary_step neurons in every layer",
+                    "value": world * args.batch * args.steps / (ms_s * 1e-3), "unit": UNIT,
+                    "ms_per_step": ms_s / args.steps,
+                    "kernels_us": {n: round(1e3 * r["ms_total"] / r["launches"], 2) for n, r in kt_s.items()
+                                   if n.startswith(("sl_up_fwd", "sl_dz_bwd"))}}
+
+    # ---- BASELINE config 3 (global batch 8192 = 1024 pairs per GPU on 8 GPUs): carried on the 8-GPU line
+    c3 = None
+    if world == 8 and args.batch != 1024 and not args.no_c3 and args.config == "vit_b16":
+        try:
+            del step_fn, state, devb, host
+            torch.cuda.empty_cache()
+            st3 = train.create_train_state(cfg, 0, device=dev)
+            b3 = [{k: v.to(dev) for k, v in train.synthetic_batch(cfg, 1024, seed=7 + rank * 100 + i, pinned=False).items()}
+                  for i in range(2)]
+            g3 = train.GraphedTrainStep(st3, b3[0], warmup=2)
+            for i in range(2):
+                g3(b3[i % 2])
+            n3 = 5
+            ms3, _ = timed(b3, n3, read_loss=False, step_fn=g3)
+            _, m3 = g3(b3[0])
+            c3 = {"global_batch": 1024 * world, "batch_per_gpu": 1024, "steps": n3, "ms_per_step": ms3 / n3,
+                  "value": world * 1024 * n3 / (ms3 * 1e-3), "unit": UNIT, "loss": float(m3["loss"].item()),
+                  "local_logits": "1024 x 8192 fp32 per rank; text embeddings all-gathered (8.4 MB bf16), column "
+                                  "log-sum-exp merged by one MAX + one SUM all-reduce, d(txt) by reduce-scatter",
+                  "peak_mem_gb": round(torch.cuda.max_memory_allocated(dev) / 2 ** 30, 1)}
+        except Exception as e:  # noqa: BLE001  (the headline line must still be printed)
+            c3 = {"error": f"{type(e).__name__}: {e}"[:300]}
+
     def finish():
         # NCCL communicators that were captured into a CUDA graph can hang in their destructor at interpreter
         # exit; everything is measured and printed by now, so synchronise, meet at a barrier and leave.
@@ -260,11 +327,19 @@ def run_gpu(args):
     roofline = None
     sl_ms = sum(r["ms_total"] for r in kt.values())
     sl_flops = sum(r["flops_total"] for r in kt.values())
-    traffic_db = {}
+    traffic_db, traffic_note = {}, "no ncu capture on record for this build"
     tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    sha = lib_sha16()
     if os.path.exists(tpath):
         with open(tpath) as f:
-            traffic_db = json.load(f)
+            tj = json.load(f)
+        if tj.get("lib_sha256_16") == sha:      # only quote DRAM bytes captured on THIS build of the library
+            traffic_db = tj.get("kernels", {})
+            traffic_note = (f"dram__bytes_read.sum + dram__bytes_write.sum per launch, one ncu --set full capture of "
+                            f"library {sha} ({tj.get('source', 'profiles/')})")
+        else:
+            traffic_note = (f"profiles/ncu_traffic.json was captured on library {tj.get('lib_sha256_16')}, this run "
+                            f"loads {sha}: not quoted")
     if kt:
         dom = max(kt, key=lambda n: kt[n]["ms_total"])
         r = kt[dom]
@@ -275,20 +350,17 @@ def run_gpu(args):
                     "flops_per_launch": r["flops_total"] / r["launches"], "launches": r["launches"],
                     "us_per_launch": round(1e3 * r["ms_total"] / r["launches"], 2),
                     "traffic": traffic_db.get(dom, {}).get("traffic_bytes"),
-                    "traffic_note": "DRAM read+write bytes per launch from one ncu --set full capture "
-                                    "(profiles/ncu_traffic.json); algorithmic bytes 2(Md+dH+2MH) = 702 MB at C2 vision"}
+                    "algorithmic_bytes": traffic_db.get(dom, {}).get("algorithmic_bytes"),
+                    "traffic_note": traffic_note}
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": f"FORDE {cfg.name} dual-encoder train step: ViT {cfg.image_size}px/p{cfg.patch_size} "
-                               f"d={cfg.vision.width} H={cfg.vision.hidden} L={cfg.vision.layers} + text S={cfg.text_len} "
-                               f"d={cfg.text.width} H={cfg.text.hidden} L={cfg.text.layers}, embed {cfg.embed_dim}",
-                   "batch_per_gpu": args.batch, "global_batch": args.batch * world, "parallelism": f"dp{world}",
-                   "optimizer": "clip_by_global_norm(1.0)+AdamW fp32 master, bf16 compute",
-                   "launch": "whole step replayed as one CUDA graph" if graphed else "eager launches",
-                   "ms_per_step_eager_instrumented": ms_eager / args.steps,
-                   "l2": "per-step working set (activations + weights, several GB) exceeds the 126 MB L2; no flush"},
+        "config": workload_config(cfg, args.batch, world),
+        "run": {"launch": "whole step replayed as one CUDA graph" if graphed else "eager launches",
+                "ms_per_step_eager_instrumented": ms_eager / args.steps, "lib_sha256_16": sha,
+                "brain_map": "all-generalist (every layer's initial map, D7); see smoothed_map for a post-slow-loop map",
+                "grad_exchange": (os.environ.get("FORDE_GRAD_COMM", "bf16") if world > 1 else "none (1 GPU)")},
         "clocks": clocks,
         "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": ms_e2e / args.steps, "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": 4, "loss": loss},
@@ -300,6 +372,10 @@ def run_gpu(args):
                            "frac_of_sustained_peak": round(sl_flops / (sl_ms * 1e-3) / 1e12 / peaks["sustained"], 4) if sl_ms else None,
                            "kernels": kernels},
     }
+    if smoothed is not None:
+        line["smoothed_map"] = smoothed
+    if c3 is not None:
+        line["c3_global_batch_8192"] = c3
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(cfg, args)
     print(json.dumps(line), flush=True)
@@ -322,13 +398,14 @@ def cpu_baseline(cfg, args):
     tr.step(img, b["input_ids"])
     t0 = time.perf_counter()
     n = 0
-    while n < 3 or (time.perf_counter() - t0 < 10.0 and n < 50):
+    while n < 2 or (time.perf_counter() - t0 < 12.0 and n < 50):
         tr.step(img, b["input_ids"])
         n += 1
     dt = time.perf_counter() - t0
     return {"value": sample * n / dt, "unit": UNIT, "cores": cores, "kind": "port",
             "sample": f"{n} steps of {sample} synthetic pairs of the {cfg.name} workload (fwd+bwd+sensing pass+AdamW), "
-                      "torch CPU fp32 port of the restated reference (JAX not installable here)"}
+                      f"{1e3 * dt / n / sample:.1f} ms per pair; torch CPU fp32 port of the restated reference on all "
+                      "host cores (JAX not installable here)"}
 
 
 def main():
@@ -339,7 +416,9 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--config", default="vit_b16", choices=["tiny", "vit_b16", "vit_l14"])
     ap.add_argument("--batch", type=int, default=256, help="pairs per GPU per step")
-    ap.add_argument("--cpu-batch", type=int, default=8, help="pairs per step of the CPU port's bounded sample")
+    ap.add_argument("--cpu-batch", type=int, default=32, help="pairs per step of the CPU port's bounded sample")
+    ap.add_argument("--no-smoothed-map", action="store_true", help="skip the second measurement on a mixed brain map")
+    ap.add_argument("--no-c3", action="store_true", help="on 8 GPUs: skip the extra global-batch-8192 measurement")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of the CUDA-graph replay")
     args = ap.parse_args()

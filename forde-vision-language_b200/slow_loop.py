@@ -14,8 +14,16 @@ accelerated (out of scope).  What is kept is the 
     tests/verify_reset.py:61-67).
 
 Multi-GPU: the raw-moment accumulators are additive, so ranks all-reduce(SUM) ``moments`` and ``sample_count``
-(never the finished statistics, Hoyer and variance are non-linear) and every rank then runs the same
-deterministic slow loop with the same seed, which keeps ``neuron_assignments`` replicated without a broadcast.
+(never the finished statistics, Hoyer and variance are non-linear) -- ONE fp64 all-reduce for all layers -- and every
+rank then runs the same seeded slow loop.  Replicas are kept identical by construction AND by a broadcast of rank 0's
+new maps before Actuate (``SlowLoopConfig.broadcast``): bit-identical scikit-learn fits on every rank are likely but
+not something to stake the replicas' consistency on.
+
+Deviations from the reference's slow loop, all switchable: ``canonicalize`` (D10) relabels
+the GMM's arbitrary cluster ids by ascending mean grad_gini so that id 0/1/2 keep meaning relu/tanh/step from one
+update to the next (``cluster_neurons_gmm`` returns raw ids); ``pooled`` senses from raw moments pooled over the
+interval and the ranks instead of ``neuron_stats / step_count`` (moe_slow_loop.py:298).  ``canonicalize=False,
+pooled=False`` is the reference's behaviour.
 """
 from __future__ import annotations
 
@@ -39,6 +47,7 @@ class SlowLoopConfig:
     canonicalize: bool = True        # D10: relabel clusters by ascending mean grad_gini -> 0 relu, 1 tanh, 2 step
     forde_lite: bool = False         # README.md:58-59 ablation: is_spec = grad_gini > threshold, no GMM
     forde_lite_threshold: float = 0.8
+    broadcast: bool = True           # multi-rank: rank 0's new maps are broadcast before Actuate (one int32 tensor)
 
 
 def default_grid(H: int) -> Tuple[int, int]:
@@ -101,47 +110,74 @@ def _seed_from_key(key) -> int:
     return int(key) % (2 ** 31 - 1)
 
 
+def _world(group) -> int:
+    return dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
+
+
 def sense_layer(stats_leaf: Dict[str, torch.Tensor], pooled: bool, group=None) -> Optional[np.ndarray]:
     """(H,5) [grad_gini, grad_gdp, act_gini, act_gdp, act_variance] for one layer, or None if nothing was
     accumulated.  With `pooled`, the raw moments are all-reduced across ranks first."""
-    world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
+    return _sense_layers([stats_leaf], pooled, group)[0]
+
+
+def _sense_layers(leaves, pooled: bool, group=None):
+    """Sense a list of stats_buffer leaf dicts with ONE cross-rank all-reduce and ONE device-to-host copy (the slow
+    loop stalls the training thread, so no per-layer synchronisation).  Returns a list of (H,5) arrays / None."""
+    if not leaves:
+        return []
+    world = _world(group)
+    dev = leaves[0]["moments"].device
+    sizes = [int(l["moments"].shape[0]) for l in leaves]
     if pooled:
-        # fp64 = high + low fp32 parts of the double-single accumulator; the cross-rank SUM runs in fp64 too
-        moments, count = ops.pooled_moments(stats_leaf), stats_leaf["sample_count"]
+        # fp64 = high + low fp32 parts of the double-single accumulators; counts ride along (exact in fp64)
+        flat = torch.cat([ops.pooled_moments(l).reshape(-1) for l in leaves] +
+                         [torch.stack([l["sample_count"].double() for l in leaves])])
         if world > 1:
-            count = count.clone()
-            dist.all_reduce(moments, op=dist.ReduceOp.SUM, group=group)
-            dist.all_reduce(count, op=dist.ReduceOp.SUM, group=group)
-        if int(count.item()) == 0:
-            return None
-        # finalisation runs in the CUDA kernel (ops rejects host tensors: no CPU fallback)
-        return ops.stats_from_moments(moments.contiguous(), count.reshape(1).contiguous()).cpu().numpy()
-    steps = int(stats_leaf["step_count"].item())
-    if steps == 0:
-        return None
-    s = stats_leaf["neuron_stats"] / steps
-    if world > 1:
-        s = s.clone()
-        dist.all_reduce(s, op=dist.ReduceOp.SUM, group=group)
-        s = s / world
-    return s.cpu().numpy()
+            dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+        counts = flat[-len(leaves):].to(torch.int32)
+        out = torch.zeros((sum(sizes), 5), dtype=torch.float32, device=dev)
+        off = 0
+        for i, H in enumerate(sizes):
+            # finalisation runs in the CUDA kernel (ops rejects host tensors: no CPU fallback); zero counts give zeros
+            ops.stats_from_moments(flat[off * 5:(off + H) * 5].view(H, 5), counts[i:i + 1], out=out[off:off + H])
+            off += H
+        host, counts_h = out.cpu().numpy(), counts.cpu().numpy()
+    else:
+        flat = torch.cat([l["neuron_stats"].reshape(-1) for l in leaves] +
+                         [torch.stack([l["step_count"].float() for l in leaves])])
+        steps = flat[-len(leaves):].clone()
+        if world > 1:       # mean over ranks of each rank's mean over steps (moe_slow_loop.py:298 per rank)
+            dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+        host = flat[:-len(leaves)].view(-1, 5).cpu().numpy()
+        counts_h = steps.cpu().numpy()
+    res, off = [], 0
+    for i, H in enumerate(sizes):
+        if counts_h[i] == 0:
+            res.append(None)
+        elif pooled:
+            res.append(host[off:off + H].copy())
+        else:
+            res.append(host[off:off + H] / (float(counts_h[i]) * world))
+        off += H
+    return res
 
 
 def slow_loop_sense(mutable_variables, config: SlowLoopConfig, group=None):
-    """SENSE for every layer (device work + the cross-rank all-reduce, in a fixed order on every rank).
+    """SENSE for every layer (device work + one cross-rank all-reduce, layers in a fixed order on every rank).
     Returns the job list [(layer path, (H,5) stats on the host or None, that layer's assignment leaf dict)]."""
-    jobs = []
+    found = []
 
     def walk(st, asg, path):
         if isinstance(st, dict) and "neuron_stats" in st:
-            jobs.append(("/".join(path), sense_layer(st, config.pooled, group), asg))
+            found.append(("/".join(path), st, asg))
             return
         if isinstance(st, dict):
             for k in sorted(st):
                 walk(st[k], asg[k], path + (k,))
 
     walk(mutable_variables["stats_buffer"], mutable_variables["neuron_assignments"], ())
-    return jobs
+    stats = _sense_layers([st for _, st, _ in found], config.pooled, group)
+    return [(name, s, asg) for (name, _, asg), s in zip(found, stats)]
 
 
 def slow_loop_compute(jobs, config: SlowLoopConfig, seed: int):
@@ -176,20 +212,35 @@ def slow_loop_compute(jobs, config: SlowLoopConfig, seed: int):
         return dict(zip([n for n, _ in todo], pool.map(lambda t: cluster_and_smooth(t[1]), todo)))
 
 
-def slow_loop_actuate(jobs, results, config: SlowLoopConfig, diagnostics) -> None:
-    """ACTUATE in layer order: overwrite each layer's ``assignments`` in place and fill ``diagnostics["layers"]``."""
+def slow_loop_actuate(jobs, results, config: SlowLoopConfig, diagnostics, group=None) -> None:
+    """ACTUATE in layer order: overwrite each layer's ``assignments`` in place and fill ``diagnostics["layers"]``.
+    Multi-rank with ``config.broadcast``: the maps every rank writes are rank 0's (one broadcast of all layers)."""
     k = config.num_clusters
-    for name, stats, asg in jobs:
+    live = [(name, stats, asg) for name, stats, asg in jobs if stats is not None]
+    for name, stats, _ in jobs:
         if stats is None:
             diagnostics["layers"][name] = {"skipped": "no statistics accumulated"}
-            continue
+    if not live:
+        return
+    dev = live[0][2]["assignments"].device
+    new_maps = [results[name][1].reshape(-1).astype(np.int32) for name, _, _ in live]
+    if _world(group) > 1 and config.broadcast:
+        flat = torch.from_numpy(np.concatenate(new_maps)).to(dev)
+        dist.broadcast(flat, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+        flat_h, off = flat.cpu().numpy(), 0
+        for i, m in enumerate(new_maps):
+            new_maps[i] = flat_h[off:off + m.size]
+            off += m.size
+    old = torch.cat([asg["assignments"].reshape(-1) for _, _, asg in live]).cpu().numpy()    # one device-to-host copy
+    off = 0
+    for (name, stats, asg), new in zip(live, new_maps):
         labels, smoothed, gmm_params = results[name]
-        tgt = asg["assignments"]
-        new = torch.from_numpy(smoothed.reshape(-1).astype(np.int32)).to(tgt.device)
-        changed = int((new != tgt).sum().item())
-        tgt.copy_(new)                                                                  # in place: bumps _version
+        smoothed = new.reshape(smoothed.shape)
+        changed = int((old[off:off + new.size] != new).sum())
+        off += new.size
+        asg["assignments"].copy_(torch.from_numpy(new))                                 # in place: bumps _version
         diagnostics["layers"][name] = {
-            "census": np.bincount(smoothed.reshape(-1), minlength=k).tolist(),          # README.md:66 "The Census"
+            "census": np.bincount(new, minlength=k).tolist(),                           # README.md:66 "The Census"
             "raw_census": np.bincount(labels, minlength=k).tolist(),
             "changed": changed,
             "brain_scan": smoothed,                                                     # README.md:64
@@ -212,11 +263,18 @@ def slow_loop_step(params, mutable_variables, config: SlowLoopConfig, key, epoch
     """One brain update: Sense -> Cluster -> Smooth -> Actuate -> Reset.  `mutable_variables` holds ``stats_buffer``
     and ``neuron_assignments`` trees keyed by ``layer_{i}`` (any nesting above that is walked).
     Returns (params, mutable_variables, diagnostics)."""
+    import time
+    t0 = time.perf_counter()
     diagnostics = {"epoch": epoch, "step": step, "layers": {}}
     jobs = slow_loop_sense(mutable_variables, config, group)
+    t1 = time.perf_counter()
     results = slow_loop_compute(jobs, config, _seed_from_key(key))
-    slow_loop_actuate(jobs, results, config, diagnostics)
+    t2 = time.perf_counter()
+    slow_loop_actuate(jobs, results, config, diagnostics, group)
     _zero_tree(mutable_variables["stats_buffer"])
+    t3 = time.perf_counter()
+    # host seconds the training thread spent in this update (the device idles meanwhile)
+    diagnostics["seconds"] = {"sense": t1 - t0, "cluster_smooth": t2 - t1, "actuate_reset": t3 - t2, "total": t3 - t0}
     return params, mutable_variables, diagnostics
 
 
@@ -246,10 +304,13 @@ class OverlappedSlowLoop:
     def start(self, mutable_variables, key, epoch: int = 0, step: int = 0):
         """Sense + Reset now, Cluster + Smooth in the background.  Returns the diagnostics of a still-pending
         earlier update that had to be actuated first (None normally)."""
+        import time
         flushed = self.flush()
+        t0 = time.perf_counter()
         diagnostics = {"epoch": epoch, "step": step, "layers": {}}
         jobs = slow_loop_sense(mutable_variables, self.config, self.group)
         _zero_tree(mutable_variables["stats_buffer"])
+        diagnostics["seconds"] = {"sense": time.perf_counter() - t0}
         fut = self._pool.submit(slow_loop_compute, jobs, self.config, _seed_from_key(key))
         self._pending = (fut, step + self.delay, jobs, diagnostics)
         return flushed
@@ -265,9 +326,15 @@ class OverlappedSlowLoop:
         """Actuate a pending update now, whatever the step (end of training, or a new update is due)."""
         if self._pending is None:
             return None
+        import time
         fut, due, jobs, diagnostics = self._pending
         self._pending = None
-        slow_loop_actuate(jobs, fut.result(), self.config, diagnostics)
+        t0 = time.perf_counter()
+        results = fut.result()                 # normally done long ago; the wait (if any) is training-thread time
+        slow_loop_actuate(jobs, results, self.config, diagnostics, self.group)
+        sec = diagnostics.setdefault("seconds", {})
+        sec["actuate_reset"] = time.perf_counter() - t0
+        sec["total"] = sec.get("sense", 0.0) + sec["actuate_reset"]     # on the training thread; Cluster+Smooth overlapped
         diagnostics["actuated_at_step"] = due
         return diagnostics
 

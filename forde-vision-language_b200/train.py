@@ -421,7 +421,8 @@ def _tree_copy_(dst, src):
 
 
 def fit(state: TrainState, batches, max_steps: int, slow_loop_interval: int = 100, slow_loop_config=None, key: int = 0,
-        use_cuda_graph: bool = True, log=None, plot_dir: Optional[str] = None, slow_loop_overlap_steps: int = 0):
+        use_cuda_graph: bool = True, log=None, plot_dir: Optional[str] = None, slow_loop_overlap_steps: int = 0,
+        step_fn=None):
     """The reference's outer loop (src/training/train.py:320-399): fast steps, and every ``slow_loop_interval`` steps
     (train.py:219-224 default 100; ``step > 0 and step % interval == 0``, train.py:365-369) the slow loop -- Sense
     (all-reduced pooled moments) -> Cluster -> Smooth -> Actuate -> Reset -- which rewrites ``neuron_assignments`` in
@@ -432,6 +433,8 @@ def fit(state: TrainState, batches, max_steps: int, slow_loop_interval: int = 10
     ViT-B/16 sizes = 5 fast steps) off the training thread: statistics are sensed and reset at the slow-loop step,
     clustered on a worker thread while fast steps continue, and the new maps take effect exactly k steps later on
     every rank (slow_loop.OverlappedSlowLoop).  0 = the reference's synchronous update.
+    ``step_fn``: an already captured ``GraphedTrainStep`` of this state to reuse (otherwise one is captured from the
+    first batch).  Every slow-loop diagnostics dict carries ``seconds``: host time the training thread spent in it.
     Returns (state, history) with history = list of (step, loss) and the slow-loop diagnostics."""
     from .brain_scan import plot_brain_scan, plot_feature_space
     from .slow_loop import OverlappedSlowLoop, SlowLoopConfig, slow_loop_step
@@ -459,7 +462,6 @@ def fit(state: TrainState, batches, max_steps: int, slow_loop_interval: int = 10
                 plot_brain_scan(d["brain_scan"], diag["step"], 0, out_dir=sub)
                 plot_feature_space(d["features"], d["brain_scan"].reshape(-1), diag["step"], 0, out_dir=sub)
 
-    step_fn = None
     it = iter(batches)
     for step in range(max_steps):
         try:

@@ -71,7 +71,12 @@ class _FakeOps:
     @staticmethod
     def stats_from_moments(moments, sample_count, out=None):
         assert moments.dtype == torch.float64          # the cross-rank SUM of the accumulators runs in fp64
-        return torch.from_numpy(O.stats_from_moments(moments.numpy(), int(sample_count.reshape(-1)[0])))
+        n = int(sample_count.reshape(-1)[0])
+        res = torch.from_numpy(O.stats_from_moments(moments.numpy(), n)) if n > 0 else torch.zeros((moments.shape[0], 5))
+        if out is not None:
+            out.copy_(res)
+            return out
+        return res
 
 
 def _clip_worker(rank, world, port, q):
