@@ -68,6 +68,11 @@ SIGNATURES = {
     "forde_grad_sqnorm": (_i, [_vp, _vp, _vp, _ll, _vp, _vp]),
     "forde_adamw_clip_step": (_i, [_vp] * 7 + [_ll, _vp, _i, _f, _f, _f, _f, _f, _f, _vp, _vp]),
     "forde_cast_f32_bf16": (_i, [_vp, _vp, _vp, _ll]),
+    "forde_patchify": (_i, [_vp, _vp, _vp, _ll, _i, _i, _i]),
+    "forde_vision_assemble_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i]),
+    "forde_vision_assemble_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i]),
+    "forde_embed_tokens_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i]),
+    "forde_embed_tokens_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i]),
 }
 
 

@@ -102,20 +102,21 @@ def _deliver_dense_grads(w, b, x2t, dy2):
 
 
 class _Dense(torch.autograd.Function):
-    """y = x W + b for bf16 activations.  Forward, input gradient and weight gradient run on this repository's tcgen05
+    """y = x W (+ b) for bf16 activations.  Forward, input gradient and weight gradient run on this repository's tcgen05
     GEMM engine (bias fused in the epilogue; dW accumulated in fp32 straight into the gradient sink), the bias
-    gradient on the column-sum kernel.  `w16` is the bf16 mirror (in, out)."""
+    gradient on the column-sum kernel.  `w16` is the bf16 mirror (in, out); `b` may be None (projection heads)."""
 
     @staticmethod
     def forward(ctx, x, w, b, w16, b16):
         x2 = x.reshape(-1, x.shape[-1])
-        if not x2.is_contiguous():
-            x2 = x2.contiguous()
-        y = ops.gemm_bf16(x2, w16, False, True, bias_col=b.detach().float())
+        if x2.stride(1) != 1 or x2.stride(0) % 8 != 0 or x2.data_ptr() % 16 != 0:
+            x2 = x2.contiguous()        # (a row-pitched view such as the padded patch rows is fine for TMA as it is)
+        y = ops.gemm_bf16(x2, w16, False, True, bias_col=None if b is None else b.detach().float())
         ctx.save_for_backward(x2, w16)
         ctx.lead = x.shape[:-1]
         ctx.masters = (w, b)
-        return y.view(*x.shape[:-1], w16.shape[1])
+        ctx.needs_dx = ctx.needs_input_grad[0]
+        return y.reshape(*x.shape[:-1], w16.shape[1])
 
     @staticmethod
     def backward(ctx, dy):
@@ -123,9 +124,70 @@ class _Dense(torch.autograd.Function):
         dy2 = dy.reshape(-1, dy.shape[-1])
         if not dy2.is_contiguous():
             dy2 = dy2.contiguous()
-        dx = ops.gemm_bf16(dy2, w16, False, False).view(*ctx.lead, w16.shape[0])     # dx = dy W^T
-        dw, db = _deliver_dense_grads(ctx.masters[0], ctx.masters[1], x2.t(), dy2)
+        if dy2.dtype != torch.bfloat16:
+            dy2 = dy2.to(torch.bfloat16)
+        dx = None
+        if ctx.needs_dx:                                                             # dx = dy W^T
+            dx = ops.gemm_bf16(dy2, w16, False, False).reshape(*ctx.lead, w16.shape[0])
+        w, b = ctx.masters
+        if b is None:
+            sw = grad_sink(w)
+            dw = sw if sw is not None else torch.zeros(w.shape, dtype=torch.float32, device=dy2.device)
+            ops.gemm_f32(x2, dy2, True, True, out=dw, accumulate=True)               # dW += x^T dy
+            if sw is not None:
+                grad_delivered(w)
+                dw = None
+            return dx, dw, None, None, None
+        dw, db = _deliver_dense_grads(w, b, x2.t(), dy2)
         return dx, dw, db, None, None
+
+
+class _VisionAssemble(torch.autograd.Function):
+    """x[b] = [cls + pos[0] ; patch tokens + pos[1:]] (README.md:30-34) on the front-end kernels of csrc/forde_frontend.cu;
+    d(cls), d(pos_embed) are accumulated in fp32 straight into their gradient sinks."""
+
+    @staticmethod
+    def forward(ctx, tok, cls, pos, cls16, pos16, B):
+        ctx.masters = (cls, pos)
+        return ops.vision_assemble_fwd(tok.contiguous(), cls16.contiguous(), pos16.contiguous(), B)
+
+    @staticmethod
+    def backward(ctx, dx):
+        cls, pos = ctx.masters
+        sc, sp = grad_sink(cls), grad_sink(pos)
+        direct = sc is not None and sp is not None
+        d_cls = sc if direct else torch.zeros(cls.shape, dtype=torch.float32, device=dx.device)
+        d_pos = sp if direct else torch.zeros(pos.shape, dtype=torch.float32, device=dx.device)
+        d_tok = ops.vision_assemble_bwd(dx.contiguous(), d_cls, d_pos)
+        if direct:
+            grad_delivered(cls); grad_delivered(pos)
+            return d_tok, None, None, None, None, None
+        return d_tok, d_cls, d_pos, None, None, None
+
+
+class _TokenEmbed(torch.autograd.Function):
+    """x[b][t] = token_embed[ids[b][t]] + pos_embed[t] and its scatter-add backward (fp32 red.add into the sinks)."""
+
+    @staticmethod
+    def forward(ctx, ids, table, pos, table16, pos16):
+        ids = ids.to(torch.int32).contiguous()
+        ctx.masters = (table, pos)
+        ctx.save_for_backward(ids)
+        return ops.embed_tokens_fwd(ids, table16.contiguous(), pos16.contiguous())
+
+    @staticmethod
+    def backward(ctx, dx):
+        (ids,) = ctx.saved_tensors
+        table, pos = ctx.masters
+        st, sp = grad_sink(table), grad_sink(pos)
+        direct = st is not None and sp is not None
+        d_table = st if direct else torch.zeros(table.shape, dtype=torch.float32, device=dx.device)
+        d_pos = sp if direct else torch.zeros(pos.shape, dtype=torch.float32, device=dx.device)
+        ops.embed_tokens_bwd(ids, dx.contiguous(), d_table, d_pos)
+        if direct:
+            grad_delivered(table); grad_delivered(pos)
+            return None, None, None, None, None
+        return None, d_table, d_pos, None, None
 
 
 class _QKVDense(torch.autograd.Function):
@@ -310,28 +372,41 @@ class FORDEDualEncoder:
         p = variables["params"]["vision"]
         p16 = params_bf16["vision"] if params_bf16 is not None else None
         B = images.shape[0]
-        g, ps = cfg.image_size // cfg.patch_size, cfg.patch_size
-        x = images.to(torch.bfloat16).view(B, g, ps, g, ps, 3).permute(0, 1, 3, 2, 4, 5).reshape(B, g * g, ps * ps * 3)
-        x = F.linear(x, self._w(p["patch_embed"], p16 and p16["patch_embed"], "kernel").t(),
-                     p["patch_embed"]["bias"].to(torch.bfloat16))
-        cls = p["cls"].to(torch.bfloat16).expand(B, 1, -1)
-        x = torch.cat([cls, x], dim=1) + p["pos_embed"].to(torch.bfloat16)
+
+        def m16(*path):      # bf16 compute mirror of a master leaf (the train state's pre-cast one when there is one)
+            t, t16 = p, p16
+            for k in path:
+                t = t[k]
+                t16 = t16[k] if t16 is not None else None
+            return t16 if t16 is not None else t.detach().to(torch.bfloat16)
+
+        # patchify (layout only) -> patch-embedding GEMM on the tcgen05 engine -> +CLS, +pos (README.md:30-34)
+        patches = ops.patchify(images.to(torch.bfloat16).contiguous(), cfg.patch_size)
+        tok = _Dense.apply(patches, p["patch_embed"]["kernel"], p["patch_embed"]["bias"], m16("patch_embed", "kernel"),
+                           None)
+        x = _VisionAssemble.apply(tok, p["cls"], p["pos_embed"], m16("cls"), m16("pos_embed"), B)
         for i in range(cfg.vision.layers):
             x = self._block(f"vision/layer_{i}", x, p[f"layer_{i}"], p16 and p16[f"layer_{i}"], cfg.vision.heads,
                             variables, sense)
-        return F.linear(x[:, 0], self._w(p["proj"], p16 and p16["proj"], "kernel").t())
+        return _Dense.apply(x[:, 0], p["proj"]["kernel"], None, m16("proj", "kernel"), None)     # [CLS] -> embed_dim
 
     def encode_text(self, variables, input_ids, sense=True, params_bf16=None):
         """input_ids (B, S) int (src/data/download_to_drive.py:106-108); token 0 is [CLS]."""
         cfg = self.cfg
         p = variables["params"]["text"]
         p16 = params_bf16["text"] if params_bf16 is not None else None
-        emb = self._w(p, p16, "token_embed")
-        x = F.embedding(input_ids.long(), emb) + p["pos_embed"].to(torch.bfloat16)[: input_ids.shape[1]]
+        def m16(*path):
+            t, t16 = p, p16
+            for k in path:
+                t = t[k]
+                t16 = t16[k] if t16 is not None else None
+            return t16 if t16 is not None else t.detach().to(torch.bfloat16)
+
+        x = _TokenEmbed.apply(input_ids, p["token_embed"], p["pos_embed"], m16("token_embed"), m16("pos_embed"))
         for i in range(cfg.text.layers):
             x = self._block(f"text/layer_{i}", x, p[f"layer_{i}"], p16 and p16[f"layer_{i}"], cfg.text.heads,
                             variables, sense)
-        return F.linear(x[:, 0], self._w(p["proj"], p16 and p16["proj"], "kernel").t())
+        return _Dense.apply(x[:, 0], p["proj"]["kernel"], None, m16("proj", "kernel"), None)     # token 0 = [CLS]
 
     def apply(self, variables, images, input_ids, mutable=False, params_bf16=None, group=None):
         """Returns the global-batch contrastive loss (and the mutable collections when asked, Flax style)."""

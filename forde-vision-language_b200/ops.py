@@ -29,6 +29,16 @@ def _req(t: torch.Tensor, dtype, name: str) -> None:
         raise _lib.FordeError(f"{name} must be contiguous")
 
 
+def _req_rows(t: torch.Tensor, dtype, name: str) -> None:
+    """A 2-D GEMM operand: unit column stride and a 16-byte aligned row pitch (TMA); rows need not be packed."""
+    if not t.is_cuda:
+        raise _lib.FordeError(f"{name} must be a CUDA tensor (the FORDE hot path has no CPU fallback)")
+    if t.dtype != dtype:
+        raise _lib.FordeError(f"{name} must be {dtype}, got {t.dtype}")
+    if t.dim() != 2 or t.stride(1) != 1 or (t.shape[0] > 1 and t.stride(0) < t.shape[1]):
+        raise _lib.FordeError(f"{name} must be a 2-D tensor with contiguous rows")
+
+
 # ---- optional per-kernel CUDA-event timing (bench.py's live roofline measurement); off by default -----------
 _TIMING = None
 
@@ -108,7 +118,7 @@ def gemm_bf16(A: torch.Tensor, B: torch.Tensor, a_mn_major: bool, b_mn_major: bo
     """D[M,N] = sum_k A(m,k) B(n,k) (+ bias_col) -> bf16.  K-major operands are [rows, K]; MN-major operands are
     [K, rows].  With ``add_to`` (a contiguous bf16 [M, N] tensor, N % 8 == 0) the product is accumulated into it in
     place and it is returned."""
-    _req(A, torch.bfloat16, "A"); _req(B, torch.bfloat16, "B")
+    _req_rows(A, torch.bfloat16, "A"); _req_rows(B, torch.bfloat16, "B")
     M, K = (A.shape[1], A.shape[0]) if a_mn_major else (A.shape[0], A.shape[1])
     N, Kb = (B.shape[1], B.shape[0]) if b_mn_major else (B.shape[0], B.shape[1])
     assert K == Kb, "reduction extents differ"
@@ -131,7 +141,7 @@ def gemm_bf16(A: torch.Tensor, B: torch.Tensor, a_mn_major: bool, b_mn_major: bo
 
 
 def gemm_f32(A, B, a_mn_major, b_mn_major, out=None, scale=1.0, accumulate=False, row_scale=None, col_scale=None):
-    _req(A, torch.bfloat16, "A"); _req(B, torch.bfloat16, "B")
+    _req_rows(A, torch.bfloat16, "A"); _req_rows(B, torch.bfloat16, "B")
     M, K = (A.shape[1], A.shape[0]) if a_mn_major else (A.shape[0], A.shape[1])
     N, Kb = (B.shape[1], B.shape[0]) if b_mn_major else (B.shape[0], B.shape[1])
     assert K == Kb, "reduction extents differ"
@@ -439,6 +449,61 @@ def add_layernorm_bwd(dy, x, r, gamma, mean, rstd, d_gamma=None, d_beta=None):
                                              d_gamma.data_ptr(), d_beta.data_ptr(), rows, cols)
     _lib.check(rc, "forde_add_layernorm_bwd")
     return ds, d_gamma, d_beta
+
+
+# ------------------------------------------------------------------------------------------ tower front ends
+def patchify(images, patch: int):
+    """images (B, S, S, 3) bf16 NHWC -> patch rows (B * g * g, round_up(p*p*3, 8)) bf16, first p*p*3 columns valid."""
+    _req(images, torch.bfloat16, "images")
+    B, S = images.shape[0], images.shape[1]
+    g = S // patch
+    k = patch * patch * 3
+    ld = round_up(k, 8)
+    out = torch.empty((B * g * g, ld), dtype=torch.bfloat16, device=images.device)
+    rc = _lib.load().forde_patchify(_stream(), images.data_ptr(), out.data_ptr(), ld, B, S, patch)
+    _lib.check(rc, "forde_patchify")
+    return out[:, :k]
+
+
+def vision_assemble_fwd(tok, cls16, pos16, B: int):
+    _req(tok, torch.bfloat16, "patch tokens"); _req(cls16, torch.bfloat16, "cls"); _req(pos16, torch.bfloat16, "pos_embed")
+    G, w = tok.shape[0] // B, tok.shape[1]
+    x = torch.empty((B, G + 1, w), dtype=torch.bfloat16, device=tok.device)
+    rc = _lib.load().forde_vision_assemble_fwd(_stream(), tok.data_ptr(), cls16.data_ptr(), pos16.data_ptr(), x.data_ptr(),
+                                               B, G, w)
+    _lib.check(rc, "forde_vision_assemble_fwd")
+    return x
+
+
+def vision_assemble_bwd(dx, d_cls, d_pos):
+    """dx (B, G+1, w) bf16 -> d_patch_tok (B*G, w) bf16; d_cls (w,), d_pos (G+1, w) fp32 accumulated into."""
+    _req(dx, torch.bfloat16, "dx"); _req(d_cls, torch.float32, "d_cls"); _req(d_pos, torch.float32, "d_pos")
+    B, T, w = dx.shape
+    d_tok = torch.empty((B * (T - 1), w), dtype=torch.bfloat16, device=dx.device)
+    rc = _lib.load().forde_vision_assemble_bwd(_stream(), dx.data_ptr(), d_tok.data_ptr(), d_cls.data_ptr(),
+                                               d_pos.data_ptr(), B, T - 1, w)
+    _lib.check(rc, "forde_vision_assemble_bwd")
+    return d_tok
+
+
+def embed_tokens_fwd(ids, table16, pos16):
+    _req(ids, torch.int32, "input_ids"); _req(table16, torch.bfloat16, "token_embed"); _req(pos16, torch.bfloat16, "pos_embed")
+    B, T = ids.shape
+    V, w = table16.shape
+    x = torch.empty((B, T, w), dtype=torch.bfloat16, device=ids.device)
+    rc = _lib.load().forde_embed_tokens_fwd(_stream(), ids.data_ptr(), table16.data_ptr(), pos16.data_ptr(), x.data_ptr(),
+                                            B, T, w, V)
+    _lib.check(rc, "forde_embed_tokens_fwd")
+    return x
+
+
+def embed_tokens_bwd(ids, dx, d_table, d_pos):
+    _req(ids, torch.int32, "input_ids"); _req(dx, torch.bfloat16, "dx")
+    _req(d_table, torch.float32, "d_table"); _req(d_pos, torch.float32, "d_pos")
+    B, T, w = dx.shape
+    rc = _lib.load().forde_embed_tokens_bwd(_stream(), ids.data_ptr(), dx.data_ptr(), d_table.data_ptr(), d_pos.data_ptr(),
+                                            B, T, w, d_table.shape[0])
+    _lib.check(rc, "forde_embed_tokens_bwd")
 
 
 # ------------------------------------------------------------------------------------------ MoE variant

@@ -269,6 +269,27 @@ int forde_adamw_clip_step(void* stream, float* p32, const float* g32, const void
                           float b2, float eps, float wd, const int* step_count, float* grad_norm_out);
 int forde_cast_f32_bf16(void* stream, const float* src, void* dst, long long n);
 
+/* ---- front ends of the two towers (README.md:30-34; layouts of src/data/download_to_drive.py:106-108,
+ *      171-178: image (S,S,3) NHWC, input_ids int32).  HBM-bound gathers / scatters; the patch-embedding and projection
+ *      head GEMMs run on forde_gemm_bf16 / forde_gemm_f32.  Gradients are accumulated (fp32 red.add) into the caller's
+ *      buffers like every other weight gradient.
+ *   patchify:            patches[b*g*g + gy*g + gx][(py*p + px)*3 + ch] = images[b][gy*p+py][gx*p+px][ch], g = S/p;
+ *                        ld = output row pitch in elements (>= p*p*3; round it up to 8 for the GEMM)
+ *   vision_assemble_fwd: x[b][0] = cls + pos[0]; x[b][1+i] = patch_tok[b*G + i] + pos[1+i]       (bf16, w % 8 == 0)
+ *   vision_assemble_bwd: d_patch_tok[b*G+i] = dx[b][1+i]; d_pos[t] += sum_b dx[b][t]; d_cls += sum_b dx[b][0]
+ *                        (d_patch_tok, d_cls, d_pos may each be NULL)
+ *   embed_tokens_fwd:    x[b][t] = table[ids[b][t]] + pos[t]   (ids clamped into [0, V))
+ *   embed_tokens_bwd:    d_table[ids[b][t]] += dx[b][t]; d_pos[t] += sum_b dx[b][t]   (d_pos may be NULL) */
+int forde_patchify(void* stream, const void* images, void* patches, long long ld, int B, int S, int p);
+int forde_vision_assemble_fwd(void* stream, const void* patch_tok, const void* cls, const void* pos, void* x, int B,
+                              int G, int w);
+int forde_vision_assemble_bwd(void* stream, const void* dx, void* d_patch_tok, float* d_cls, float* d_pos, int B, int G,
+                              int w);
+int forde_embed_tokens_fwd(void* stream, const int* ids, const void* table, const void* pos, void* x, int B, int T,
+                           int w, int V);
+int forde_embed_tokens_bwd(void* stream, const int* ids, const void* dx, float* d_table, float* d_pos, int B, int T,
+                           int w, int V);
+
 #ifdef __cplusplus
 }
 #endif

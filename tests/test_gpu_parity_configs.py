@@ -253,3 +253,57 @@ def test_train_state_takes_one_optax_step_per_batch(ops):
     np.testing.assert_allclose(f32(st.opt_state["mu"]), rmu, rtol=2e-6, atol=1e-12)
     assert int(st.opt_state["count"].item()) == 1 and st.step == 1
     assert torch.equal(st.flat_p16, st.flat_p32.detach().bfloat16())
+
+
+# ------------------------------------------------------------------------------------------ tower front ends (8(f)-3)
+@pytest.mark.parametrize("B,S,p,w", [(4, 32, 16, 128), (3, 224, 16, 768), (2, 224, 14, 1024)])
+def test_vision_front_end_matches_plain_restatement(ops, B, S, p, w):
+    """patchify -> patch-embedding GEMM -> +CLS, +pos (README.md:30-34) against a plain torch restatement (reshape /
+    permute / matmul / cat in fp32 on the same bf16 inputs), forward and backward.  patchify is pure data movement:
+    bit-exact.  p = 14 exercises the 588-wide (not 16-byte) patch rows of ViT-L/14."""
+    from forde_b200.dual_encoder import _Dense, _VisionAssemble
+    g_ = torch.Generator(device="cuda").manual_seed(B * S)
+    g, k = S // p, p * p * 3
+    img = torch.randn((B, S, S, 3), device="cuda", generator=g_).bfloat16()
+    patches = ops.patchify(img, p)
+    ref_patches = img.view(B, g, p, g, p, 3).permute(0, 1, 3, 2, 4, 5).reshape(B * g * g, k)
+    assert torch.equal(patches, ref_patches)
+    wk = (torch.randn((k, w), device="cuda", generator=g_) / k ** 0.5).requires_grad_(True)
+    bk = (torch.randn(w, device="cuda", generator=g_) * 0.1).requires_grad_(True)
+    cls = (torch.randn(w, device="cuda", generator=g_) * 0.02).requires_grad_(True)
+    pos = (torch.randn((g * g + 1, w), device="cuda", generator=g_) * 0.02).requires_grad_(True)
+    tok = _Dense.apply(patches, wk, bk, wk.detach().bfloat16(), None)
+    x = _VisionAssemble.apply(tok, cls, pos, cls.detach().bfloat16(), pos.detach().bfloat16(), B)
+    dx = torch.randn(x.shape, device="cuda", generator=g_).bfloat16()
+    x.backward(dx)
+    torch.cuda.synchronize()
+    # restatement
+    wr = wk.detach().bfloat16().float().requires_grad_(True); br = bk.detach().clone().requires_grad_(True)
+    cr = cls.detach().bfloat16().float().requires_grad_(True); pr = pos.detach().bfloat16().float().requires_grad_(True)
+    tok_r = (ref_patches.float() @ wr + br).bfloat16().float()
+    tok_r = tok_r + ((ref_patches.float() @ wr + br) - (ref_patches.float() @ wr + br).detach())   # straight-through rounding
+    x_r = torch.cat([cr.expand(B, 1, w), tok_r.view(B, g * g, w)], 1) + pr
+    x_r.backward(dx.float())
+    assert_close_bf16(f32(x), f32(x_r.detach().bfloat16().float()), "x")
+    assert relerr(f32(wk.grad), f32(wr.grad)) < 2e-3 and relerr(f32(bk.grad), f32(br.grad)) < 2e-3
+    assert relerr(f32(cls.grad), f32(cr.grad)) < 1e-3 and relerr(f32(pos.grad), f32(pr.grad)) < 1e-3
+
+
+def test_token_embedding_front_end_matches_plain_restatement(ops):
+    """x = token_embed[ids] + pos_embed (README.md:30-34) and its scatter-add backward against torch's embedding."""
+    from forde_b200.dual_encoder import _TokenEmbed
+    B, T, w, V = 64, 77, 512, 30522
+    g_ = torch.Generator(device="cuda").manual_seed(3)
+    ids = torch.randint(0, V, (B, T), device="cuda", generator=g_, dtype=torch.int32)
+    ids[:, 0] = 101                                            # a token shared by every caption ([CLS]): hot row
+    table = (torch.randn((V, w), device="cuda", generator=g_) * 0.02).requires_grad_(True)
+    pos = (torch.randn((T, w), device="cuda", generator=g_) * 0.01).requires_grad_(True)
+    x = _TokenEmbed.apply(ids, table, pos, table.detach().bfloat16(), pos.detach().bfloat16())
+    dx = torch.randn(x.shape, device="cuda", generator=g_).bfloat16()
+    x.backward(dx)
+    torch.cuda.synchronize()
+    tr = table.detach().bfloat16().float().requires_grad_(True); pr = pos.detach().bfloat16().float().requires_grad_(True)
+    x_r = torch.nn.functional.embedding(ids.long(), tr) + pr
+    x_r.backward(dx.float())
+    assert torch.equal(x, x_r.detach().bfloat16())             # one fp32 add, one rounding: bit-exact
+    assert relerr(f32(table.grad), f32(tr.grad)) < 1e-5 and relerr(f32(pos.grad), f32(pr.grad)) < 1e-5
