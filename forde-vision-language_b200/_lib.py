@@ -43,7 +43,7 @@ SIGNATURES = {
     "forde_colsum_bf16": (_i, [_vp, _vp, _ll, _vp, _i, _i]),
     "forde_sl_bwd": (_i, [_vp] * 15 + [_i, _i, _i, _ll]),
     "forde_sl_topk_sparsify": (_i, [_vp, _vp, _ll, _i, _i, _i, _vp, _vp, _vp]),
-    "forde_sl_topk_mask": (_i, [_vp, _vp, _ll, _i, _i, _vp, _vp]),
+    "forde_sl_dz_bwd_topk": (_i, [_vp] * 11 + [_i, _i, _i, _ll]),
     "forde_stats_finalize": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "forde_stats_from_moments": (_i, [_vp, _vp, _vp, _i, _vp]),
     "forde_clip_fwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i] + [_vp] * 10),
@@ -66,7 +66,7 @@ SIGNATURES = {
     "forde_add_layernorm_bwd": (_i, [_vp] * 11 + [_i, _i]),
     "forde_optim_num_partials": (_i, [_ll]),
     "forde_grad_sqnorm": (_i, [_vp, _vp, _vp, _ll, _vp, _vp]),
-    "forde_adamw_clip_step": (_i, [_vp] * 7 + [_ll, _vp, _i, _f, _f, _f, _f, _f, _f, _vp, _vp]),
+    "forde_adamw_clip_step": (_i, [_vp] * 7 + [_ll, _vp, _i] + [ctypes.c_double] * 6 + [_vp, _vp]),
     "forde_cast_f32_bf16": (_i, [_vp, _vp, _vp, _ll]),
     "forde_patchify": (_i, [_vp, _vp, _vp, _ll, _i, _i, _i]),
     "forde_vision_assemble_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i]),

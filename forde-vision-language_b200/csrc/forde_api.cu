@@ -169,9 +169,21 @@ static int launch_inst(const GemmParams& p, cudaStream_t stream) {
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
+  GemmParams q = p;
+  q.clc = 0;
   if (PAIR) {
+    // dynamic scheduling: one cluster per work item, resident clusters take over the not yet launched ones
+    // (forde_gemm.cuh, "Tile scheduling"); FORDE_CLC=0 restores the static persistent grid for A/B runs
+    static const bool clc_on = [] {
+      const char* e = std::getenv("FORDE_CLC");
+      return e == nullptr || std::atoi(e) != 0;
+    }();
     int pairs = sms / 2;
     if (total < pairs) pairs = total;
+    if (clc_on && total > pairs) {
+      pairs = total;
+      q.clc = 1;
+    }
     cfg.gridDim = dim3(2 * pairs);
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2;
@@ -182,7 +194,7 @@ static int launch_inst(const GemmParams& p, cudaStream_t stream) {
   } else {
     cfg.gridDim = dim3(total < sms ? total : sms);
   }
-  cudaError_t e = cudaLaunchKernelEx(&cfg, forde_gemm_kernel<A_MN, B_MN, EPI, PAIR>, p);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, forde_gemm_kernel<A_MN, B_MN, EPI, PAIR>, q);
   if (e != cudaSuccess) {
     record_cuda_error("cudaLaunchKernelEx(forde_gemm_kernel)", cudaGetErrorString(e));
     return FORDE_ECUDA;
@@ -456,7 +468,7 @@ int forde_sl_fwd(void* stream, const void* x, const void* w_up, const float* b_u
 // dzT[H][M] = (dy . w_down^T)^T * (F'(z) + gate) : A = w_down [H][d] (m = neuron, k = d) K-major ; B = dy [M][d] K-major
 static int sl_dz_bwd_impl(void* stream, const void* dy, const void* w_down, const void* zT, const void* hT,
                           const uint32_t* sign_bits, const int8_t* assign, void* dzT, float* grad_partials, int M,
-                          int d, int H, long long ldz) {
+                          int d, int H, long long ldz, const uint32_t* keep_bits = nullptr) {
   if (assign == nullptr || zT == nullptr || dzT == nullptr || ldz < M) return FORDE_EINVAL;
   if (hT == nullptr && sign_bits == nullptr) return FORDE_EINVAL;
   if (sign_bits != nullptr && (reinterpret_cast<uintptr_t>(sign_bits) & 15) != 0) return FORDE_EALIGN;
@@ -475,6 +487,7 @@ static int sl_dz_bwd_impl(void* stream, const void* dy, const void* w_down, cons
   p.partials = grad_partials;
   p.sign_bits = const_cast<uint32_t*>(sign_bits);
   p.sign_ld = forde_sl_sign_words(M);
+  p.keep_bits = keep_bits;
   return launch_epi<EPI_DZ_BWD>(p, false, false, static_cast<cudaStream_t>(stream));
 }
 
@@ -489,6 +502,14 @@ int forde_sl_dz_bwd_signs(void* stream, const void* dy, const void* w_down, cons
                           int d, int H, long long ldz) {
   if (sign_bits == nullptr) return FORDE_EINVAL;
   return sl_dz_bwd_impl(stream, dy, w_down, zT, nullptr, sign_bits, assign, dzT, grad_partials, M, d, H, ldz);
+}
+
+int forde_sl_dz_bwd_topk(void* stream, const void* dy, const void* w_down, const void* zT, const void* hT,
+                         const uint32_t* sign_bits, const uint32_t* keep_bits, const int8_t* assign, void* dzT,
+                         float* grad_partials, int M, int d, int H, long long ldz) {
+  if (keep_bits == nullptr || (hT == nullptr && sign_bits == nullptr)) return FORDE_EINVAL;
+  return sl_dz_bwd_impl(stream, dy, w_down, zT, sign_bits != nullptr ? nullptr : hT, sign_bits, assign, dzT,
+                        grad_partials, M, d, H, ldz, keep_bits);
 }
 
 // dx[M][d] = dz . w_up^T : A = dzT [H][M] (m = sample, k = neuron) MN-major ; B = w_up [d][H] (n = d, k = neuron) K-major

@@ -452,10 +452,13 @@ int forde_l2norm_bwd(void* stream, const void* u, const float* inv_norm, const f
 // Optional (off by default): per token keep the k largest |h| over the H neurons, zero the rest.  hT is neuron-major
 // [H][ld]; a block stages 16 token columns x H neurons in shared memory, one warp per token then
 //   1. finds the k-th largest magnitude by a 15-step bitwise radix search on the bf16 magnitude bits,
-//   2. keeps everything above it and the lowest-indexed ties (jax.lax.top_k tie rule), zeroes the rest of hT in
-//      place and records a kept-bitmask [ceil(H/32)][M] for the backward,
+//   2. keeps everything above it and the lowest-indexed ties (jax.lax.top_k tie rule), zeroes the rest IN THE STAGED
+//      TILE and records a kept-bitmask [ceil(H/32)][M] (consumed by the dz epilogue of the backward GEMM: no
+//      masking pass over dz^T, and the gradient statistics are taken of the masked dL/dz directly),
 //   3. writes the kept indices ordered like lax.top_k (|value| descending, equal -> lower index first) and the
-//      per-token Hoyer sparsity of the dense h (sensing.py:5-32 formula over the H axis).
+//      per-token Hoyer sparsity of the dense h (sensing.py:5-32 formula over the H axis);
+// the block then writes the masked tile back with the access pattern it was read with (32-byte runs per neuron row):
+// one read and one write of h^T in total, no scattered 2-byte read-modify-writes.
 namespace forde {
 
 constexpr int TK_TOK = 16;  // tokens per block (one warp each)
@@ -475,104 +478,86 @@ topk_sparsify_kernel(__nv_bfloat16* __restrict__ hT, long long ld, int M, int H,
   }
   __syncthreads();
   const int m = m0 + warp;
-  if (m >= M) return;
-  const uint16_t* col = tile + warp * H;
-  int* scratch = scratch_all + warp * k;
-  float l1 = 0.f, l2 = 0.f;
-  for (int h = lane; h < H; h += 32) {
-    const float v = __uint_as_float(static_cast<uint32_t>(col[h]) << 16);
-    l1 += fabsf(v);
-    l2 = fmaf(v, v, l2);
-  }
-  l1 = warp_sum(l1);
-  l2 = sqrtf(warp_sum(l2));
-  if (lane == 0 && hoyer_out != nullptr) {
-    const float sn = sqrtf(static_cast<float>(H));
-    hoyer_out[m] = (H == 1 || l2 == 0.f) ? 0.f : (sn - l1 / l2) / (sn - 1.f);
-  }
-  // 1. radix search: after the loop `thr` is the key of the k-th largest magnitude and `need` of the elements equal
-  //    to it are kept
-  uint32_t thr = 0;
-  int need = k;
-  for (int bit = 14; bit >= 0; --bit) {
-    const uint32_t cand = thr | (1u << bit);
-    const uint32_t hi_mask = (~((1u << bit) - 1u)) & 0x7FFFu;
-    int cnt = 0;
-    for (int h = lane; h < H; h += 32) cnt += (((static_cast<uint32_t>(col[h]) & 0x7FFFu) & hi_mask) == cand) ? 1 : 0;
+  if (m < M) {
+    uint16_t* col = tile + warp * H;
+    int* scratch = scratch_all + warp * k;
+    float l1 = 0.f, l2 = 0.f;
+    for (int h = lane; h < H; h += 32) {
+      const float v = __uint_as_float(static_cast<uint32_t>(col[h]) << 16);
+      l1 += fabsf(v);
+      l2 = fmaf(v, v, l2);
+    }
+    l1 = warp_sum(l1);
+    l2 = sqrtf(warp_sum(l2));
+    if (lane == 0 && hoyer_out != nullptr) {
+      const float sn = sqrtf(static_cast<float>(H));
+      hoyer_out[m] = (H == 1 || l2 == 0.f) ? 0.f : (sn - l1 / l2) / (sn - 1.f);
+    }
+    // 1. radix search: after the loop `thr` is the key of the k-th largest magnitude and `need` of the elements
+    //    equal to it are kept
+    uint32_t thr = 0;
+    int need = k;
+    for (int bit = 14; bit >= 0; --bit) {
+      const uint32_t cand = thr | (1u << bit);
+      const uint32_t hi_mask = (~((1u << bit) - 1u)) & 0x7FFFu;
+      int cnt = 0;
+      for (int h = lane; h < H; h += 32) cnt += (((static_cast<uint32_t>(col[h]) & 0x7FFFu) & hi_mask) == cand) ? 1 : 0;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
-    if (cnt >= need) thr = cand;
-    else need -= cnt;
-  }
-  // 2. keep mask, in-place zeroing, unsorted list of kept indices (ascending index) in shared scratch
-  int n_kept = 0, n_tie = 0;
-  for (int h0 = 0; h0 < H; h0 += 32) {
-    const int h = h0 + lane;
-    const uint32_t key = (h < H) ? (static_cast<uint32_t>(col[h]) & 0x7FFFu) : 0u;
-    const bool above = (h < H) && key > thr;
-    const bool tie = (h < H) && key == thr;
-    const unsigned bt = __ballot_sync(0xffffffffu, tie);
-    const bool keep = above || (tie && (n_tie + __popc(bt & ((1u << lane) - 1u))) < need);
-    const unsigned bk = __ballot_sync(0xffffffffu, keep);
-    if (keep) scratch[n_kept + __popc(bk & ((1u << lane) - 1u))] = h;
-    if (h < H && !keep) h16[static_cast<size_t>(h) * ld + m] = 0;
-    if (keep_bits != nullptr && lane == 0) keep_bits[static_cast<size_t>(h0 >> 5) * M + m] = bk;
-    n_kept += __popc(bk);
-    n_tie += __popc(bt);
-  }
-  __syncwarp();
-  // 3. lax.top_k order by counting rank: (|value| descending, index ascending); ranks are a permutation of 0..k-1
-  if (idx_out != nullptr) {
-    for (int a = lane; a < k; a += 32) {
-      const int ia = scratch[a];
-      const uint32_t ka = static_cast<uint32_t>(col[ia]) & 0x7FFFu;
-      int rank = 0;
-      for (int b = 0; b < k; ++b) {
-        const int ib = scratch[b];
-        const uint32_t kb = static_cast<uint32_t>(col[ib]) & 0x7FFFu;
-        rank += (kb > ka || (kb == ka && ib < ia)) ? 1 : 0;
+      for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+      if (cnt >= need) thr = cand;
+      else need -= cnt;
+    }
+    // 2. keep mask and the unsorted list of kept indices (ascending index) in shared scratch.  The ranking of step 3
+    //    needs the kept magnitudes, so dropped entries are zeroed in the tile only after it (`drop` remembers them:
+    //    one bit per 32-neuron group and lane).
+    int n_kept = 0, n_tie = 0;
+    for (int h0 = 0; h0 < H; h0 += 32) {
+      const int h = h0 + lane;
+      const uint32_t key = (h < H) ? (static_cast<uint32_t>(col[h]) & 0x7FFFu) : 0u;
+      const bool above = (h < H) && key > thr;
+      const bool tie = (h < H) && key == thr;
+      const unsigned bt = __ballot_sync(0xffffffffu, tie);
+      const bool keep = above || (tie && (n_tie + __popc(bt & ((1u << lane) - 1u))) < need);
+      const unsigned bk = __ballot_sync(0xffffffffu, keep);
+      if (keep) scratch[n_kept + __popc(bk & ((1u << lane) - 1u))] = h;
+      if (keep_bits != nullptr && lane == 0) keep_bits[static_cast<size_t>(h0 >> 5) * M + m] = bk;
+      n_kept += __popc(bk);
+      n_tie += __popc(bt);
+    }
+    __syncwarp();
+    // 3. lax.top_k order by counting rank: (|value| descending, index ascending); ranks are a permutation of 0..k-1
+    if (idx_out != nullptr) {
+      for (int a = lane; a < k; a += 32) {
+        const int ia = scratch[a];
+        const uint32_t ka = static_cast<uint32_t>(col[ia]) & 0x7FFFu;
+        int rank = 0;
+        for (int b = 0; b < k; ++b) {
+          const int ib = scratch[b];
+          const uint32_t kb = static_cast<uint32_t>(col[ib]) & 0x7FFFu;
+          rank += (kb > ka || (kb == ka && ib < ia)) ? 1 : 0;
+        }
+        idx_out[static_cast<size_t>(m) * k + rank] = ia;
       }
-      idx_out[static_cast<size_t>(m) * k + rank] = ia;
+    }
+    __syncwarp();
+    // 4. zero the dropped entries in the staged tile: everything below the threshold, and the ties beyond the first
+    //    `need` (the same walk as step 2)
+    n_tie = 0;
+    for (int h0 = 0; h0 < H; h0 += 32) {
+      const int h = h0 + lane;
+      const uint32_t key = (h < H) ? (static_cast<uint32_t>(col[h]) & 0x7FFFu) : 0u;
+      const bool tie = (h < H) && key == thr;
+      const unsigned bt = __ballot_sync(0xffffffffu, tie);
+      const bool keep = (h < H) && (key > thr || (tie && (n_tie + __popc(bt & ((1u << lane) - 1u))) < need));
+      if (h < H && !keep) col[h] = 0;
+      n_tie += __popc(bt);
     }
   }
-}
-
-// dzT[h][m] = 0 where the forward dropped h[h][m]; optionally re-takes the per-neuron gradient sums of the MASKED dz
-// in the layout of the GEMM epilogue's partials ([P][3][H], one slot per `sps` samples).  One warp per (neuron,
-// slot), sps / 32 samples per lane.
-__global__ void topk_mask_kernel(__nv_bfloat16* __restrict__ dzT, long long ld, int M, int H,
-                                 const uint32_t* __restrict__ keep_bits, float* __restrict__ partials, int sps) {
-  const int lane = threadIdx.x & 31;
-  const int h = blockIdx.y * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  const int pb = blockIdx.x;  // slot (block of sps samples)
-  if (h >= H) return;
-  float s_abs = 0.f, s_sum = 0.f, s_sq = 0.f;
-  for (int i = 0; i < sps / 32; ++i) {
-    const int m = pb * sps + i * 32 + lane;
-    if (m < M) {
-      const uint32_t w = keep_bits[static_cast<size_t>(h >> 5) * M + m];
-      uint16_t* p = reinterpret_cast<uint16_t*>(dzT) + static_cast<size_t>(h) * ld + m;
-      uint16_t bits = *p;
-      if (((w >> (h & 31)) & 1u) == 0u) {
-        bits = 0;
-        *p = 0;
-      }
-      const float v = __uint_as_float(static_cast<uint32_t>(bits) << 16);
-      s_abs += fabsf(v);
-      s_sum += v;
-      s_sq = fmaf(v, v, s_sq);
-    }
-  }
-  if (partials != nullptr) {
-    s_abs = warp_sum(s_abs);
-    s_sum = warp_sum(s_sum);
-    s_sq = warp_sum(s_sq);
-    if (lane == 0) {
-      float* dst = partials + (static_cast<size_t>(pb) * 3) * H + h;
-      dst[0] = s_abs;
-      dst[H] = s_sum;
-      dst[2 * static_cast<size_t>(H)] = s_sq;
-    }
+  __syncthreads();
+  for (int i = threadIdx.x; i < H * TK_TOK; i += blockDim.x) {  // masked tile back, same runs as the load
+    const int h = i / TK_TOK, t = i - h * TK_TOK;
+    const int mm = m0 + t;
+    if (mm < M) h16[static_cast<size_t>(h) * ld + mm] = tile[t * H + h];
   }
 }
 
@@ -593,16 +578,6 @@ int forde_sl_topk_sparsify(void* stream, void* hT, long long ldz, int M, int H, 
                                 static_cast<cudaStream_t>(stream)>>>(static_cast<__nv_bfloat16*>(hT), ldz, M, H, k,
                                                                      idx_out, hoyer_out, keep_bits);
   return forde::check_launch("topk_sparsify_kernel");
-}
-
-int forde_sl_topk_mask(void* stream, void* dzT, long long ldz, int M, int H, const uint32_t* keep_bits,
-                       float* grad_partials) {
-  if (dzT == nullptr || keep_bits == nullptr || M <= 0 || H <= 0 || ldz < M) return FORDE_EINVAL;
-  const int P = forde_sl_num_partials(M);             // slots (trailing ones beyond M get zeros)
-  const int sps = 256 / forde_sl_num_partials(256);   // samples per slot: the GEMM epilogues' partials layout
-  forde::topk_mask_kernel<<<dim3(P, (H + 7) / 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<__nv_bfloat16*>(dzT), ldz, M, H, keep_bits, grad_partials, sps);
-  return forde::check_launch("topk_mask_kernel");
 }
 
 }  // extern "C"

@@ -22,6 +22,19 @@
 // The accumulator is double buffered in TMEM (2 x 256 columns) so the epilogue of tile i overlaps the
 // main loop of tile i+1.
 //
+// Tile scheduling.  Static (single-CTA instantiations, grouped MoE modes): one CTA per SM, work item t = worker,
+// worker + #workers, ...  Dynamic (CTA-pair instantiations, `clc`): the grid has ONE CLUSTER PER WORK ITEM, a cluster
+// processes its own item and then keeps asking the hardware for further, not yet launched clusters of the grid
+// (clusterlaunchcontrol.try_cancel, SASS UGETNEXTWORKID) and does their work too.  Resident clusters therefore behave
+// like a persistent grid (prologue once per SM), but the schedule adapts to SMs that are not available: when an NCCL
+// kernel of the overlapped gradient exchange holds some SMs, the clusters that cannot become resident there simply never
+// start and their tiles are taken by the others, instead of delaying a static 1/74 share of the tiles to the end of the
+// kernel (measured round 2: +1.4 ms per step at 2 GPUs whatever NCCL's footprint, profiles/r2_n2_*.md).
+// The leader CTA's producer thread issues the query for item j+1 when it STARTS loading item j (one item of
+// lookahead, so early clusters cannot hoard work); the response is multicast into a 4-slot ring in both CTAs and
+// every role (2 producers, MMA issuer, 2 x 8 epilogue warps) consumes every response once, releasing the slot on the
+// leader's `clc_empty` barrier.
+//
 // Either operand may be K-major (reduction index contiguous in global memory) or MN-major (row index
 // contiguous); the smem tile layout and the UMMA descriptors are derived from that, so no operand is ever
 // transposed in HBM.
@@ -72,6 +85,7 @@ __host__ __device__ constexpr int stage_bytes(bool pair) { return A_TILE_BYTES +
 constexpr int CHUNK = 64;                         // epilogue column chunk (one 128-byte bf16 row)
 constexpr int BOX_BYTES = 32 * CHUNK * 2;         // one warp's staging box: 32 rows x 64 bf16 = 4 KB
 constexpr int TMEM_COLS = 512;
+constexpr int CLC_SLOTS = 4;                      // ring of cluster-launch-control responses (dynamic scheduling)
 // Epilogue warps per CTA.  The fused epilogues are instruction/latency heavy (bf16 round trip, multiplex, gate FMA,
 // three running sums per element); 8 warps = 2 per SM sub-partition, 16 = 4 (one 64-column chunk each per tile).
 // More warps cost staging smem, i.e. main-loop stages; the trade-off differs per kernel, see below.
@@ -157,8 +171,9 @@ __host__ __device__ constexpr int gemm_stages(int epi, bool pair) {
                                                     : (pair ? 6 : 4);
 }
 __host__ __device__ constexpr int gemm_smem_bytes(int epi, bool pair) {
-  // ring + staging + column bias (BN fp32) + barriers/pointers (512 B) + 1 KB alignment slack
-  return gemm_stages(epi, pair) * stage_bytes(pair) + epi_warps(epi, pair) * epi_warp_staging_bytes(epi, pair) + BN * 4 + 512 + 1024;
+  // ring + staging + column bias (BN fp32) + barriers/pointers (512 B) + CLC responses (64 B, padded to 128)
+  // + 1 KB alignment slack
+  return gemm_stages(epi, pair) * stage_bytes(pair) + epi_warps(epi, pair) * epi_warp_staging_bytes(epi, pair) + BN * 4 + 512 + 128 + 1024;
 }
 static_assert(gemm_smem_bytes(EPI_STORE, false) <= 232448 && gemm_smem_bytes(EPI_STORE, true) <= 232448, "smem");
 static_assert(gemm_smem_bytes(EPI_UP_FWD, false) <= 232448 && gemm_smem_bytes(EPI_UP_FWD, true) <= 232448, "smem");
@@ -178,6 +193,7 @@ struct GemmParams {
   int split_k, kb_per_split;
   int raster_m_fast;  // 1: consecutive work items walk M first (share the B slab), 0: walk N first
   int pair;           // 1: launched as 2-CTA clusters (256-row tiles, cta_group::2)
+  int clc;            // 1: one cluster per work item + cluster launch control (pair kernels only), 0: static schedule
   int save_z;         // EPI_UP_FWD: 1 = store every z box; 0 = only the boxes the backward needs (warps with tanh neurons)
   // Optional sign bits of z, word-major [sign_ld words][M rows = neurons] u32; word w of a neuron covers samples
   // 32 w .. 32 w + 31 in the interleaved bit order described at sign_index() (forde_sl_sign_layout() == 3).
@@ -185,6 +201,9 @@ struct GemmParams {
   // per neuron and 64-sample chunk instead of TMA-loading the h^T box (1/16 of the bytes).  Null = off.
   uint32_t* sign_bits;
   int sign_ld;        // row pitch in u32 words: 8 * ceil(N / 256)
+  // EPI_DZ_BWD, top-k mode (D8): kept mask of the forward, [ceil(M / 32)][N] u32, bit (row % 32) of word
+  // [row / 32][col] = neuron `row` of sample `col` survived.  Null = off.
+  const uint32_t* keep_bits;
   // grouped modes (MoE experts); all null / 0 otherwise
   const int* m_blocks_dev;     // grouped-M: number of valid 128-row blocks (device scalar)
   const int* group_of_mblock;  // grouped-M: expert of each 128-row block
@@ -320,9 +339,11 @@ __device__ __forceinline__ void up_fwd_8(const uint32_t* v, float bias_r, const 
 // backward, 8 columns: dz = acc * (F_a'(z) + gate_a).  Samples beyond N have acc == 0 exactly (TMA zero fill), so
 // they add nothing to the sums and need no masking.  m_pos / m_neg are the per-neuron multipliers for z > 0 / z <= 0:
 // relu (1 + gate, gate), binary step with the straight-through estimator (1 + gate both), tanh computed per element.
-template <bool HAS_TANH>
+// KEEP: top-k activation sparsification (D8) -- bit c of `keep8` says whether column c of these 8 survived the
+// forward's per-token top-k; dropped entries have h = 0 downstream, so their dL/dz is zero.
+template <bool HAS_TANH, bool KEEP>
 __device__ __forceinline__ void dz_bwd_8(const uint32_t* v, const uint32_t* zw, float m_pos, float m_neg,
-                                         const ActConst& act, uint32_t* dw, RunningSums& rs) {
+                                         const ActConst& act, uint32_t* dw, RunningSums& rs, uint32_t keep8) {
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const float z0 = bf16lo_to_f32(zw[i]), z1 = bf16hi_to_f32(zw[i]);
@@ -332,6 +353,10 @@ __device__ __forceinline__ void dz_bwd_8(const uint32_t* v, const uint32_t* zw, 
       const float t0 = tanh_approx(z0), t1 = tanh_approx(z1);
       m0 = act.is_tanh ? (fmaf(-t0, t0, 1.f) + act.gate) : m0;
       m1 = act.is_tanh ? (fmaf(-t1, t1, 1.f) + act.gate) : m1;
+    }
+    if (KEEP) {
+      m0 = (keep8 >> (2 * i)) & 1u ? m0 : 0.f;
+      m1 = (keep8 >> (2 * i + 1)) & 1u ? m1 : 0.f;
     }
     const uint32_t dp = pack_bf16x2(__uint_as_float(v[2 * i]) * m0, __uint_as_float(v[2 * i + 1]) * m1);
     dw[i] = dp;
@@ -345,12 +370,17 @@ __device__ __forceinline__ void dz_bwd_8(const uint32_t* v, const uint32_t* zw, 
 
 // backward from the sign bits (no tanh neuron in the warp): bit i of `bits8` = (z > 0) for column i of these 8
 // (interleaved layout: bits i and 16 + i for columns 2 i and 2 i + 1)
+template <bool KEEP>
 __device__ __forceinline__ void dz_bwd_8_bits(const uint32_t* v, uint32_t bits8, float m_pos, float m_neg,
-                                              uint32_t* dw, RunningSums& rs) {
+                                              uint32_t* dw, RunningSums& rs, uint32_t keep8) {
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    const float m0 = (bits8 & (1u << i)) ? m_pos : m_neg;
-    const float m1 = (bits8 & (1u << (16 + i))) ? m_pos : m_neg;
+    float m0 = (bits8 & (1u << i)) ? m_pos : m_neg;
+    float m1 = (bits8 & (1u << (16 + i))) ? m_pos : m_neg;
+    if (KEEP) {
+      m0 = (keep8 >> (2 * i)) & 1u ? m0 : 0.f;
+      m1 = (keep8 >> (2 * i + 1)) & 1u ? m1 : 0.f;
+    }
     const uint32_t dp = pack_bf16x2(__uint_as_float(v[2 * i]) * m0, __uint_as_float(v[2 * i + 1]) * m1);
     dw[i] = dp;
     const float d0 = bf16lo_to_f32(dp), d1 = bf16hi_to_f32(dp);
@@ -360,6 +390,36 @@ __device__ __forceinline__ void dz_bwd_8_bits(const uint32_t* v, uint32_t bits8,
     rs.s_sq = fmaf(d1, d1, rs.s_sq);
   }
 }
+
+// Per-thread view of the work-item sequence of this CTA (pair).  Static: t, t + step, ...  Dynamic: the j-th call of
+// advance() consumes the j-th cluster-launch-control response (slot j % CLC_SLOTS, phase (j / CLC_SLOTS) & 1).
+struct TileSched {
+  int t;            // current work item
+  int step, total;  // static schedule
+  bool clc;
+  uint32_t j;       // responses consumed (= index of the current item in this cluster's sequence)
+  uint64_t* full;   // [CLC_SLOTS] local: response j has landed
+  uint64_t* empty;  // [CLC_SLOTS] in the LEADER CTA: every consumer of both CTAs has read response j
+  uint32_t resp;    // shared address of the response ring
+  // `arriver`: this thread releases the slot (exactly one thread per consumer agent); warp_collective: every lane
+  // of the warp calls this together
+  __device__ __forceinline__ bool advance(bool arriver, bool warp_collective) {
+    if (!clc) {
+      t += step;
+      return t < total;
+    }
+    const uint32_t s = j % CLC_SLOTS;
+    mbar_wait(&full[s], (j / CLC_SLOTS) & 1u);
+    int x;
+    const bool valid = clc_read(resp + 16u * s, x);
+    fence_proxy_async_smem();  // our (generic-proxy) read is ordered before the next async-proxy write of this slot
+    if (warp_collective) __syncwarp();
+    if (arriver) mbar_arrive_leader(&empty[s]);
+    ++j;
+    t = x >> 1;  // cluster index = first CTA's blockIdx.x / 2
+    return valid;
+  }
+};
 
 template <bool A_MN, bool B_MN, int EPI, bool PAIR>
 __global__ void __launch_bounds__(num_threads(EPI, PAIR), 1) forde_gemm_kernel(const __grid_constant__ GemmParams p) {
@@ -382,8 +442,12 @@ __global__ void __launch_bounds__(num_threads(EPI, PAIR), 1) forde_gemm_kernel(c
   uint64_t* tempty_bar = tfull_bar + 2;      // [2]
   constexpr int ZR = dz_ring(PAIR), ZD = dz_dist(PAIR);
   uint64_t* z_bar = tempty_bar + 2;          // [EPI_WARPS][ZR]
-  uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(z_bar + 2 * 16);
-  static_assert(2 * 6 + 4 + 2 * 16 <= 62, "barrier block is 512 bytes");
+  uint64_t* clc_full = z_bar + 2 * 16;       // [CLC_SLOTS]
+  uint64_t* clc_empty = clc_full + CLC_SLOTS;  // [CLC_SLOTS] (the leader CTA's are used)
+  uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(clc_empty + CLC_SLOTS);
+  static_assert(2 * 6 + 4 + 2 * 16 + 2 * CLC_SLOTS <= 62, "barrier block is 512 bytes");
+  const uint32_t clc_resp = smem_u32(reinterpret_cast<uint8_t*>(bars) + 512);  // [CLC_SLOTS] x 16 B, 16-byte aligned
+  const bool clc = PAIR && p.clc != 0;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -393,6 +457,8 @@ __global__ void __launch_bounds__(num_threads(EPI, PAIR), 1) forde_gemm_kernel(c
   const int m_off = cta_rank * BM;
   const int worker = PAIR ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
   const int num_workers = PAIR ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
+  // every role walks the same item sequence through its own copy of this
+  const TileSched sched0{worker, num_workers, total_work, clc, 0u, clc_full, clc_empty, clc_resp};
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.tmA);
@@ -410,6 +476,10 @@ __global__ void __launch_bounds__(num_threads(EPI, PAIR), 1) forde_gemm_kernel(c
       mbar_init(&tempty_bar[a], PAIR ? 2 * EPI_WARPS : EPI_WARPS);  // pair: both CTAs' epilogues release the leader
     }
     for (int i = 0; i < ZR * EPI_WARPS; ++i) mbar_init(&z_bar[i], 1);
+    for (int i = 0; i < CLC_SLOTS; ++i) {
+      mbar_init(&clc_full[i], 1);
+      mbar_init(&clc_empty[i], 2 + 1 + 2 * EPI_WARPS);  // both producers, the MMA issuer, both CTAs' epilogue warps
+    }
     fence_mbar_init();
   }
   if (warp == 1) {
@@ -432,7 +502,16 @@ __global__ void __launch_bounds__(num_threads(EPI, PAIR), 1) forde_gemm_kernel(c
     if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int t = worker; t < total_work; t += num_workers) {
+      TileSched sc = sched0;
+      for (bool more = true; more; more = sc.advance(true, false)) {
+        const int t = sc.t;
+        if (clc) {
+          // ask for the NEXT item now, one item ahead: the answer is back long before this item's loads are issued
+          const uint32_t s = sc.j % CLC_SLOTS;
+          if (cta_rank == 0) mbar_wait(&clc_empty[s], ((sc.j / CLC_SLOTS) & 1u) ^ 1u);  // slot read by everyone
+          mbar_expect_tx(&clc_full[s], 16);  // each CTA arms its own barrier; the response is multicast to both
+          if (cta_rank == 0) clc_try_cancel_multicast(clc_resp + 16u * s, &clc_full[s]);
+        }
         const WorkItem w = decode_work(p, t, TILE_M, m_off, m_blocks);
         // first B row (D column) this CTA stages (+ the expert's slice of n-stacked weights)
         const int nb0 = w.n0 + (PAIR ? cta_rank * BNL : 0) + w.group * p.b_n_group_stride;
@@ -479,7 +558,9 @@ __global__ void __launch_bounds__(num_threads(EPI, PAIR), 1) forde_gemm_kernel(c
     uint32_t phase = 0;
     int it = 0;
     if (!PAIR || cta_rank == 0) {  // in a pair only the leader issues; its MMAs drive both SMs' tensor cores
-      for (int t = worker; t < total_work; t += num_workers, ++it) {
+      TileSched sc = sched0;
+      for (bool more = true; more; more = sc.advance(lane == 0, true), ++it) {
+        const int t = sc.t;
         const WorkItem w = decode_work(p, t, TILE_M, m_off, m_blocks);
         const int as = it & 1;
         const uint32_t aphase = (it >> 1) & 1;
@@ -537,9 +618,13 @@ __global__ void __launch_bounds__(num_threads(EPI, PAIR), 1) forde_gemm_kernel(c
     // Warp-collective.  The backward only needs z itself for tanh neurons (F' = 1 - tanh^2 z); for relu neurons the
     // sign of h = z + relu(z) is the sign of z and the straight-through step needs nothing, so a warp without tanh
     // neurons reads the h^T box (which the forward stores anyway) and the forward never has to write its z^T box.
+    // item sequence of this warp, read one item ahead (the z^T prefetch of a tile's last chunk targets the next item)
+    TileSched sc = sched0;
+    int cur_t = sc.t;
+    int next_t = sc.advance(lane == 0, true) ? sc.t : -1;
     auto z_prefetch = [&](int gi, bool wait_for_store) {
-      const int nt = worker + (gi / CPW) * num_workers;
-      if (nt >= total_work) return;
+      const int nt = (gi / CPW == it) ? cur_t : next_t;  // chunk gi lies in the current item or in the next one
+      if (nt < 0) return;
       const WorkItem wn = decode_work(p, nt, TILE_M, m_off, m_blocks);
       bool use_z = true;
       if (EPI == EPI_DZ_BWD) {
@@ -561,7 +646,8 @@ __global__ void __launch_bounds__(num_threads(EPI, PAIR), 1) forde_gemm_kernel(c
       for (int i = 0; i < ZD; ++i) z_prefetch(i, false);
     }
 
-    for (int t = worker; t < total_work; t += num_workers, ++it) {
+    for (; cur_t >= 0; ++it) {
+      const int t = cur_t;
       const WorkItem w = decode_work(p, t, TILE_M, m_off, m_blocks);
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
@@ -639,6 +725,18 @@ __global__ void __launch_bounds__(num_threads(EPI, PAIR), 1) forde_gemm_kernel(c
         __syncwarp();
         uint8_t* obuf = epi_z_ring(EPI) ? (wst + (g % ZR) * BOX_BYTES) : wst;
         const uint32_t orow_s = smem_u32(obuf) + lane * 128;
+        // top-k mode: the kept words of this chunk's 64 samples for this warp's 32-neuron group (lane l holds the
+        // words of samples col0 + l and col0 + 32 + l; bit (row % 32) is this thread's neuron)
+        uint32_t kw[2] = {0u, 0u};
+        const bool use_keep = (EPI == EPI_DZ_BWD) && p.keep_bits != nullptr;
+        if (use_keep && w.m0 + q * 32 < p.M) {
+          const uint32_t* kp = p.keep_bits + static_cast<long long>((w.m0 + q * 32) >> 5) * p.N;
+#pragma unroll
+          for (int hh = 0; hh < 2; ++hh) {
+            const int col = col0 + hh * 32 + lane;
+            kw[hh] = col < p.N ? __ldg(kp + col) : 0u;
+          }
+        }
 
         // the 64-column chunk is drained in two 32-column halves to keep the live registers low
         auto drain_half = [&](const uint32_t* v_in, const int half) {
@@ -774,29 +872,46 @@ __global__ void __launch_bounds__(num_threads(EPI, PAIR), 1) forde_gemm_kernel(c
               st_shared_v4(orow_s + off, dw[0], dw[1], dw[2], dw[3]);
             }
           } else {  // EPI_DZ_BWD: dz over z, in place (same thread, same bytes)
-            auto run = [&](auto has_tanh) {
+            // kept bits of columns j8 * 8 .. + 7 for this thread's neuron (warp-collective: every lane asks lane j)
+            auto keep8_of = [&](int j8) {
+              uint32_t k8 = 0u;
+#pragma unroll
+              for (int c8 = 0; c8 < 8; ++c8)
+                k8 |= ((__shfl_sync(0xffffffffu, kw[half], j8 * 8 + c8) >> (row & 31)) & 1u) << c8;
+              return k8;
+            };
+            auto run = [&](auto has_tanh, auto keep) {
 #pragma unroll
               for (int j8 = 0; j8 < 4; ++j8) {
                 const uint32_t off = (static_cast<uint32_t>(half * 4 + j8) ^ sw) << 4;
                 uint32_t zw[4], dw[4];
+                const uint32_t k8 = decltype(keep)::value ? keep8_of(j8) : 0u;
                 ld_shared_v4(orow_s + off, zw[0], zw[1], zw[2], zw[3]);
-                dz_bwd_8<decltype(has_tanh)::value>(v + j8 * 8, zw, m_pos, m_neg, act, dw, rs);
+                dz_bwd_8<decltype(has_tanh)::value, decltype(keep)::value>(v + j8 * 8, zw, m_pos, m_neg, act, dw, rs, k8);
                 st_shared_v4(orow_s + off, dw[0], dw[1], dw[2], dw[3]);
               }
             };
-            if (bits_path) {
+            auto run_bits = [&](auto keep) {
               uint32_t word = mw[half];
               if (CPW > 1 && cc == 1) word = mw[2 + half];
 #pragma unroll
               for (int j8 = 0; j8 < 4; ++j8) {
                 uint32_t dw[4];
-                dz_bwd_8_bits(v + j8 * 8, word >> (j8 * 4), m_pos, m_neg, dw, rs);
+                const uint32_t k8 = decltype(keep)::value ? keep8_of(j8) : 0u;
+                dz_bwd_8_bits<decltype(keep)::value>(v + j8 * 8, word >> (j8 * 4), m_pos, m_neg, dw, rs, k8);
                 st_shared_v4(orow_s + ((static_cast<uint32_t>(half * 4 + j8) ^ sw) << 4), dw[0], dw[1], dw[2], dw[3]);
               }
-            } else if (warp_has_tanh) {
-              run(std::true_type{});
+            };
+            using T = std::true_type;
+            using F = std::false_type;
+            if (use_keep) {  // warp-uniform
+              if (bits_path) run_bits(T{});
+              else if (warp_has_tanh) run(T{}, T{});
+              else run(F{}, T{});
             } else {
-              run(std::false_type{});
+              if (bits_path) run_bits(F{});
+              else if (warp_has_tanh) run(T{}, F{});
+              else run(F{}, F{});
             }
           }
         };
@@ -858,6 +973,8 @@ __global__ void __launch_bounds__(num_threads(EPI, PAIR), 1) forde_gemm_kernel(c
         if (PAIR) mbar_arrive_leader(&tempty_bar[as]);
         else mbar_arrive(&tempty_bar[as]);
       }
+      cur_t = next_t;
+      if (cur_t >= 0) next_t = sc.advance(lane == 0, true) ? sc.t : -1;
     }
     if (EPI != EPI_F32 && lane == 0) tma_wait_all<0>();
   }

@@ -75,7 +75,8 @@ __global__ void __launch_bounds__(OPT_THREADS)
 adamw_clip_kernel(float* __restrict__ p32, const float* __restrict__ g32, const __nv_bfloat16* __restrict__ g16,
                   float* __restrict__ mu, float* __restrict__ nu, __nv_bfloat16* __restrict__ p16, long long n,
                   const float* __restrict__ partials, int num_partials, float max_norm, float lr, float b1, float b2,
-                  float eps, float wd, const int* __restrict__ step_count, float* __restrict__ grad_norm_out) {
+                  float omb1, float omb2, float eps, float wd, const int* __restrict__ step_count,
+                  float* __restrict__ grad_norm_out) {
   __shared__ double red[OPT_THREADS];
   __shared__ float s_scale, s_c1, s_c2;
   // the same fixed-order reduction in every block -> every block sees the identical norm
@@ -109,8 +110,8 @@ adamw_clip_kernel(float* __restrict__ p32, const float* __restrict__ g32, const 
     float* vv = reinterpret_cast<float*>(&v);
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      mm[k] = b1 * mm[k] + (1.f - b1) * g[k];
-      vv[k] = b2 * vv[k] + (1.f - b2) * g[k] * g[k];
+      mm[k] = b1 * mm[k] + omb1 * g[k];            // omb = 1 - b evaluated in double on the host, as optax's
+      vv[k] = b2 * vv[k] + omb2 * g[k] * g[k];     // Python-float (1 - decay) is before it meets the fp32 arrays
       const float u = (mm[k] * c1) / (sqrtf(vv[k] * c2) + eps) + wd * pp[k];
       pp[k] = pp[k] - lr * u;
     }
@@ -175,8 +176,8 @@ int forde_grad_sqnorm(void* stream, const float* g32, const void* g16, long long
 }
 
 int forde_adamw_clip_step(void* stream, float* p32, const float* g32, const void* g16, float* mu, float* nu, void* p16,
-                          long long n, const float* partials, int num_partials, float max_norm, float lr, float b1,
-                          float b2, float eps, float wd, const int* step_count, float* grad_norm_out) {
+                          long long n, const float* partials, int num_partials, double max_norm, double lr, double b1,
+                          double b2, double eps, double wd, const int* step_count, float* grad_norm_out) {
   if (p32 == nullptr || (g32 == nullptr) == (g16 == nullptr) || mu == nullptr || nu == nullptr ||
       partials == nullptr || step_count == nullptr || n <= 0 || num_partials <= 0)
     return FORDE_EINVAL;
@@ -188,7 +189,9 @@ int forde_adamw_clip_step(void* stream, float* p32, const float* g32, const void
   if (blocks <= 0) return FORDE_ENODEV;
   adamw_clip_kernel<<<blocks, OPT_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(
       p32, g32, static_cast<const __nv_bfloat16*>(g16), mu, nu, static_cast<__nv_bfloat16*>(p16), n, partials,
-      num_partials, max_norm, lr, b1, b2, eps, wd, step_count, grad_norm_out);
+      num_partials, static_cast<float>(max_norm), static_cast<float>(lr), static_cast<float>(b1),
+      static_cast<float>(b2), static_cast<float>(1.0 - b1), static_cast<float>(1.0 - b2), static_cast<float>(eps),
+      static_cast<float>(wd), step_count, grad_norm_out);
   return check_launch("adamw_clip_kernel");
 }
 

@@ -73,6 +73,38 @@ __device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & kPeerBitMask) : "memory");
 }
 
+// ---------------------------------------------------------------- cluster launch control (dynamic tile scheduling)
+// Ask the hardware to cancel a cluster of this grid that has not been launched yet; the 16-byte response is written
+// (async proxy) to the same shared-memory offset in EVERY CTA of the requesting cluster and completes 16 transaction
+// bytes on the mbarrier at `bar`'s offset in every CTA.  Must not be issued again once a response said "nothing left".
+__device__ __forceinline__ void clc_try_cancel_multicast(uint32_t resp_smem_addr, uint64_t* bar) {
+  asm volatile(
+      "clusterlaunchcontrol.try_cancel.async.shared::cta.mbarrier::complete_tx::bytes.multicast::cluster::all.b128"
+      " [%0], [%1];" ::"r"(resp_smem_addr),
+      "r"(smem_u32(bar))
+      : "memory");
+}
+// Decode a response: true and the x index of the cancelled cluster's first CTA, or false when nothing was pending.
+__device__ __forceinline__ bool clc_read(uint32_t resp_smem_addr, int& first_ctaid_x) {
+  uint32_t valid = 0, x = 0;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p1;\n\t"
+      ".reg .b128 r;\n\t"
+      ".reg .b32 y, z;\n\t"
+      "mov.b32 %0, 0;\n\t"
+      "ld.shared.b128 r, [%2];\n\t"
+      "clusterlaunchcontrol.query_cancel.is_canceled.pred.b128 p1, r;\n\t"
+      "selp.u32 %1, 1, 0, p1;\n\t"
+      "@p1 clusterlaunchcontrol.query_cancel.get_first_ctaid.v4.b32.b128 {%0, y, z, _}, r;\n\t"
+      "}\n"
+      : "=r"(x), "=r"(valid)
+      : "r"(resp_smem_addr)
+      : "memory");
+  first_ctaid_x = static_cast<int>(x);
+  return valid != 0;
+}
+
 // ---------------------------------------------------------------- proxies / fences
 __device__ __forceinline__ void fence_proxy_async_smem() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");

@@ -193,11 +193,24 @@ def sl_down_fwd(hT, w_down, b_down, y, M):
     _lib.check(rc, "forde_sl_down_fwd")
 
 
-def sl_dz_bwd(dy, w_down, zT, hT, assign_i8, dzT, grad_partials, sign_bits=None):
-    """With ``sign_bits`` (written by ``sl_up_fwd(..., sign_bits=...)``) h^T is not read and may be None."""
+def sl_dz_bwd(dy, w_down, zT, hT, assign_i8, dzT, grad_partials, sign_bits=None, keep_bits=None):
+    """With ``sign_bits`` (written by ``sl_up_fwd(..., sign_bits=...)``) h^T is not read and may be None.
+    With ``keep_bits`` (from ``sl_topk_sparsify``) dL/dz is zeroed where the forward's top-k dropped h, in the same
+    epilogue, and the gradient partial sums are those of the masked dL/dz."""
     M, d = dy.shape
     H = w_down.shape[0]
     _req(dy, torch.bfloat16, "dy"); _req(zT, torch.bfloat16, "zT"); _req(dzT, torch.bfloat16, "dzT")
+    if keep_bits is not None:
+        _req(keep_bits, torch.int32, "keep_bits")
+        assert tuple(keep_bits.shape) == ((H + 31) // 32, M)
+        if sign_bits is not None:
+            _req(sign_bits, torch.int32, "sign_bits")
+        with _Timed(f"sl_dz_bwd[{M}x{d}x{H}]", 2.0 * M * d * H):
+            rc = _lib.load().forde_sl_dz_bwd_topk(_stream(), dy.data_ptr(), w_down.data_ptr(), zT.data_ptr(), _ptr(hT),
+                                                  _ptr(sign_bits), keep_bits.data_ptr(), assign_i8.data_ptr(),
+                                                  dzT.data_ptr(), _ptr(grad_partials), M, d, H, zT.stride(0))
+        _lib.check(rc, "forde_sl_dz_bwd_topk")
+        return
     if sign_bits is not None:
         _req(sign_bits, torch.int32, "sign_bits")
         assert tuple(sign_bits.shape) == sign_shape(M, H) and sign_bits.is_contiguous()
@@ -262,13 +275,6 @@ def sl_topk_sparsify(hT, M: int, k: int, want_indices: bool = True):
                                             keep.data_ptr())
     _lib.check(rc, "forde_sl_topk_sparsify")
     return idx, hoyer, keep
-
-
-def sl_topk_mask(dzT, M: int, keep_bits, grad_partials=None):
-    _req(dzT, torch.bfloat16, "dzT")
-    rc = _lib.load().forde_sl_topk_mask(_stream(), dzT.data_ptr(), dzT.stride(0), M, dzT.shape[0], keep_bits.data_ptr(),
-                                        _ptr(grad_partials))
-    _lib.check(rc, "forde_sl_topk_mask")
 
 
 def colsum_bf16(a, out):

@@ -174,11 +174,9 @@ class _StatefulLayerFn(torch.autograd.Function):
         H = ws.H
         dev = x2d.device
         dzT = _dz_scratch(H, ws.ld, dev)
-        if ctx.keep_bits is None:
-            ops.sl_dz_bwd(dy, w_down16, ws.zT, ws.hT, assign_i8, dzT, ws.grad_partials, sign_bits=ws.signs)
-        else:  # top-k path: dL/dz is zero where h was dropped; the gradient sums are re-taken after masking
-            ops.sl_dz_bwd(dy, w_down16, ws.zT, ws.hT, assign_i8, dzT, None, sign_bits=ws.signs)
-            ops.sl_topk_mask(dzT, M, ctx.keep_bits, ws.grad_partials)
+        # top-k path (keep_bits): dL/dz is zero where h was dropped, applied in the same epilogue
+        ops.sl_dz_bwd(dy, w_down16, ws.zT, ws.hT, assign_i8, dzT, ws.grad_partials, sign_bits=ws.signs,
+                      keep_bits=ctx.keep_bits)
         d_out = dy.shape[1]
         sinks = [grad_sink(m) for m in ctx.masters]
         direct = all(s is not None for s in sinks)      # accumulate straight into the train state's gradient views

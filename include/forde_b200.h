@@ -128,17 +128,18 @@ int forde_sl_bwd(void* stream, const void* x, const void* dy, const void* w_up, 
 
 /* ---- optional top-k activation sparsification (nearest reference code: lax.top_k at moe.py:130) ------
  * sparsify: per token (column of hT) keep the k largest |h| over the H neurons and zero the rest IN PLACE (call it
- *   between forde_sl_up_fwd and forde_sl_down_fwd).  idx_out [M][k] i32 = kept neuron indices in jax.lax.top_k order of
- *   |h| (descending, equal values -> lower index first; may be NULL); hoyer_out [M] f32 = Hoyer sparsity of the dense
- *   h of each token (may be NULL); keep_bits [ceil(H/32)][M] u32 = kept mask for the backward (may be NULL).
- * mask: dzT[h][m] = 0 where the forward dropped (h, m): call it after forde_sl_dz_bwd (which then gets NULL
- *   grad_partials) and before dx / dW_up.  grad_partials (may be NULL) receives the per-neuron sums of the MASKED
- *   dL/dz in the same [P][3][H] layout, so forde_stats_finalize works unchanged.  This is an extra pass over dzT and
- *   only exists on the optional top-k path. */
+ *   between forde_sl_up_fwd and forde_sl_down_fwd; one read and one write of hT).  idx_out [M][k] i32 = kept neuron
+ *   indices in jax.lax.top_k order of |h| (descending, equal values -> lower index first; may be NULL); hoyer_out [M]
+ *   f32 = Hoyer sparsity of the dense h of each token (may be NULL); keep_bits [ceil(H/32)][M] u32 = kept mask.
+ * dz_bwd_topk: forde_sl_dz_bwd / forde_sl_dz_bwd_signs with that mask applied in the same epilogue: dL/dz = 0 where the
+ *   forward dropped (h, m), and grad_partials are the sums of the MASKED dL/dz -- no extra pass over dzT.  Exactly one
+ *   of hT / sign_bits is the source of sign(z) for the neuron groups without a tanh neuron (the other may be NULL;
+ *   sign_bits wins when both are given). */
 int forde_sl_topk_sparsify(void* stream, void* hT, long long ldz, int M, int H, int k, int* idx_out, float* hoyer_out,
                            uint32_t* keep_bits);
-int forde_sl_topk_mask(void* stream, void* dzT, long long ldz, int M, int H, const uint32_t* keep_bits,
-                       float* grad_partials);
+int forde_sl_dz_bwd_topk(void* stream, const void* dy, const void* w_down, const void* zT, const void* hT,
+                         const uint32_t* sign_bits, const uint32_t* keep_bits, const int8_t* assign, void* dzT,
+                         float* grad_partials, int M, int d, int H, long long ldz);
 
 /* ---- sensing finalisation (sensing.py:5-69) --------------------------------------------------------
  * Reduces the partials in a fixed order and produces this step's (H,5) statistics
@@ -261,12 +262,14 @@ int forde_add_layernorm_bwd(void* stream, const void* dy, const void* x, const v
  *                           p -= lr * (mu/(1-b1^t) / (sqrt(nu/(1-b2^t)) + eps) + wd * p), t = *step_count (already
  *                           incremented by forde_grad_sqnorm); p16 (may be NULL) = bf16(p), the compute mirror;
  *                           grad_norm_out[1] (may be NULL) = the pre-clip norm.  max_norm <= 0 disables clipping.
+ *                           Hyper-parameters are doubles (Python floats in optax): 1 - b is formed in double before
+ *                           it is rounded to fp32, exactly as optax's weakly typed scalars are.
  *   forde_cast_f32_bf16   : dst = bf16(src) (gradient buckets before a bf16 all-reduce). */
 int forde_optim_num_partials(long long n);
 int forde_grad_sqnorm(void* stream, const float* g32, const void* g16, long long n, float* partials, int* step_count);
 int forde_adamw_clip_step(void* stream, float* p32, const float* g32, const void* g16, float* mu, float* nu, void* p16,
-                          long long n, const float* partials, int num_partials, float max_norm, float lr, float b1,
-                          float b2, float eps, float wd, const int* step_count, float* grad_norm_out);
+                          long long n, const float* partials, int num_partials, double max_norm, double lr, double b1,
+                          double b2, double eps, double wd, const int* step_count, float* grad_norm_out);
 int forde_cast_f32_bf16(void* stream, const float* src, void* dst, long long n);
 
 /* ---- front ends of the two towers (README.md:30-34; layouts of src/data/download_to_drive.py:106-108,

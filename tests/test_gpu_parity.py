@@ -372,6 +372,38 @@ def test_topk_sparsify_matches_lax_top_k_semantics(ops, M, H, k):
     np.testing.assert_array_equal(kept.T, ref_kept)
 
 
+@pytest.mark.parametrize("use_signs", [False, True])
+@pytest.mark.parametrize("shape", [(300, 64, 256, 32), (1000, 256, 640, 64), (2048, 512, 2048, 128)])
+def test_dz_epilogue_applies_the_topk_mask_bit_exactly(ops, shape, use_signs):
+    """forde_sl_dz_bwd_topk: dL/dz == (dL/dz of the dense backward) where the forward's top-k kept h, exactly 0
+    elsewhere -- bit for bit -- and the gradient partial sums are those of the masked tensor (no separate masking pass)."""
+    M, d, H, k = shape
+    a = np.random.RandomState(5).randint(0, 3, H)
+    t = run_layer(ops, M, d, H, a, seed=8)                       # dense forward + backward, every z box stored
+    hT = t["hT"].clone()
+    idx, hoyer, keep = ops.sl_topk_sparsify(hT, M, k)
+    kb = keep.cpu().numpy().view(np.uint32)
+    kept = ((kb[np.arange(H)[:, None] >> 5, np.arange(M)[None, :]] >> (np.arange(H)[:, None] & 31)) & 1).astype(bool)  # (H, M)
+    assert (kept.sum(0) == k).all()
+    np.testing.assert_array_equal(f32(hT[:, :M]), f32(t["hT"][:, :M]) * kept)     # masked tile written back whole
+    signs = None
+    zT = t["zT"]
+    if use_signs:
+        signs = torch.zeros(ops.sign_shape(M, H), device="cuda", dtype=torch.int32)
+        zT2 = torch.full_like(t["zT"], float("nan")); h2 = torch.zeros_like(hT); ap = torch.zeros_like(t["actp"])
+        ops.sl_up_fwd(t["x"], t["w_up"], t["b_up"], t["assign"], zT2, h2, ap, save_z=False, sign_bits=signs)
+        zT = zT2
+    dzT = torch.zeros_like(t["dzT"]); gp = torch.zeros_like(t["gradp"])
+    ops.sl_dz_bwd(t["dy"], t["w_down"], zT, hT, t["assign"], dzT, gp, sign_bits=signs, keep_bits=keep)
+    torch.cuda.synchronize()
+    want = f32(t["dzT"][:, :M]) * kept
+    np.testing.assert_array_equal(f32(dzT[:, :M]), want)
+    sums = f32(gp).sum(0)                                                          # (3, H): sum|dz|, sum dz, sum dz^2
+    np.testing.assert_allclose(sums[0], np.abs(want).astype(np.float64).sum(1), rtol=1e-4, atol=1e-4)
+    np.testing.assert_allclose(sums[1], want.astype(np.float64).sum(1), rtol=1e-4, atol=1e-3)
+    np.testing.assert_allclose(sums[2], (want.astype(np.float64) ** 2).sum(1), rtol=1e-4, atol=1e-5)
+
+
 def test_stateful_layer_with_topk_masks_gradients_and_statistics(ops):
     from forde_b200.stateful_layer import StatefulLayer
     M, d, H, k = 300, 64, 256, 32

@@ -280,8 +280,8 @@ def test_vision_front_end_matches_plain_restatement(ops, B, S, p, w):
     # restatement
     wr = wk.detach().bfloat16().float().requires_grad_(True); br = bk.detach().clone().requires_grad_(True)
     cr = cls.detach().bfloat16().float().requires_grad_(True); pr = pos.detach().bfloat16().float().requires_grad_(True)
-    tok_r = (ref_patches.float() @ wr + br).bfloat16().float()
-    tok_r = tok_r + ((ref_patches.float() @ wr + br) - (ref_patches.float() @ wr + br).detach())   # straight-through rounding
+    t_ = ref_patches.float() @ wr + br
+    tok_r = t_ + (t_.detach().bfloat16().float() - t_.detach())     # value: bf16-rounded like the stored tokens; grad: identity
     x_r = torch.cat([cr.expand(B, 1, w), tok_r.view(B, g * g, w)], 1) + pr
     x_r.backward(dx.float())
     assert_close_bf16(f32(x), f32(x_r.detach().bfloat16().float()), "x")
