@@ -43,7 +43,7 @@ SIGNATURES = {
     "forde_colsum_bf16": (_i, [_vp, _vp, _ll, _vp, _i, _i]),
     "forde_sl_bwd": (_i, [_vp] * 15 + [_i, _i, _i, _ll]),
     "forde_sl_topk_sparsify": (_i, [_vp, _vp, _ll, _i, _i, _i, _vp, _vp, _vp]),
-    "forde_sl_dz_bwd_topk": (_i, [_vp] * 11 + [_i, _i, _i, _ll]),
+    "forde_sl_dz_bwd_topk": (_i, [_vp] * 10 + [_i, _i, _i, _ll]),
     "forde_stats_finalize": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "forde_stats_from_moments": (_i, [_vp, _vp, _vp, _i, _vp]),
     "forde_clip_fwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i] + [_vp] * 10),
@@ -53,7 +53,8 @@ SIGNATURES = {
     "forde_l2norm_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i]),
     "forde_moe_capacity_rows": (_i, [_i, _i, _i]),
     "forde_moe_num_prob_partials": (_i, [_i]),
-    "forde_moe_route": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _f] + [_vp] * 14),
+    "forde_moe_route": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _f] + [_vp] * 15),
+    "forde_moe_plan_scratch_ints": (_i, [_i, _i, _i]),
     "forde_moe_gather": (_i, [_vp, _vp, _vp, _i, _vp, _i, _i]),
     "forde_moe_scatter": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _i, _i]),
     "forde_moe_combine": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i]),

@@ -134,20 +134,42 @@ moe_router_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __re
   }
 }
 
-// ------------------------------------------------------------------ routing plan (one block)
+// ------------------------------------------------------------------ routing plan (three small kernels)
 // counts -> 128-aligned expert segments, block -> expert map, auxiliary loss (moe.py:212-222), expert-usage
 // accumulation (moe.py:277-279) and a STABLE slot for every (token, j) entry (entries of an expert keep token order).
-__global__ void __launch_bounds__(1024)
-moe_plan_kernel(const int* __restrict__ topk_idx, const int* __restrict__ counts,
-                const float* __restrict__ prob_partials, int n_partials, int M, int k, int E, int r_cap,
-                float aux_weight, int* __restrict__ seg_offsets, int* __restrict__ n_blocks_dev,
-                int* __restrict__ block_expert, int* __restrict__ slot_of, int* __restrict__ src_of_slot,
-                float* __restrict__ aux_loss, float* __restrict__ expert_usage, int* __restrict__ step_count) {
+// The (token, j) entries are cut into chunks of PLAN_CHUNK; a chunk is one thread block:
+//   1. moe_plan_count_kernel : per-chunk, per-expert entry counts (and the -1 fill of src_of_slot)
+//   2. moe_plan_scan_kernel  : one block; segments, aux loss, usage, and the exclusive scan of the chunk counts
+//                              -> chunk_base[chunk][e] = first slot of chunk's entries for expert e
+//   3. moe_plan_assign_kernel: per chunk, rank of every entry among the chunk's entries of the same expert
+//                              (warp match + prefix over the warps) + chunk_base -> slot
+// (round 1 did all of it in one 1024-thread block, 16 serial passes at C4: 35 us of a 430 us slot.)
+constexpr int PLAN_CHUNK = 1024;
+
+__global__ void __launch_bounds__(PLAN_CHUNK)
+moe_plan_count_kernel(const int* __restrict__ topk_idx, int total, int E, int r_cap, int* __restrict__ chunk_counts,
+                      int* __restrict__ src_of_slot) {
+  __shared__ int cnt_s[MOE_MAX_E];
+  const int tid = threadIdx.x;
+  if (tid < E) cnt_s[tid] = 0;
+  __syncthreads();
+  const int i = blockIdx.x * PLAN_CHUNK + tid;
+  const int e = (i < total) ? topk_idx[i] : -1;
+  const unsigned peers = __match_any_sync(0xffffffffu, e);
+  if (e >= 0 && (peers & ((1u << (tid & 31)) - 1u)) == 0u) atomicAdd(&cnt_s[e], __popc(peers));  // warp leader per expert
+  __syncthreads();
+  if (tid < E) chunk_counts[blockIdx.x * E + tid] = cnt_s[tid];
+  for (int s = blockIdx.x * PLAN_CHUNK + tid; s < r_cap; s += gridDim.x * PLAN_CHUNK) src_of_slot[s] = -1;
+}
+
+__global__ void __launch_bounds__(256)
+moe_plan_scan_kernel(const int* __restrict__ counts, const float* __restrict__ prob_partials, int n_partials, int M,
+                     int k, int E, int r_cap, float aux_weight, int n_chunks, int* __restrict__ chunk_counts,
+                     int* __restrict__ seg_offsets, int* __restrict__ n_blocks_dev, int* __restrict__ block_expert,
+                     float* __restrict__ aux_loss, float* __restrict__ expert_usage, int* __restrict__ step_count) {
   __shared__ int seg_s[MOE_MAX_E + 1];
-  __shared__ int base_s[MOE_MAX_E];
-  __shared__ int wcnt_s[32][MOE_MAX_E];
   __shared__ float aux_s[MOE_MAX_E];
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tid = threadIdx.x;
   if (tid == 0) {
     int off = 0;
     for (int e = 0; e < E; ++e) {
@@ -172,42 +194,48 @@ moe_plan_kernel(const int* __restrict__ topk_idx, const int* __restrict__ counts
     *aux_loss = a * static_cast<float>(E) * aux_weight;
   }
   if (tid <= E) seg_offsets[tid] = seg_s[tid];
-  if (tid < E) base_s[tid] = seg_s[tid];
-  for (int s = tid; s < r_cap; s += blockDim.x) src_of_slot[s] = -1;
+  if (tid < E) {  // exclusive scan of this expert's chunk counts, in place: chunk_counts becomes chunk_base
+    int run = seg_s[tid];
+    for (int c = 0; c < n_chunks; ++c) {
+      const int v = chunk_counts[c * E + tid];
+      chunk_counts[c * E + tid] = run;
+      run += v;
+    }
+  }
   for (int b = tid; b < r_cap / SEG_ALIGN; b += blockDim.x) {
     int e_of = -1;
     for (int e = 0; e < E; ++e)
       if (b * SEG_ALIGN >= seg_s[e] && b * SEG_ALIGN < seg_s[e + 1]) e_of = e;
     block_expert[b] = e_of;
   }
+}
+
+__global__ void __launch_bounds__(PLAN_CHUNK)
+moe_plan_assign_kernel(const int* __restrict__ topk_idx, int total, int E, const int* __restrict__ chunk_base,
+                       int* __restrict__ slot_of, int* __restrict__ src_of_slot) {
+  __shared__ int wcnt_s[PLAN_CHUNK / 32][MOE_MAX_E];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int i = blockIdx.x * PLAN_CHUNK + tid;
+  const int e = (i < total) ? topk_idx[i] : -1;
+  for (int j = lane; j < E; j += 32) wcnt_s[warp][j] = 0;
+  __syncwarp();
+  const unsigned peers = __match_any_sync(0xffffffffu, e);
+  const int rank = __popc(peers & ((1u << lane) - 1u));
+  if (e >= 0 && rank == 0) wcnt_s[warp][e] = __popc(peers);
   __syncthreads();
-  const int total = M * k;
-  for (int i0 = 0; i0 < total; i0 += blockDim.x) {
-    const int i = i0 + tid;
-    const int e = (i < total) ? topk_idx[i] : -1;
-    for (int j = lane; j < E; j += 32) wcnt_s[warp][j] = 0;
-    __syncwarp();
-    const unsigned peers = __match_any_sync(0xffffffffu, e);
-    const int rank = __popc(peers & ((1u << lane) - 1u));
-    if (e >= 0 && rank == 0) wcnt_s[warp][e] = __popc(peers);
-    __syncthreads();
-    // exclusive prefix over the warps, per expert (thread e owns expert e); afterwards wcnt_s holds warp bases
-    if (tid < E) {
-      int run = base_s[tid];
-      for (int w = 0; w < 32; ++w) {
-        const int c = wcnt_s[w][tid];
-        wcnt_s[w][tid] = run;
-        run += c;
-      }
-      base_s[tid] = run;
+  if (tid < E) {  // exclusive prefix over the warps, per expert; afterwards wcnt_s holds each warp's first slot
+    int run = chunk_base[blockIdx.x * E + tid];
+    for (int w = 0; w < PLAN_CHUNK / 32; ++w) {
+      const int c = wcnt_s[w][tid];
+      wcnt_s[w][tid] = run;
+      run += c;
     }
-    __syncthreads();
-    if (e >= 0) {
-      const int slot = wcnt_s[warp][e] + rank;
-      slot_of[i] = slot;
-      src_of_slot[slot] = i;
-    }
-    __syncthreads();
+  }
+  __syncthreads();
+  if (e >= 0) {
+    const int slot = wcnt_s[warp][e] + rank;
+    slot_of[i] = slot;
+    src_of_slot[slot] = i;
   }
 }
 
@@ -410,12 +438,18 @@ int forde_moe_num_prob_partials(int M) {
   return need < 4 * sms ? need : 4 * sms;
 }
 
+int forde_moe_plan_scratch_ints(int M, int k, int E) {
+  if (M <= 0 || k <= 0 || E <= 0) return 0;
+  return ((M * k + PLAN_CHUNK - 1) / PLAN_CHUNK) * E;
+}
+
 int forde_moe_route(void* stream, const void* x, const void* w_r, const float* b_r, int M, int d, int E, int k,
                     float aux_weight, float* logits, float* probs, int* topk_idx, float* topk_w, int* counts,
-                    float* prob_partials, int* seg_offsets, int* n_blocks_dev, int* block_expert, int* slot_of,
-                    int* src_of_slot, float* aux_loss, float* expert_usage, int* step_count) {
+                    float* prob_partials, int* plan_scratch, int* seg_offsets, int* n_blocks_dev, int* block_expert,
+                    int* slot_of, int* src_of_slot, float* aux_loss, float* expert_usage, int* step_count) {
   if (x == nullptr || w_r == nullptr || b_r == nullptr || logits == nullptr || probs == nullptr ||
       topk_idx == nullptr || topk_w == nullptr || counts == nullptr || prob_partials == nullptr ||
+      plan_scratch == nullptr ||
       seg_offsets == nullptr || n_blocks_dev == nullptr || block_expert == nullptr || slot_of == nullptr ||
       src_of_slot == nullptr || aux_loss == nullptr || M <= 0 || d <= 0)
     return FORDE_EINVAL;
@@ -440,10 +474,14 @@ int forde_moe_route(void* stream, const void* x, const void* w_r, const float* b
   else FORDE_ROUTER(16);
 #undef FORDE_ROUTER
   const int r_cap = forde_moe_capacity_rows(M, k, E);
-  moe_plan_kernel<<<1, 1024, 0, st>>>(topk_idx, counts, prob_partials, grid, M, k, E, r_cap, aux_weight, seg_offsets,
-                                      n_blocks_dev, block_expert, slot_of, src_of_slot, aux_loss, expert_usage,
-                                      step_count);
-  return check_launch("moe_router_kernel + moe_plan_kernel", 2);
+  const int total = M * k;
+  const int n_chunks = (total + PLAN_CHUNK - 1) / PLAN_CHUNK;
+  moe_plan_count_kernel<<<n_chunks, PLAN_CHUNK, 0, st>>>(topk_idx, total, E, r_cap, plan_scratch, src_of_slot);
+  moe_plan_scan_kernel<<<1, 256, 0, st>>>(counts, prob_partials, grid, M, k, E, r_cap, aux_weight, n_chunks,
+                                          plan_scratch, seg_offsets, n_blocks_dev, block_expert, aux_loss,
+                                          expert_usage, step_count);
+  moe_plan_assign_kernel<<<n_chunks, PLAN_CHUNK, 0, st>>>(topk_idx, total, E, plan_scratch, slot_of, src_of_slot);
+  return check_launch("moe_router_kernel + moe_plan kernels", 4);
 }
 
 int forde_moe_gather(void* stream, const void* x, const int* src_of_slot, int k, void* xg, int rows, int d) {

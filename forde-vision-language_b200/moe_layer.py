@@ -107,6 +107,46 @@ class MoEStatefulLayer:
         return {"up_proj": {"kernel": e["up_proj"]["kernel"][i], "bias": e["up_proj"]["bias"][i]},
                 "down_proj": {"kernel": e["down_proj"]["kernel"][i], "bias": e["down_proj"]["bias"][i]}}
 
+    @staticmethod
+    def from_reference_params(tree) -> Dict[str, dict]:
+        """Convert the reference's Flax parameter tree of one MoEStatefulLayer into this module's ``params``.
+
+        The reference nests ``MoELayer_0/{MoERouter_0/router_linear, expert_0 .. expert_{E-1}}/...`` with one
+        ``{up_proj, down_proj}/{kernel, bias}`` per expert (src/forde/moe.py:17-29,88,96-104,254-260); here the experts
+        are stacked along a leading axis.  Any nesting above ``router_linear`` / ``expert_{i}`` is accepted; leaves may
+        be torch tensors or array-likes (NumPy / JAX arrays of a loaded checkpoint)."""
+        found = {"router": None, "experts": {}}
+
+        def walk(node):
+            if not isinstance(node, dict):
+                return
+            for k, v in node.items():
+                if k == "router_linear":
+                    found["router"] = v
+                elif k.startswith("expert_") and k[7:].isdigit():
+                    found["experts"][int(k[7:])] = v
+                else:
+                    walk(v)
+
+        walk(tree)
+        E = len(found["experts"])
+        if found["router"] is None or E == 0 or sorted(found["experts"]) != list(range(E)):
+            raise ValueError("not a MoEStatefulLayer parameter tree: need router_linear and expert_0 .. expert_{E-1}")
+        t = lambda a: a if torch.is_tensor(a) else torch.as_tensor(__import__("numpy").asarray(a))
+        stack = lambda proj, leaf: torch.stack([t(found["experts"][i][proj][leaf]) for i in range(E)])
+        return {"router": {"router_linear": {"kernel": t(found["router"]["kernel"]), "bias": t(found["router"]["bias"])}},
+                "experts": {"up_proj": {"kernel": stack("up_proj", "kernel"), "bias": stack("up_proj", "bias")},
+                            "down_proj": {"kernel": stack("down_proj", "kernel"), "bias": stack("down_proj", "bias")}}}
+
+    @staticmethod
+    def to_reference_params(params: Dict[str, dict]) -> Dict[str, dict]:
+        """The inverse: this module's ``params`` as the reference's nested tree (views of the stacked arrays)."""
+        E = params["experts"]["up_proj"]["kernel"].shape[0]
+        inner = {"MoERouter_0": {"router_linear": dict(params["router"]["router_linear"])}}
+        for i in range(E):
+            inner[f"expert_{i}"] = MoEStatefulLayer.expert_view(params, i)
+        return {"MoELayer_0": inner}
+
     def apply(self, variables, x: torch.Tensor, mutable: Union[bool, Iterable[str]] = False, return_routing=False):
         p = variables["params"]
         mut = set(mutable) if not isinstance(mutable, bool) else (set(variables) - {"params"} if mutable else set())

@@ -533,6 +533,7 @@ def moe_route(x, w_r16, b_r, k: int, aux_weight: float, expert_usage=None, step_
         "topk_idx": torch.empty((M, k), **i32), "topk_w": torch.empty((M, k), **f32),
         "counts": torch.empty(E, **i32),
         "prob_partials": torch.empty((lib.forde_moe_num_prob_partials(M), E), **f32),
+        "plan_scratch": torch.empty(lib.forde_moe_plan_scratch_ints(M, k, E), **i32),
         "seg_offsets": torch.empty(E + 1, **i32), "n_blocks": torch.empty(1, **i32),
         "block_expert": torch.empty(R // 128, **i32), "slot_of": torch.empty(M * k, **i32),
         "src_of_slot": torch.empty(R, **i32), "aux_loss": torch.empty(1, **f32),
@@ -540,7 +541,7 @@ def moe_route(x, w_r16, b_r, k: int, aux_weight: float, expert_usage=None, step_
     rc = lib.forde_moe_route(_stream(), x.data_ptr(), w_r16.data_ptr(), b_r.data_ptr(), M, d, E, k, float(aux_weight),
                              r["logits"].data_ptr(), r["probs"].data_ptr(), r["topk_idx"].data_ptr(),
                              r["topk_w"].data_ptr(), r["counts"].data_ptr(), r["prob_partials"].data_ptr(),
-                             r["seg_offsets"].data_ptr(), r["n_blocks"].data_ptr(), r["block_expert"].data_ptr(),
+                             r["plan_scratch"].data_ptr(), r["seg_offsets"].data_ptr(), r["n_blocks"].data_ptr(), r["block_expert"].data_ptr(),
                              r["slot_of"].data_ptr(), r["src_of_slot"].data_ptr(), r["aux_loss"].data_ptr(),
                              _ptr(expert_usage), _ptr(step_count))
     _lib.check(rc, "forde_moe_route")

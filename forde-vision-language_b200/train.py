@@ -150,12 +150,9 @@ class _GradBuckets:
     is issued asynchronously (NCCL's own stream, ordered after the kernels that produced the gradients), so it runs
     under the rest of the backward.  `finish()` issues whatever did not fire and makes the compute stream wait."""
 
-    def __init__(self, leaves, offs, total, flat_g32, group, layers_per_bucket: Optional[int] = None, flat_g16=None):
-        if layers_per_bucket is None:
-            layers_per_bucket = int(os.environ.get("FORDE_BUCKET_LAYERS", "4"))
-        # FORDE_BUCKET_TAPER=1: the layers whose gradients arrive LAST (layer 1, layer 0 of a tower) get buckets of
-        # their own, so the exchange that cannot hide under any remaining backward work is small
-        taper = os.environ.get("FORDE_BUCKET_TAPER", "1") == "1"
+    def __init__(self, leaves, offs, total, flat_g32, group, layers_per_bucket: int = 4, flat_g16=None):
+        # (bucket shapes were swept on 2 GPUs in round 2 -- 1, 2, 4, 12 layers per bucket, tapered tails -- with no
+        # measurable effect on the step, profiles/r2_n2_bucket_variants.md: four layers per bucket stays)
         self.flat, self.group = flat_g32, group
         self.flat16 = flat_g16      # when set, a bucket is cast to bf16 on the side stream and exchanged as bf16
         ranges = []  # (key, start, end, count)
@@ -163,12 +160,9 @@ class _GradBuckets:
             tower = path[0]
             layer = next((k for k in path if k.startswith("layer_")), None)
             if layer is not None:
-                li = int(layer.split("_")[1])
-                idx = li // layers_per_bucket
-                if taper and li < 2:
-                    idx = -3 if li == 1 else -2     # layer 1 and layer 0: a bucket each
+                idx = int(layer.split("_")[1]) // layers_per_bucket
             elif len(path) > 1 and ("embed" in path[1] or path[1] == "cls"):
-                idx = -4            # front end of the tower: its gradients arrive last
+                idx = -1            # front end of the tower: its gradients arrive last
             else:
                 idx = 10 ** 6       # projection head / log-temperature: arrive first
             key = (tower, idx)
@@ -187,7 +181,6 @@ class _GradBuckets:
         self.mode = os.environ.get("FORDE_BUCKET_MODE", "stream")
         # FORDE_GRAD_OVERLAP=0: exchange every bucket after the backward instead of under it (A/B of the overlap)
         self.overlap = os.environ.get("FORDE_GRAD_OVERLAP", "1") != "0"
-        self.skip = os.environ.get("FORDE_SKIP_GRAD_EXCHANGE", "0") == "1"
 
     def attach(self, params_in_order):
         """params_in_order: the leaf tensors in the same order as `leaves`.  The hook fires from autograd's
@@ -217,9 +210,6 @@ class _GradBuckets:
 
     def _fire(self, bi):
         _, a, b, _ = self.ranges[bi]
-        if self.skip:                   # FORDE_SKIP_GRAD_EXCHANGE=1: timing experiments only (gradients stay local)
-            self.fired[bi] = True
-            return
         if self.flat.is_cuda and self.mode == "stream":
             # explicit side stream: it waits for everything enqueued so far on the compute stream (the kernels that
             # produced this bucket's gradients), the collective is ordered on it, finish() joins it back

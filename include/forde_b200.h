@@ -210,10 +210,11 @@ int forde_l2norm_bwd(void* stream, const void* u, const float* inv_norm, const f
  *          db_up_all [E][H] +=, db_down_all [E][d] +=), then combine(dxg, slot_of, NULL) sums the k copies into dx. */
 int forde_moe_capacity_rows(int M, int k, int E);
 int forde_moe_num_prob_partials(int M);
+int forde_moe_plan_scratch_ints(int M, int k, int E); /* ints of plan_scratch: per-chunk, per-expert entry counts */
 int forde_moe_route(void* stream, const void* x, const void* w_r, const float* b_r, int M, int d, int E, int k,
                     float aux_weight, float* logits, float* probs, int* topk_idx, float* topk_w, int* counts,
-                    float* prob_partials, int* seg_offsets, int* n_blocks_dev, int* block_expert, int* slot_of,
-                    int* src_of_slot, float* aux_loss, float* expert_usage, int* step_count);
+                    float* prob_partials, int* plan_scratch, int* seg_offsets, int* n_blocks_dev, int* block_expert,
+                    int* slot_of, int* src_of_slot, float* aux_loss, float* expert_usage, int* step_count);
 int forde_moe_gather(void* stream, const void* x, const int* src_of_slot, int k, void* xg, int rows, int d);
 int forde_moe_scatter(void* stream, const void* dout, const int* src_of_slot, const float* topk_w, int k, void* dyg,
                       int rows, int d);

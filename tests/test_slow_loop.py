@@ -300,3 +300,30 @@ def test_overlapped_slow_loop_actuates_after_a_fixed_delay(monkeypatch):
 def test_overlapped_slow_loop_rejects_zero_delay():
     with pytest.raises(ValueError):
         SL.OverlappedSlowLoop(SL.SlowLoopConfig(), 0)
+
+
+def test_moe_parameter_tree_converts_to_and_from_the_reference_layout():
+    """The reference's per-expert Flax tree (MoELayer_0/{MoERouter_0/router_linear, expert_i/{up,down}_proj},
+    src/forde/moe.py:17-29,88,96-104) loads into the stacked layout and back without loss."""
+    from forde_b200.moe_layer import MoEStatefulLayer
+    rng = np.random.RandomState(0)
+    E, d, H = 4, 8, 16
+    ref = {"MoELayer_0": {"MoERouter_0": {"router_linear": {"kernel": rng.randn(d, E).astype(np.float32),
+                                                             "bias": rng.randn(E).astype(np.float32)}}}}
+    for i in range(E):
+        ref["MoELayer_0"][f"expert_{i}"] = {
+            "up_proj": {"kernel": rng.randn(d, H).astype(np.float32), "bias": rng.randn(H).astype(np.float32)},
+            "down_proj": {"kernel": rng.randn(H, d).astype(np.float32), "bias": rng.randn(d).astype(np.float32)}}
+    p = MoEStatefulLayer.from_reference_params(ref)
+    assert p["experts"]["up_proj"]["kernel"].shape == (E, d, H) and p["experts"]["down_proj"]["bias"].shape == (E, d)
+    np.testing.assert_array_equal(p["experts"]["down_proj"]["kernel"][2].numpy(), ref["MoELayer_0"]["expert_2"]["down_proj"]["kernel"])
+    back = MoEStatefulLayer.to_reference_params(p)
+    for i in range(E):
+        for proj in ("up_proj", "down_proj"):
+            for leaf in ("kernel", "bias"):
+                np.testing.assert_array_equal(back["MoELayer_0"][f"expert_{i}"][proj][leaf].numpy(),
+                                              ref["MoELayer_0"][f"expert_{i}"][proj][leaf])
+    np.testing.assert_array_equal(back["MoELayer_0"]["MoERouter_0"]["router_linear"]["kernel"].numpy(),
+                                  ref["MoELayer_0"]["MoERouter_0"]["router_linear"]["kernel"])
+    with pytest.raises(ValueError):
+        MoEStatefulLayer.from_reference_params({"MoELayer_0": {"expert_0": {}, "expert_2": {}}})
