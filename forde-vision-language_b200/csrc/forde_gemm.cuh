@@ -86,25 +86,13 @@ constexpr int CHUNK = 64;                         // epilogue column chunk (one 
 constexpr int BOX_BYTES = 32 * CHUNK * 2;         // one warp's staging box: 32 rows x 64 bf16 = 4 KB
 constexpr int TMEM_COLS = 512;
 constexpr int CLC_SLOTS = 4;                      // ring of cluster-launch-control responses (dynamic scheduling)
-// Epilogue warps per CTA.  The fused epilogues are instruction/latency heavy (bf16 round trip, multiplex, gate FMA,
-// three running sums per element); 8 warps = 2 per SM sub-partition, 16 = 4 (one 64-column chunk each per tile).
-// More warps cost staging smem, i.e. main-loop stages; the trade-off differs per kernel, see below.
-// Measured at C2 dims: with the first (heavier) epilogues dz_bwd preferred 16 warps / 3 stages (226 us vs 245 us,
-// profiles/r1_exp7_variants.txt); after the warp-uniform, branch-free epilogues 8 warps / 5 stages wins for both
-// fused kernels (dz_bwd 192 us vs 221 us, profiles/r1_exp11_dz_variants.txt): the main loop starves with 3 stages.
-// -D overrides are for A/B builds.
-#ifndef FORDE_UP_WARPS
-#define FORDE_UP_WARPS 8
-#endif
-#ifndef FORDE_DZ_WARPS
-#define FORDE_DZ_WARPS 8
-#endif
-#ifndef FORDE_UP_STAGES
-#define FORDE_UP_STAGES 5
-#endif
-#ifndef FORDE_DZ_STAGES
-#define FORDE_DZ_STAGES 5
-#endif
+// Epilogue warps per CTA: 8 = 2 per SM sub-partition, each draining two adjacent 64-column chunks of a tile; the fused
+// kernels keep a 5-stage operand ring next to their staging boxes.  16 warps / 3 stages was measured twice and lost
+// both times: at C2 vision dims once the epilogues were warp-uniform (dz_bwd 221 vs 192 us, profiles/r1_exp11) and at
+// the text-tower dims in round 2 (K = 512: up_fwd 57.3 vs 43.6 us, dz_bwd 51.8 vs 46.2 us, profiles/r2_w16_text_dims.txt)
+// -- the main loop starves with 3 stages and the extra warps do not shorten the per-tile store chain.
+constexpr int FUSED_EPI_WARPS = 8;
+constexpr int FUSED_STAGES = 5;
 // Software pipelining of the accumulator reads (tcgen05.ld) in the fused epilogues: 0 = load a 32-column half, use
 // it, load the next; 1 = the chunk's second half is in flight while the first is processed; 2 = additionally the next
 // chunk's first half is requested before the second half is processed (64 more live registers, still no spills).
@@ -134,13 +122,12 @@ __device__ __forceinline__ long long sign_index(long long row, long long word, i
 __host__ __device__ constexpr int tmem_pipe(int epi) {
   return epi == 1 /*EPI_UP_FWD*/ ? FORDE_TMEM_PIPE_UP : epi == 2 /*EPI_DZ_BWD*/ ? FORDE_TMEM_PIPE_DZ : 0;
 }
-// Per-neuron partial-sum slots per 256-column tile.  With 8 epilogue warps each warp drains two adjacent 64-column
-// chunks and sums them into ONE slot (2 slots of 128 samples per tile: half the partials traffic and half of what
-// forde_stats_finalize reads); A/B builds with 16 warps keep one slot per chunk.
-constexpr int PARTIALS_PER_TILE = (FORDE_UP_WARPS == 8 && FORDE_DZ_WARPS == 8) ? 2 : 4;
+// Per-neuron partial-sum slots per 256-column tile: each epilogue warp drains two adjacent 64-column chunks and sums
+// them into ONE slot (2 slots of 128 samples per tile).
+constexpr int PARTIALS_PER_TILE = 2;
 constexpr int CHUNKS_PER_SLOT = (BN / CHUNK) / PARTIALS_PER_TILE;
 __host__ __device__ constexpr int epi_warps(int epi, bool pair) {
-  return !pair ? 8 : epi == EPI_UP_FWD ? FORDE_UP_WARPS : epi == EPI_DZ_BWD ? FORDE_DZ_WARPS : 8;
+  return FUSED_EPI_WARPS;
 }
 __host__ __device__ constexpr int num_threads(int epi, bool pair) { return 64 + 32 * epi_warps(epi, pair); }
 
@@ -164,8 +151,8 @@ __host__ __device__ constexpr int epi_warp_staging_bytes(int epi, bool pair) {
 }
 
 __host__ __device__ constexpr int gemm_stages(int epi, bool pair) {
-  return epi == EPI_UP_FWD ? (pair ? FORDE_UP_STAGES : 3)
-         : epi == EPI_DZ_BWD ? (pair ? FORDE_DZ_STAGES : 3)
+  return epi == EPI_UP_FWD ? (pair ? FUSED_STAGES : 3)
+         : epi == EPI_DZ_BWD ? (pair ? FUSED_STAGES : 3)
          : (epi == EPI_MOE_UP || epi == EPI_MOE_DZ) ? 3
          : epi == EPI_STORE_ADD                     ? (pair ? 5 : 3)
                                                     : (pair ? 6 : 4);
@@ -401,6 +388,9 @@ struct TileSched {
   uint64_t* full;   // [CLC_SLOTS] local: response j has landed
   uint64_t* empty;  // [CLC_SLOTS] in the LEADER CTA: every consumer of both CTAs has read response j
   uint32_t resp;    // shared address of the response ring
+  // the first item: every launched cluster of a dynamic grid owns one; a static worker may have none (grouped-M
+  // kernels size their grid for the row capacity and read the number of valid row blocks from device memory)
+  __device__ __forceinline__ bool first_valid() const { return clc || t < total; }
   // `arriver`: this thread releases the slot (exactly one thread per consumer agent); warp_collective: every lane
   // of the warp calls this together
   __device__ __forceinline__ bool advance(bool arriver, bool warp_collective) {
@@ -503,7 +493,7 @@ __global__ void __launch_bounds__(num_threads(EPI, PAIR), 1) forde_gemm_kernel(c
       int stage = 0;
       uint32_t phase = 0;
       TileSched sc = sched0;
-      for (bool more = true; more; more = sc.advance(true, false)) {
+      for (bool more = sc.first_valid(); more; more = sc.advance(true, false)) {
         const int t = sc.t;
         if (clc) {
           // ask for the NEXT item now, one item ahead: the answer is back long before this item's loads are issued
@@ -559,7 +549,7 @@ __global__ void __launch_bounds__(num_threads(EPI, PAIR), 1) forde_gemm_kernel(c
     int it = 0;
     if (!PAIR || cta_rank == 0) {  // in a pair only the leader issues; its MMAs drive both SMs' tensor cores
       TileSched sc = sched0;
-      for (bool more = true; more; more = sc.advance(lane == 0, true), ++it) {
+      for (bool more = sc.first_valid(); more; more = sc.advance(lane == 0, true), ++it) {
         const int t = sc.t;
         const WorkItem w = decode_work(p, t, TILE_M, m_off, m_blocks);
         const int as = it & 1;
@@ -620,8 +610,8 @@ __global__ void __launch_bounds__(num_threads(EPI, PAIR), 1) forde_gemm_kernel(c
     // neurons reads the h^T box (which the forward stores anyway) and the forward never has to write its z^T box.
     // item sequence of this warp, read one item ahead (the z^T prefetch of a tile's last chunk targets the next item)
     TileSched sc = sched0;
-    int cur_t = sc.t;
-    int next_t = sc.advance(lane == 0, true) ? sc.t : -1;
+    int cur_t = sc.first_valid() ? sc.t : -1;
+    int next_t = (cur_t >= 0 && sc.advance(lane == 0, true)) ? sc.t : -1;
     auto z_prefetch = [&](int gi, bool wait_for_store) {
       const int nt = (gi / CPW == it) ? cur_t : next_t;  // chunk gi lies in the current item or in the next one
       if (nt < 0) return;

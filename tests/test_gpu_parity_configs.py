@@ -221,9 +221,11 @@ def test_fused_clip_adamw_matches_the_optax_restatement(ops, grad_dtype, gscale)
         rp, rmu, rnu, rc, rnorm = O.optax_clip_adamw_step(rp, f32(grads), rmu, rnu, rc, lr, wd)
         assert int(count.item()) == rc
         assert abs(float(gn.item()) - float(rnorm)) <= 1e-5 * float(rnorm)
-        np.testing.assert_allclose(f32(mu), rmu, rtol=2e-6, atol=1e-12)
-        np.testing.assert_allclose(f32(nu), rnu, rtol=2e-6, atol=1e-20)
-        np.testing.assert_allclose(f32(p), rp, rtol=2e-6, atol=2e-7)
+        # (the kernel contracts b * m + (1 - b) * g into one FMA, NumPy rounds twice: ~1e-7 of the larger term, which
+        # is a large RELATIVE error only where the two terms cancel)
+        np.testing.assert_allclose(f32(mu), rmu, rtol=2e-6, atol=1e-6 * float(np.abs(rmu).max()))
+        np.testing.assert_allclose(f32(nu), rnu, rtol=2e-6, atol=1e-6 * float(np.abs(rnu).max()))
+        np.testing.assert_allclose(f32(p), rp, rtol=2e-6, atol=1e-6)
         assert torch.equal(p16, p.bfloat16())                         # the compute mirror is bf16(p) exactly
     # deterministic: the same inputs give the same bits
     q1, q2 = p.clone(), p.clone()
@@ -249,8 +251,8 @@ def test_train_state_takes_one_optax_step_per_batch(ops):
     g = f32(st.flat_g32)
     rp, rmu, rnu, rc, rnorm = O.optax_clip_adamw_step(p0, g, np.zeros_like(p0), np.zeros_like(p0), 0, 1e-3, 0.05)
     assert abs(float(m["grad_norm"].item()) - float(rnorm)) <= 1e-5 * float(rnorm)
-    np.testing.assert_allclose(f32(st.flat_p32), rp, rtol=2e-6, atol=2e-7)
-    np.testing.assert_allclose(f32(st.opt_state["mu"]), rmu, rtol=2e-6, atol=1e-12)
+    np.testing.assert_allclose(f32(st.flat_p32), rp, rtol=2e-6, atol=1e-6)
+    np.testing.assert_allclose(f32(st.opt_state["mu"]), rmu, rtol=2e-6, atol=1e-6 * float(np.abs(rmu).max()))
     assert int(st.opt_state["count"].item()) == 1 and st.step == 1
     assert torch.equal(st.flat_p16, st.flat_p32.detach().bfloat16())
 

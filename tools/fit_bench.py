@@ -65,6 +65,24 @@ def stream():
         yield batches[i % 2]
 
 
+# fast steps alone (no slow loop): the baseline the fit() figure is compared with
+barrier()
+f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+f0.record()
+for i in range(20):
+    g(batches[i % 2])
+f1.record()
+barrier()
+ms_fast = torch.tensor([f0.elapsed_time(f1) / 20], device=dev)
+if world > 1:
+    dist.all_reduce(ms_fast, op=dist.ReduceOp.MAX)
+ms_fast = float(ms_fast.item())
+for tower in st.variables["stats_buffer"].values():
+    for l in tower.values():
+        for t in l["stateful_layer"].values():
+            t.zero_()
+st.step = 0
+
 barrier()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 t0 = time.perf_counter()
@@ -88,6 +106,8 @@ if rank == 0:
         "ms_total_device_max_over_ranks": ms, "wall_s_rank0": wall,
         "pairs_per_s_including_slow_loops": world * a.batch * a.steps / (ms * 1e-3),
         "ms_per_step_including_slow_loops": ms / a.steps,
+        "ms_per_fast_step_alone": ms_fast, "pairs_per_s_fast_steps_alone": world * a.batch / (ms_fast * 1e-3),
+        "slow_loop_overhead_fraction": (ms / a.steps - ms_fast) / ms_fast,
         "slow_loop_seconds_on_training_thread": [d.get("seconds") for d in loops],
         "slow_loop_share_of_wall": slow_s / (ms * 1e-3),
         "final_loss": hist["loss"][-1][1] if hist["loss"] else None,

@@ -64,6 +64,29 @@ for name, f in stages:
     print(f"  {name:36s} {us:8.1f} us")
 fl = 12.0 * M * k * d * H
 print(f"  total fwd+bwd {tot:8.1f} us ; routed-token GEMM work 12*M*k*d*H = {fl / 1e9:.1f} GFLOP -> {fl / (tot * 1e-6) / 1e12:.1f} TFLOP/s")
+print("  (stage times above are eager launches from Python with the GPU idle in between: they include the launch latency of")
+print("   every kernel of the stage; the device-side cost is the CUDA-graph replay below)")
+# the whole slot (fwd + bwd, 25 kernels) as ONE CUDA graph: nothing in it synchronises with the host (the routing plan
+# stays on the device), so it replays back to back
+side = torch.cuda.Stream()
+side.wait_stream(torch.cuda.current_stream())
+with torch.cuda.stream(side):
+    run()
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph, stream=side):
+        run()
+    for _ in range(3):
+        graph.replay()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n = 50
+    a.record()
+    for _ in range(n):
+        graph.replay()
+    b.record(); torch.cuda.synchronize()
+    us = 1e3 * a.elapsed_time(b) / n
+print(f"  whole slot fwd+bwd replayed as one CUDA graph: {us:8.1f} us -> {fl / (us * 1e-6) / 1e12:.1f} TFLOP/s on the routed work")
 
 if "--profile" in sys.argv:
     from torch.profiler import ProfilerActivity, profile
