@@ -74,6 +74,9 @@ SIGNATURES = {
     "forde_vision_assemble_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i]),
     "forde_embed_tokens_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i]),
     "forde_embed_tokens_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i]),
+    "forde_attn_max_tokens": (_i, []),
+    "forde_attn_fwd": (_i, [_vp] * 6 + [_i, _i, _i, _ll]),
+    "forde_attn_bwd": (_i, [_vp] * 9 + [_i, _i, _i, _ll]),
 }
 
 

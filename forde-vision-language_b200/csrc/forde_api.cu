@@ -137,6 +137,75 @@ int make_tmap_bf16(CUtensorMap* out, const void* ptr, uint64_t inner, uint64_t o
   return FORDE_OK;
 }
 
+// 3-D bf16 tensor [d2][d1][d0] (d0 contiguous; pitches ld1, ld2 in elements), box {b0, b1, 1}, 128B swizzle, zero OOB
+// fill: the per-(batch, head) token tiles of the attention kernels (rows beyond the sequence read as zeros).
+int make_tmap_bf16_3d(CUtensorMap* out, const void* ptr, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t ld1,
+                      uint64_t ld2, uint32_t b0, uint32_t b1) {
+  static std::mutex mu;
+  struct Key3 {
+    const void* ptr;
+    uint64_t d0, d1, d2, ld1, ld2;
+    uint32_t b0, b1;
+    int dev;
+    bool operator==(const Key3& o) const {
+      return ptr == o.ptr && d0 == o.d0 && d1 == o.d1 && d2 == o.d2 && ld1 == o.ld1 && ld2 == o.ld2 && b0 == o.b0 &&
+             b1 == o.b1 && dev == o.dev;
+    }
+  };
+  struct Key3Hash {
+    size_t operator()(const Key3& k) const {
+      size_t h = reinterpret_cast<size_t>(k.ptr);
+      auto mix = [&h](uint64_t v) { h ^= v + 0x9e3779b97f4a7c15ull + (h << 6) + (h >> 2); };
+      mix(k.d0); mix(k.d1); mix(k.d2); mix(k.ld1); mix(k.ld2); mix(k.b0); mix(k.b1); mix(static_cast<uint64_t>(k.dev));
+      return h;
+    }
+  };
+  static std::unordered_map<Key3, CUtensorMap, Key3Hash> cache;
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) != 0 || (ld1 % 8) != 0 || (ld2 % 8) != 0) return FORDE_EALIGN;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  Key3 key{ptr, d0, d1, d2, ld1, ld2, b0, b1, dev};
+  {
+    std::lock_guard<std::mutex> lock(mu);
+    auto it = cache.find(key);
+    if (it != cache.end()) {
+      std::memcpy(out, &it->second, sizeof(CUtensorMap));
+      return FORDE_OK;
+    }
+  }
+  static thread_local bool ctx_bound = false;
+  if (!ctx_bound) {
+    cudaFree(nullptr);
+    ctx_bound = true;
+  }
+  EncodeTiledFn enc = get_encode_fn();
+  if (enc == nullptr) {
+    record_cuda_error("cuTensorMapEncodeTiled", "driver entry point not available");
+    return FORDE_ECUDA;
+  }
+  cuuint64_t dims[3] = {d0, d1, d2};
+  cuuint64_t strides[2] = {ld1 * 2, ld2 * 2};
+  cuuint32_t box[3] = {b0, b1, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUtensorMap m;
+  CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    char buf[64];
+    std::snprintf(buf, sizeof(buf), "CUresult %d (3-D map)", static_cast<int>(r));
+    record_cuda_error("cuTensorMapEncodeTiled", buf);
+    return FORDE_ECUDA;
+  }
+  {
+    std::lock_guard<std::mutex> lock(mu);
+    if (cache.size() > 4096) cache.clear();
+    cache[key] = m;
+  }
+  std::memcpy(out, &m, sizeof(CUtensorMap));
+  return FORDE_OK;
+}
+
 // operand map: `rows` is the M (or N) extent, `k` the reduction extent.
 //   K-major : memory [rows][k]  -> dims {k, rows},  box {64, tile_rows}
 //   MN-major: memory [k][rows]  -> dims {rows, k},  box {64, 64}

@@ -1,5 +1,6 @@
 // Host-side helpers shared between the translation units of libforde_b200.so.
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <cstdint>
 
@@ -9,6 +10,10 @@ void record_cuda_error(const char* what, const char* msg);
 // records a launch error (if any) and counts `kernels` successful kernel launches (forde_launch_count)
 int check_launch(const char* what, int kernels = 1);
 int sm_count();
+
+// cached TMA descriptor of a 3-D bf16 tensor (see forde_api.cu)
+int make_tmap_bf16_3d(CUtensorMap* out, const void* ptr, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t ld1,
+                      uint64_t ld2, uint32_t b0, uint32_t b1);
 
 struct GemmArgs {
   const void* A;

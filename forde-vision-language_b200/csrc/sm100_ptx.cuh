@@ -135,6 +135,14 @@ __device__ __forceinline__ void tma_load_2d(const void* tmap, uint64_t* bar, voi
         "l"(hint)
       : "memory");
 }
+// 3-D tiled load (attention: {head columns, token rows, batch})
+__device__ __forceinline__ void tma_load_3d(const void* tmap, uint64_t* bar, void* smem_dst, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      :
+      : "r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
 // Same, issued by either CTA of a pair: data lands in the issuing CTA's shared memory, the transaction bytes are
 // counted on the LEADER CTA's barrier (the one the cta_group::2 MMA issuer waits on).
 __device__ __forceinline__ void tma_load_2d_pair(const void* tmap, uint64_t* bar, void* smem_dst, int c0, int c1,

@@ -142,6 +142,33 @@ class _Dense(torch.autograd.Function):
         return dx, dw, db, None, None
 
 
+class _ShortAttention(torch.autograd.Function):
+    """softmax(q k^T / sqrt(d_head)) v for sequences of at most ops.attn_max_tokens() tokens and d_head = 64 (the text
+    tower): csrc/forde_attn.cu, one tcgen05 tile per (batch, head).  q, k, v: (B, T, w) bf16, heads packed along w."""
+
+    @staticmethod
+    def forward(ctx, q, k, v, heads):
+        B, T, w = q.shape
+        q2, k2, v2 = (t.reshape(B * T, w) for t in (q, k, v))
+        q2, k2, v2 = (t if t.is_contiguous() else t.contiguous() for t in (q2, k2, v2))
+        o, lse = ops.attn_fwd(q2, k2, v2, B, T, heads)
+        ctx.save_for_backward(q2, k2, v2, lse)
+        ctx.dims = (B, T, heads, w)
+        return o.view(B, T, w)
+
+    @staticmethod
+    def backward(ctx, d_o):
+        q2, k2, v2, lse = ctx.saved_tensors
+        B, T, heads, w = ctx.dims
+        d2 = d_o.reshape(B * T, w)
+        if d2.dtype != torch.bfloat16:
+            d2 = d2.to(torch.bfloat16)
+        if not d2.is_contiguous():
+            d2 = d2.contiguous()
+        dq, dk, dv = ops.attn_bwd(q2, k2, v2, d2, lse, B, T, heads)
+        return dq.view(B, T, w), dk.view(B, T, w), dv.view(B, T, w), None
+
+
 class _VisionAssemble(torch.autograd.Function):
     """x[b] = [cls + pos[0] ; patch tokens + pos[1:]] (README.md:30-34) on the front-end kernels of csrc/forde_frontend.cu;
     d(cls), d(pos_embed) are accumulated in fp32 straight into their gradient sinks."""
@@ -345,10 +372,12 @@ class FORDEDualEncoder:
                                   pa["value"]["kernel"], pa["value"]["bias"], mirror("query", "kernel"),
                                   mirror("query", "bias"), mirror("key", "kernel"), mirror("key", "bias"),
                                   mirror("value", "kernel"), mirror("value", "bias"), holder)
-        q, k, v = (t.view(B, T, heads, w // heads).transpose(1, 2) for t in (q, k, v))
-        a = F.scaled_dot_product_attention(q, k, v)
-        a = _Dense.apply(a.transpose(1, 2).reshape(B, T, w), pa["out"]["kernel"], pa["out"]["bias"],
-                         mirror("out", "kernel"), mirror("out", "bias"))
+        if w // heads == 64 and T <= ops.attn_max_tokens() and q.is_cuda:
+            a = _ShortAttention.apply(q, k, v, heads)          # text tower: whole sequence in one tcgen05 tile
+        else:                                                 # vision tower: library flash attention (cuDNN)
+            q, k, v = (t.view(B, T, heads, w // heads).transpose(1, 2) for t in (q, k, v))
+            a = F.scaled_dot_product_attention(q, k, v).transpose(1, 2).reshape(B, T, w)
+        a = _Dense.apply(a, pa["out"]["kernel"], pa["out"]["bias"], mirror("out", "kernel"), mirror("out", "bias"))
         x = _AddLayerNorm.apply(x, a, p["ln_1"]["scale"], p["ln_1"]["bias"], holder)
         tower, lname = key.split("/")
         sl_vars = {

@@ -457,6 +457,33 @@ def add_layernorm_bwd(dy, x, r, gamma, mean, rstd, d_gamma=None, d_beta=None):
     return ds, d_gamma, d_beta
 
 
+# ------------------------------------------------------------------------------------------ short-sequence attention
+def attn_max_tokens() -> int:
+    return _lib.load().forde_attn_max_tokens()
+
+
+def attn_fwd(q, k, v, B: int, T: int, heads: int):
+    """q, k, v: bf16 [B*T, heads*64].  Returns (o [B*T, heads*64] bf16, lse [B, heads, T] fp32)."""
+    for t, n in ((q, "q"), (k, "k"), (v, "v")):
+        _req(t, torch.bfloat16, n)
+    assert q.shape == k.shape == v.shape == (B * T, heads * 64)
+    o = torch.empty_like(q)
+    lse = torch.empty((B, heads, T), dtype=torch.float32, device=q.device)
+    rc = _lib.load().forde_attn_fwd(_stream(), q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr(), lse.data_ptr(),
+                                    B, T, heads, q.stride(0))
+    _lib.check(rc, "forde_attn_fwd")
+    return o, lse
+
+
+def attn_bwd(q, k, v, d_o, lse, B: int, T: int, heads: int):
+    _req(d_o, torch.bfloat16, "d_o"); _req(lse, torch.float32, "lse")
+    dq, dk, dv = torch.empty_like(q), torch.empty_like(q), torch.empty_like(q)
+    rc = _lib.load().forde_attn_bwd(_stream(), q.data_ptr(), k.data_ptr(), v.data_ptr(), d_o.data_ptr(), lse.data_ptr(),
+                                    dq.data_ptr(), dk.data_ptr(), dv.data_ptr(), B, T, heads, q.stride(0))
+    _lib.check(rc, "forde_attn_bwd")
+    return dq, dk, dv
+
+
 # ------------------------------------------------------------------------------------------ tower front ends
 def patchify(images, patch: int):
     """images (B, S, S, 3) bf16 NHWC -> patch rows (B * g * g, round_up(p*p*3, 8)) bf16, first p*p*3 columns valid."""

@@ -41,6 +41,27 @@ def test_every_declared_symbol_is_exported_and_bound(lib):
     assert not extra, f"bound in _lib.SIGNATURES but not declared in the header: {extra}"
 
 
+def test_binding_arity_and_argument_kinds_match_the_header():
+    """Every ctypes signature in _lib.SIGNATURES has as many arguments as the header declares, and pointers / integers
+    / floating-point parameters line up position by position (a wrong count only shows up as a TypeError on the GPU)."""
+    import ctypes
+    from forde_b200 import _lib
+    src = re.sub(r"/\*.*?\*/", "", open(HEADER).read(), flags=re.S)
+    decls = dict(re.findall(r"\b(forde_[a-z0-9_]+)\s*\(([^)]*)\)\s*;", src))
+    for name, (_, args) in _lib.SIGNATURES.items():
+        params = [p.strip() for p in decls[name].split(",")] if decls[name].strip() not in ("", "void") else []
+        assert len(params) == len(args), f"{name}: header has {len(params)} parameters, binding {len(args)}"
+        for i, (p, a) in enumerate(zip(params, args)):
+            kind = "ptr" if "*" in p else ("fp" if re.match(r"(const\s+)?(float|double)\b", p) else "int")
+            want = {"ptr": (ctypes.c_void_p, ctypes.c_char_p), "fp": (ctypes.c_float, ctypes.c_double),
+                    "int": (ctypes.c_int, ctypes.c_longlong)}[kind]
+            assert a in want, f"{name}: parameter {i} '{p}' is bound as {a}"
+            if kind == "fp":
+                assert (a is ctypes.c_double) == ("double" in p), f"{name}: parameter {i} '{p}' float/double mismatch"
+            if kind == "int":
+                assert (a is ctypes.c_longlong) == ("long long" in p), f"{name}: parameter {i} '{p}' int width mismatch"
+
+
 def test_pure_host_entry_points(lib):
     assert lib.forde_version() >= 100
     assert lib.forde_error_string(0) == b"ok"

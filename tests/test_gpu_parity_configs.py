@@ -309,3 +309,36 @@ def test_token_embedding_front_end_matches_plain_restatement(ops):
     x_r.backward(dx.float())
     assert torch.equal(x, x_r.detach().bfloat16())             # one fp32 add, one rounding: bit-exact
     assert relerr(f32(table.grad), f32(tr.grad)) < 1e-5 and relerr(f32(pos.grad), f32(pr.grad)) < 1e-5
+
+
+# ------------------------------------------------------------------------------------------ short-sequence attention
+@pytest.mark.parametrize("B,T,heads", [(4, 77, 8), (3, 16, 2), (2, 128, 4), (5, 1, 1), (256, 77, 8), (2, 100, 12)])
+def test_short_attention_forward_backward_against_plain_softmax_attention(ops, B, T, heads):
+    """csrc/forde_attn.cu against plain fp32 softmax(q k^T / 8) v and its autograd gradients on the same bf16 inputs.
+    Tolerance: the probabilities are staged in bf16 (2^-8 relative each), outputs and gradients are bf16: relative
+    Frobenius error <= 1e-2, and every element within 2^-6 |ref| + 5e-2 rms(ref) (dS = p (dP - D) is rounded to bf16
+    after a cancellation, so a handful of the 10^7 gradient elements of the full-size case sit at 2-3 % of the rms)."""
+    w = heads * 64
+    g_ = torch.Generator(device="cuda").manual_seed(T * 131 + B)
+    q, k, v = ((torch.randn((B, T, w), device="cuda", generator=g_) * s).bfloat16() for s in (1.5, 1.5, 1.0))
+    d_o = torch.randn((B, T, w), device="cuda", generator=g_).bfloat16()
+    o, lse = ops.attn_fwd(q.view(B * T, w), k.view(B * T, w), v.view(B * T, w), B, T, heads)
+    dq, dk, dv = ops.attn_bwd(q.view(B * T, w), k.view(B * T, w), v.view(B * T, w), d_o.view(B * T, w), lse, B, T, heads)
+    torch.cuda.synchronize()
+    qf, kf, vf = (t.float().view(B, T, heads, 64).transpose(1, 2).detach().requires_grad_(True) for t in (q, k, v))
+    s = (qf @ kf.transpose(-1, -2)) * 0.125
+    ref_lse = torch.logsumexp(s, -1)
+    ref = torch.softmax(s, -1) @ vf
+    ref.backward(d_o.float().view(B, T, heads, 64).transpose(1, 2))
+    back = lambda t: t.transpose(1, 2).reshape(B * T, w)
+
+    def close(got, want, name):
+        got, want = f32(got), f32(want)
+        assert relerr(got, want) <= 1e-2, f"{name}: rel Frobenius {relerr(got, want):.3e}"
+        rms = float(np.sqrt(np.mean(want.astype(np.float64) ** 2)))
+        bad = np.abs(got - want) > 2.0 ** -6 * np.abs(want) + 5e-2 * rms
+        assert not bad.any(), f"{name}: {bad.sum()} of {bad.size} elements off"
+
+    np.testing.assert_allclose(f32(lse), f32(ref_lse), rtol=1e-3, atol=2e-3)
+    close(o, back(ref), "o")
+    close(dq, back(qf.grad), "dq"); close(dk, back(kf.grad), "dk"); close(dv, back(vf.grad), "dv")
