@@ -17,6 +17,11 @@
 //             TMEM instead of keeping 256 values per thread)                         -> P, dS (bf16) in shared memory
 //             dV = P^T dO, dK = dS^T Q, dQ = dS K                                     -> TMEM [0,64), [64,128), [128,192)
 //             (operand tiles double buffered: the next head's 64 KB load while this one computes)
+// What bounds it: TMEM reads (64 B/clk per SM).  A backward item reads S and dP twice and the three gradients once,
+// ~300 KB = 2.4 us of the ~7 us an item takes; more CTAs per SM do not help (measured in round 2 with compact
+// Tpad-row tiles, 2-3 CTAs per SM: forward 38 -> 65 us, backward 101 -> 108 us per text layer, reverted), nor does
+// double-buffering the operand loads much (107 -> 101 us, kept).  Shipped: forward 38 us + backward 101 us per
+// text layer at C2 against 207 us for cuDNN's kernels.
 // Rows / keys beyond T: TMA zero-fills them (3-D tensor map {columns, tokens, batch}), masked keys get p = 0, and the
 // padded query rows of P / dS are written as zeros because they are reduction (K) indices of dV and dK.
 // Roles: warps 0-3 = one thread per row (TMEM lane quarter = warp), warp 4 = TMA + MMA issue (one thread).
