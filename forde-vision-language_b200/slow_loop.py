@@ -80,8 +80,10 @@ def warm_up() -> None:
     """Import scikit-learn / SciPy and run one tiny fit so the first slow loop does not pay ~4 s of imports.
     ``train.fit`` calls this on a background thread while the first fast steps run."""
     rng = np.random.RandomState(0)
-    gmm_cluster(rng.rand(32, 5).astype(np.float32), 3, 0)
-    box_smooth(np.zeros((4, 8), np.int32), 3, 3)
+    # a realistically sized job through the same code path as an update (thread pool, threadpoolctl, sklearn's
+    # lazily imported linear algebra): the first real update otherwise pays seconds of one-time set-up
+    jobs = [(f"warm_{i}", rng.rand(1024, 5).astype(np.float32), None) for i in range(2)]
+    slow_loop_compute(jobs, SlowLoopConfig(), 0)
 
 
 def gmm_cluster(stats: np.ndarray, num_clusters: int, seed: int):
@@ -120,51 +122,73 @@ def sense_layer(stats_leaf: Dict[str, torch.Tensor], pooled: bool, group=None) -
     return _sense_layers([stats_leaf], pooled, group)[0]
 
 
-def _sense_layers(leaves, pooled: bool, group=None):
-    """Sense a list of stats_buffer leaf dicts with ONE cross-rank all-reduce and ONE device-to-host copy (the slow
-    loop stalls the training thread, so no per-layer synchronisation).  Returns a list of (H,5) arrays / None."""
-    if not leaves:
-        return []
+def _sense_layers_device(leaves, pooled: bool, group=None):
+    """Device half of Sense for a list of stats_buffer leaf dicts: ONE cross-rank all-reduce, the finalisation kernels
+    and ONE device-to-host copy into pinned memory, all enqueued on the current stream without waiting for them.
+    Returns a handle for ``_sense_layers_host``."""
     world = _world(group)
     dev = leaves[0]["moments"].device
     sizes = [int(l["moments"].shape[0]) for l in leaves]
+    n = len(leaves)
     if pooled:
         # fp64 = high + low fp32 parts of the double-single accumulators; counts ride along (exact in fp64)
         flat = torch.cat([ops.pooled_moments(l).reshape(-1) for l in leaves] +
                          [torch.stack([l["sample_count"].double() for l in leaves])])
         if world > 1:
             dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
-        counts = flat[-len(leaves):].to(torch.int32)
+        counts = flat[-n:].to(torch.int32)
         out = torch.zeros((sum(sizes), 5), dtype=torch.float32, device=dev)
         off = 0
         for i, H in enumerate(sizes):
             # finalisation runs in the CUDA kernel (ops rejects host tensors: no CPU fallback); zero counts give zeros
             ops.stats_from_moments(flat[off * 5:(off + H) * 5].view(H, 5), counts[i:i + 1], out=out[off:off + H])
             off += H
-        host, counts_h = out.cpu().numpy(), counts.cpu().numpy()
+        counts = counts.float()
     else:
         flat = torch.cat([l["neuron_stats"].reshape(-1) for l in leaves] +
                          [torch.stack([l["step_count"].float() for l in leaves])])
-        steps = flat[-len(leaves):].clone()
+        counts = flat[-n:].clone()
         if world > 1:       # mean over ranks of each rank's mean over steps (moe_slow_loop.py:298 per rank)
             dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
-        host = flat[:-len(leaves)].view(-1, 5).cpu().numpy()
-        counts_h = steps.cpu().numpy()
+        out = flat[:-n].view(-1, 5)
+    pin = dev.type == "cuda"
+    host = torch.empty(out.shape, dtype=torch.float32, pin_memory=pin)
+    counts_h = torch.empty(n, dtype=torch.float32, pin_memory=pin)
+    host.copy_(out, non_blocking=True)
+    counts_h.copy_(counts, non_blocking=True)
+    event = None
+    if dev.type == "cuda":
+        event = torch.cuda.Event()
+        event.record()
+    return {"host": host, "counts": counts_h, "event": event, "sizes": sizes, "pooled": pooled, "world": world}
+
+
+def _sense_layers_host(handle):
+    """Host half: wait for the copy (only this thread blocks) and cut the flat array into per-layer (H,5) arrays."""
+    if handle["event"] is not None:
+        handle["event"].synchronize()
+    host, counts_h = handle["host"].numpy(), handle["counts"].numpy()
     res, off = [], 0
-    for i, H in enumerate(sizes):
+    for i, H in enumerate(handle["sizes"]):
         if counts_h[i] == 0:
             res.append(None)
-        elif pooled:
+        elif handle["pooled"]:
             res.append(host[off:off + H].copy())
         else:
-            res.append(host[off:off + H] / (float(counts_h[i]) * world))
+            res.append(host[off:off + H] / (float(counts_h[i]) * handle["world"]))
         off += H
     return res
 
 
-def slow_loop_sense(mutable_variables, config: SlowLoopConfig, group=None):
-    """SENSE for every layer (device work + one cross-rank all-reduce, layers in a fixed order on every rank).
-    Returns the job list [(layer path, (H,5) stats on the host or None, that layer's assignment leaf dict)]."""
+def _sense_layers(leaves, pooled: bool, group=None):
+    """Sense a list of stats_buffer leaf dicts with ONE cross-rank all-reduce and ONE device-to-host copy (the slow
+    loop stalls the training thread, so no per-layer synchronisation).  Returns a list of (H,5) arrays / None."""
+    if not leaves:
+        return []
+    return _sense_layers_host(_sense_layers_device(leaves, pooled, group))
+
+
+def _find_layers(mutable_variables):
     found = []
 
     def walk(st, asg, path):
@@ -176,6 +200,13 @@ def slow_loop_sense(mutable_variables, config: SlowLoopConfig, group=None):
                 walk(st[k], asg[k], path + (k,))
 
     walk(mutable_variables["stats_buffer"], mutable_variables["neuron_assignments"], ())
+    return found
+
+
+def slow_loop_sense(mutable_variables, config: SlowLoopConfig, group=None):
+    """SENSE for every layer (device work + one cross-rank all-reduce, layers in a fixed order on every rank).
+    Returns the job list [(layer path, (H,5) stats on the host or None, that layer's assignment leaf dict)]."""
+    found = _find_layers(mutable_variables)
     stats = _sense_layers([st for _, st, _ in found], config.pooled, group)
     return [(name, s, asg) for (name, _, asg), s in zip(found, stats)]
 
@@ -308,11 +339,22 @@ class OverlappedSlowLoop:
         flushed = self.flush()
         t0 = time.perf_counter()
         diagnostics = {"epoch": epoch, "step": step, "layers": {}}
-        jobs = slow_loop_sense(mutable_variables, self.config, self.group)
+        # Sense is only ENQUEUED here (all-reduce, finalisation kernels, copy into pinned memory, then Reset, all
+        # stream-ordered behind the fast step in flight): the training thread does not wait for the device, the
+        # worker thread does before it clusters.
+        found = _find_layers(mutable_variables)
+        handle = _sense_layers_device([st for _, st, _ in found], self.config.pooled, self.group) if found else None
         _zero_tree(mutable_variables["stats_buffer"])
         diagnostics["seconds"] = {"sense": time.perf_counter() - t0}
-        fut = self._pool.submit(slow_loop_compute, jobs, self.config, _seed_from_key(key))
-        self._pending = (fut, step + self.delay, jobs, diagnostics)
+        config, seed = self.config, _seed_from_key(key)
+
+        def work():
+            stats = _sense_layers_host(handle) if handle is not None else []
+            jobs = [(name, st, asg) for (name, _, asg), st in zip(found, stats)]
+            return jobs, slow_loop_compute(jobs, config, seed)
+
+        fut = self._pool.submit(work)
+        self._pending = (fut, step + self.delay, None, diagnostics)
         return flushed
 
     def poll(self, step: int):
@@ -327,10 +369,10 @@ class OverlappedSlowLoop:
         if self._pending is None:
             return None
         import time
-        fut, due, jobs, diagnostics = self._pending
+        fut, due, _, diagnostics = self._pending
         self._pending = None
         t0 = time.perf_counter()
-        results = fut.result()                 # normally done long ago; the wait (if any) is training-thread time
+        jobs, results = fut.result()           # normally done long ago; the wait (if any) is training-thread time
         slow_loop_actuate(jobs, results, self.config, diagnostics, self.group)
         sec = diagnostics.setdefault("seconds", {})
         sec["actuate_reset"] = time.perf_counter() - t0
