@@ -243,9 +243,19 @@ def slow_loop_compute(jobs, config: SlowLoopConfig, seed: int):
         return dict(zip([n for n, _ in todo], pool.map(lambda t: cluster_and_smooth(t[1]), todo)))
 
 
+def computes_here(config: SlowLoopConfig, group=None) -> bool:
+    """With ``broadcast`` only rank 0 clusters and smooths (its maps are the ones every rank writes anyway); eight ranks
+    each running the same scikit-learn fits on 16 host threads oversubscribe the box's cores and stretch an update
+    from 0.7 s to 3 s (measured at 4 and 8 ranks, profiles/r2_c5_fit_*)."""
+    if _world(group) > 1 and config.broadcast:
+        return dist.get_rank(group) == 0
+    return True
+
+
 def slow_loop_actuate(jobs, results, config: SlowLoopConfig, diagnostics, group=None) -> None:
     """ACTUATE in layer order: overwrite each layer's ``assignments`` in place and fill ``diagnostics["layers"]``.
-    Multi-rank with ``config.broadcast``: the maps every rank writes are rank 0's (one broadcast of all layers)."""
+    Multi-rank with ``config.broadcast``: the maps every rank writes are rank 0's (one broadcast of all layers);
+    the other ranks pass empty ``results``."""
     k = config.num_clusters
     live = [(name, stats, asg) for name, stats, asg in jobs if stats is not None]
     for name, stats, _ in jobs:
@@ -254,7 +264,8 @@ def slow_loop_actuate(jobs, results, config: SlowLoopConfig, diagnostics, group=
     if not live:
         return
     dev = live[0][2]["assignments"].device
-    new_maps = [results[name][1].reshape(-1).astype(np.int32) for name, _, _ in live]
+    new_maps = [results[name][1].reshape(-1).astype(np.int32) if name in results
+                else np.zeros(stats.shape[0], np.int32) for name, stats, _ in live]
     if _world(group) > 1 and config.broadcast:
         flat = torch.from_numpy(np.concatenate(new_maps)).to(dev)
         dist.broadcast(flat, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
@@ -265,14 +276,14 @@ def slow_loop_actuate(jobs, results, config: SlowLoopConfig, diagnostics, group=
     old = torch.cat([asg["assignments"].reshape(-1) for _, _, asg in live]).cpu().numpy()    # one device-to-host copy
     off = 0
     for (name, stats, asg), new in zip(live, new_maps):
-        labels, smoothed, gmm_params = results[name]
-        smoothed = new.reshape(smoothed.shape)
+        labels, _, gmm_params = results.get(name, (None, None, None))
+        smoothed = new.reshape(default_grid(new.size))
         changed = int((old[off:off + new.size] != new).sum())
         off += new.size
-        asg["assignments"].copy_(torch.from_numpy(new))                                 # in place: bumps _version
+        asg["assignments"].copy_(torch.from_numpy(np.ascontiguousarray(new)))           # in place: bumps _version
         diagnostics["layers"][name] = {
             "census": np.bincount(new, minlength=k).tolist(),                           # README.md:66 "The Census"
-            "raw_census": np.bincount(labels, minlength=k).tolist(),
+            "raw_census": np.bincount(labels, minlength=k).tolist() if labels is not None else None,
             "changed": changed,
             "brain_scan": smoothed,                                                     # README.md:64
             "features": stats,                                                          # README.md:65
@@ -299,7 +310,7 @@ def slow_loop_step(params, mutable_variables, config: SlowLoopConfig, key, epoch
     diagnostics = {"epoch": epoch, "step": step, "layers": {}}
     jobs = slow_loop_sense(mutable_variables, config, group)
     t1 = time.perf_counter()
-    results = slow_loop_compute(jobs, config, _seed_from_key(key))
+    results = slow_loop_compute(jobs, config, _seed_from_key(key)) if computes_here(config, group) else {}
     t2 = time.perf_counter()
     slow_loop_actuate(jobs, results, config, diagnostics, group)
     _zero_tree(mutable_variables["stats_buffer"])
@@ -347,11 +358,12 @@ class OverlappedSlowLoop:
         _zero_tree(mutable_variables["stats_buffer"])
         diagnostics["seconds"] = {"sense": time.perf_counter() - t0}
         config, seed = self.config, _seed_from_key(key)
+        here = computes_here(config, self.group)
 
         def work():
             stats = _sense_layers_host(handle) if handle is not None else []
             jobs = [(name, st, asg) for (name, _, asg), st in zip(found, stats)]
-            return jobs, slow_loop_compute(jobs, config, seed)
+            return jobs, (slow_loop_compute(jobs, config, seed) if here else {})
 
         fut = self._pool.submit(work)
         self._pending = (fut, step + self.delay, None, diagnostics)

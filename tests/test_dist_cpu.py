@@ -230,3 +230,54 @@ def test_two_rank_bucketed_gradient_allreduce():
             np.testing.assert_array_equal(g[off:off + n], np.full(n, 3.0 * (i + 1), np.float32))   # (1 + 2) * (i+1)
         off, n = layout[-2]
         np.testing.assert_array_equal(g[off:off + n], np.zeros(n, np.float32))
+
+
+def _slow_loop_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import forde_b200  # noqa: F401
+        from forde_b200 import slow_loop as SL
+        from forde_b200.stateful_layer import new_stats_buffer
+        SL.ops = _FakeOps
+        if rank != 0:                      # with broadcast only rank 0 may cluster; anything else is a bug
+            def boom(*a, **k):
+                raise AssertionError("slow_loop_compute ran on a rank other than 0")
+            SL.slow_loop_compute = boom
+        rng = np.random.RandomState(3)
+        H = 64
+        z = (rng.randn(256, H) * np.linspace(0.2, 2.0, H)).astype(np.float32)
+        g = (rng.randn(256, H) * np.where(np.arange(H) % 3 == 0, 1.0, 0.05)).astype(np.float32)
+        sl = slice(rank * 128, (rank + 1) * 128)                 # each rank sensed its own half of the samples
+        m, n = O.raw_moments(z[sl], g[sl])
+        mv = {"stats_buffer": {"layer_0": {"stateful_layer": new_stats_buffer(H, "cpu")}},
+              "neuron_assignments": {"layer_0": {"stateful_layer": {"assignments": torch.zeros(H, dtype=torch.int32)}}}}
+        sb = mv["stats_buffer"]["layer_0"]["stateful_layer"]
+        hi = m.astype(np.float32)
+        sb["moments"] += torch.from_numpy(hi); sb["moments_lo"] += torch.from_numpy((m - hi).astype(np.float32))
+        sb["sample_count"] += n; sb["step_count"] += 1
+        _, mv, diag = SL.slow_loop_step({}, mv, SL.SlowLoopConfig(), key=5, step=100)
+        a = mv["neuron_assignments"]["layer_0"]["stateful_layer"]["assignments"].numpy().copy()
+        d = diag["layers"]["layer_0/stateful_layer"]
+        q.put((rank, a, d["census"], d["raw_census"] is not None, float(sb["moments"].abs().sum())))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_slow_loop_rank0_clusters_and_broadcasts_the_maps():
+    """Sense pools both ranks' moments; only rank 0 runs Cluster + Smooth; every rank actuates rank 0's map; Reset."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_slow_loop_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=180) for _ in procs], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    (_, a0, c0, raw0, m0), (_, a1, c1, raw1, m1) = res
+    np.testing.assert_array_equal(a0, a1)
+    assert c0 == c1 and sum(c0) == 64 and len(set(a0.tolist())) > 1      # a non-trivial map, identical on both ranks
+    assert raw0 is True and raw1 is False                                # only rank 0 holds the GMM's own labels
+    assert m0 == 0.0 and m1 == 0.0                                       # Reset on both
