@@ -34,6 +34,7 @@ SIGNATURES = {
     "forde_gemm_f32": (_i, [_vp, _vp, _i, _ll, _vp, _i, _ll, _vp, _ll, _vp, _vp, _f, _i, _i, _i, _i]),
     "forde_sl_up_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _ll, _i]),
     "forde_sl_down_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _ll]),
+    "forde_sl_down_fwd_add": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _ll]),
     "forde_sl_fwd": (_i, [_vp] * 11 + [_i, _i, _i, _ll, _i]),
     "forde_sl_dz_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _ll]),
     "forde_sl_dx_bwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _ll]),

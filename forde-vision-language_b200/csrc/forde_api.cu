@@ -526,6 +526,15 @@ int forde_sl_down_fwd(void* stream, const void* hT, const void* w_down, const fl
   return gemm_store_bf16(static_cast<cudaStream_t>(stream), g, y, d, b_down);
 }
 
+// y = h . w_down + b + residual : the block's `x + StatefulLayer(x)` is formed in the epilogue, so the add/norm that
+// follows reads ONE tensor instead of two
+int forde_sl_down_fwd_add(void* stream, const void* hT, const void* w_down, const float* b_down, const void* residual,
+                          void* y, int M, int d, int H, long long ldz) {
+  if (ldz < M || residual == nullptr) return FORDE_EINVAL;
+  GemmArgs g{hT, true, ldz, w_down, true, d, M, d, H, /*raster_m_fast=*/false, kEvictFirst, kEvictLast};
+  return gemm_store_bf16(static_cast<cudaStream_t>(stream), g, y, d, b_down, residual);
+}
+
 int forde_sl_fwd(void* stream, const void* x, const void* w_up, const float* b_up, const void* w_down,
                  const float* b_down, const int8_t* assign, void* zT, void* hT, void* y, float* act_partials,
                  int M, int d, int H, long long ldz, int save_z) {

@@ -1,3 +1,6 @@
+// (round 2) The arithmetic is written with Blackwell's packed fp32 pair instructions (FFMA2 / FADD2 / FMUL2 through
+// __ffma2_rn / __fadd2_rn / __fmul2_rn): the kernels were issue-bound, not bandwidth-bound (the backward streamed
+// 232 MB in 80 us = 2.9 TB/s), and a bf16 pair unpacks straight into a float2.
 // Fused residual-add + LayerNorm (the `add/norm` either side of the StatefulLayer in a FORDE block,
 // README.md:42-43).  HBM-bound streaming kernels: one warp per token row, 16-byte vector accesses, the row
 // stays in registers between the statistics and the normalisation, persistent grid (a multiple of the SM
@@ -34,6 +37,16 @@ __device__ __forceinline__ void unpack8(const uint4& q, float* f) {
     f[2 * i + 1] = __uint_as_float(w[i] & 0xFFFF0000u);
   }
 }
+// a packed bf16 pair -> float2 {low element, high element}
+__device__ __forceinline__ float2 unpack2(uint32_t w) {
+  return make_float2(__uint_as_float(w << 16), __uint_as_float(w & 0xFFFF0000u));
+}
+__device__ __forceinline__ uint32_t pack2(float2 v) {
+  __nv_bfloat162 b = __floats2bfloat162_rn(v.x, v.y);
+  return *reinterpret_cast<uint32_t*>(&b);
+}
+__device__ __forceinline__ float2 splat2(float v) { return make_float2(v, v); }
+
 __device__ __forceinline__ uint4 pack8(const float* f) {
   uint32_t w[4];
 #pragma unroll
@@ -44,7 +57,7 @@ __device__ __forceinline__ uint4 pack8(const float* f) {
   return make_uint4(w[0], w[1], w[2], w[3]);
 }
 
-template <int NV>  // 16-byte vectors per lane actually used: ceil(cols / 256)
+template <int NV, bool HAS_R>  // NV: 16-byte vectors per lane actually used, ceil(cols / 256); HAS_R: r != NULL
 __global__ void __launch_bounds__(LN_WARPS * 32)
 add_layernorm_fwd_kernel(const uint4* __restrict__ x, const uint4* __restrict__ r, const float* __restrict__ gamma,
                          const float* __restrict__ beta, uint4* __restrict__ out, float* __restrict__ mean_out,
@@ -52,41 +65,62 @@ add_layernorm_fwd_kernel(const uint4* __restrict__ x, const uint4* __restrict__ 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int nvec = cols >> 3;
   const float inv_n = 1.f / static_cast<float>(cols);
-  for (int row = blockIdx.x * LN_WARPS + warp; row < rows; row += gridDim.x * LN_WARPS) {
-    const size_t base = static_cast<size_t>(row) * nvec;
-    float s[NV][8];
-    float sum = 0.f;
+  const int stride = gridDim.x * LN_WARPS;
+  constexpr bool has_r = HAS_R;
+  uint4 cx[NV], cr[NV];
+  auto load_row = [&](int rw, uint4* ax, uint4* ar) {
+    const size_t b0 = static_cast<size_t>(rw) * nvec;
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
       const int v = lane + i * 32;
       if (v < nvec) {
-        float a[8], b[8];
-        unpack8(__ldg(x + base + v), a);
-        if (r != nullptr) {
-          unpack8(__ldg(r + base + v), b);
-#pragma unroll
-          for (int k = 0; k < 8; ++k) a[k] += b[k];
-        }
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          s[i][k] = a[k];
-          sum += a[k];
-        }
+        ax[i] = __ldg(x + b0 + v);
+        if (has_r) ar[i] = __ldg(r + b0 + v);
       }
     }
-    const float mean = wsum(sum) * inv_n;
-    float sq = 0.f;
+  };
+  int row = blockIdx.x * LN_WARPS + warp;
+  if (row < rows) load_row(row, cx, cr);
+  for (; row < rows; row += stride) {
+    const size_t base = static_cast<size_t>(row) * nvec;
+    uint4 nx[NV], nr[NV];
+    if (row + stride < rows) load_row(row + stride, nx, nr);   // the next row's loads fly while this one is normalised
+    float2 s[NV][4];
+    float2 sum2 = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int v = lane + i * 32;
+      if (v < nvec) {
+        const uint4 qx = cx[i];
+        const uint32_t wx[4] = {qx.x, qx.y, qx.z, qx.w};
+        if (has_r) {
+          const uint4 qr = cr[i];
+          const uint32_t wr[4] = {qr.x, qr.y, qr.z, qr.w};
+#pragma unroll
+          for (int k = 0; k < 4; ++k) s[i][k] = __fadd2_rn(unpack2(wx[k]), unpack2(wr[k]));
+        } else {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) s[i][k] = unpack2(wx[k]);
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) sum2 = __fadd2_rn(sum2, s[i][k]);
+      }
+    }
+    const float mean = wsum(sum2.x + sum2.y) * inv_n;
+    const float2 nmean2 = splat2(-mean);
+    float2 sq2 = make_float2(0.f, 0.f);
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
       if (lane + i * 32 < nvec) {
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          const float dlt = s[i][k] - mean;
-          sq = fmaf(dlt, dlt, sq);
+        for (int k = 0; k < 4; ++k) {
+          const float2 dlt = __fadd2_rn(s[i][k], nmean2);
+          sq2 = __ffma2_rn(dlt, dlt, sq2);
         }
       }
     }
-    const float rstd = rsqrtf(wsum(sq) * inv_n + eps);
+    const float rstd = rsqrtf(wsum(sq2.x + sq2.y) * inv_n + eps);
+    const float2 rstd2 = splat2(rstd), nmr2 = splat2(-mean * rstd);
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
       const int v = lane + i * 32;
@@ -95,17 +129,22 @@ add_layernorm_fwd_kernel(const uint4* __restrict__ x, const uint4* __restrict__ 
         const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma) + 2 * v + 1);
         const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta) + 2 * v);
         const float4 b1 = __ldg(reinterpret_cast<const float4*>(beta) + 2 * v + 1);
-        const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
-        const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-        float o[8];
+        const float2 g[4] = {make_float2(g0.x, g0.y), make_float2(g0.z, g0.w), make_float2(g1.x, g1.y), make_float2(g1.z, g1.w)};
+        const float2 b[4] = {make_float2(b0.x, b0.y), make_float2(b0.z, b0.w), make_float2(b1.x, b1.y), make_float2(b1.z, b1.w)};
+        uint32_t o[4];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) o[k] = fmaf((s[i][k] - mean) * rstd, g[k], b[k]);
-        out[base + v] = pack8(o);
+        for (int k = 0; k < 4; ++k) o[k] = pack2(__ffma2_rn(__ffma2_rn(s[i][k], rstd2, nmr2), g[k], b[k]));
+        out[base + v] = make_uint4(o[0], o[1], o[2], o[3]);
       }
     }
     if (lane == 0) {
       mean_out[row] = mean;
       rstd_out[row] = rstd;
+    }
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      cx[i] = nx[i];
+      if (has_r) cr[i] = nr[i];
     }
   }
 }
@@ -145,61 +184,198 @@ add_layernorm_bwd_kernel(const uint4* __restrict__ dy, const uint4* __restrict__
       }
     }
     const float mean = mean_in[row], rstd = rstd_in[row];
-    float c1 = 0.f, c2 = 0.f;
+    const float2 rstd2 = splat2(rstd), nmr2 = splat2(-mean * rstd);
+    const bool has_r = (r != nullptr);   // uniform
+    float2 c1_2 = make_float2(0.f, 0.f), c2_2 = make_float2(0.f, 0.f);
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
       const int v = lane + i * 32;
       if (v < nvec) {
-        float a[8], b[8], d[8];
-        unpack8(px[i], a);
-        unpack8(pr[i], b);
-        unpack8(pd[i], d);
-        float4* dgp = reinterpret_cast<float4*>(dg_s + v * 8);
-        float4* dbp = reinterpret_cast<float4*>(db_s + v * 8);
-        const float4* gp = reinterpret_cast<const float4*>(gam_s + v * 8);
-        float4 g0 = dgp[0], g1 = dgp[1], b0 = dbp[0], b1 = dbp[1];
-        const float4 w0 = gp[0], w1 = gp[1];
-        float dgv[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
-        float dbv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-        const float gw[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+        const uint32_t wx[4] = {px[i].x, px[i].y, px[i].z, px[i].w};
+        const uint32_t wr[4] = {pr[i].x, pr[i].y, pr[i].z, pr[i].w};
+        const uint32_t wd[4] = {pd[i].x, pd[i].y, pd[i].z, pd[i].w};
+        float2* dgp = reinterpret_cast<float2*>(dg_s + v * 8);
+        float2* dbp = reinterpret_cast<float2*>(db_s + v * 8);
+        const float2* gp = reinterpret_cast<const float2*>(gam_s + v * 8);
+        float4 g01 = reinterpret_cast<float4*>(dgp)[0], g23 = reinterpret_cast<float4*>(dgp)[1];
+        float4 b01 = reinterpret_cast<float4*>(dbp)[0], b23 = reinterpret_cast<float4*>(dbp)[1];
+        const float4 w01 = reinterpret_cast<const float4*>(gp)[0], w23 = reinterpret_cast<const float4*>(gp)[1];
+        float2 dgv[4] = {make_float2(g01.x, g01.y), make_float2(g01.z, g01.w), make_float2(g23.x, g23.y), make_float2(g23.z, g23.w)};
+        float2 dbv[4] = {make_float2(b01.x, b01.y), make_float2(b01.z, b01.w), make_float2(b23.x, b23.y), make_float2(b23.z, b23.w)};
+        const float2 gw[4] = {make_float2(w01.x, w01.y), make_float2(w01.z, w01.w), make_float2(w23.x, w23.y), make_float2(w23.z, w23.w)};
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          const float h = (a[k] + b[k] - mean) * rstd;
-          dgv[k] = fmaf(d[k], h, dgv[k]);
-          dbv[k] += d[k];
-          const float t = d[k] * gw[k];
-          c1 += t;
-          c2 = fmaf(t, h, c2);
+        for (int k = 0; k < 4; ++k) {
+          float2 a = unpack2(wx[k]);
+          if (has_r) a = __fadd2_rn(a, unpack2(wr[k]));
+          const float2 d = unpack2(wd[k]);
+          const float2 h = __ffma2_rn(a, rstd2, nmr2);      // (x + r - mean) * rstd
+          dgv[k] = __ffma2_rn(d, h, dgv[k]);
+          dbv[k] = __fadd2_rn(dbv[k], d);
+          const float2 t = __fmul2_rn(d, gw[k]);
+          c1_2 = __fadd2_rn(c1_2, t);
+          c2_2 = __ffma2_rn(t, h, c2_2);
         }
-        dgp[0] = make_float4(dgv[0], dgv[1], dgv[2], dgv[3]);
-        dgp[1] = make_float4(dgv[4], dgv[5], dgv[6], dgv[7]);
-        dbp[0] = make_float4(dbv[0], dbv[1], dbv[2], dbv[3]);
-        dbp[1] = make_float4(dbv[4], dbv[5], dbv[6], dbv[7]);
+        reinterpret_cast<float4*>(dgp)[0] = make_float4(dgv[0].x, dgv[0].y, dgv[1].x, dgv[1].y);
+        reinterpret_cast<float4*>(dgp)[1] = make_float4(dgv[2].x, dgv[2].y, dgv[3].x, dgv[3].y);
+        reinterpret_cast<float4*>(dbp)[0] = make_float4(dbv[0].x, dbv[0].y, dbv[1].x, dbv[1].y);
+        reinterpret_cast<float4*>(dbp)[1] = make_float4(dbv[2].x, dbv[2].y, dbv[3].x, dbv[3].y);
       }
     }
-    c1 = wsum(c1) * inv_n;
-    c2 = wsum(c2) * inv_n;
+    const float c1 = wsum(c1_2.x + c1_2.y) * inv_n;
+    const float c2 = wsum(c2_2.x + c2_2.y) * inv_n;
+    const float2 nc2_2 = splat2(-c2), nc1r2 = splat2(-c1 * rstd);
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
       const int v = lane + i * 32;
       if (v < nvec) {
-        float a[8], b[8], d[8], o[8];
-        unpack8(px[i], a);
-        unpack8(pr[i], b);
-        unpack8(pd[i], d);
-        const float4* gp = reinterpret_cast<const float4*>(gam_s + v * 8);
-        const float4 w0 = gp[0], w1 = gp[1];
-        const float gw[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+        const uint32_t wx[4] = {px[i].x, px[i].y, px[i].z, px[i].w};
+        const uint32_t wr[4] = {pr[i].x, pr[i].y, pr[i].z, pr[i].w};
+        const uint32_t wd[4] = {pd[i].x, pd[i].y, pd[i].z, pd[i].w};
+        const float4 w01 = reinterpret_cast<const float4*>(gam_s + v * 8)[0];
+        const float4 w23 = reinterpret_cast<const float4*>(gam_s + v * 8)[1];
+        const float2 gw[4] = {make_float2(w01.x, w01.y), make_float2(w01.z, w01.w), make_float2(w23.x, w23.y), make_float2(w23.z, w23.w)};
+        uint32_t o[4];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          const float h = (a[k] + b[k] - mean) * rstd;
-          o[k] = rstd * (d[k] * gw[k] - c1 - h * c2);
+        for (int k = 0; k < 4; ++k) {
+          float2 a = unpack2(wx[k]);
+          if (has_r) a = __fadd2_rn(a, unpack2(wr[k]));
+          const float2 h = __ffma2_rn(a, rstd2, nmr2);
+          const float2 t = __fmul2_rn(unpack2(wd[k]), gw[k]);
+          // rstd * (t - c1 - h * c2)
+          o[k] = pack2(__ffma2_rn(__ffma2_rn(h, nc2_2, t), rstd2, nc1r2));
         }
-        ds[base + v] = pack8(o);
+        ds[base + v] = make_uint4(o[0], o[1], o[2], o[3]);
       }
     }
   }
   // CTA reduction of d_gamma / d_beta over the warps, fixed order
+  __syncthreads();
+  for (int c = threadIdx.x; c < 2 * cols; c += blockDim.x) {
+    const int which = c / cols, col = c - which * cols;
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < LN_WARPS; ++w) t += red[(w * 2 + which) * cols + col];
+    partials[(static_cast<size_t>(blockIdx.x) * 2 + which) * cols + col] = t;
+  }
+}
+
+// Round-2 variant of the backward: per-lane REGISTER accumulators for d_gamma / d_beta (each lane owns its columns;
+// flushed to shared memory once, at the end) and the next row's loads issued before the current row is processed.
+// ncu of the shared-memory-accumulator version above: short-scoreboard (LDS -> FMA -> STS chains on the accumulators)
+// and MIO-throttle stalls dominate, 232 MB streamed at 3.0 TB/s.
+template <int NV, bool HAS_R>
+__global__ void __launch_bounds__(LN_WARPS * 32, HAS_R ? 1 : 2)
+add_layernorm_bwd_reg_kernel(const uint4* __restrict__ dy, const uint4* __restrict__ x, const uint4* __restrict__ r,
+                             const float* __restrict__ gamma, const float* __restrict__ mean_in,
+                             const float* __restrict__ rstd_in, uint4* __restrict__ ds, float* __restrict__ partials,
+                             int rows, int cols) {
+  extern __shared__ float red[];  // [LN_WARPS][2][cols] (used once, at the end), then [cols] gamma
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nvec = cols >> 3;
+  const float inv_n = 1.f / static_cast<float>(cols);
+  float* gam_s = red + LN_WARPS * 2 * cols;
+  for (int c = threadIdx.x; c < cols; c += blockDim.x) gam_s[c] = gamma[c];
+  __syncthreads();
+  float2 dg[NV][4], db[NV][4];
+#pragma unroll
+  for (int i = 0; i < NV; ++i)
+#pragma unroll
+    for (int k = 0; k < 4; ++k) dg[i][k] = db[i][k] = make_float2(0.f, 0.f);
+
+  const int stride = gridDim.x * LN_WARPS;
+  int row = blockIdx.x * LN_WARPS + warp;
+  uint4 px[NV], pr[NV], pd[NV];
+  auto load_row = [&](int rw, uint4* ax, uint4* ar, uint4* ad) {
+    const size_t base = static_cast<size_t>(rw) * nvec;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int v = lane + i * 32;
+      if (v < nvec) {
+        ax[i] = __ldg(x + base + v);
+        if (HAS_R) ar[i] = __ldg(r + base + v);
+        ad[i] = __ldg(dy + base + v);
+      }
+    }
+  };
+  if (row < rows) load_row(row, px, pr, pd);
+  while (row < rows) {
+    const int nrow = row + stride;
+    uint4 nx[NV], nr[NV], nd[NV];
+    if (nrow < rows) load_row(nrow, nx, nr, nd);   // in flight while this row is processed
+    const size_t base = static_cast<size_t>(row) * nvec;
+    const float mean = mean_in[row], rstd = rstd_in[row];
+    const float2 rstd2 = splat2(rstd), nmr2 = splat2(-mean * rstd);
+    float2 c1_2 = make_float2(0.f, 0.f), c2_2 = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int v = lane + i * 32;
+      if (v < nvec) {
+        const uint32_t wx[4] = {px[i].x, px[i].y, px[i].z, px[i].w};
+        const uint32_t wr[4] = {pr[i].x, pr[i].y, pr[i].z, pr[i].w};
+        const uint32_t wd[4] = {pd[i].x, pd[i].y, pd[i].z, pd[i].w};
+        const float4 w01 = reinterpret_cast<const float4*>(gam_s + v * 8)[0];
+        const float4 w23 = reinterpret_cast<const float4*>(gam_s + v * 8)[1];
+        const float2 gw[4] = {make_float2(w01.x, w01.y), make_float2(w01.z, w01.w), make_float2(w23.x, w23.y), make_float2(w23.z, w23.w)};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          float2 a = unpack2(wx[k]);
+          if (HAS_R) a = __fadd2_rn(a, unpack2(wr[k]));
+          const float2 d = unpack2(wd[k]);
+          const float2 h = __ffma2_rn(a, rstd2, nmr2);      // (x + r - mean) * rstd
+          dg[i][k] = __ffma2_rn(d, h, dg[i][k]);
+          db[i][k] = __fadd2_rn(db[i][k], d);
+          const float2 t = __fmul2_rn(d, gw[k]);
+          c1_2 = __fadd2_rn(c1_2, t);
+          c2_2 = __ffma2_rn(t, h, c2_2);
+        }
+      }
+    }
+    const float c1 = wsum(c1_2.x + c1_2.y) * inv_n;
+    const float c2 = wsum(c2_2.x + c2_2.y) * inv_n;
+    const float2 nc2_2 = splat2(-c2), nc1r2 = splat2(-c1 * rstd);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int v = lane + i * 32;
+      if (v < nvec) {
+        const uint32_t wx[4] = {px[i].x, px[i].y, px[i].z, px[i].w};
+        const uint32_t wr[4] = {pr[i].x, pr[i].y, pr[i].z, pr[i].w};
+        const uint32_t wd[4] = {pd[i].x, pd[i].y, pd[i].z, pd[i].w};
+        const float4 w01 = reinterpret_cast<const float4*>(gam_s + v * 8)[0];
+        const float4 w23 = reinterpret_cast<const float4*>(gam_s + v * 8)[1];
+        const float2 gw[4] = {make_float2(w01.x, w01.y), make_float2(w01.z, w01.w), make_float2(w23.x, w23.y), make_float2(w23.z, w23.w)};
+        uint32_t o[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          float2 a = unpack2(wx[k]);
+          if (HAS_R) a = __fadd2_rn(a, unpack2(wr[k]));
+          const float2 h = __ffma2_rn(a, rstd2, nmr2);
+          const float2 t = __fmul2_rn(unpack2(wd[k]), gw[k]);
+          o[k] = pack2(__ffma2_rn(__ffma2_rn(h, nc2_2, t), rstd2, nc1r2));   // rstd * (t - c1 - h * c2)
+        }
+        ds[base + v] = make_uint4(o[0], o[1], o[2], o[3]);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      px[i] = nx[i];
+      if (HAS_R) pr[i] = nr[i];
+      pd[i] = nd[i];
+    }
+    row = nrow;
+  }
+  // flush the lane-owned accumulators, then the fixed-order CTA reduction over the warps
+  float* dg_s = red + (warp * 2 + 0) * cols;
+  float* db_s = red + (warp * 2 + 1) * cols;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int v = lane + i * 32;
+    if (v < nvec) {
+      reinterpret_cast<float4*>(dg_s + v * 8)[0] = make_float4(dg[i][0].x, dg[i][0].y, dg[i][1].x, dg[i][1].y);
+      reinterpret_cast<float4*>(dg_s + v * 8)[1] = make_float4(dg[i][2].x, dg[i][2].y, dg[i][3].x, dg[i][3].y);
+      reinterpret_cast<float4*>(db_s + v * 8)[0] = make_float4(db[i][0].x, db[i][0].y, db[i][1].x, db[i][1].y);
+      reinterpret_cast<float4*>(db_s + v * 8)[1] = make_float4(db[i][2].x, db[i][2].y, db[i][3].x, db[i][3].y);
+    }
+  }
   __syncthreads();
   for (int c = threadIdx.x; c < 2 * cols; c += blockDim.x) {
     const int which = c / cols, col = c - which * cols;
@@ -266,12 +442,31 @@ static int bwd_grid(int rows, int cols) {
                                : resident_blocks_per_sm(add_layernorm_bwd_kernel<4>, smem);
   return clamp_grid(per_sm, rows);
 }
-static int fwd_grid(int rows, int cols) {
+template <int NV, bool HAS_R>
+static int launch_bwd_reg(cudaStream_t st, const void* dy, const void* x, const void* r, const float* gamma,
+                          const float* mean, const float* rstd, void* ds, float* partials, int rows, int cols,
+                          int* grid_out) {
+  static std::once_flag once;
+  std::call_once(once, [] {
+    cudaFuncSetAttribute(add_layernorm_bwd_reg_kernel<NV, HAS_R>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         bwd_smem(32 * LN_MAXV * 8));
+  });
+  const int smem = bwd_smem(cols);
+  const int grid = clamp_grid(resident_blocks_per_sm(add_layernorm_bwd_reg_kernel<NV, HAS_R>, smem), rows);
+  if (grid <= 0) return FORDE_ENODEV;
+  add_layernorm_bwd_reg_kernel<NV, HAS_R><<<grid, LN_WARPS * 32, smem, st>>>(
+      static_cast<const uint4*>(dy), static_cast<const uint4*>(x), static_cast<const uint4*>(r), gamma, mean, rstd,
+      static_cast<uint4*>(ds), partials, rows, cols);
+  *grid_out = grid;
+  return FORDE_OK;
+}
+
+static int fwd_grid(int rows, int cols, bool has_r) {
   const int nv = (cols / 8 + 31) / 32;
-  const int per_sm = nv == 1   ? resident_blocks_per_sm(add_layernorm_fwd_kernel<1>, 0)
-                     : nv == 2 ? resident_blocks_per_sm(add_layernorm_fwd_kernel<2>, 0)
-                     : nv == 3 ? resident_blocks_per_sm(add_layernorm_fwd_kernel<3>, 0)
-                               : resident_blocks_per_sm(add_layernorm_fwd_kernel<4>, 0);
+#define FORDE_LN_OCC(NV) \
+  (has_r ? resident_blocks_per_sm(add_layernorm_fwd_kernel<NV, true>, 0) : resident_blocks_per_sm(add_layernorm_fwd_kernel<NV, false>, 0))
+  const int per_sm = nv == 1 ? FORDE_LN_OCC(1) : nv == 2 ? FORDE_LN_OCC(2) : nv == 3 ? FORDE_LN_OCC(3) : FORDE_LN_OCC(4);
+#undef FORDE_LN_OCC
   return clamp_grid(per_sm, rows);
 }
 
@@ -295,13 +490,20 @@ int forde_add_layernorm_fwd(void* stream, const void* x, const void* r, const fl
       (reinterpret_cast<uintptr_t>(r) & 15) != 0 || (reinterpret_cast<uintptr_t>(out) & 15) != 0 ||
       (reinterpret_cast<uintptr_t>(gamma) & 15) != 0 || (reinterpret_cast<uintptr_t>(beta) & 15) != 0)
     return FORDE_EALIGN;
-  const int grid = fwd_grid(rows, cols);
+  const int grid = fwd_grid(rows, cols, r != nullptr);
   if (grid <= 0) return FORDE_ENODEV;
   const int nv = (cols / 8 + 31) / 32;
-#define FORDE_LN_FWD(NV)                                                                                      \
-  add_layernorm_fwd_kernel<NV><<<grid, LN_WARPS * 32, 0, static_cast<cudaStream_t>(stream)>>>(               \
-      static_cast<const uint4*>(x), static_cast<const uint4*>(r), gamma, beta, static_cast<uint4*>(out), mean, \
-      rstd, rows, cols, eps)
+#define FORDE_LN_FWD(NV)                                                                                        \
+  do {                                                                                                          \
+    if (r != nullptr)                                                                                           \
+      add_layernorm_fwd_kernel<NV, true><<<grid, LN_WARPS * 32, 0, static_cast<cudaStream_t>(stream)>>>(        \
+          static_cast<const uint4*>(x), static_cast<const uint4*>(r), gamma, beta, static_cast<uint4*>(out),    \
+          mean, rstd, rows, cols, eps);                                                                         \
+    else                                                                                                        \
+      add_layernorm_fwd_kernel<NV, false><<<grid, LN_WARPS * 32, 0, static_cast<cudaStream_t>(stream)>>>(       \
+          static_cast<const uint4*>(x), static_cast<const uint4*>(r), gamma, beta, static_cast<uint4*>(out),    \
+          mean, rstd, rows, cols, eps);                                                                         \
+  } while (0)
   if (nv == 1) FORDE_LN_FWD(1);
   else if (nv == 2) FORDE_LN_FWD(2);
   else if (nv == 3) FORDE_LN_FWD(3);
@@ -320,11 +522,27 @@ int forde_add_layernorm_bwd(void* stream, const void* dy, const void* x, const v
       (reinterpret_cast<uintptr_t>(r) & 15) != 0 || (reinterpret_cast<uintptr_t>(dy) & 15) != 0 ||
       (reinterpret_cast<uintptr_t>(ds) & 15) != 0)
     return FORDE_EALIGN;
-  const int grid = bwd_grid(rows, cols);
+  int grid = bwd_grid(rows, cols);
   if (grid <= 0) return FORDE_ENODEV;
   const int smem = bwd_smem(cols);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int nv = (cols / 8 + 31) / 32;
+  // Input already summed (r == NULL, what the FORDE block passes since the skip connection is added in the producing
+  // GEMM's epilogue): register accumulators + next-row prefetch, 86 -> 66 us at 50 432 x 768.  With a separate
+  // residual the extra row registers push that variant to one CTA per SM (105 us), so the shared-memory-accumulator
+  // kernel stays for it (90 us).  profiles/r2_ln_variants.txt
+  if (r == nullptr && nv <= 3) {   // (4 vectors per lane spill at two CTAs per SM: 147 us vs ~138 us at 65 792 x 1024)
+    int rc = FORDE_OK;
+#define FORDE_LN_BWD_REG(NV) \
+  rc = launch_bwd_reg<NV, false>(st, dy, x, r, gamma, mean, rstd, ds, partials, rows, cols, &grid)
+    if (nv == 1) FORDE_LN_BWD_REG(1);
+    else if (nv == 2) FORDE_LN_BWD_REG(2);
+    else FORDE_LN_BWD_REG(3);
+#undef FORDE_LN_BWD_REG
+    if (rc != FORDE_OK) return rc;
+    ln_param_grad_kernel<<<(2 * cols + 31) / 32, dim3(32, 32), 0, st>>>(partials, grid, cols, d_gamma, d_beta);
+    return check_launch("add_layernorm_bwd_reg_kernel", 2);
+  }
 #define FORDE_LN_BWD(NV)                                                                                         \
   add_layernorm_bwd_kernel<NV><<<grid, LN_WARPS * 32, smem, st>>>(                                               \
       static_cast<const uint4*>(dy), static_cast<const uint4*>(x), static_cast<const uint4*>(r), gamma, mean, rstd, \

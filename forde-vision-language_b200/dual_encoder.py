@@ -107,15 +107,26 @@ class _Dense(torch.autograd.Function):
     gradient on the column-sum kernel.  `w16` is the bf16 mirror (in, out); `b` may be None (projection heads)."""
 
     @staticmethod
-    def forward(ctx, x, w, b, w16, b16):
+    def forward(ctx, x, w, b, w16, b16, residual=None, skip_holder=None):
+        """``residual`` (shape of the output): y = x W + b + residual, added in the GEMM epilogue; its gradient is the
+        output gradient itself.  It is returned to autograd, or -- with ``skip_holder``, a dict shared with the
+        _QKVDense of the same block -- left in the holder so that _QKVDense.backward accumulates its GEMMs on top of it
+        in their epilogues instead of autograd adding it with a separate pass."""
         x2 = x.reshape(-1, x.shape[-1])
         if x2.stride(1) != 1 or x2.stride(0) % 8 != 0 or x2.data_ptr() % 16 != 0:
             x2 = x2.contiguous()        # (a row-pitched view such as the padded patch rows is fine for TMA as it is)
-        y = ops.gemm_bf16(x2, w16, False, True, bias_col=None if b is None else b.detach().float())
+        r2 = None
+        if residual is not None:
+            r2 = residual.reshape(-1, residual.shape[-1])
+            r2 = r2 if r2.is_contiguous() else r2.contiguous()
+        y = ops.gemm_bf16(x2, w16, False, True, bias_col=None if b is None else b.detach().float(), residual=r2)
         ctx.save_for_backward(x2, w16)
         ctx.lead = x.shape[:-1]
         ctx.masters = (w, b)
         ctx.needs_dx = ctx.needs_input_grad[0]
+        ctx.has_residual = residual is not None
+        ctx.skip_holder = skip_holder if residual is not None else None
+        ctx.res_shape = residual.shape if residual is not None else None
         return y.reshape(*x.shape[:-1], w16.shape[1])
 
     @staticmethod
@@ -130,6 +141,12 @@ class _Dense(torch.autograd.Function):
         if ctx.needs_dx:                                                             # dx = dy W^T
             dx = ops.gemm_bf16(dy2, w16, False, False).reshape(*ctx.lead, w16.shape[0])
         w, b = ctx.masters
+        d_res = None
+        if ctx.has_residual:
+            if ctx.skip_holder is not None:
+                ctx.skip_holder["ds"] = dy2.view(ctx.res_shape)      # picked up (and accumulated onto) by _QKVDense
+            else:
+                d_res = dy2.view(ctx.res_shape)
         if b is None:
             sw = grad_sink(w)
             dw = sw if sw is not None else torch.zeros(w.shape, dtype=torch.float32, device=dy2.device)
@@ -137,9 +154,9 @@ class _Dense(torch.autograd.Function):
             if sw is not None:
                 grad_delivered(w)
                 dw = None
-            return dx, dw, None, None, None
+            return dx, dw, None, None, None, d_res, None
         dw, db = _deliver_dense_grads(w, b, x2.t(), dy2)
-        return dx, dw, db, None, None
+        return dx, dw, db, None, None, d_res, None
 
 
 class _ShortAttention(torch.autograd.Function):
@@ -257,7 +274,8 @@ class _QKVDense(torch.autograd.Function):
 
 
 class _AddLayerNorm(torch.autograd.Function):
-    """LayerNorm(x + r) on the fused sm_100a kernel (csrc/forde_norm.cu); gamma / beta are fp32 masters."""
+    """LayerNorm(x + r) on the fused sm_100a kernel (csrc/forde_norm.cu); gamma / beta are fp32 masters.  With
+    ``r = None`` the input is already the sum (formed in the producing GEMM's epilogue)."""
 
     @staticmethod
     def forward(ctx, x, r, gamma, beta, skip_holder=None):
@@ -265,10 +283,12 @@ class _AddLayerNorm(torch.autograd.Function):
         # not returned to autograd (which would add it to the projections' input gradient with a separate pass) but
         # left in the holder, and _QKVDense.backward accumulates its GEMMs on top of it.
         ctx.skip_holder = skip_holder
-        x = x.contiguous(); r = r.contiguous()
+        x = x.contiguous()
+        r = r.contiguous() if r is not None else None
         out, mean, rstd = ops.add_layernorm_fwd(x, r, gamma, beta, 1e-6)
         ctx.save_for_backward(x, r, gamma, mean, rstd)
         ctx.masters = (gamma, beta)
+        ctx.has_r = r is not None
         return out
 
     @staticmethod
@@ -282,10 +302,11 @@ class _AddLayerNorm(torch.autograd.Function):
         if ctx.skip_holder is not None:
             ctx.skip_holder["ds"] = ds
             dx_skip = None
+        dr = ds if ctx.has_r else None
         if direct:
             grad_delivered(ctx.masters[0]); grad_delivered(ctx.masters[1])
-            return dx_skip, ds, None, None, None
-        return dx_skip, ds, dg, db, None
+            return dx_skip, dr, None, None, None
+        return dx_skip, dr, dg, db, None
 
 
 def _flatten(tree, prefix=""):
@@ -377,8 +398,10 @@ class FORDEDualEncoder:
         else:                                                 # vision tower: library flash attention (cuDNN)
             q, k, v = (t.view(B, T, heads, w // heads).transpose(1, 2) for t in (q, k, v))
             a = F.scaled_dot_product_attention(q, k, v).transpose(1, 2).reshape(B, T, w)
-        a = _Dense.apply(a, pa["out"]["kernel"], pa["out"]["bias"], mirror("out", "kernel"), mirror("out", "bias"))
-        x = _AddLayerNorm.apply(x, a, p["ln_1"]["scale"], p["ln_1"]["bias"], holder)
+        # x + attention(x): the skip connection is added in the out-projection's epilogue, the add/norm streams the sum
+        s_ = _Dense.apply(a, pa["out"]["kernel"], pa["out"]["bias"], mirror("out", "kernel"), mirror("out", "bias"), x,
+                          holder)
+        x = _AddLayerNorm.apply(s_, None, p["ln_1"]["scale"], p["ln_1"]["bias"], None)
         tower, lname = key.split("/")
         sl_vars = {
             "params": p["stateful_layer"],

@@ -114,10 +114,11 @@ def sample_pitch(M: int) -> int:
 
 
 # ------------------------------------------------------------------------------------------ generic GEMM
-def gemm_bf16(A: torch.Tensor, B: torch.Tensor, a_mn_major: bool, b_mn_major: bool, bias_col=None, add_to=None) -> torch.Tensor:
+def gemm_bf16(A: torch.Tensor, B: torch.Tensor, a_mn_major: bool, b_mn_major: bool, bias_col=None, add_to=None,
+              residual=None) -> torch.Tensor:
     """D[M,N] = sum_k A(m,k) B(n,k) (+ bias_col) -> bf16.  K-major operands are [rows, K]; MN-major operands are
     [K, rows].  With ``add_to`` (a contiguous bf16 [M, N] tensor, N % 8 == 0) the product is accumulated into it in
-    place and it is returned."""
+    place and it is returned; with ``residual`` (same shape) a NEW tensor D = product + bias + residual is returned."""
     _req_rows(A, torch.bfloat16, "A"); _req_rows(B, torch.bfloat16, "B")
     M, K = (A.shape[1], A.shape[0]) if a_mn_major else (A.shape[0], A.shape[1])
     N, Kb = (B.shape[1], B.shape[0]) if b_mn_major else (B.shape[0], B.shape[1])
@@ -134,6 +135,14 @@ def gemm_bf16(A: torch.Tensor, B: torch.Tensor, a_mn_major: bool, b_mn_major: bo
         return add_to
     ldd = round_up(N, 8)
     D = torch.empty((M, ldd), dtype=torch.bfloat16, device=A.device)
+    if residual is not None:
+        _req(residual, torch.bfloat16, "residual")
+        assert tuple(residual.shape) == (M, N) and ldd == N
+        rc = _lib.load().forde_gemm_bf16_add(_stream(), A.data_ptr(), int(a_mn_major), A.stride(0), B.data_ptr(),
+                                             int(b_mn_major), B.stride(0), D.data_ptr(), ldd, residual.data_ptr(),
+                                             _ptr(bias_col), M, N, K)
+        _lib.check(rc, "forde_gemm_bf16_add")
+        return D
     rc = _lib.load().forde_gemm_bf16(_stream(), A.data_ptr(), int(a_mn_major), A.stride(0), B.data_ptr(),
                                      int(b_mn_major), B.stride(0), D.data_ptr(), ldd, _ptr(bias_col), M, N, K)
     _lib.check(rc, "forde_gemm_bf16")
@@ -182,14 +191,20 @@ def sl_up_fwd(x, w_up, b_up, assign_i8, zT, hT, act_partials, save_z: bool = Tru
     _lib.check(rc, "forde_sl_up_fwd")
 
 
-def sl_down_fwd(hT, w_down, b_down, y, M):
+def sl_down_fwd(hT, w_down, b_down, y, M, residual=None):
+    """y = h . w_down + b_down (+ residual: the block's skip connection, added in the epilogue)."""
     H, d = w_down.shape
     _req(hT, torch.bfloat16, "hT"); _req(w_down, torch.bfloat16, "w_down"); _req(y, torch.bfloat16, "y")
     if b_down is not None:
         _req(b_down, torch.float32, "b_down")
     with _Timed(f"sl_down_fwd[{M}x{d}x{H}]", 2.0 * M * d * H):
-        rc = _lib.load().forde_sl_down_fwd(_stream(), hT.data_ptr(), w_down.data_ptr(), _ptr(b_down), y.data_ptr(),
-                                           M, d, H, hT.stride(0))
+        if residual is None:
+            rc = _lib.load().forde_sl_down_fwd(_stream(), hT.data_ptr(), w_down.data_ptr(), _ptr(b_down), y.data_ptr(),
+                                               M, d, H, hT.stride(0))
+        else:
+            _req(residual, torch.bfloat16, "residual")
+            rc = _lib.load().forde_sl_down_fwd_add(_stream(), hT.data_ptr(), w_down.data_ptr(), _ptr(b_down),
+                                                   residual.data_ptr(), y.data_ptr(), M, d, H, hT.stride(0))
     _lib.check(rc, "forde_sl_down_fwd")
 
 

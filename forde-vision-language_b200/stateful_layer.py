@@ -122,13 +122,16 @@ class _StatefulLayerFn(torch.autograd.Function):
         ctx.keep_bits = None
         if layer.top_k is not None:  # D8: keep the k largest |h| per token, zero the rest (in place)
             layer.last_topk_indices, layer.last_row_hoyer, ctx.keep_bits = ops.sl_topk_sparsify(ws.hT, M, layer.top_k)
-        ops.sl_down_fwd(ws.hT, w_down16, b_down32, y, M)
         ctx.with_norm = ln_g is not None
         if ctx.with_norm:
-            out, mean, rstd = ops.add_layernorm_fwd(x2d, y, ln_g, ln_b, 1e-6)
+            # y = x + layer(x): the skip connection is added in the down projection's epilogue, so the add/norm
+            # (forward and backward) streams one tensor instead of two
+            ops.sl_down_fwd(ws.hT, w_down16, b_down32, y, M, residual=x2d)
+            out, mean, rstd = ops.add_layernorm_fwd(y, None, ln_g, ln_b, 1e-6)
             ctx.save_for_backward(x2d, w_up16, w_down16, y, ln_g, mean, rstd)
             ctx.ln_masters = (ln_g, ln_b)
         else:
+            ops.sl_down_fwd(ws.hT, w_down16, b_down32, y, M)
             out = y
             ctx.save_for_backward(x2d, w_up16, w_down16)
         ctx.layer, ctx.ws, ctx.stats, ctx.assign_i8 = layer, ws, stats, assign_i8
@@ -161,7 +164,7 @@ class _StatefulLayerFn(torch.autograd.Function):
             sg, sb = grad_sink(ctx.ln_masters[0]), grad_sink(ctx.ln_masters[1])
             direct_ln = sg is not None and sb is not None
             # d(x + y): the gradient of the layer's output AND of the skip path
-            dy, dg, db = ops.add_layernorm_bwd(dy, x2d, y, ln_g, mean, rstd, d_gamma=sg if direct_ln else None,
+            dy, dg, db = ops.add_layernorm_bwd(dy, y, None, ln_g, mean, rstd, d_gamma=sg if direct_ln else None,
                                                d_beta=sb if direct_ln else None)
             skip = dy
             if direct_ln:

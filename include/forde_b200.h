@@ -74,6 +74,10 @@ int forde_sl_up_fwd(void* stream, const void* x, const void* w_up, const float* 
                     void* zT, void* hT, float* act_partials, int M, int d, int H, long long ldz, int save_z);
 int forde_sl_down_fwd(void* stream, const void* hT, const void* w_down, const float* b_down, void* y, int M,
                       int d, int H, long long ldz);
+/* y = h . w_down + b_down + residual (residual [M][d] bf16, may be y itself): the FORDE block's `x + layer(x)`
+ * (README.md:43) formed in the GEMM epilogue, so the add/norm that follows streams one tensor instead of two */
+int forde_sl_down_fwd_add(void* stream, const void* hT, const void* w_down, const float* b_down, const void* residual,
+                          void* y, int M, int d, int H, long long ldz);
 /* Sign-bit variant of the save_z = 0 forward (what the module uses by default).  Where the z box is not written the
  * kernel also records (z > 0), one bit per neuron and sample, in sign_bits: H * forde_sl_sign_words(M) u32 words,
  * 16-byte aligned, word-major [forde_sl_sign_words(M)][H] so that a warp (32 consecutive neurons) touches one

@@ -11,9 +11,10 @@ G.build()
 import forde_b200  # noqa: E402,F401
 from forde_b200 import ops  # noqa: E402
 
-rows, cols = (50432, 768) if len(sys.argv) < 3 else (int(sys.argv[1]), int(sys.argv[2]))
+_pos = [a for a in sys.argv[1:] if not a.startswith("--")]
+rows, cols = (50432, 768) if len(_pos) < 2 else (int(_pos[0]), int(_pos[1]))
 x = torch.randn((rows, cols), device="cuda").bfloat16()
-r = torch.randn((rows, cols), device="cuda").bfloat16()
+r = None if "--no-r" in sys.argv else torch.randn((rows, cols), device="cuda").bfloat16()   # --no-r: the input is already the sum
 dy = torch.randn((rows, cols), device="cuda").bfloat16()
 g = torch.ones(cols, device="cuda"); b = torch.zeros(cols, device="cuda")
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
@@ -22,8 +23,9 @@ if "--once" in sys.argv:
     ops.add_layernorm_bwd(dy, x, r, g, mean, rstd)
     torch.cuda.synchronize()
     sys.exit(0)
-for name, f, nbytes in [("fwd", lambda: ops.add_layernorm_fwd(x, r, g, b), 3 * rows * cols * 2),
-                        ("bwd", lambda: ops.add_layernorm_bwd(dy, x, r, g, mean, rstd), 4 * rows * cols * 2)]:
+nt = 2 if r is None else 3
+for name, f, nbytes in [("fwd", lambda: ops.add_layernorm_fwd(x, r, g, b), nt * rows * cols * 2),
+                        ("bwd", lambda: ops.add_layernorm_bwd(dy, x, r, g, mean, rstd), (nt + 1) * rows * cols * 2)]:
     for _ in range(3):
         f()
     t = 0.0
