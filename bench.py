@@ -230,12 +230,16 @@ def run_gpu(args):
     # ---- per-kernel pass (eager launches, CUDA events around every StatefulLayer kernel on the launching stream):
     #      the same K steps as the timed region below, which replays them as one CUDA graph and so cannot be
     #      instrumented per kernel.  Launch counts come from this pass too (a replay launches the same kernels).
+    #      Kernels are timed one at a time: both towers on ONE stream here (the measured step overlaps them).
+    concurrent = state.model.concurrent_towers
+    state.model.concurrent_towers = False
     ops.enable_timing(True)
     l0 = ops.launch_count()
     ms_eager, _ = timed(devb, args.steps, read_loss=False)
     launches = ops.launch_count() - l0
     kt = ops.timing_summary()
     ops.enable_timing(False)
+    state.model.concurrent_towers = concurrent
 
     step_fn, graphed = None, False
     if not args.no_graph:
@@ -273,10 +277,12 @@ def run_gpu(args):
         for i in range(2):
             (step_fn or (lambda b: train.train_step(state, b)))(devb[i % 2])
         ms_s, _ = timed(devb, args.steps, read_loss=False, step_fn=step_fn)
+        state.model.concurrent_towers = False
         ops.enable_timing(True)
         timed(devb, min(args.steps, 3), read_loss=False)
         kt_s = ops.timing_summary()
         ops.enable_timing(False)
+        state.model.concurrent_towers = concurrent
         smoothed = {"map": "contiguous thirds of relu / tanh / binary_step neurons in every layer",
                     "value": world * args.batch * args.steps / (ms_s * 1e-3), "unit": UNIT,
                     "ms_per_step": ms_s / args.steps,
@@ -359,6 +365,8 @@ def run_gpu(args):
         "config": workload_config(cfg, args.batch, world),
         "run": {"launch": "whole step replayed as one CUDA graph" if graphed else "eager launches",
                 "ms_per_step_eager_instrumented": ms_eager / args.steps, "lib_sha256_16": sha,
+                "towers": ("text tower on its own CUDA stream, forward and backward (fork/join inside the graph); the "
+                           "per-kernel pass runs both towers on one stream") if concurrent else "one stream",
                 "brain_map": "all-generalist (every layer's initial map, D7); see smoothed_map for a post-slow-loop map",
                 "grad_exchange": (os.environ.get("FORDE_GRAD_COMM", "bf16") if world > 1 else "none (1 GPU)")},
         "clocks": clocks,

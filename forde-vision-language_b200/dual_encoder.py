@@ -16,6 +16,7 @@ src/forde/moe_slow_loop.py:145-170).
 from __future__ import annotations
 
 import math
+import os
 from dataclasses import dataclass, field
 from typing import Dict, Optional
 
@@ -309,6 +310,24 @@ class _AddLayerNorm(torch.autograd.Function):
         return dx_skip, dr, dg, db, None
 
 
+class _JoinTowerStreams(torch.autograd.Function):
+    """Identity on the text embedding, applied on the caller's stream after the forward join.  Its backward is the
+    first node of the text tower's backward pass: it queues an engine callback that runs when the whole backward has
+    been enqueued and makes the stream ``backward()`` was called on wait for the text tower's stream (that tower's
+    parameter gradients are accumulated in place by its kernels, so autograd itself has nothing to synchronise on)."""
+
+    @staticmethod
+    def forward(ctx, t, model, device):
+        ctx.model, ctx.device = model, device
+        return t.view_as(t)
+
+    @staticmethod
+    def backward(ctx, g):
+        model, device = ctx.model, ctx.device
+        torch.autograd.Variable._execution_engine.queue_callback(lambda: model.join_streams(device))
+        return g, None, None
+
+
 def _flatten(tree, prefix=""):
     out = {}
     for k in sorted(tree):
@@ -322,8 +341,15 @@ def _flatten(tree, prefix=""):
 
 
 class FORDEDualEncoder:
-    def __init__(self, cfg: DualEncoderConfig):
+    def __init__(self, cfg: DualEncoderConfig, concurrent_towers: Optional[bool] = None):
+        """``concurrent_towers`` (default on, env FORDE_TOWER_STREAMS=0 turns it off): the two towers are independent
+        until the contrastive loss, so the text tower is enqueued on its own CUDA stream, forward and backward (autograd
+        runs a node's backward on its forward's stream).  Its GEMMs have partial last waves (154 tiles on 74 CTA pairs at
+        C2) and the vision tower's tiles fill those SMs; inside a captured step this is a fork/join of the graph."""
         self.cfg = cfg
+        self.concurrent_towers = (os.environ.get("FORDE_TOWER_STREAMS", "1") != "0") if concurrent_towers is None \
+            else bool(concurrent_towers)
+        self._tower_streams: Dict[str, "torch.cuda.Stream"] = {}
         self.layers: Dict[str, StatefulLayer] = {}
         for tower, tc in (("vision", cfg.vision), ("text", cfg.text)):
             for i in range(tc.layers):
@@ -370,6 +396,22 @@ class FORDEDualEncoder:
             params[tower], assigns[tower], stats[tower] = tp, ta, ts
         params["log_temp"] = torch.tensor(INIT_LOG_TEMP, device=dev)
         return {"params": params, "neuron_assignments": assigns, "stats_buffer": stats}
+
+    # ------------------------------------------------------------------ streams
+    def tower_stream(self, device) -> "torch.cuda.Stream":
+        """The text tower's stream on ``device`` (created on first use)."""
+        key = str(torch.device(device))
+        s = self._tower_streams.get(key)
+        if s is None:
+            s = self._tower_streams[key] = torch.cuda.Stream(device=device)
+        return s
+
+    def join_streams(self, device) -> None:
+        """Make the current stream wait for the text tower's stream (call after ``loss.backward()``: the text tower's
+        backward ran there, and its gradients were accumulated in place, not handed to autograd)."""
+        s = self._tower_streams.get(str(torch.device(device)))
+        if s is not None:
+            torch.cuda.current_stream(device).wait_stream(s)
 
     # ------------------------------------------------------------------ forward
     @staticmethod
@@ -464,8 +506,20 @@ class FORDEDualEncoder:
         """Returns the global-batch contrastive loss (and the mutable collections when asked, Flax style)."""
         mut = set(mutable) if not isinstance(mutable, bool) else (set(variables) - {"params"} if mutable else set())
         sense = "stats_buffer" in mut
-        img = self.encode_image(variables, images, sense, params_bf16)
-        txt = self.encode_text(variables, input_ids, sense, params_bf16)
+        if self.concurrent_towers and images.is_cuda:
+            cur = torch.cuda.current_stream(images.device)
+            side = self.tower_stream(images.device)
+            side.wait_stream(cur)                     # fork: the text tower sees everything enqueued so far
+            with torch.cuda.stream(side):
+                txt = self.encode_text(variables, input_ids, sense, params_bf16)
+            img = self.encode_image(variables, images, sense, params_bf16)
+            cur.wait_stream(side)                     # join before the loss reads both embeddings
+            txt.record_stream(cur)
+            if txt.requires_grad:
+                txt = _JoinTowerStreams.apply(txt, self, images.device)
+        else:
+            img = self.encode_image(variables, images, sense, params_bf16)
+            txt = self.encode_text(variables, input_ids, sense, params_bf16)
         loss = clip_contrastive_loss(img, txt, variables["params"]["log_temp"], group)
         if isinstance(mutable, bool) and not mutable:
             return loss

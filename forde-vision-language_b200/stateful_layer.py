@@ -72,12 +72,13 @@ class _WorkspaceLease:
             ws.in_flight = False
 
 
-_DZ_POOL: Dict[Tuple[int, int, str], torch.Tensor] = {}
+_DZ_POOL: Dict[Tuple[int, int, str, str], torch.Tensor] = {}
 
 
-def _dz_scratch(H: int, ld: int, device) -> torch.Tensor:
-    """dz^T is consumed inside one layer's backward, so every layer of the same shape shares one buffer."""
-    key = (H, ld, str(device))
+def _dz_scratch(H: int, ld: int, device, group: str = "") -> torch.Tensor:
+    """dz^T is consumed inside one layer's backward, so every layer of the same shape AND the same group (the tower:
+    towers may run concurrently on different streams) shares one buffer."""
+    key = (H, ld, str(device), group)
     t = _DZ_POOL.get(key)
     if t is None:
         t = torch.empty((H, ld), dtype=torch.bfloat16, device=device)
@@ -176,7 +177,7 @@ class _StatefulLayerFn(torch.autograd.Function):
         M, d = x2d.shape
         H = ws.H
         dev = x2d.device
-        dzT = _dz_scratch(H, ws.ld, dev)
+        dzT = _dz_scratch(H, ws.ld, dev, layer.name.split('/')[0])
         # top-k path (keep_bits): dL/dz is zero where h was dropped, applied in the same epilogue
         ops.sl_dz_bwd(dy, w_down16, ws.zT, ws.hT, assign_i8, dzT, ws.grad_partials, sign_bits=ws.signs,
                       keep_bits=ctx.keep_bits)

@@ -274,9 +274,13 @@ def train_step(state: TrainState, batch: Dict[str, torch.Tensor], sense: bool = 
     if state.buckets is not None:
         state.buckets.begin()
         loss.backward()
+        if dev.type == "cuda":
+            state.model.join_streams(dev)   # the text tower's backward ran on its own stream
         state.buckets.finish()          # bucketed SUM all-reduce, overlapped with the backward
     else:
         loss.backward()
+        if dev.type == "cuda":
+            state.model.join_streams(dev)
         sync_gradients(state.flat_g32, state.group)
     gnorm = apply_gradients(state)      # clip_by_global_norm(1.0) -> AdamW -> bf16 mirror, two fused passes
     state.step += 1
