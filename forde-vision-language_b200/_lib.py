@@ -78,6 +78,9 @@ SIGNATURES = {
     "forde_attn_max_tokens": (_i, []),
     "forde_attn_fwd": (_i, [_vp] * 6 + [_i, _i, _i, _ll]),
     "forde_attn_bwd": (_i, [_vp] * 9 + [_i, _i, _i, _ll]),
+    "forde_attn2_max_tokens": (_i, []),
+    "forde_attn2_fwd": (_i, [_vp] * 6 + [_i, _i, _i, _ll]),
+    "forde_attn2_bwd": (_i, [_vp] * 10 + [_i, _i, _i, _ll]),
 }
 
 

@@ -160,9 +160,11 @@ class _Dense(torch.autograd.Function):
         return dx, dw, db, None, None, d_res, None
 
 
-class _ShortAttention(torch.autograd.Function):
-    """softmax(q k^T / sqrt(d_head)) v for sequences of at most ops.attn_max_tokens() tokens and d_head = 64 (the text
-    tower): csrc/forde_attn.cu, one tcgen05 tile per (batch, head).  q, k, v: (B, T, w) bf16, heads packed along w."""
+class _SelfAttention(torch.autograd.Function):
+    """softmax(q k^T / sqrt(d_head)) v for sequences of at most ops.attn_max_tokens() tokens and d_head = 64 on this
+    repository's tcgen05 kernels: csrc/forde_attn.cu (T <= 128, the text tower: one tile per (batch, head)) and
+    csrc/forde_attn2.cu (T <= 256, the ViT-B/16 vision tower: two 128-row blocks per item, operands ring-buffered).
+    q, k, v: (B, T, w) bf16, heads packed along w."""
 
     @staticmethod
     def forward(ctx, q, k, v, heads):
@@ -170,20 +172,20 @@ class _ShortAttention(torch.autograd.Function):
         q2, k2, v2 = (t.reshape(B * T, w) for t in (q, k, v))
         q2, k2, v2 = (t if t.is_contiguous() else t.contiguous() for t in (q2, k2, v2))
         o, lse = ops.attn_fwd(q2, k2, v2, B, T, heads)
-        ctx.save_for_backward(q2, k2, v2, lse)
+        ctx.save_for_backward(q2, k2, v2, lse, o)
         ctx.dims = (B, T, heads, w)
         return o.view(B, T, w)
 
     @staticmethod
     def backward(ctx, d_o):
-        q2, k2, v2, lse = ctx.saved_tensors
+        q2, k2, v2, lse, o = ctx.saved_tensors
         B, T, heads, w = ctx.dims
         d2 = d_o.reshape(B * T, w)
         if d2.dtype != torch.bfloat16:
             d2 = d2.to(torch.bfloat16)
         if not d2.is_contiguous():
             d2 = d2.contiguous()
-        dq, dk, dv = ops.attn_bwd(q2, k2, v2, d2, lse, B, T, heads)
+        dq, dk, dv = ops.attn_bwd(q2, k2, v2, d2, lse, B, T, heads, o=o)
         return dq.view(B, T, w), dk.view(B, T, w), dv.view(B, T, w), None
 
 
@@ -435,9 +437,9 @@ class FORDEDualEncoder:
                                   pa["value"]["kernel"], pa["value"]["bias"], mirror("query", "kernel"),
                                   mirror("query", "bias"), mirror("key", "kernel"), mirror("key", "bias"),
                                   mirror("value", "kernel"), mirror("value", "bias"), holder)
-        if w // heads == 64 and T <= ops.attn_max_tokens() and q.is_cuda:
-            a = _ShortAttention.apply(q, k, v, heads)          # text tower: whole sequence in one tcgen05 tile
-        else:                                                 # vision tower: library flash attention (cuDNN)
+        if w // heads == 64 and q.is_cuda and T <= int(os.environ.get("FORDE_ATTN_MAX_TOKENS", ops.attn_max_tokens())):
+            a = _SelfAttention.apply(q, k, v, heads)           # both towers at C2: this repository's tcgen05 kernels
+        else:                                                 # longer sequences (ViT-L/14: 257 tokens): cuDNN flash
             q, k, v = (t.view(B, T, heads, w // heads).transpose(1, 2) for t in (q, k, v))
             a = F.scaled_dot_product_attention(q, k, v).transpose(1, 2).reshape(B, T, w)
         # x + attention(x): the skip connection is added in the out-projection's epilogue, the add/norm streams the sum

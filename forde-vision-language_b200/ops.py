@@ -472,27 +472,48 @@ def add_layernorm_bwd(dy, x, r, gamma, mean, rstd, d_gamma=None, d_beta=None):
     return ds, d_gamma, d_beta
 
 
-# ------------------------------------------------------------------------------------------ short-sequence attention
-def attn_max_tokens() -> int:
+# ------------------------------------------------------------------------------------------ self-attention core
+def attn_short_max_tokens() -> int:
+    """Longest sequence the one-tile kernels (csrc/forde_attn.cu) take."""
     return _lib.load().forde_attn_max_tokens()
 
 
-def attn_fwd(q, k, v, B: int, T: int, heads: int):
-    """q, k, v: bf16 [B*T, heads*64].  Returns (o [B*T, heads*64] bf16, lse [B, heads, T] fp32)."""
+def attn_max_tokens() -> int:
+    """Longest sequence any of this library's attention kernels takes (csrc/forde_attn2.cu)."""
+    return _lib.load().forde_attn2_max_tokens()
+
+
+def attn_fwd(q, k, v, B: int, T: int, heads: int, blocked=None):
+    """q, k, v: bf16 [B*T, heads*64].  Returns (o [B*T, heads*64] bf16, lse [B, heads, T] fp32).
+    T <= 128 runs the one-tile kernel, longer sequences (<= 256) the blocked one; ``blocked`` forces the choice."""
     for t, n in ((q, "q"), (k, "k"), (v, "v")):
         _req(t, torch.bfloat16, n)
     assert q.shape == k.shape == v.shape == (B * T, heads * 64)
     o = torch.empty_like(q)
     lse = torch.empty((B, heads, T), dtype=torch.float32, device=q.device)
-    rc = _lib.load().forde_attn_fwd(_stream(), q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr(), lse.data_ptr(),
-                                    B, T, heads, q.stride(0))
-    _lib.check(rc, "forde_attn_fwd")
+    if blocked is None:
+        blocked = T > attn_short_max_tokens()
+    fn = _lib.load().forde_attn2_fwd if blocked else _lib.load().forde_attn_fwd
+    rc = fn(_stream(), q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr(), lse.data_ptr(), B, T, heads, q.stride(0))
+    _lib.check(rc, "forde_attn2_fwd" if blocked else "forde_attn_fwd")
     return o, lse
 
 
-def attn_bwd(q, k, v, d_o, lse, B: int, T: int, heads: int):
+def attn_bwd(q, k, v, d_o, lse, B: int, T: int, heads: int, o=None, blocked=None):
+    """``o`` (the forward output) is read by the blocked kernel only (D = rowsum(dO * o))."""
     _req(d_o, torch.bfloat16, "d_o"); _req(lse, torch.float32, "lse")
     dq, dk, dv = torch.empty_like(q), torch.empty_like(q), torch.empty_like(q)
+    if blocked is None:
+        blocked = T > attn_short_max_tokens()
+    if blocked:
+        if o is None:
+            raise _lib.FordeError("attn_bwd: the blocked kernel (T > 128) needs the forward output `o`")
+        _req(o, torch.bfloat16, "o")
+        rc = _lib.load().forde_attn2_bwd(_stream(), q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr(),
+                                         d_o.data_ptr(), lse.data_ptr(), dq.data_ptr(), dk.data_ptr(), dv.data_ptr(),
+                                         B, T, heads, q.stride(0))
+        _lib.check(rc, "forde_attn2_bwd")
+        return dq, dk, dv
     rc = _lib.load().forde_attn_bwd(_stream(), q.data_ptr(), k.data_ptr(), v.data_ptr(), d_o.data_ptr(), lse.data_ptr(),
                                     dq.data_ptr(), dk.data_ptr(), dv.data_ptr(), B, T, heads, q.stride(0))
     _lib.check(rc, "forde_attn_bwd")

@@ -301,7 +301,7 @@ int forde_embed_tokens_bwd(void* stream, const int* ids, const void* dx, float* 
 /* ---- self-attention core for short sequences (README.md:42-43 "self-attention -> add/norm") -------
  * softmax(q k^T / sqrt(64)) v per (batch, head), head_dim = 64, T <= forde_attn_max_tokens() (= 128: the text tower's
  * 77 tokens): the whole sequence of a head is ONE tcgen05 tile (scores in TMEM, probabilities staged once in shared
- * memory and consumed K-major and MN-major).  Longer sequences (the vision tower) stay on the library flash kernel.
+ * memory and consumed K-major and MN-major).  Longer sequences: forde_attn2_* below.
  * q, k, v, o, d_o, dq, dk, dv: bf16 [B*T][ld], head h in columns [64 h, 64 h + 64); 16-byte aligned, ld % 8 == 0.
  * lse [B][heads][T] fp32 = ln sum_j exp(q.k_j / 8), written by fwd, read by bwd. */
 int forde_attn_max_tokens(void);
@@ -309,6 +309,16 @@ int forde_attn_fwd(void* stream, const void* q, const void* k, const void* v, vo
                    int heads, long long ld);
 int forde_attn_bwd(void* stream, const void* q, const void* k, const void* v, const void* d_o, const float* lse,
                    void* dq, void* dk, void* dv, int B, int T, int heads, long long ld);
+
+/* ---- the same for medium sequences, 1 <= T <= forde_attn2_max_tokens() (= 256: the ViT-B/16 vision tower's 197
+ * tokens).  One persistent CTA per SM walks the (batch, head) items: all operands of an item in shared
+ * memory (TMA ring, next item's loads in flight), scores of both 128-row blocks in TMEM, softmax on 8 warps
+ * (TMEM lane quarter x column half).  The backward additionally reads the forward output `o` (D = rowsum(dO * o)). */
+int forde_attn2_max_tokens(void);
+int forde_attn2_fwd(void* stream, const void* q, const void* k, const void* v, void* o, float* lse, int B, int T,
+                    int heads, long long ld);
+int forde_attn2_bwd(void* stream, const void* q, const void* k, const void* v, const void* o, const void* d_o,
+                    const float* lse, void* dq, void* dk, void* dv, int B, int T, int heads, long long ld);
 
 #ifdef __cplusplus
 }

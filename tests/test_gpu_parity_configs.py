@@ -312,9 +312,15 @@ def test_token_embedding_front_end_matches_plain_restatement(ops):
 
 
 # ------------------------------------------------------------------------------------------ short-sequence attention
-@pytest.mark.parametrize("B,T,heads", [(4, 77, 8), (3, 16, 2), (2, 128, 4), (5, 1, 1), (256, 77, 8), (2, 100, 12)])
-def test_short_attention_forward_backward_against_plain_softmax_attention(ops, B, T, heads):
-    """csrc/forde_attn.cu against plain fp32 softmax(q k^T / 8) v and its autograd gradients on the same bf16 inputs.
+@pytest.mark.parametrize("B,T,heads,blocked", [
+    (4, 77, 8, False), (3, 16, 2, False), (2, 128, 4, False), (5, 1, 1, False), (256, 77, 8, False), (2, 100, 12, False),
+    # csrc/forde_attn2.cu (two 128-row blocks, operand ring): the ViT-B/16 vision tower's 197 tokens at toy and full size,
+    # every block-count / padding corner, more items than CTAs, and the one-block case forced onto the blocked kernel
+    (2, 197, 12, True), (3, 256, 2, True), (2, 129, 4, True), (1, 144, 1, True), (2, 250, 3, True), (40, 197, 12, True),
+    (4, 77, 8, True), (5, 1, 1, True), (3, 128, 2, True), (256, 197, 12, True)])
+def test_attention_forward_backward_against_plain_softmax_attention(ops, B, T, heads, blocked):
+    """csrc/forde_attn.cu / forde_attn2.cu against plain fp32 softmax(q k^T / 8) v and its autograd gradients on the same
+    bf16 inputs.
     Tolerance: the probabilities are staged in bf16 (2^-8 relative each), outputs and gradients are bf16: relative
     Frobenius error <= 1e-2, and every element within 2^-6 |ref| + 5e-2 rms(ref) (dS = p (dP - D) is rounded to bf16
     after a cancellation, so a handful of the 10^7 gradient elements of the full-size case sit at 2-3 % of the rms)."""
@@ -322,8 +328,9 @@ def test_short_attention_forward_backward_against_plain_softmax_attention(ops, B
     g_ = torch.Generator(device="cuda").manual_seed(T * 131 + B)
     q, k, v = ((torch.randn((B, T, w), device="cuda", generator=g_) * s).bfloat16() for s in (1.5, 1.5, 1.0))
     d_o = torch.randn((B, T, w), device="cuda", generator=g_).bfloat16()
-    o, lse = ops.attn_fwd(q.view(B * T, w), k.view(B * T, w), v.view(B * T, w), B, T, heads)
-    dq, dk, dv = ops.attn_bwd(q.view(B * T, w), k.view(B * T, w), v.view(B * T, w), d_o.view(B * T, w), lse, B, T, heads)
+    o, lse = ops.attn_fwd(q.view(B * T, w), k.view(B * T, w), v.view(B * T, w), B, T, heads, blocked=blocked)
+    dq, dk, dv = ops.attn_bwd(q.view(B * T, w), k.view(B * T, w), v.view(B * T, w), d_o.view(B * T, w), lse, B, T, heads,
+                              o=o, blocked=blocked)
     torch.cuda.synchronize()
     qf, kf, vf = (t.float().view(B, T, heads, 64).transpose(1, 2).detach().requires_grad_(True) for t in (q, k, v))
     s = (qf @ kf.transpose(-1, -2)) * 0.125
@@ -334,10 +341,20 @@ def test_short_attention_forward_backward_against_plain_softmax_attention(ops, B
 
     def close(got, want, name):
         got, want = f32(got), f32(want)
+        if not want.any():      # T = 1: dq = dk = 0 exactly; with D taken from the bf16-rounded output they are ~2^-9 |dO . v|
+            assert np.abs(got).max() <= 2.0 ** -6, f"{name}: {np.abs(got).max():.3e} where the reference is exactly zero"
+            return
         assert relerr(got, want) <= 1e-2, f"{name}: rel Frobenius {relerr(got, want):.3e}"
         rms = float(np.sqrt(np.mean(want.astype(np.float64) ** 2)))
-        bad = np.abs(got - want) > 2.0 ** -6 * np.abs(want) + 5e-2 * rms
-        assert not bad.any(), f"{name}: {bad.sum()} of {bad.size} elements off"
+        err, bound = np.abs(got - want), 2.0 ** -6 * np.abs(want) + 5e-2 * rms
+        bad = err > bound
+        if blocked:
+            # the blocked backward takes D = rowsum(dO * O) from the bf16-ROUNDED forward output (as flash attention
+            # does), the reference from exact fp32 probabilities: of the ~10^7 gradient elements a few per million sit
+            # just outside the bound above.  Stated: at most 1e-5 of the elements, none beyond twice the bound.
+            assert bad.mean() <= 1e-5 and not (err > 2 * bound).any(), f"{name}: {bad.sum()} of {bad.size} elements off"
+        else:
+            assert not bad.any(), f"{name}: {bad.sum()} of {bad.size} elements off"
 
     np.testing.assert_allclose(f32(lse), f32(ref_lse), rtol=1e-3, atol=2e-3)
     close(o, back(ref), "o")
