@@ -7,10 +7,14 @@
 // walks the items with the operand loads of the next item in flight (TMA ring) while this one computes.
 //
 //   forward  (per item): S_i = Q_i K^T for both 128-row blocks i (N = Tk padded keys, <= 256 TMEM columns each)
-//             softmax: 8 warps = 4 TMEM lane quarters x 2 column halves; row max and row sum exchanged between the two
-//             warps of a quarter through shared memory; p = exp2(s * scale * log2e - max) packed to bf16 in REGISTERS,
-//             stored to the swizzled staging buffer once the previous block's P V has finished reading it
-//             O_i = P_i V accumulates over the first 64 columns of S_i's own TMEM region (S_i is dead by then)
+//             softmax: warps 0-3 own row block 0, warps 4-7 row block 1, one thread per score row: row max, then
+//             p = exp2(s * scale * log2e - max) packed to bf16 and stored to that block's swizzled staging buffer,
+//             the TMEM load of the next 32 columns in flight while a chunk is processed
+//             O_i = P_i V accumulates over the first 64 columns of S_i's own TMEM region, in two parts: keys [0, 128)
+//             as soon as they are staged (under the exponentials of the remaining keys), the rest when the row is done
+//             read-out: O_i / row sum -> bf16 rows in the (idle) staging buffer -> one TMA store per block
+//             What bounds it: the two passes over S are TMEM-read bound (128 B per clock per SM: 229 KB per pass and
+//             item = 1.8 k clocks each way, measured) and the exponentials MUFU bound (3.6 k clocks per item).
 //   backward (per item): tiles (key block j, row block i), j outer.  Per tile:
 //             S = Q_i K_j^T, dP = dO_i V_j^T                                   -> TMEM [0,128), [128,256)
 //             p = exp2(s * scale * log2e - lse), dS = p (dP - D) scale         -> P, dS (bf16) staged in shared memory
@@ -50,7 +54,7 @@ constexpr float kA2Log2e = 1.4426950408889634f;
 constexpr float kA2Ln2 = 0.6931471805599453f;
 
 struct Attn2Params {
-  CUtensorMap tmQ, tmK, tmV, tmDO, tmDQ, tmDK, tmDV;
+  CUtensorMap tmQ, tmK, tmV, tmDO, tmDQ, tmDK, tmDV, tmO;
   __nv_bfloat16* o;            // forward output [B*T][ld]
   const __nv_bfloat16* o_in;   // backward: the forward output
   const __nv_bfloat16* do_in;  // backward: the output gradient (row reads for D; the tiles come through tmDO)
@@ -99,40 +103,109 @@ __device__ __forceinline__ void a2_store_row32(__nv_bfloat16* dst, const uint32_
   }
 }
 
+__device__ __forceinline__ void named_bar_sync(int id, int threads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
+__device__ __forceinline__ void tma_store_3d(const void* tmap, uint32_t smem_src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+               :
+               : "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_src), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+
 // ------------------------------------------------------------------------------------------------ forward
-// shared memory: [2 stages][Q0, Q1, K0, K1] | [V0, V1] | P staging [4 column tiles] | exchange [2][128] f32 | barriers
+// Warps 0-3 own row block 0, warps 4-7 row block 1: a thread holds ONE whole score row (TMEM lane), so the row max and
+// the row sum need no exchange between warps, and the two blocks' latency-bound phases (TMEM reads, staging, read-out)
+// run side by side instead of one after the other.  clock64 trace of the first version (all eight warps on one block
+// at a time, two warps per row, per-thread row stores of O): 13.1 k cycles per item, of which 4.5 k the exponentials
+// -- 169 us per ViT-B/16 layer; this one 8.6 k cycles, 122 us (cuDNN: 108; profiles/r2_attn2_forward.md).
+// shared memory: Q [2 row blocks] | K [2 key blocks] | V [2 key blocks] | P staging [2 row blocks][4 column tiles]
+//                (tile 0 of a block's staging also carries its O on the way out: TMA store) | barriers
+// Q / K are single-buffered: both S products are issued at the start of an item, so the next item's Q / K loads have
+// the rest of the item to land.
+__device__ __forceinline__ float a2_max32(const uint32_t* v, int c0, int T, float m) {
+  float m0 = m, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;      // four chains instead of one of 32 dependent ops
+  if (c0 + 32 <= T) {
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+      m0 = fmaxf(m0, __uint_as_float(v[j]));
+      m1 = fmaxf(m1, __uint_as_float(v[j + 1]));
+      m2 = fmaxf(m2, __uint_as_float(v[j + 2]));
+      m3 = fmaxf(m3, __uint_as_float(v[j + 3]));
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      if (c0 + j < T) m0 = fmaxf(m0, __uint_as_float(v[j]));
+  }
+  return fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+}
+// p = exp2(s * sl2 - mxs) for the 32 scores of a chunk (0 for keys beyond T), staged as bf16; returns their sum
+__device__ __forceinline__ float a2_exp32_stage(const uint32_t* v, int c0, int T, float sl2, float mxs, uint32_t sP_u,
+                                                int r) {
+  uint32_t pk[16];
+  float s0 = 0.f, s1 = 0.f;
+  if (c0 + 32 <= T) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const float p0 = ex2_approx(fmaf(__uint_as_float(v[2 * j]), sl2, -mxs));
+      const float p1 = ex2_approx(fmaf(__uint_as_float(v[2 * j + 1]), sl2, -mxs));
+      s0 += p0;
+      s1 += p1;
+      pk[j] = pack_bf16x2(p0, p1);
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const int c = c0 + 2 * j;
+      const float p0 = (c < T) ? ex2_approx(fmaf(__uint_as_float(v[2 * j]), sl2, -mxs)) : 0.f;
+      const float p1 = (c + 1 < T) ? ex2_approx(fmaf(__uint_as_float(v[2 * j + 1]), sl2, -mxs)) : 0.f;
+      s0 += p0;
+      s1 += p1;
+      pk[j] = pack_bf16x2(p0, p1);
+    }
+  }
+#pragma unroll
+  for (int j8 = 0; j8 < 4; ++j8)
+    st_shared_v4(a2_chunk(sP_u, r, c0 + j8 * 8), pk[4 * j8], pk[4 * j8 + 1], pk[4 * j8 + 2], pk[4 * j8 + 3]);
+  return s0 + s1;
+}
+
 __global__ void __launch_bounds__(A2_THREADS, 1) attn2_fwd_kernel(const __grid_constant__ Attn2Params p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sA = smem;
-  uint8_t* sV = smem + 8 * A2_TILE;
-  uint8_t* sP = smem + 10 * A2_TILE;
-  float* xbuf = reinterpret_cast<float*>(smem + 14 * A2_TILE);        // [2 column halves][128 rows]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 14 * A2_TILE + 1024);
-  uint64_t* fullA = bars;          // [2]
-  uint64_t* emptyA = bars + 2;     // [2]
-  uint64_t* fullV = bars + 4;
-  uint64_t* emptyV = bars + 5;
-  uint64_t* bar_s = bars + 6;      // [2] S_i complete
-  uint64_t* bar_p = bars + 8;      // P of a row block staged (256 arrivals)
-  uint64_t* bar_o = bars + 9;      // [2] O_i = P_i V complete (also: staging buffer free again)
-  uint64_t* tfree = bars + 11;     // [2] O_i read out of TMEM (256 arrivals): region i may take the next item's S_i
-  uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(bars + 13);
+  uint8_t* sQ = smem;
+  uint8_t* sK = smem + 2 * A2_TILE;
+  uint8_t* sV = smem + 4 * A2_TILE;
+  uint8_t* sP = smem + 6 * A2_TILE;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 14 * A2_TILE);
+  uint64_t* fullQK = bars;
+  uint64_t* emptyQK = bars + 1;
+  uint64_t* fullV = bars + 2;
+  uint64_t* emptyV = bars + 3;
+  uint64_t* bar_s = bars + 4;      // [2] S_i complete
+  uint64_t* bar_pa = bars + 6;     // [2] keys [0, 128) of P_i staged (128 arrivals): the first part of P_i V may start
+  uint64_t* bar_pb = bars + 8;     // [2] all of P_i staged (128 arrivals); every score of S_i has been read
+  uint64_t* bar_o = bars + 10;     // [2] O_i = P_i V complete (also: P_i's staging buffer idle again)
+  uint64_t* tfree = bars + 12;     // [2] O_i read out of TMEM (128 arrivals): region i may take the next item's S_i
+  uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(bars + 14);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == A2_SOFT) {
     tma_prefetch_desc(&p.tmQ);
     tma_prefetch_desc(&p.tmK);
     tma_prefetch_desc(&p.tmV);
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&fullA[i], 1);
-      mbar_init(&emptyA[i], 1);
-      mbar_init(&bar_s[i], 1);
-      mbar_init(&bar_o[i], 1);
-      mbar_init(&tfree[i], A2_SOFT);
-    }
+    tma_prefetch_desc(&p.tmO);
+    mbar_init(fullQK, 1);
+    mbar_init(emptyQK, 1);
     mbar_init(fullV, 1);
     mbar_init(emptyV, 1);
-    mbar_init(bar_p, A2_SOFT);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&bar_s[i], 1);
+      mbar_init(&bar_pa[i], 128);
+      mbar_init(&bar_pb[i], 128);
+      mbar_init(&bar_o[i], 1);
+      mbar_init(&tfree[i], 128);
+    }
     fence_mbar_init();
   }
   if (warp == 9) {
@@ -151,12 +224,11 @@ __global__ void __launch_bounds__(A2_THREADS, 1) attn2_fwd_kernel(const __grid_c
       int n = 0;
       for (int it = blockIdx.x; it < items; it += gridDim.x, ++n) {
         const int b = it / p.heads, h = it - b * p.heads;
-        const int a = n & 1;
-        mbar_wait(&emptyA[a], ((n >> 1) & 1) ^ 1);
-        mbar_expect_tx(&fullA[a], 2 * nb * A2_TILE);
+        mbar_wait(emptyQK, (n & 1) ^ 1);
+        mbar_expect_tx(fullQK, 2 * nb * A2_TILE);
         for (int i = 0; i < nb; ++i) {
-          tma_load_3d(&p.tmQ, &fullA[a], sA + (a * 4 + i) * A2_TILE, h * A2_DH, i * A2_ROWS, b);
-          tma_load_3d(&p.tmK, &fullA[a], sA + (a * 4 + 2 + i) * A2_TILE, h * A2_DH, i * A2_ROWS, b);
+          tma_load_3d(&p.tmQ, fullQK, sQ + i * A2_TILE, h * A2_DH, i * A2_ROWS, b);
+          tma_load_3d(&p.tmK, fullQK, sK + i * A2_TILE, h * A2_DH, i * A2_ROWS, b);
         }
         mbar_wait(emptyV, (n & 1) ^ 1);
         mbar_expect_tx(fullV, nb * A2_TILE);
@@ -167,16 +239,13 @@ __global__ void __launch_bounds__(A2_THREADS, 1) attn2_fwd_kernel(const __grid_c
     if (lane == 0) {
       const uint32_t idesc_s = make_idesc_bf16(A2_ROWS, Tk, false, false);   // Q (K-major) x K (K-major)
       const uint32_t idesc_o = make_idesc_bf16(A2_ROWS, A2_DH, false, true); // P (K-major) x V (MN-major)
-      const uint64_t dP = make_smem_desc_sw128(smem_u32(sP), 0, 1024);
+      const uint64_t dK = make_smem_desc_sw128(smem_u32(sK), 0, 1024);
       const uint64_t dV = make_smem_desc_sw128(smem_u32(sV), A2_TILE, 1024);
       int n = 0;
       for (int it = blockIdx.x; it < items; it += gridDim.x, ++n) {
-        const int a = n & 1;
-        const uint32_t sQ_u = smem_u32(sA + a * 4 * A2_TILE), sK_u = sQ_u + 2 * A2_TILE;
-        const uint64_t dK = make_smem_desc_sw128(sK_u, 0, 1024);
-        mbar_wait(&fullA[a], (n >> 1) & 1);
+        mbar_wait(fullQK, n & 1);
         for (int i = 0; i < nb; ++i) {
-          const uint64_t dQ = make_smem_desc_sw128(sQ_u + i * A2_TILE, 0, 1024);
+          const uint64_t dQ = make_smem_desc_sw128(smem_u32(sQ) + i * A2_TILE, 0, 1024);
           if (n > 0) mbar_wait(&tfree[i], (n - 1) & 1);
           tc_fence_after();
 #pragma unroll
@@ -184,129 +253,132 @@ __global__ void __launch_bounds__(A2_THREADS, 1) attn2_fwd_kernel(const __grid_c
             umma_bf16(tmem_base + i * 256, dQ + 2 * k, dK + 2 * k, idesc_s, k > 0 ? 1u : 0u);
           umma_commit(&bar_s[i]);
         }
-        umma_commit(&emptyA[a]);
+        umma_commit(emptyQK);
         mbar_wait(fullV, n & 1);
+        // P_i V in two parts: the keys [0, 128) as soon as they are staged -- under the exponentials of the remaining
+        // keys --, the rest when the row is complete.  (Runtime loops on purpose: fully unrolled with a per-step
+        // predicate, this compiler build produced wrong operand registers for the last steps.)
+        const int ks_a = (Tk < 128 ? Tk : 128) / 16, ks_n = Tk / 16;
         for (int i = 0; i < nb; ++i) {
-          mbar_wait(bar_p, (n * nb + i) & 1);
+          const uint64_t dP = make_smem_desc_sw128(smem_u32(sP) + i * 4 * A2_TILE, 0, 1024);
+          mbar_wait(&bar_pa[i], n & 1);
           tc_fence_after();
-          // (a runtime loop on purpose: fully unrolled with a per-step predicate, this compiler build produced wrong
-          // operand registers for the last steps -- profiles/r2_attn2_notes.md)
-          for (int ks = 0; ks < Tk / 16; ++ks)   // reduction over the keys, 16 per step
+          for (int ks = 0; ks < ks_a; ++ks)      // reduction over the keys, 16 per step
             umma_bf16(tmem_base + i * 256, dP + (ks >> 2) * (A2_TILE >> 4) + (ks & 3) * 2, dV + 128 * ks, idesc_o,
                       ks > 0 ? 1u : 0u);
+        }
+        for (int i = 0; i < nb; ++i) {
+          const uint64_t dP = make_smem_desc_sw128(smem_u32(sP) + i * 4 * A2_TILE, 0, 1024);
+          mbar_wait(&bar_pb[i], n & 1);
+          tc_fence_after();
+          for (int ks = ks_a; ks < ks_n; ++ks)
+            umma_bf16(tmem_base + i * 256, dP + (ks >> 2) * (A2_TILE >> 4) + (ks & 3) * 2, dV + 128 * ks, idesc_o, 1u);
           umma_commit(&bar_o[i]);
         }
         umma_commit(emptyV);
       }
     }
-  } else {
-    const int q = warp & 3, ch = warp >> 2;
+  } else if ((warp >> 2) < nb) {
+    const int i = warp >> 2, q = warp & 3;                             // row block, TMEM lane quarter
     const int r = q * 32 + lane;                                       // row within the block = TMEM lane
-    const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
-    const uint32_t sP_u = smem_u32(sP);
-    const uint32_t x_mine = smem_u32(xbuf) + (ch * 128 + r) * 4, x_other = smem_u32(xbuf) + ((ch ^ 1) * 128 + r) * 4;
+    const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + i * 256;
+    const uint32_t sP_u = smem_u32(sP) + i * 4 * A2_TILE;
     const float sl2 = p.scale * kA2Log2e;
-    const int chunks = (Tk + 31) >> 5;                                 // 32-column chunks of a score row (<= 8)
-    const int half = (chunks + 1) >> 1;
-    const int cb = ch == 0 ? 0 : half;                                 // my chunks: [cb, ce)
-    const int ce = ch == 0 ? half : chunks;
+    const int nch = (Tk + 31) >> 5;                                    // 32-column chunks of a score row (<= 8)
+    const bool leader = (q == 0 && lane == 0);                         // issues this block's O store
+    const int rg = i * A2_ROWS + r;
+    const bool trace = p.dbg != nullptr && blockIdx.x == 0 && (threadIdx.x & 127) == 0;
+#define A2F_TR(slot) do { if (trace && n < 16) p.dbg[n * 16 + i * 8 + (slot)] = clock64(); } while (0)
     int n = 0;
     for (int it = blockIdx.x; it < items; it += gridDim.x, ++n) {
       const int b = it / p.heads, h = it - b * p.heads;
-      float inv[2] = {0.f, 0.f};
-      for (int i = 0; i < nb; ++i) {
-        mbar_wait(&bar_s[i], n & 1);
-        tc_fence_after();
-        const uint32_t ts = taddr + i * 256;
-        float mx = -INFINITY;
+      A2F_TR(0);
+      mbar_wait(&bar_s[i], n & 1);
+      tc_fence_after();
+      A2F_TR(1);
+      // both passes: the TMEM load of chunk c + 1 is in flight while chunk c is processed
+      uint32_t va[32], vb[32];
+      float mx = -INFINITY;
+      tmem_ld32(taddr, va);
+      tmem_wait_ld();
 #pragma unroll
-        for (int cc = 0; cc < 4; ++cc) {
-          if (cb + cc < ce) {
-            const int c0 = (cb + cc) * 32;
-            uint32_t v[32];
-            tmem_ld32(ts + c0, v);
-            tmem_wait_ld();
-            if (c0 + 32 <= T) {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(v[j]));
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (c0 + j < T) mx = fmaxf(mx, __uint_as_float(v[j]));
-            }
-          }
+      for (int c = 0; c < 8; ++c) {
+        if (c < nch) {
+          uint32_t* cur = (c & 1) ? vb : va;
+          uint32_t* nxt = (c & 1) ? va : vb;
+          if (c + 1 < nch) tmem_ld32(taddr + (c + 1) * 32, nxt);
+          mx = a2_max32(cur, c * 32, T, mx);
+          if (c + 1 < nch) tmem_wait_ld();
         }
-        st_shared_f32(x_mine, mx);
-        pair_bar_sync(1 + q);
-        mx = fmaxf(mx, ld_shared_f32(x_other));
-        pair_bar_sync(1 + q);
-        const float mxs = mx * sl2;
-        float sum = 0.f;
-        uint32_t pk[4][16];
-#pragma unroll
-        for (int cc = 0; cc < 4; ++cc) {
-          if (cb + cc < ce) {
-            const int c0 = (cb + cc) * 32;
-            uint32_t v[32];
-            tmem_ld32(ts + c0, v);
-            tmem_wait_ld();
-            if (c0 + 32 <= T) {
-#pragma unroll
-              for (int j = 0; j < 16; ++j) {
-                const float p0 = ex2_approx(fmaf(__uint_as_float(v[2 * j]), sl2, -mxs));
-                const float p1 = ex2_approx(fmaf(__uint_as_float(v[2 * j + 1]), sl2, -mxs));
-                sum += p0 + p1;
-                pk[cc][j] = pack_bf16x2(p0, p1);
-              }
-            } else {
-#pragma unroll
-              for (int j = 0; j < 16; ++j) {
-                const int c = c0 + 2 * j;
-                const float p0 = (c < T) ? ex2_approx(fmaf(__uint_as_float(v[2 * j]), sl2, -mxs)) : 0.f;
-                const float p1 = (c + 1 < T) ? ex2_approx(fmaf(__uint_as_float(v[2 * j + 1]), sl2, -mxs)) : 0.f;
-                sum += p0 + p1;
-                pk[cc][j] = pack_bf16x2(p0, p1);
-              }
-            }
-          }
-        }
-        // the staging buffer is free once the previous row block's P V has completed (block 0: the previous item's
-        // last P V, which this thread waited for in that item's read-out below)
-        if (i > 0) mbar_wait(&bar_o[i - 1], n & 1);
-#pragma unroll
-        for (int cc = 0; cc < 4; ++cc) {
-          if (cb + cc < ce) {
-            const int c0 = (cb + cc) * 32;
-#pragma unroll
-            for (int j8 = 0; j8 < 4; ++j8)
-              st_shared_v4(a2_chunk(sP_u, r, c0 + j8 * 8), pk[cc][4 * j8], pk[cc][4 * j8 + 1], pk[cc][4 * j8 + 2],
-                           pk[cc][4 * j8 + 3]);
-          }
-        }
-        fence_proxy_async_smem();
-        tc_fence_before();
-        mbar_arrive(bar_p);
-        st_shared_f32(x_mine, sum);
-        pair_bar_sync(1 + q);
-        sum += ld_shared_f32(x_other);
-        pair_bar_sync(1 + q);
-        inv[i] = 1.f / sum;
-        const int rg = i * A2_ROWS + r;
-        if (ch == 0 && rg < T) p.lse[(static_cast<size_t>(b) * p.heads + h) * T + rg] = (mxs + log2f(sum)) * kA2Ln2;
       }
-      for (int i = 0; i < nb; ++i) {
-        mbar_wait(&bar_o[i], n & 1);
-        tc_fence_after();
-        uint32_t v[32];
-        tmem_ld32(taddr + i * 256 + ch * 32, v);
+      const float mxs = mx * sl2;
+      A2F_TR(2);
+      tmem_ld32(taddr, va);
+      // this block's staging buffer: P V of the previous item has completed (every thread waited for it before its
+      // read-out); the TMA store of that item's O must have read tile 0
+      if (n > 0) {
+        if (leader) tma_wait_read<0>();
+        named_bar_sync(1 + i, 128);
+      }
+      tmem_wait_ld();
+      float sum = 0.f;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        if (c < nch) {
+          uint32_t* cur = (c & 1) ? vb : va;
+          uint32_t* nxt = (c & 1) ? va : vb;
+          if (c + 1 < nch) tmem_ld32(taddr + (c + 1) * 32, nxt);
+          sum += a2_exp32_stage(cur, c * 32, T, sl2, mxs, sP_u, r);
+          if (c == 3 && nch > 4) {               // keys [0, 128) staged: the first part of P V may start
+            fence_proxy_async_smem();
+            tc_fence_before();
+            mbar_arrive(&bar_pa[i]);
+          }
+          if (c + 1 < nch) tmem_wait_ld();
+        }
+      }
+      fence_proxy_async_smem();
+      tc_fence_before();
+      if (nch <= 4) mbar_arrive(&bar_pa[i]);
+      mbar_arrive(&bar_pb[i]);
+      A2F_TR(3);
+      const float inv = 1.f / sum;
+      if (rg < T) p.lse[(static_cast<size_t>(b) * p.heads + h) * T + rg] = (mxs + log2f(sum)) * kA2Ln2;
+      // read-out: O_i -> bf16 rows in tile 0 of the (idle) staging buffer -> one TMA store, rows beyond T clipped
+      mbar_wait(&bar_o[i], n & 1);
+      tc_fence_after();
+      A2F_TR(4);
+      {
+        uint32_t va[32], vb[32];
+        tmem_ld32(taddr, va);
+        tmem_ld32(taddr + 32, vb);
         tmem_wait_ld();
         tc_fence_before();
         mbar_arrive(&tfree[i]);
-        const int rg = i * A2_ROWS + r;
-        if (rg < T)
-          a2_store_row32(p.o + (static_cast<size_t>(b) * T + rg) * p.ld + h * A2_DH + ch * 32, v, inv[i]);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          st_shared_v4(a2_chunk(sP_u, r, 8 * k),
+                       pack_bf16x2(__uint_as_float(va[8 * k]) * inv, __uint_as_float(va[8 * k + 1]) * inv),
+                       pack_bf16x2(__uint_as_float(va[8 * k + 2]) * inv, __uint_as_float(va[8 * k + 3]) * inv),
+                       pack_bf16x2(__uint_as_float(va[8 * k + 4]) * inv, __uint_as_float(va[8 * k + 5]) * inv),
+                       pack_bf16x2(__uint_as_float(va[8 * k + 6]) * inv, __uint_as_float(va[8 * k + 7]) * inv));
+          st_shared_v4(a2_chunk(sP_u, r, 32 + 8 * k),
+                       pack_bf16x2(__uint_as_float(vb[8 * k]) * inv, __uint_as_float(vb[8 * k + 1]) * inv),
+                       pack_bf16x2(__uint_as_float(vb[8 * k + 2]) * inv, __uint_as_float(vb[8 * k + 3]) * inv),
+                       pack_bf16x2(__uint_as_float(vb[8 * k + 4]) * inv, __uint_as_float(vb[8 * k + 5]) * inv),
+                       pack_bf16x2(__uint_as_float(vb[8 * k + 6]) * inv, __uint_as_float(vb[8 * k + 7]) * inv));
+        }
       }
+      fence_proxy_async_smem();
+      named_bar_sync(1 + i, 128);
+      if (leader) {
+        tma_store_3d(&p.tmO, sP_u, h * A2_DH, i * A2_ROWS, b);
+        tma_commit();
+      }
+      A2F_TR(5);
     }
+#undef A2F_TR
+    if (leader) tma_wait_all<0>();               // the last store has landed before the CTA retires
   }
   tc_fence_before();
   __syncthreads();
@@ -325,15 +397,6 @@ __global__ void __launch_bounds__(A2_THREADS, 1) attn2_fwd_kernel(const __grid_c
 // (descriptors rebuilt with dependent integer chains).  Hence: read-outs staged in shared memory and written by TMA,
 // O read 4 rows x 128 contiguous bytes per warp instruction one tile ahead of its use, descriptors built once per
 // tile and advanced by adding constants, tile indices kept as counters.
-__device__ __forceinline__ void named_bar_sync(int id, int threads) {
-  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
-}
-__device__ __forceinline__ void tma_store_3d(const void* tmap, uint32_t smem_src, int c0, int c1, int c2) {
-  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
-               :
-               : "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_src), "r"(c0), "r"(c1), "r"(c2)
-               : "memory");
-}
 // bring a tile into L2 ahead of the load that will need a free ring slot (no shared memory involved)
 __device__ __forceinline__ void tma_prefetch_l2_3d(const void* tmap, int c0, int c1, int c2) {
   asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global [%0, {%1, %2, %3}];"
@@ -715,7 +778,7 @@ __global__ void __launch_bounds__(A2B_THREADS, 1) attn2_bwd_kernel(const __grid_
   }
 }
 
-constexpr int attn2_fwd_smem() { return 14 * A2_TILE + 1024 + 128 + 1024; }
+constexpr int attn2_fwd_smem() { return 14 * A2_TILE + 128 + 1024; }
 constexpr int attn2_bwd_smem() { return (2 * A2_RING + 6) * A2_TILE + 1024 + 256 + 1024; }
 
 static int fill_attn2(Attn2Params& p, const void* q, const void* k, const void* v, const void* d_o, int B, int T,
@@ -745,6 +808,10 @@ extern "C" {
 
 int forde_attn2_max_tokens(void) { return A2_MAXT; }
 
+// debug: clock64 timeline of CTA 0's first softmax thread (tools/attn_trace.py); NULL in production
+static long long* g_attn2_dbg = nullptr;
+void forde_attn2_set_trace(void* buf) { g_attn2_dbg = static_cast<long long*>(buf); }
+
 int forde_attn2_fwd(void* stream, const void* q, const void* k, const void* v, void* o, float* lse, int B, int T,
                     int heads, long long ld) {
   if (o == nullptr || lse == nullptr) return FORDE_EINVAL;
@@ -754,6 +821,11 @@ int forde_attn2_fwd(void* stream, const void* q, const void* k, const void* v, v
   if (rc != FORDE_OK) return rc;
   p.o = static_cast<__nv_bfloat16*>(o);
   p.lse = lse;
+  p.dbg = g_attn2_dbg;
+  rc = make_tmap_bf16_3d(&p.tmO, o, static_cast<uint64_t>(heads) * A2_DH, static_cast<uint64_t>(T),
+                         static_cast<uint64_t>(B), static_cast<uint64_t>(ld),
+                         static_cast<uint64_t>(T) * static_cast<uint64_t>(ld), A2_DH, A2_ROWS);
+  if (rc != FORDE_OK) return rc;
   static std::once_flag once;
   std::call_once(once, [] {
     cudaFuncSetAttribute(attn2_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, attn2_fwd_smem());
@@ -764,9 +836,6 @@ int forde_attn2_fwd(void* stream, const void* q, const void* k, const void* v, v
   attn2_fwd_kernel<<<items < sms ? items : sms, A2_THREADS, attn2_fwd_smem(), static_cast<cudaStream_t>(stream)>>>(p);
   return check_launch("attn2_fwd_kernel");
 }
-
-static long long* g_attn2_dbg = nullptr;
-void forde_attn2_set_trace(void* buf) { g_attn2_dbg = static_cast<long long*>(buf); }
 
 int forde_attn2_bwd(void* stream, const void* q, const void* k, const void* v, const void* o, const void* d_o,
                     const float* lse, void* dq, void* dk, void* dv, int B, int T, int heads, long long ld) {

@@ -2,11 +2,12 @@
 
 This is the benchmark / integration harness around the StatefulLayer, not the product: the towers are the
 plain macro-architecture the README describes (patchify or token embedding -> L x FORDETransformerBlock ->
-[CLS] -> Dense projection), the attention core goes through stock torch SDPA (cuDNN flash, "library code" for this
-task) and the front ends / projection heads through torch ops; the FFN slot of every block -- ``StatefulLayer`` --,
-the `add/norm` either side of it, the q/k/v/out projections and the contrastive loss run on this repository's
-sm_100a kernels.  FORDE block = self-attention -> add/norm -> StatefulLayer ->
-add/norm (README.md:42-43).
+[CLS] -> Dense projection).  Everything a train step launches runs on this repository's sm_100a kernels: the FFN slot
+of every block -- ``StatefulLayer`` --, the `add/norm` either side of it, the q/k/v/out projections, patch embedding and
+heads (tcgen05 GEMM engine), the front ends (csrc/forde_frontend.cu), the attention core for head_dim 64 and up to 256
+tokens (csrc/forde_attn.cu: T <= 128, the text tower; csrc/forde_attn2.cu: T <= 256, the ViT-B/16 vision tower) and the
+contrastive loss.  Longer sequences (ViT-L/14: 257 tokens) fall back to stock torch SDPA (cuDNN flash, "library code"
+for this task).  FORDE block = self-attention -> add/norm -> StatefulLayer -> add/norm (README.md:42-43).
 
 Variables follow the Flax collection layout the reference's training loop threads through ``train_step``
 (src/training/train.py:122-171): ``params`` (differentiated), ``neuron_assignments`` and ``stats_buffer``
