@@ -65,6 +65,17 @@ def lib_sha16():
         return None
 
 
+def lib_src16():
+    """First 16 hex digits of the hash of the SOURCES the loaded library was built from (__graft_entry__.build() records
+    it next to the library); unlike the binary's hash it does not depend on the directory the build ran in."""
+    path = os.environ.get("FORDE_LIB", os.path.join(ROOT, "forde-vision-language_b200", "libforde_b200.so")) + ".srchash"
+    try:
+        with open(path) as f:
+            return f.read().strip()[:16] or None
+    except OSError:
+        return None
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
 
@@ -335,17 +346,21 @@ def run_gpu(args):
     sl_flops = sum(r["flops_total"] for r in kt.values())
     traffic_db, traffic_note = {}, "no ncu capture on record for this build"
     tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
-    sha = lib_sha16()
+    sha, src = lib_sha16(), lib_src16()
     if os.path.exists(tpath):
         with open(tpath) as f:
             tj = json.load(f)
-        if tj.get("lib_sha256_16") == sha:      # only quote DRAM bytes captured on THIS build of the library
+        # only quote DRAM bytes captured on THIS build of the library: the same binary, or one built from the same sources
+        same_bin = tj.get("lib_sha256_16") is not None and tj.get("lib_sha256_16") == sha
+        same_src = tj.get("src_sha256_16") is not None and tj.get("src_sha256_16") == src
+        if same_bin or same_src:
             traffic_db = tj.get("kernels", {})
             traffic_note = (f"dram__bytes_read.sum + dram__bytes_write.sum per launch, one ncu --set full capture of "
-                            f"library {sha} ({tj.get('source', 'profiles/')})")
+                            f"library {tj.get('lib_sha256_16')} built from sources {tj.get('src_sha256_16')} "
+                            f"({'same binary' if same_bin else 'same sources'}; {tj.get('source', 'profiles/')})")
         else:
-            traffic_note = (f"profiles/ncu_traffic.json was captured on library {tj.get('lib_sha256_16')}, this run "
-                            f"loads {sha}: not quoted")
+            traffic_note = (f"profiles/ncu_traffic.json was captured on library {tj.get('lib_sha256_16')} (sources "
+                            f"{tj.get('src_sha256_16')}), this run loads {sha} (sources {src}): not quoted")
     if kt:
         dom = max(kt, key=lambda n: kt[n]["ms_total"])
         r = kt[dom]
@@ -364,7 +379,7 @@ def run_gpu(args):
         "dtype": "bf16", "data": "synthetic",
         "config": workload_config(cfg, args.batch, world),
         "run": {"launch": "whole step replayed as one CUDA graph" if graphed else "eager launches",
-                "ms_per_step_eager_instrumented": ms_eager / args.steps, "lib_sha256_16": sha,
+                "ms_per_step_eager_instrumented": ms_eager / args.steps, "lib_sha256_16": sha, "src_sha256_16": src,
                 "towers": ("text tower on its own CUDA stream, forward and backward (fork/join inside the graph); the "
                            "per-kernel pass runs both towers on one stream") if concurrent else "one stream",
                 "brain_map": "all-generalist (every layer's initial map, D7); see smoothed_map for a post-slow-loop map",

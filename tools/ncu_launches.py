@@ -1,5 +1,6 @@
 """Aggregate an `ncu --metrics gpu__time_duration.sum --csv` launch list by kernel name.
-Usage: python tools/ncu_launches.py launches.csv [steps] > summary.md"""
+Usage: python tools/ncu_launches.py launches.csv [steps] > summary.md
+Launches before the first kernel of this repository (parameter initialisation fills) are dropped."""
 import csv
 import re
 import sys
@@ -11,6 +12,8 @@ with open(sys.argv[1], newline="") as f:
         if len(r) > 10 and r[0].isdigit():
             rows.append(r)
 steps = float(sys.argv[2]) if len(sys.argv) > 2 else 1.0
+first = next((i for i, r in enumerate(rows) if "forde::" in r[4]), 0)
+rows = rows[first:]
 agg = defaultdict(lambda: [0, 0.0])
 for r in rows:
     name = r[4]

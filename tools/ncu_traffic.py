@@ -68,7 +68,11 @@ for name, r in zip(ORDER, gemm_rows):
         "inst_executed": val(r, "smsp__inst_executed.sum"),
     }
 sha = hashlib.sha256(open(a.lib, "rb").read()).hexdigest()[:16]
-out = {"lib_sha256_16": sha, "brain_map": a.map, "dims": {"M": M, "d": d, "H": H},
+try:   # hash of the sources the library was built from (written by __graft_entry__.build(); path-independent)
+    src = open(a.lib + ".srchash").read().strip()[:16] or None
+except OSError:
+    src = None
+out = {"lib_sha256_16": sha, "src_sha256_16": src, "brain_map": a.map, "dims": {"M": M, "d": d, "H": H},
        "source": f"{os.path.relpath(a.raw_csv, ROOT)} (ncu --set full --clock-control none, one launch per kernel, "
                  f"tools/layer_bench.py --once --assign {a.map})",
        "kernels": kernels}
