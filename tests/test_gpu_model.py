@@ -125,3 +125,31 @@ def test_fit_runs_fast_and_slow_loops_together(built, tmp_path):
     # statistics restarted after the last slow loop (step 6): nothing accumulated since
     sb = st.variables["stats_buffer"]["vision"]["layer_0"]["stateful_layer"]
     assert int(sb["step_count"].item()) == 0
+
+
+def test_text_tower_on_its_own_stream_is_the_same_computation(built):
+    """dual_encoder.FORDEDualEncoder(concurrent_towers=True) forks the text tower onto a side stream (forward and
+    backward) and joins it before the loss / before the optimizer reads the gradients.  Same seed, same batches: the
+    losses, gradient norms, parameters and sensing statistics after three steps must equal the one-stream run (up to
+    the fp32 accumulation order of the split-K weight-gradient adds)."""
+    from forde_b200 import dual_encoder, train
+
+    cfg = dual_encoder.config_tiny()
+    b = {k: v.cuda() for k, v in train.synthetic_batch(cfg, 32, pinned=False).items()}
+    runs = {}
+    for concurrent in (True, False):
+        st = train.create_train_state(cfg, 11, device="cuda")
+        st.model.concurrent_towers = concurrent
+        out = []
+        for _ in range(3):
+            _, m = train.train_step(st, b)
+            out.append((float(m["loss"].item()), float(m["grad_norm"].item())))
+        torch.cuda.synchronize()
+        sb = st.variables["stats_buffer"]["text"]["layer_1"]["stateful_layer"]
+        runs[concurrent] = (out, st.flat_p32.detach().cpu().numpy(), sb["moments"].cpu().numpy(),
+                            int(sb["step_count"].item()))
+    (o1, p1, m1, c1), (o0, p0, m0, c0) = runs[True], runs[False]
+    np.testing.assert_allclose(np.array(o1), np.array(o0), rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(p1, p0, rtol=0, atol=2e-5)
+    np.testing.assert_allclose(m1, m0, rtol=1e-3, atol=1e-4)
+    assert c1 == c0 == 3
