@@ -13,8 +13,12 @@
 //             O_i = P_i V accumulates over the first 64 columns of S_i's own TMEM region, in two parts: keys [0, 128)
 //             as soon as they are staged (under the exponentials of the remaining keys), the rest when the row is done
 //             read-out: O_i / row sum -> bf16 rows in the (idle) staging buffer -> one TMA store per block
-//             What bounds it: the two passes over S are TMEM-read bound (128 B per clock per SM: 229 KB per pass and
-//             item = 1.8 k clocks each way, measured) and the exponentials MUFU bound (3.6 k clocks per item).
+//             issue order: row block 1 runs half an item behind row block 0 (S_0(n), P_1 V of item n - 1, S_1(n),
+//             P_0 V of item n), so one block's exponentials run under the other's max pass and P V / read-out tail
+//             What bounds it (ncu, profiles/r2_ncu_full_aux_kernels.md): neither pipe saturates (MUFU 38 %, tensor
+//             17 %); with 2.5 warps per scheduler the per-warp dependency chains are exposed (7 cycles per issued
+//             instruction: fixed-latency waits 1.9, TMEM / barrier scoreboard 1.5).  Per item and block: max pass
+//             1.9 k clocks, exp pass 4.7 k, P V wait + read-out 1.4 k (clock64 trace).
 //   backward (per item): tiles (key block j, row block i), j outer.  Per tile:
 //             S = Q_i K_j^T, dP = dO_i V_j^T                                   -> TMEM [0,128), [128,256)
 //             p = exp2(s * scale * log2e - lse), dS = p (dP - D) scale         -> P, dS (bf16) staged in shared memory
@@ -43,6 +47,9 @@
 
 namespace forde {
 
+#ifndef FORDE_ATTN2_STAGGER
+#define FORDE_ATTN2_STAGGER 1
+#endif
 constexpr int A2_ROWS = 128;
 constexpr int A2_DH = 64;
 constexpr int A2_TILE = A2_ROWS * A2_DH * 2;     // 16 KB: 128 rows x 64 bf16, 128-byte swizzle
@@ -118,7 +125,7 @@ __device__ __forceinline__ void tma_store_3d(const void* tmap, uint32_t smem_src
 // the row sum need no exchange between warps, and the two blocks' latency-bound phases (TMEM reads, staging, read-out)
 // run side by side instead of one after the other.  clock64 trace of the first version (all eight warps on one block
 // at a time, two warps per row, per-thread row stores of O): 13.1 k cycles per item, of which 4.5 k the exponentials
-// -- 169 us per ViT-B/16 layer; this one 8.6 k cycles, 122 us (cuDNN: 108; profiles/r2_attn2_forward.md).
+// -- 169 us per ViT-B/16 layer; this one 8.2 k cycles, 114 us (cuDNN: 108; profiles/r2_attn2_forward.md).
 // shared memory: Q [2 row blocks] | K [2 key blocks] | V [2 key blocks] | P staging [2 row blocks][4 column tiles]
 //                (tile 0 of a block's staging also carries its O on the way out: TMA store) | barriers
 // Q / K are single-buffered: both S products are issued at the start of an item, so the next item's Q / K loads have
@@ -241,42 +248,67 @@ __global__ void __launch_bounds__(A2_THREADS, 1) attn2_fwd_kernel(const __grid_c
       const uint32_t idesc_o = make_idesc_bf16(A2_ROWS, A2_DH, false, true); // P (K-major) x V (MN-major)
       const uint64_t dK = make_smem_desc_sw128(smem_u32(sK), 0, 1024);
       const uint64_t dV = make_smem_desc_sw128(smem_u32(sV), A2_TILE, 1024);
+      // Issue order.  Row block 1 runs half an item behind row block 0: per item S_0(n), P_1 V of item n - 1, S_1(n),
+      // P_0 V of item n.  The two blocks' softmax groups are then in different phases -- one block's exponentials (MUFU)
+      // run under the other's TMEM-read-bound max pass and its P V / read-out tail -- instead of both hitting the same
+      // unit at the same time (FORDE_ATTN2_STAGGER=0 at build time: both blocks of an item issued together).
+      // P_i V goes in two parts: the keys [0, 128) as soon as they are staged -- under the exponentials of the remaining
+      // keys --, the rest when the row is complete.  (Runtime loops on purpose: fully unrolled with a per-step
+      // predicate, this compiler build produced wrong operand registers for the last steps.)
+      const int ks_a = (Tk < 128 ? Tk : 128) / 16, ks_n = Tk / 16;
+      auto issue_s = [&](int i, int n) {
+        const uint64_t dQ = make_smem_desc_sw128(smem_u32(sQ) + i * A2_TILE, 0, 1024);
+        if (n > 0) mbar_wait(&tfree[i], (n - 1) & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < A2_DH / 16; ++k)
+          umma_bf16(tmem_base + i * 256, dQ + 2 * k, dK + 2 * k, idesc_s, k > 0 ? 1u : 0u);
+        umma_commit(&bar_s[i]);
+      };
+      auto issue_pv = [&](int i, int n, bool first_part) {
+        const uint64_t dP = make_smem_desc_sw128(smem_u32(sP) + i * 4 * A2_TILE, 0, 1024);
+        mbar_wait(first_part ? &bar_pa[i] : &bar_pb[i], n & 1);
+        tc_fence_after();
+        const int k0 = first_part ? 0 : ks_a, k1 = first_part ? ks_a : ks_n;
+        for (int ks = k0; ks < k1; ++ks)         // reduction over the keys, 16 per step
+          umma_bf16(tmem_base + i * 256, dP + (ks >> 2) * (A2_TILE >> 4) + (ks & 3) * 2, dV + 128 * ks, idesc_o,
+                    ks > 0 ? 1u : 0u);
+        if (!first_part) umma_commit(&bar_o[i]);
+      };
       int n = 0;
+#if FORDE_ATTN2_STAGGER
       for (int it = blockIdx.x; it < items; it += gridDim.x, ++n) {
         mbar_wait(fullQK, n & 1);
-        for (int i = 0; i < nb; ++i) {
-          const uint64_t dQ = make_smem_desc_sw128(smem_u32(sQ) + i * A2_TILE, 0, 1024);
-          if (n > 0) mbar_wait(&tfree[i], (n - 1) & 1);
-          tc_fence_after();
-#pragma unroll
-          for (int k = 0; k < A2_DH / 16; ++k)
-            umma_bf16(tmem_base + i * 256, dQ + 2 * k, dK + 2 * k, idesc_s, k > 0 ? 1u : 0u);
-          umma_commit(&bar_s[i]);
+        issue_s(0, n);
+        if (nb > 1) {
+          if (n > 0) {                           // block 1 of the previous item: its V is released here
+            issue_pv(1, n - 1, true);
+            issue_pv(1, n - 1, false);
+            umma_commit(emptyV);
+          }
+          issue_s(1, n);
         }
         umma_commit(emptyQK);
         mbar_wait(fullV, n & 1);
-        // P_i V in two parts: the keys [0, 128) as soon as they are staged -- under the exponentials of the remaining
-        // keys --, the rest when the row is complete.  (Runtime loops on purpose: fully unrolled with a per-step
-        // predicate, this compiler build produced wrong operand registers for the last steps.)
-        const int ks_a = (Tk < 128 ? Tk : 128) / 16, ks_n = Tk / 16;
-        for (int i = 0; i < nb; ++i) {
-          const uint64_t dP = make_smem_desc_sw128(smem_u32(sP) + i * 4 * A2_TILE, 0, 1024);
-          mbar_wait(&bar_pa[i], n & 1);
-          tc_fence_after();
-          for (int ks = 0; ks < ks_a; ++ks)      // reduction over the keys, 16 per step
-            umma_bf16(tmem_base + i * 256, dP + (ks >> 2) * (A2_TILE >> 4) + (ks & 3) * 2, dV + 128 * ks, idesc_o,
-                      ks > 0 ? 1u : 0u);
-        }
-        for (int i = 0; i < nb; ++i) {
-          const uint64_t dP = make_smem_desc_sw128(smem_u32(sP) + i * 4 * A2_TILE, 0, 1024);
-          mbar_wait(&bar_pb[i], n & 1);
-          tc_fence_after();
-          for (int ks = ks_a; ks < ks_n; ++ks)
-            umma_bf16(tmem_base + i * 256, dP + (ks >> 2) * (A2_TILE >> 4) + (ks & 3) * 2, dV + 128 * ks, idesc_o, 1u);
-          umma_commit(&bar_o[i]);
-        }
+        issue_pv(0, n, true);
+        issue_pv(0, n, false);
+        if (nb == 1) umma_commit(emptyV);
+      }
+      if (nb > 1 && n > 0) {                     // the last item's block 1
+        issue_pv(1, n - 1, true);
+        issue_pv(1, n - 1, false);
+      }
+#else
+      for (int it = blockIdx.x; it < items; it += gridDim.x, ++n) {
+        mbar_wait(fullQK, n & 1);
+        for (int i = 0; i < nb; ++i) issue_s(i, n);
+        umma_commit(emptyQK);
+        mbar_wait(fullV, n & 1);
+        for (int i = 0; i < nb; ++i) issue_pv(i, n, true);
+        for (int i = 0; i < nb; ++i) issue_pv(i, n, false);
         umma_commit(emptyV);
       }
+#endif
     }
   } else if ((warp >> 2) < nb) {
     const int i = warp >> 2, q = warp & 3;                             // row block, TMEM lane quarter
