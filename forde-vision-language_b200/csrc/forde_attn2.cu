@@ -47,9 +47,6 @@
 
 namespace forde {
 
-#ifndef FORDE_ATTN2_STAGGER
-#define FORDE_ATTN2_STAGGER 1
-#endif
 constexpr int A2_ROWS = 128;
 constexpr int A2_DH = 64;
 constexpr int A2_TILE = A2_ROWS * A2_DH * 2;     // 16 KB: 128 rows x 64 bf16, 128-byte swizzle
@@ -251,7 +248,7 @@ __global__ void __launch_bounds__(A2_THREADS, 1) attn2_fwd_kernel(const __grid_c
       // Issue order.  Row block 1 runs half an item behind row block 0: per item S_0(n), P_1 V of item n - 1, S_1(n),
       // P_0 V of item n.  The two blocks' softmax groups are then in different phases -- one block's exponentials (MUFU)
       // run under the other's TMEM-read-bound max pass and its P V / read-out tail -- instead of both hitting the same
-      // unit at the same time (FORDE_ATTN2_STAGGER=0 at build time: both blocks of an item issued together).
+      // unit at the same time (both blocks of an item issued together: 122 instead of 114 us per ViT-B/16 layer).
       // P_i V goes in two parts: the keys [0, 128) as soon as they are staged -- under the exponentials of the remaining
       // keys --, the rest when the row is complete.  (Runtime loops on purpose: fully unrolled with a per-step
       // predicate, this compiler build produced wrong operand registers for the last steps.)
@@ -276,7 +273,6 @@ __global__ void __launch_bounds__(A2_THREADS, 1) attn2_fwd_kernel(const __grid_c
         if (!first_part) umma_commit(&bar_o[i]);
       };
       int n = 0;
-#if FORDE_ATTN2_STAGGER
       for (int it = blockIdx.x; it < items; it += gridDim.x, ++n) {
         mbar_wait(fullQK, n & 1);
         issue_s(0, n);
@@ -298,17 +294,6 @@ __global__ void __launch_bounds__(A2_THREADS, 1) attn2_fwd_kernel(const __grid_c
         issue_pv(1, n - 1, true);
         issue_pv(1, n - 1, false);
       }
-#else
-      for (int it = blockIdx.x; it < items; it += gridDim.x, ++n) {
-        mbar_wait(fullQK, n & 1);
-        for (int i = 0; i < nb; ++i) issue_s(i, n);
-        umma_commit(emptyQK);
-        mbar_wait(fullV, n & 1);
-        for (int i = 0; i < nb; ++i) issue_pv(i, n, true);
-        for (int i = 0; i < nb; ++i) issue_pv(i, n, false);
-        umma_commit(emptyV);
-      }
-#endif
     }
   } else if ((warp >> 2) < nb) {
     const int i = warp >> 2, q = warp & 3;                             // row block, TMEM lane quarter
