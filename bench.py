@@ -353,11 +353,17 @@ def run_gpu(args):
         # only quote DRAM bytes captured on THIS build of the library: the same binary, or one built from the same sources
         same_bin = tj.get("lib_sha256_16") is not None and tj.get("lib_sha256_16") == sha
         same_src = tj.get("src_sha256_16") is not None and tj.get("src_sha256_16") == src
-        if same_bin or same_src:
+        # ... or one whose GEMM engine (the only kernels in the table) is built from the same files and flags, when the
+        # loaded library is the one build() made from this tree
+        import __graft_entry__ as G
+        same_gemm = (tj.get("gemm_src_sha256_16") is not None and src == G.source_hash()[:16]
+                     and tj.get("gemm_src_sha256_16") == G.source_hash(G.GEMM_SOURCES)[:16])
+        if same_bin or same_src or same_gemm:
             traffic_db = tj.get("kernels", {})
+            how = "same binary" if same_bin else "same sources" if same_src else "same GEMM-engine sources"
             traffic_note = (f"dram__bytes_read.sum + dram__bytes_write.sum per launch, one ncu --set full capture of "
                             f"library {tj.get('lib_sha256_16')} built from sources {tj.get('src_sha256_16')} "
-                            f"({'same binary' if same_bin else 'same sources'}; {tj.get('source', 'profiles/')})")
+                            f"({how}; {tj.get('source', 'profiles/')})")
         else:
             traffic_note = (f"profiles/ncu_traffic.json was captured on library {tj.get('lib_sha256_16')} (sources "
                             f"{tj.get('src_sha256_16')}), this run loads {sha} (sources {src}): not quoted")

@@ -67,7 +67,6 @@ struct Attn2Params {
   int B, T, heads, Tk, nb;     // Tk = T rounded up to 16; nb = number of 128-row blocks (1 or 2)
   long long ld;
   float scale;
-  int l2_prefetch;  // backward: pull the next item's tiles into L2 a whole item ahead
   long long* dbg;   // optional clock64 trace of CTA 0 (tools/attn_trace.py); NULL in production
 };
 
@@ -414,13 +413,6 @@ __global__ void __launch_bounds__(A2_THREADS, 1) attn2_fwd_kernel(const __grid_c
 // (descriptors rebuilt with dependent integer chains).  Hence: read-outs staged in shared memory and written by TMA,
 // O read 4 rows x 128 contiguous bytes per warp instruction one tile ahead of its use, descriptors built once per
 // tile and advanced by adding constants, tile indices kept as counters.
-// bring a tile into L2 ahead of the load that will need a free ring slot (no shared memory involved)
-__device__ __forceinline__ void tma_prefetch_l2_3d(const void* tmap, int c0, int c1, int c2) {
-  asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global [%0, {%1, %2, %3}];"
-               :
-               : "l"(reinterpret_cast<uint64_t>(tmap)), "r"(c0), "r"(c1), "r"(c2)
-               : "memory");
-}
 __device__ __forceinline__ float dot8_bf16(const uint4& a, const uint4& b) {
   float d = 0.f;
   d = fmaf(bf16lo_to_f32(a.x), bf16lo_to_f32(b.x), d); d = fmaf(bf16hi_to_f32(a.x), bf16hi_to_f32(b.x), d);
@@ -500,19 +492,9 @@ __global__ void __launch_bounds__(A2B_THREADS, 1) attn2_bwd_kernel(const __grid_
       int L = 0;
       for (int it = blockIdx.x; it < items; it += gridDim.x) {
         const int b = it / p.heads, h = it - b * p.heads;
-        // The ring holds one item, so the next item's loads are issued only a tile or two before their use -- less than
-        // an HBM round trip.  Pulling its tiles into L2 a whole item ahead removes those waits but MEASURED SLOWER
-        // (218 -> 234 us per layer, same box, alternating runs): off unless FORDE_ATTN2_L2PF=1.
-        const int nx = it + gridDim.x;
-        if (nx < items && p.l2_prefetch) {
-          const int b2 = nx / p.heads, h2 = nx - b2 * p.heads;
-          for (int i = 0; i < nb; ++i) {
-            tma_prefetch_l2_3d(&p.tmK, h2 * A2_DH, i * A2_ROWS, b2);
-            tma_prefetch_l2_3d(&p.tmV, h2 * A2_DH, i * A2_ROWS, b2);
-            tma_prefetch_l2_3d(&p.tmQ, h2 * A2_DH, i * A2_ROWS, b2);
-            tma_prefetch_l2_3d(&p.tmDO, h2 * A2_DH, i * A2_ROWS, b2);
-          }
-        }
+        // (The ring holds one item, so the next item's loads are issued only a tile or two before their use.  Pulling its
+        // tiles into L2 a whole item ahead with cp.async.bulk.prefetch removed those waits but MEASURED SLOWER -- 218 ->
+        // 234 us per layer, same box, alternating runs -- and was deleted.)
         for (int l = 0; l < lpi; ++l, ++L) {
           const int slot = L & (A2_RING - 1);
           uint8_t* dst = ring + slot * 2 * A2_TILE;
@@ -866,10 +848,6 @@ int forde_attn2_bwd(void* stream, const void* q, const void* k, const void* v, c
   if (rc != FORDE_OK) return rc;
   p.o_in = static_cast<const __nv_bfloat16*>(o);
   p.do_in = static_cast<const __nv_bfloat16*>(d_o);
-  {
-    static const int pf = [] { const char* e = getenv("FORDE_ATTN2_L2PF"); return e == nullptr ? 0 : atoi(e); }();
-    p.l2_prefetch = pf;
-  }
   p.dbg = g_attn2_dbg;
   p.lse = const_cast<float*>(lse);
   p.dq = static_cast<__nv_bfloat16*>(dq);

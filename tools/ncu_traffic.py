@@ -16,6 +16,7 @@ import csv
 import hashlib
 import json
 import os
+import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 ORDER = ["sl_up_fwd", "sl_down_fwd", "sl_dz_bwd", "sl_dx_bwd", "sl_dw_up", "sl_dw_down"]
@@ -72,7 +73,11 @@ try:   # hash of the sources the library was built from (written by __graft_entr
     src = open(a.lib + ".srchash").read().strip()[:16] or None
 except OSError:
     src = None
-out = {"lib_sha256_16": sha, "src_sha256_16": src, "brain_map": a.map, "dims": {"M": M, "d": d, "H": H},
+sys.path.insert(0, ROOT)
+import __graft_entry__ as G  # noqa: E402
+# hash of the GEMM engine's sources in THIS tree (run this right after the capture, on the tree that was profiled)
+gemm_src = G.source_hash(G.GEMM_SOURCES)[:16] if src == G.source_hash()[:16] else None
+out = {"lib_sha256_16": sha, "src_sha256_16": src, "gemm_src_sha256_16": gemm_src, "brain_map": a.map, "dims": {"M": M, "d": d, "H": H},
        "source": f"{os.path.relpath(a.raw_csv, ROOT)} (ncu --set full --clock-control none, one launch per kernel, "
                  f"tools/layer_bench.py --once --assign {a.map})",
        "kernels": kernels}
