@@ -312,8 +312,11 @@ int forde_attn_bwd(void* stream, const void* q, const void* k, const void* v, co
 
 /* ---- the same for medium sequences, 1 <= T <= forde_attn2_max_tokens() (= 256: the ViT-B/16 vision tower's 197
  * tokens).  One persistent CTA per SM walks the (batch, head) items: all operands of an item in shared
- * memory (TMA ring, next item's loads in flight), scores of both 128-row blocks in TMEM, softmax on 8 warps
- * (TMEM lane quarter x column half).  The backward additionally reads the forward output `o` (D = rowsum(dO * o)). */
+ * memory (next item's loads in flight), scores of both 128-row blocks in TMEM.  Forward: one warp group per row
+ * block, a thread owns a score row, row block 1 issued half an item behind row block 0, o written by TMA (so `o` must
+ * be a [B][T][ld] tensor the 3-D tensor map can describe: 16-byte aligned, ld % 8 == 0).  Backward: 8 softmax warps
+ * (TMEM lane quarter x column half) + 4 read-out warps; it additionally reads the forward output `o`
+ * (D = rowsum(dO * o)). */
 int forde_attn2_max_tokens(void);
 int forde_attn2_fwd(void* stream, const void* q, const void* k, const void* v, void* o, float* lse, int B, int T,
                     int heads, long long ld);
