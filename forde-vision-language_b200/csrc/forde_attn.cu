@@ -11,17 +11,21 @@
 //   forward : S = Q K^T (M = 128 query rows padded, N = Tpad keys, K = 64)           -> TMEM cols [0, 128)
 //             one thread per query row: p = exp2(S * scale * log2e - max), row sum   -> P (bf16) in shared memory
 //             O = P V (K = Tpad)                                                      -> TMEM cols [128, 192)
-//             o = O / rowsum -> bf16 -> global ; lse = ln sum_j exp(scale * s_j)
+//             o = O / rowsum -> bf16 -> the (idle) P buffer -> one TMA store ; lse = ln sum_j exp(scale * s_j)
 //   backward: S = Q K^T, dP = dO V^T                                                  -> TMEM [0,128), [128,256)
 //             p = exp2(S * scale * log2e - lse * log2e) ; D = sum_j p dP ; dS = p (dP - D) scale   (two passes over
 //             TMEM instead of keeping 256 values per thread)                         -> P, dS (bf16) in shared memory
 //             dV = P^T dO, dK = dS^T Q, dQ = dS K                                     -> TMEM [0,64), [64,128), [128,192)
+//             each gradient -> bf16 rows in a swizzled staging tile -> one TMA store (rows beyond T clipped)
 //             (operand tiles double buffered: the next head's 64 KB load while this one computes)
-// What bounds it: TMEM reads (64 B/clk per SM).  A backward item reads S and dP twice and the three gradients once,
-// ~300 KB = 2.4 us of the ~7 us an item takes; more CTAs per SM do not help (measured in round 2 with compact
-// Tpad-row tiles, 2-3 CTAs per SM: forward 38 -> 65 us, backward 101 -> 108 us per text layer, reverted), nor does
-// double-buffering the operand loads much (107 -> 101 us, kept).  Shipped: forward 38 us + backward 101 us per
-// text layer at C2 against 207 us for cuDNN's kernels.
+// What bounds it: latency.  Five warps per CTA walk an item's phases one after the other (ncu: 8 % occupancy, MUFU
+// 13 %, tensor 6 %, profiles/r2_ncu_full_aux_kernels.md); a backward item reads S and dP twice and the three gradients
+// once from TMEM (~300 KB = 2.3 k clocks at the measured 128 B/clk/SM) of the ~10 k clocks it takes.  More CTAs per SM
+// do not help (measured in round 2 with compact Tpad-row tiles, 2-3 CTAs per SM: forward 38 -> 65 us, backward 101 ->
+// 108 us per text layer, reverted) and a second item in flight per CTA does not fit (operands + P + dS = 128 KB per
+// item).  Double-buffering the operand loads (107 -> 101 us) and writing dQ / dK / dV through staged TMA stores
+// instead of per-thread 128-byte rows (104 -> 93 us, same box) are kept.  Shipped: forward 45 us + backward 93 us per
+// text layer at C2 (B = 256, 8 heads) against 50 + 195 us for cuDNN's kernels.
 // Rows / keys beyond T: TMA zero-fills them (3-D tensor map {columns, tokens, batch}), masked keys get p = 0, and the
 // padded query rows of P / dS are written as zeros because they are reduction (K) indices of dV and dK.
 // Roles: warps 0-3 = one thread per row (TMEM lane quarter = warp), warp 4 = TMA + MMA issue (one thread).
@@ -48,6 +52,7 @@ constexpr float kLn2 = 0.6931471805599453f;
 
 struct AttnParams {
   CUtensorMap tmQ, tmK, tmV, tmDO;
+  CUtensorMap tmO, tmDQ, tmDK, tmDV;   // outputs leave through shared memory and TMA stores (rows beyond T clipped)
   __nv_bfloat16* o;      // forward output [B*T][ld]
   float* lse;            // [B][heads][T]
   __nv_bfloat16 *dq, *dk, *dv;
@@ -63,21 +68,30 @@ __device__ __forceinline__ uint32_t sw128_chunk(uint32_t base, int r, int col) {
          ((static_cast<uint32_t>((col & 63) >> 3) ^ static_cast<uint32_t>(r & 7)) << 4);
 }
 
-__device__ __forceinline__ void store_row64(__nv_bfloat16* dst, const uint32_t* v0, const uint32_t* v1, float mul) {
-  // 64 fp32 accumulator values (two 32-column TMEM loads) -> 64 bf16 = 128 contiguous bytes
-  uint4* d4 = reinterpret_cast<uint4*>(dst);
+__device__ __forceinline__ void at_bar_sync(int id, int threads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
+__device__ __forceinline__ void at_tma_store_3d(const void* tmap, uint32_t smem_src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+               :
+               : "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_src), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+// 64 fp32 accumulator values of row r (two 32-column TMEM loads) -> 64 bf16 in a [128 rows][64 cols] staging tile with
+// TMA's 128-byte swizzle.  (Every thread storing its own 128-byte row to global memory -- 32 lines per store
+// instruction -- is what the first version of these kernels spent most of an item on.)
+__device__ __forceinline__ void stage_row64(uint32_t tile_u, int r, const uint32_t* v0, const uint32_t* v1, float mul) {
+  const uint32_t row = tile_u + static_cast<uint32_t>(r) * 128u, rx = static_cast<uint32_t>(r & 7);
 #pragma unroll
   for (int half = 0; half < 2; ++half) {
     const uint32_t* v = half == 0 ? v0 : v1;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      uint4 q;
-      q.x = pack_bf16x2(__uint_as_float(v[8 * j + 0]) * mul, __uint_as_float(v[8 * j + 1]) * mul);
-      q.y = pack_bf16x2(__uint_as_float(v[8 * j + 2]) * mul, __uint_as_float(v[8 * j + 3]) * mul);
-      q.z = pack_bf16x2(__uint_as_float(v[8 * j + 4]) * mul, __uint_as_float(v[8 * j + 5]) * mul);
-      q.w = pack_bf16x2(__uint_as_float(v[8 * j + 6]) * mul, __uint_as_float(v[8 * j + 7]) * mul);
-      d4[half * 4 + j] = q;
-    }
+    for (int j = 0; j < 4; ++j)
+      st_shared_v4(row + ((static_cast<uint32_t>(half * 4 + j) ^ rx) << 4),
+                   pack_bf16x2(__uint_as_float(v[8 * j + 0]) * mul, __uint_as_float(v[8 * j + 1]) * mul),
+                   pack_bf16x2(__uint_as_float(v[8 * j + 2]) * mul, __uint_as_float(v[8 * j + 3]) * mul),
+                   pack_bf16x2(__uint_as_float(v[8 * j + 4]) * mul, __uint_as_float(v[8 * j + 5]) * mul),
+                   pack_bf16x2(__uint_as_float(v[8 * j + 6]) * mul, __uint_as_float(v[8 * j + 7]) * mul));
   }
 }
 
@@ -100,6 +114,7 @@ __global__ void __launch_bounds__(AT_THREADS) attn_fwd_kernel(const __grid_const
     tma_prefetch_desc(&p.tmQ);
     tma_prefetch_desc(&p.tmK);
     tma_prefetch_desc(&p.tmV);
+    tma_prefetch_desc(&p.tmO);
     mbar_init(bar_load, 1);
     mbar_init(bar_s, 1);
     mbar_init(bar_p, 128);
@@ -164,6 +179,11 @@ __global__ void __launch_bounds__(AT_THREADS) attn_fwd_kernel(const __grid_const
         for (int j = 0; j < 32; ++j)
           if (c0 + j < T) mx = fmaxf(mx, __uint_as_float(v[j]) * sl2);
       }
+      // the P buffer also carried the previous item's O on its way out: that TMA store must have read it
+      if (it != static_cast<int>(blockIdx.x)) {
+        if (threadIdx.x == 0) tma_wait_read<0>();
+        at_bar_sync(1, 128);
+      }
       float sum = 0.f;
       for (int c0 = 0; c0 < Tpad; c0 += 32) {
         uint32_t v[32];
@@ -193,10 +213,16 @@ __global__ void __launch_bounds__(AT_THREADS) attn_fwd_kernel(const __grid_const
       tmem_ld32(taddr + 128, o0);
       tmem_ld32(taddr + 160, o1);
       tmem_wait_ld();
-      if (r < T)
-        store_row64(p.o + (static_cast<size_t>(b) * T + r) * p.ld + h * AT_DH, o0, o1, 1.f / sum);
       tc_fence_before();
+      stage_row64(sP_u, r, o0, o1, 1.f / sum);   // P V has completed: tile 0 of the P buffer is idle
+      fence_proxy_async_smem();
+      at_bar_sync(1, 128);
+      if (threadIdx.x == 0) {
+        at_tma_store_3d(&p.tmO, sP_u, h * AT_DH, 0, b);
+        tma_commit();
+      }
     }
+    if (threadIdx.x == 0) tma_wait_all<0>();     // the last store has landed before the CTA retires
   }
   tc_fence_before();
   __syncthreads();
@@ -214,7 +240,8 @@ __global__ void __launch_bounds__(AT_THREADS) attn_bwd_kernel(const __grid_const
   uint8_t* sOp = smem;                                   // [2 stages][Q, K, V, dO] x 16 KB
   uint8_t* sP = smem + 8 * AT_TILE;                      // [2][128][64] bf16
   uint8_t* sDS = smem + 10 * AT_TILE;                    // [2][128][64] bf16
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 12 * AT_TILE);
+  uint8_t* sOut = smem + 12 * AT_TILE;                   // [2] gradient tiles on their way out (TMA stores)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 14 * AT_TILE);
   uint64_t* bar_load = bars;       // [2] TMA bytes of Q, K, V, dO of a stage
   uint64_t* bar_sdp = bars + 2;    // S and dP complete
   uint64_t* bar_pds = bars + 3;    // P and dS written by the 128 row threads
@@ -227,6 +254,9 @@ __global__ void __launch_bounds__(AT_THREADS) attn_bwd_kernel(const __grid_const
     tma_prefetch_desc(&p.tmK);
     tma_prefetch_desc(&p.tmV);
     tma_prefetch_desc(&p.tmDO);
+    tma_prefetch_desc(&p.tmDQ);
+    tma_prefetch_desc(&p.tmDK);
+    tma_prefetch_desc(&p.tmDV);
     mbar_init(&bar_load[0], 1);
     mbar_init(&bar_load[1], 1);
     mbar_init(bar_sdp, 1);
@@ -305,9 +335,10 @@ __global__ void __launch_bounds__(AT_THREADS) attn_bwd_kernel(const __grid_const
   } else {
     const int r = warp * 32 + lane;                                    // query row (S, dP, dQ) / key row (dK, dV)
     const uint32_t taddr = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
-    const uint32_t sP_u = smem_u32(sP), sDS_u = smem_u32(sDS);
+    const uint32_t sP_u = smem_u32(sP), sDS_u = smem_u32(sDS), sOut_u = smem_u32(sOut);
     const float sl2 = p.scale * kLog2e;
     uint32_t ph = 0;
+    int stage = 0;                                                     // staging tiles alternate
     for (int it = blockIdx.x; it < items; it += gridDim.x, ph ^= 1u) {
       const int b = it / p.heads, h = it - b * p.heads;
       const float lse2 = (r < T) ? p.lse[(static_cast<size_t>(b) * p.heads + h) * T + r] * kLog2e : 0.f;
@@ -351,31 +382,34 @@ __global__ void __launch_bounds__(AT_THREADS) attn_bwd_kernel(const __grid_const
       mbar_arrive(bar_pds);
       mbar_wait(bar_g, ph);
       tc_fence_after();
-      const size_t row_off = (static_cast<size_t>(b) * T + r) * p.ld + h * AT_DH;
-      {
+      // dQ, dK, dV: TMEM -> bf16 rows in a swizzled staging tile -> one TMA store each (two tiles, alternating; rows
+      // beyond T are clipped by the tensor map)
+      auto read_out = [&](uint32_t tcol, const CUtensorMap* tm, bool last) {
+        if (threadIdx.x == 0) tma_wait_read<1>();      // the store that used this tile two read-outs ago has read it
+        at_bar_sync(1, 128);
         uint32_t a0[32], a1[32];
-        tmem_ld32(taddr + 128, a0);
-        tmem_ld32(taddr + 160, a1);
+        tmem_ld32(taddr + tcol, a0);
+        tmem_ld32(taddr + tcol + 32, a1);
         tmem_wait_ld();
-        if (r < T) store_row64(p.dq + row_off, a0, a1, 1.f);
-      }
-      {
-        uint32_t a0[32], a1[32];
-        tmem_ld32(taddr + 64, a0);
-        tmem_ld32(taddr + 96, a1);
-        tmem_wait_ld();
-        if (r < T) store_row64(p.dk + row_off, a0, a1, 1.f);
-      }
-      {
-        uint32_t a0[32], a1[32];
-        tmem_ld32(taddr, a0);
-        tmem_ld32(taddr + 32, a1);
-        tmem_wait_ld();
-        if (r < T) store_row64(p.dv + row_off, a0, a1, 1.f);
-      }
-      tc_fence_before();
-      mbar_arrive(bar_epi);
+        if (last) {                                    // the gradients have left TMEM: the next item's S / dP may start
+          tc_fence_before();
+          mbar_arrive(bar_epi);
+        }
+        const uint32_t tile_u = sOut_u + stage * AT_TILE;
+        stage_row64(tile_u, r, a0, a1, 1.f);
+        fence_proxy_async_smem();
+        at_bar_sync(1, 128);
+        if (threadIdx.x == 0) {
+          at_tma_store_3d(tm, tile_u, h * AT_DH, 0, b);
+          tma_commit();
+        }
+        stage ^= 1;
+      };
+      read_out(128, &p.tmDQ, false);
+      read_out(64, &p.tmDK, false);
+      read_out(0, &p.tmDV, true);
     }
+    if (threadIdx.x == 0) tma_wait_all<0>();           // the last stores have landed before the CTA retires
   }
   tc_fence_before();
   __syncthreads();
@@ -386,16 +420,17 @@ __global__ void __launch_bounds__(AT_THREADS) attn_bwd_kernel(const __grid_const
 }
 
 constexpr int attn_fwd_smem() { return 5 * AT_TILE + 256 + 1024; }
-constexpr int attn_bwd_smem() { return 12 * AT_TILE + 256 + 1024; }
+constexpr int attn_bwd_smem() { return 14 * AT_TILE + 256 + 1024; }
 
 static int fill_attn(AttnParams& p, const void* q, const void* k, const void* v, const void* d_o, int B, int T,
-                     int heads, long long ld) {
+                     int heads, long long ld, void* o = nullptr, void* dq = nullptr, void* dk = nullptr,
+                     void* dv = nullptr) {
   if (q == nullptr || k == nullptr || v == nullptr || B <= 0 || T <= 0 || heads <= 0) return FORDE_EINVAL;
   if (T > AT_ROWS || ld < static_cast<long long>(heads) * AT_DH) return FORDE_EINVAL;
   const uint64_t w = static_cast<uint64_t>(heads) * AT_DH;
-  CUtensorMap* maps[4] = {&p.tmQ, &p.tmK, &p.tmV, &p.tmDO};
-  const void* ptrs[4] = {q, k, v, d_o};
-  for (int i = 0; i < 4; ++i) {
+  CUtensorMap* maps[8] = {&p.tmQ, &p.tmK, &p.tmV, &p.tmDO, &p.tmO, &p.tmDQ, &p.tmDK, &p.tmDV};
+  const void* ptrs[8] = {q, k, v, d_o, o, dq, dk, dv};
+  for (int i = 0; i < 8; ++i) {
     if (ptrs[i] == nullptr) continue;
     const int rc = make_tmap_bf16_3d(maps[i], ptrs[i], w, static_cast<uint64_t>(T),
                                      static_cast<uint64_t>(B), static_cast<uint64_t>(ld),
@@ -420,7 +455,7 @@ int forde_attn_fwd(void* stream, const void* q, const void* k, const void* v, vo
   if (o == nullptr || lse == nullptr) return FORDE_EINVAL;
   if ((reinterpret_cast<uintptr_t>(o) & 15) != 0 || (ld & 7) != 0) return FORDE_EALIGN;
   AttnParams p = {};
-  int rc = fill_attn(p, q, k, v, nullptr, B, T, heads, ld);
+  int rc = fill_attn(p, q, k, v, nullptr, B, T, heads, ld, o);
   if (rc != FORDE_OK) return rc;
   p.o = static_cast<__nv_bfloat16*>(o);
   p.lse = lse;
@@ -443,7 +478,7 @@ int forde_attn_bwd(void* stream, const void* q, const void* k, const void* v, co
       (ld & 7) != 0)
     return FORDE_EALIGN;
   AttnParams p = {};
-  int rc = fill_attn(p, q, k, v, d_o, B, T, heads, ld);
+  int rc = fill_attn(p, q, k, v, d_o, B, T, heads, ld, nullptr, dq, dk, dv);
   if (rc != FORDE_OK) return rc;
   p.lse = const_cast<float*>(lse);
   p.dq = static_cast<__nv_bfloat16*>(dq);
