@@ -42,3 +42,19 @@ def test_gpu_arm_refuses_to_run_without_a_gpu():
         return
     r = _run("--steps", "1")
     assert r.returncode != 0 and "no CPU fallback" in (r.stderr + r.stdout)
+
+
+def test_committed_ncu_traffic_table_belongs_to_the_gemm_engine_in_this_tree():
+    """bench.py quotes `roofline.traffic` from profiles/ncu_traffic.json only when that capture was taken on a library
+    whose GEMM engine is built from the sources in the tree (or on the very binary / source set).  The committed table
+    must pass that gate, otherwise the bench line silently loses its DRAM-traffic evidence: re-capture it
+    (tools/r2_final2.sh + tools/ncu_traffic.py) after touching csrc/forde_gemm.cuh, forde_api.cu, sm100_ptx.cuh,
+    forde_host.h or include/."""
+    import __graft_entry__ as G
+    with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+        tj = json.load(f)
+    assert tj.get("gemm_src_sha256_16") == G.source_hash(G.GEMM_SOURCES)[:16], \
+        "profiles/ncu_traffic.json was captured on different GEMM-engine sources"
+    assert set(tj["kernels"]) >= {"sl_up_fwd[50432x768x3072]", "sl_dz_bwd[50432x768x3072]"}
+    for k in tj["kernels"].values():
+        assert k["traffic_bytes"] > 0 and k["algorithmic_bytes"] > 0
