@@ -483,18 +483,30 @@ def attn_max_tokens() -> int:
     return _lib.load().forde_attn2_max_tokens()
 
 
+def _attn_pitch(*tensors) -> int:
+    """The attention entry points take one row pitch for every operand and result: all of them must be row-major with
+    unit column stride and the SAME row stride (raises instead of reading or writing with the wrong pitch)."""
+    ld = tensors[0].stride(0)
+    for t in tensors:
+        if t.dim() != 2 or t.stride(1) != 1 or t.stride(0) != ld:
+            raise _lib.FordeError(f"attention operands must share one row pitch and have unit column stride "
+                                  f"(got strides {[tuple(x.stride()) for x in tensors]})")
+    return ld
+
+
 def attn_fwd(q, k, v, B: int, T: int, heads: int, blocked=None):
     """q, k, v: bf16 [B*T, heads*64].  Returns (o [B*T, heads*64] bf16, lse [B, heads, T] fp32).
     T <= 128 runs the one-tile kernel, longer sequences (<= 256) the blocked one; ``blocked`` forces the choice."""
     for t, n in ((q, "q"), (k, "k"), (v, "v")):
         _req(t, torch.bfloat16, n)
     assert q.shape == k.shape == v.shape == (B * T, heads * 64)
-    o = torch.empty_like(q)
+    ld = _attn_pitch(q, k, v)
+    o = torch.empty_strided(q.shape, (ld, 1), dtype=q.dtype, device=q.device)   # the C ABI has ONE row pitch for all
     lse = torch.empty((B, heads, T), dtype=torch.float32, device=q.device)
     if blocked is None:
         blocked = T > attn_short_max_tokens()
     fn = _lib.load().forde_attn2_fwd if blocked else _lib.load().forde_attn_fwd
-    rc = fn(_stream(), q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr(), lse.data_ptr(), B, T, heads, q.stride(0))
+    rc = fn(_stream(), q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr(), lse.data_ptr(), B, T, heads, ld)
     _lib.check(rc, "forde_attn2_fwd" if blocked else "forde_attn_fwd")
     return o, lse
 
@@ -502,7 +514,8 @@ def attn_fwd(q, k, v, B: int, T: int, heads: int, blocked=None):
 def attn_bwd(q, k, v, d_o, lse, B: int, T: int, heads: int, o=None, blocked=None):
     """``o`` (the forward output) is read by the blocked kernel only (D = rowsum(dO * o))."""
     _req(d_o, torch.bfloat16, "d_o"); _req(lse, torch.float32, "lse")
-    dq, dk, dv = torch.empty_like(q), torch.empty_like(q), torch.empty_like(q)
+    ld = _attn_pitch(q, k, v, d_o, *(() if o is None else (o,)))
+    dq, dk, dv = (torch.empty_strided(q.shape, (ld, 1), dtype=q.dtype, device=q.device) for _ in range(3))
     if blocked is None:
         blocked = T > attn_short_max_tokens()
     if blocked:
@@ -511,11 +524,11 @@ def attn_bwd(q, k, v, d_o, lse, B: int, T: int, heads: int, o=None, blocked=None
         _req(o, torch.bfloat16, "o")
         rc = _lib.load().forde_attn2_bwd(_stream(), q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr(),
                                          d_o.data_ptr(), lse.data_ptr(), dq.data_ptr(), dk.data_ptr(), dv.data_ptr(),
-                                         B, T, heads, q.stride(0))
+                                         B, T, heads, ld)
         _lib.check(rc, "forde_attn2_bwd")
         return dq, dk, dv
     rc = _lib.load().forde_attn_bwd(_stream(), q.data_ptr(), k.data_ptr(), v.data_ptr(), d_o.data_ptr(), lse.data_ptr(),
-                                    dq.data_ptr(), dk.data_ptr(), dv.data_ptr(), B, T, heads, q.stride(0))
+                                    dq.data_ptr(), dk.data_ptr(), dv.data_ptr(), B, T, heads, ld)
     _lib.check(rc, "forde_attn_bwd")
     return dq, dk, dv
 
